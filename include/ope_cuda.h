@@ -1,0 +1,145 @@
+/* ope_cuda.h — C ABI of libope_cuda.so: the B200 (sm_100a) implementation of the registration hot path of
+ * gopi-erabati/Object-Pose-Estimation.
+ *
+ * The reference has no FFI for this path: it instantiates header-only PCL templates in its own translation
+ * units. The entry points below are what the PCL-style shim classes in include/ope_pcl/ bind;
+ * each cites the reference interface it replaces (paths relative to /root/reference; VP =
+ * DetectAndLocalize/include/pcl/registration; [UPSTREAM] = un-vendored PCL, restated in SURVEY Appendix A).
+ *
+ * Conventions
+ *   - every function returns OPE_OK (0) or a negative OPE_ERR_* (include/ope_types.h); nothing throws or
+ *     aborts across the ABI; ope_last_error() returns a description of the last failure of that context;
+ *   - host buffers are caller-owned and only read/written during the call; device memory is library-owned
+ *     behind opaque handles; points are float triples `stride` BYTES apart starting at byte `offset`
+ *     (so PCL's 32-byte PointXYZRGB / 48-byte PointXYZRGBNormal structs can be passed as they are, A.9);
+ *     normals are float triples (+ curvature where stated); matrices are 4x4 column-major (Eigen::Matrix4f);
+ *   - calls are synchronous from the caller's view (like align()/compute()), one ope_ctx per host thread;
+ *   - there is NO CPU fallback: without a usable CUDA device every call fails with OPE_ERR_NO_DEVICE.
+ */
+#ifndef OPE_CUDA_H_
+#define OPE_CUDA_H_
+
+#include "ope_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ope_ctx ope_ctx;
+typedef struct ope_cloud ope_cloud;
+typedef struct ope_pose_tracker ope_pose_tracker;
+
+/* ---- context -------------------------------------------------------------------------------------- */
+/* `stream` is a cudaStream_t to run on (e.g. torch.cuda.current_stream().cuda_stream) or NULL to create one. */
+int ope_ctx_create(int device, void* stream, ope_ctx** out);
+void ope_ctx_destroy(ope_ctx* ctx);
+const char* ope_last_error(const ope_ctx* ctx);
+int ope_ctx_synchronize(ope_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int64_t ope_ctx_launch_count(const ope_ctx* ctx);
+/* library / build identification: "ope_cuda <version> sm_100a" */
+const char* ope_version(void);
+
+/* ---- clouds (device-resident float4 copies of PCL clouds) -------------------------------- */
+/* pcl::PointCloud<PointT> -> device. normals may be NULL. Replaces PCLBase::setInputCloud /
+ * Registration::setInputSource / setInputTarget (VP/registration_mod.h:150-200) as the point where data is handed over. */
+int ope_cloud_upload(ope_ctx* ctx, const void* pts, size_t n, size_t stride, size_t offset,
+                     const void* normals, size_t nstride, size_t noffset, ope_cloud** out);
+int ope_cloud_free(ope_ctx* ctx, ope_cloud* cloud);
+size_t ope_cloud_size(const ope_cloud* cloud);
+int ope_cloud_has_normals(const ope_cloud* cloud);
+/* device -> host: xyz as float triples (3*n floats), normals as nx,ny,nz,curvature (4*n floats); either may be NULL */
+int ope_cloud_download(ope_ctx* ctx, const ope_cloud* cloud, float* xyz, float* normals4);
+/* pcl::copyPointCloud(cloud, indices, out) on the device (D&L/src/poseestimator.cpp:145) */
+int ope_cloud_select(ope_ctx* ctx, const ope_cloud* cloud, const int32_t* idx, size_t n, ope_cloud** out);
+/* pcl::transformPointCloud[WithNormals] -> new cloud (D&L/src/poseestimator.cpp:68,358; VP/impl/icp_mod.hpp:48-115) */
+int ope_cloud_transform(ope_ctx* ctx, const ope_cloud* cloud, const float T[16], ope_cloud** out);
+/* attach normals computed by ope_normals_knn to the cloud (pcl::copyPointCloud(normals, pointnormal), :201) */
+int ope_cloud_set_normals(ope_ctx* ctx, ope_cloud* cloud, const float* normals4);
+
+/* ---- spatial search: replaces pcl::search::KdTree / KdTreeFLANN -------------------------- */
+/* nearestKSearch for nq host queries; out_idx/out_d2 are nq*k, padded with -1 / +inf. k <= 32. */
+int ope_knn(ope_ctx* ctx, const ope_cloud* tgt, const void* qry, size_t nq, size_t stride, size_t offset, int k,
+            int32_t* out_idx, float* out_d2);
+/* same with the queries already on the device */
+int ope_knn_cloud(ope_ctx* ctx, const ope_cloud* tgt, const ope_cloud* qry, int k, int32_t* out_idx, float* out_d2);
+/* radiusSearch (d2 < r*r, ascending index). offsets: nq+1; out_idx/out_d2 up to `capacity` entries (may be NULL
+ * to only count). Returns OPE_ERR_CAPACITY when total > capacity; *total is always set. */
+int ope_radius_cloud(ope_ctx* ctx, const ope_cloud* tgt, const ope_cloud* qry, float radius, int64_t capacity,
+                     int64_t* offsets, int32_t* out_idx, float* out_d2, int64_t* total);
+
+/* ---- down-sampling ------------------------------------------------------------------------------------ */
+/* pcl::UniformSampling::setRadiusSearch(leaf) + compute(indices) (D&L/src/poseestimator.cpp:141-144).
+ * out_idx must hold ope_cloud_size entries; ascending voxel-key order. */
+int ope_uniform_sample(ope_ctx* ctx, const ope_cloud* cloud, float leaf, int32_t* out_idx, size_t* out_n);
+/* the same, result kept on the device as a new cloud (fused copyPointCloud) */
+int ope_uniform_sample_cloud(ope_ctx* ctx, const ope_cloud* cloud, float leaf, ope_cloud** out);
+/* pcl::VoxelGrid::setLeafSize + filter (D&L/src/processingpcd.cpp:45-59). rgb: packed float per
+ * point or NULL. out_xyz holds 3*n floats, out_rgb n floats (or NULL). */
+int ope_voxel_grid(ope_ctx* ctx, const ope_cloud* cloud, const float* rgb, float lx, float ly, float lz,
+                   float* out_xyz, float* out_rgb, size_t* out_n);
+
+/* ---- features ------------------------------------------------------------------------------------------- */
+/* pcl::NormalEstimation::setKSearch(k) + compute (D&L/src/poseestimator.cpp:151-156, BM/src/regmeshpcd.cpp:74-90;
+ * SURVEY A.4). Writes the normals into the cloud (device) and, if out4 != NULL, to the host (n*4). */
+int ope_normals_knn(ope_ctx* ctx, ope_cloud* cloud, int k, const float viewpoint[3], float* out4);
+/* pcl::FPFHEstimation::setRadiusSearch + compute (D&L/src/poseestimator.cpp:121-125). The cloud must
+ * carry normals. out: n*33 floats (host). out_spfh (n*33) may be NULL. */
+int ope_fpfh(ope_ctx* ctx, const ope_cloud* cloud, float radius, float* out, float* out_spfh);
+/* KdTreeFLANN<FPFHSignature33>::nearestKSearch over whole feature sets (SAC-IA findSimilarFeatures):
+ * exact float32 L2_Simple ranking; host feature arrays (rows of `dim` floats). k <= 16. */
+int ope_feature_knn(ope_ctx* ctx, const float* ftgt, size_t nt, const float* fqry, size_t nq, int dim, int k,
+                    int32_t* out_idx, float* out_d2);
+
+/* ---- rigid transform estimation ---------------------------------------------------------------------------- */
+/* TransformationEstimationSVD::estimateRigidTransformation (D&L/src/poseestimator.cpp:306,435).
+ * isrc/itgt: n host indices each, or NULL for identity correspondences over the first n points. */
+int ope_umeyama(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const int32_t* isrc, const int32_t* itgt,
+                size_t n, float T[16]);
+
+/* ---- registration --------------------------------------------------------------------------------------------- */
+/* Registration::getFitnessScore(max_range), VP/impl/registration_mod.hpp:131-165. */
+int ope_fitness(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const float T[16], double max_range,
+                double* out);
+/* determineCorrespondences + rejector chain on the clouds as given (VP/impl/correspondence_estimation_mod.hpp:127-213,
+ * VP/impl/correspondence_estimation_normal_shooting_weighted.hpp:104-145, VP/impl/icp_mod.hpp:194-208). out: ns entries. */
+int ope_correspondences(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const ope_icp_params* prm,
+                        ope_correspondence* out, size_t* out_n);
+/* IterativeClosestPoint[WithNormals]::align(output, guess): VP/impl/registration_mod.hpp:176-219 +
+ * VP/impl/icp_mod.hpp:118-272 (variant VP/impl/icp_modCorr.hpp:118-230). guess may be NULL (identity).
+ * out_corr (ns entries, last iteration's correspondences_) and out_aligned (device cloud = `output`) may be NULL. */
+int ope_icp_align(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const ope_icp_params* prm,
+                  const float guess[16], ope_reg_result* res, ope_correspondence* out_corr, ope_cloud** out_aligned);
+/* SampleConsensusInitialAlignment::align [UPSTREAM ia_ransac.hpp] (D&L/src/poseestimator.cpp:50-64).
+ * fsrc/ftgt: host FPFHSignature33 arrays (ns*33, nt*33). table == NULL: the decisions are drawn from libc rand()
+ * exactly as PCL does (the host owns the RNG stream; the device evaluates the whole pool in one launch).
+ * prm->hypothesis_begin/end restrict the evaluated shard (multi-GPU pools); out_errors: max_iterations floats or NULL. */
+int ope_sacia_align(ope_ctx* ctx, const ope_cloud* src, const float* fsrc, const ope_cloud* tgt, const float* ftgt,
+                    const ope_sacia_params* prm, const ope_rng_table* table, ope_reg_result* res, float* out_errors);
+/* draw the SAC-IA decision table on the host from libc rand() (selectSamples + the pick of findSimilarFeatures) */
+int ope_sacia_draw(const float* src_xyz, size_t ns, size_t stride_bytes, int iterations, int nr_samples,
+                   int k_correspondences, float* min_sample_distance, int32_t* samples, int32_t* picks);
+
+/* ---- PoseEstimator (D&L/src/poseestimator.cpp:16-448) ---------------------------------------------------------- */
+int ope_pose_tracker_create(ope_ctx* ctx, const ope_pose_params* prm, ope_pose_tracker** out);
+void ope_pose_tracker_destroy(ope_pose_tracker* t);
+/* PoseEstimator::estimateFinalPose(p_sourceCloud, p_targetCloud, fitnessScore, alignStrength), :383-448.
+ * source_xyz: ns*3 floats, in/out (overwritten with alignedSource, :441); target: nt points. */
+int ope_pose_estimate_final(ope_pose_tracker* t, float* source_xyz, size_t ns, const void* target, size_t nt,
+                            size_t tstride, size_t toffset, const ope_rng_table* table, ope_pose_result* res);
+/* the same with both clouds resident on the device (bench.py `value`); *source is replaced by alignedSource. */
+int ope_pose_estimate_final_device(ope_pose_tracker* t, ope_cloud** source, const ope_cloud* target,
+                                   const ope_rng_table* table, ope_pose_result* res);
+/* per-stage device time of the last call in milliseconds (CUDA events; same slots as the oracle's stage list:
+ * [0] down-sample [1] normals [2] fpfh [3] sac-ia [4] icp [5] fitness [6] dense umeyama + transforms [7] total) */
+int ope_pose_stage_ms(const ope_pose_tracker* t, double out[8]);
+
+/* defaults of the reference classes (include/ope_types.h) */
+void ope_icp_params_default(ope_icp_params* p);
+void ope_sacia_params_default(ope_sacia_params* p);
+void ope_pose_params_default(ope_pose_params* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPE_CUDA_H_ */

@@ -1,0 +1,409 @@
+// features.cu — NormalEstimation (K4), SPFH/FPFH (K5) and the exact float32 feature-space k-NN (K6 ranking stage).
+//
+// Rooflines: normals read 16 B and write 16 B per point plus a k-neighbour gather that stays in
+// L2; SPFH/FPFH move 428 B per point compulsory (16 pts + 16 normals + 132 SPFH write + 132 SPFH read +
+// 132 FPFH write) plus an m-neighbour gather of 32 B (SPFH pass) / 136 B (FPFH pass) per neighbour from L2.
+#include <algorithm>
+
+#include "ope_host.cuh"
+
+namespace ope {
+
+// ------------------------------------------------------------------------------------------ normals ----
+// thread per point: exact k-NN on the cloud's own grid (the point itself is neighbour 0), covariance summed
+// sequentially in the sorted neighbour order, eigen33, flip toward the viewpoint.
+__global__ void normals_kernel(GridView g, const float4* __restrict__ pts, int n, int k, float vpx, float vpy, float vpz,
+                               float4* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 q = __ldg(pts + i);
+  const float nan = __int_as_float(0x7fc00000);
+  float r[4] = {nan, nan, nan, nan};
+  if (finite3(q.x, q.y, q.z)) {
+    float bd[32];
+    int bi[32];
+    int cnt = grid_knn<32>(g, q.x, q.y, q.z, k, bd, bi);
+    if (cnt >= 3) {
+      CovAccum acc;
+      acc.reset();
+      for (int j = 0; j < cnt; ++j) {
+        float4 p = __ldg(pts + bi[j]);
+        acc.add(p.x, p.y, p.z);
+      }
+      normal_from_accum(acc, cnt, q.x, q.y, q.z, vpx, vpy, vpz, r);
+    }
+  }
+  out[i] = make_float4(r[0], r[1], r[2], r[3]);
+}
+
+// ------------------------------------------------------------------------------------------- SPFH ------
+// warp per point. Lanes stride over the candidate points of each grid row; every in-radius neighbour's three
+// bin indices go to a per-warp shared-memory histogram of integer counts. Because every increment of one
+// point's histogram is the same float (100/(m-1)), the reference's sequence of float additions depends only
+// on the count, so the float bin value is rebuilt exactly by repeated addition afterwards.
+static constexpr int kWarpsPerBlock = 8;
+
+__global__ void spfh_kernel(GridView g, const float4* __restrict__ pts, const float4* __restrict__ nrm, int n, float r2,
+                            int rings, float* __restrict__ spfh) {
+  __shared__ int hist[kWarpsPerBlock][33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p_idx = blockIdx.x * kWarpsPerBlock + warp;
+  if (p_idx >= n) return;
+  hist[warp][lane] = 0;
+  if (lane == 0) hist[warp][32] = 0;
+  __syncwarp();
+  const float4 q = __ldg(pts + p_idx);
+  int nb_count = 0;
+  if (finite3(q.x, q.y, q.z)) {
+    const float4 qn4 = __ldg(nrm + p_idx);
+    const float qn[3] = {qn4.x, qn4.y, qn4.z};
+    const int cx = grid_cell_coord(q.x, g.ox, g.inv_h), cy = grid_cell_coord(q.y, g.oy, g.inv_h),
+              cz = grid_cell_coord(q.z, g.oz, g.inv_h);
+    const int z0 = max(cz - rings, 0), z1 = min(cz + rings, g.nz - 1);
+    const int y0 = max(cy - rings, 0), y1 = min(cy + rings, g.ny - 1);
+    const int x0 = max(cx - rings, 0), x1 = min(cx + rings, g.nx - 1);
+    if (x0 <= x1)
+      for (int z = z0; z <= z1; ++z)
+        for (int y = y0; y <= y1; ++y) {
+          const int row = (z * g.ny + y) * g.nx;
+          const int b = __ldg(g.cell_start + row + x0), e = __ldg(g.cell_start + row + x1 + 1);
+          for (int i = b + lane; i < e; i += 32) {
+            const float4 c = __ldg(g.pts + i);
+            const float d2 = dist2(q.x, q.y, q.z, c.x, c.y, c.z);
+            if (d2 < r2) {
+              ++nb_count;
+              const int j = __float_as_int(c.w);
+              if (j != p_idx) {
+                const float4 cn4 = __ldg(nrm + j);
+                const float cn[3] = {cn4.x, cn4.y, cn4.z};
+                int h1, h2, h3;
+                pair_feature_bins(q.x, q.y, q.z, qn, c.x, c.y, c.z, cn, h1, h2, h3);
+                atomicAdd(&hist[warp][h1], 1);
+                atomicAdd(&hist[warp][11 + h2], 1);
+                atomicAdd(&hist[warp][22 + h3], 1);
+              }
+            }
+          }
+        }
+  }
+  for (int o = 16; o > 0; o >>= 1) nb_count += __shfl_xor_sync(0xffffffffu, nb_count, o);
+  __syncwarp();
+  const float incr = 100.0f / (float)(nb_count - 1);
+  for (int b = lane; b < 33; b += 32) {
+    const int c = hist[warp][b];
+    float v = 0.0f;
+    for (int t = 0; t < c; ++t) v += incr;
+    spfh[(size_t)p_idx * 33 + b] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- FPFH ------
+// warp per point, lane = histogram bin (lane 0 also carries bin 32). Candidates are examined 32 at a time
+// (one per lane, coalesced float4 loads); the in-radius ones are then consumed in order, each as one
+// coalesced 132-byte read of its SPFH row, weighted by 1/d2 and accumulated in float like the reference
+// (weightPointSPFHSignature). The three normalisation sums are carried in double.
+__global__ void fpfh_kernel(GridView g, const float4* __restrict__ pts, int n, float r2, int rings,
+                            const float* __restrict__ spfh, float* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p_idx = blockIdx.x * kWarpsPerBlock + warp;
+  if (p_idx >= n) return;
+  const float4 q = __ldg(pts + p_idx);
+  float acc = 0.0f, acc32 = 0.0f;
+  double sum = 0.0, sum32 = 0.0;
+  const bool ok = finite3(q.x, q.y, q.z);
+  int found = 0;
+  if (ok) {
+    const int cx = grid_cell_coord(q.x, g.ox, g.inv_h), cy = grid_cell_coord(q.y, g.oy, g.inv_h),
+              cz = grid_cell_coord(q.z, g.oz, g.inv_h);
+    const int z0 = max(cz - rings, 0), z1 = min(cz + rings, g.nz - 1);
+    const int y0 = max(cy - rings, 0), y1 = min(cy + rings, g.ny - 1);
+    const int x0 = max(cx - rings, 0), x1 = min(cx + rings, g.nx - 1);
+    if (x0 <= x1)
+      for (int z = z0; z <= z1; ++z)
+        for (int y = y0; y <= y1; ++y) {
+          const int row = (z * g.ny + y) * g.nx;
+          const int b = __ldg(g.cell_start + row + x0), e = __ldg(g.cell_start + row + x1 + 1);
+          for (int base = b; base < e; base += 32) {
+            const int i = base + lane;
+            float d2 = FLT_MAX;
+            int j = -1;
+            if (i < e) {
+              const float4 c = __ldg(g.pts + i);
+              d2 = dist2(q.x, q.y, q.z, c.x, c.y, c.z);
+              j = __float_as_int(c.w);
+            }
+            const bool inr = d2 < r2;
+            unsigned in_mask = __ballot_sync(0xffffffffu, inr);
+            found += __popc(in_mask);
+            unsigned use_mask = __ballot_sync(0xffffffffu, inr && d2 != 0.0f);
+            while (use_mask) {
+              const int src = __ffs(use_mask) - 1;
+              use_mask &= use_mask - 1;
+              const float dj = __shfl_sync(0xffffffffu, d2, src);
+              const int jj = __shfl_sync(0xffffffffu, j, src);
+              const float w = 1.0f / dj;
+              const float* hrow = spfh + (size_t)jj * 33;
+              const float val = __ldg(hrow + lane) * w;
+              sum += val;
+              acc += val;
+              if (lane == 0) {
+                const float v32 = __ldg(hrow + 32) * w;
+                sum32 += v32;
+                acc32 += v32;
+              }
+            }
+          }
+        }
+  }
+  // per-sub-histogram sums: bins 0-10 | 11-21 | 22-32
+  const unsigned full = 0xffffffffu;
+  double s1 = (lane <= 10) ? sum : 0.0, s2 = (lane >= 11 && lane <= 21) ? sum : 0.0, s3 = (lane >= 22) ? sum : 0.0;
+  if (lane == 0) s3 += sum32;
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(full, s1, o);
+    s2 += __shfl_xor_sync(full, s2, o);
+    s3 += __shfl_xor_sync(full, s3, o);
+  }
+  if (s1 != 0) s1 = 100.0 / s1;
+  if (s2 != 0) s2 = 100.0 / s2;
+  if (s3 != 0) s3 = 100.0 / s3;
+  const float nan = __int_as_float(0x7fc00000);
+  float* o = out + (size_t)p_idx * 33;
+  if (!ok || found == 0) {
+    o[lane] = nan;
+    if (lane == 0) o[32] = nan;
+    return;
+  }
+  const double sc = lane <= 10 ? s1 : (lane <= 21 ? s2 : s3);
+  o[lane] = acc * (float)sc;
+  if (lane == 0) o[32] = acc32 * (float)s3;
+}
+
+// ------------------------------------------------------------------------------- feature-space k-NN ----
+// Exact float32 ranking: d = sum_c (q_c - t_c)^2 accumulated left to right (FLANN L2_Simple over 33 floats),
+// ties on the smaller index. One thread per query; the block streams target tiles through shared memory
+// (coalesced 16 KB tiles, every thread reads the same target row -> shared-memory broadcast). The target
+// range is split over blockIdx.y so small query sets still fill the SMs; a merge kernel combines the splits.
+static constexpr int kFkQueries = 128;   // threads per block = queries per block
+static constexpr int kFkTile = 64;       // targets per shared-memory tile
+static constexpr int kFkMaxDim = 64;
+static constexpr int kFkMaxK = 16;
+
+__global__ void feature_knn_kernel(const float* __restrict__ ftgt, int nt, const float* __restrict__ fqry, int nq, int dim,
+                                   int k, int t_per_split, int* __restrict__ part_idx, float* __restrict__ part_d2) {
+  extern __shared__ float tile[];  // kFkTile * dim
+  const int qi = blockIdx.x * kFkQueries + threadIdx.x;
+  const int t_begin = blockIdx.y * t_per_split, t_end = min(nt, t_begin + t_per_split);
+  float q[kFkMaxDim];
+  if (qi < nq)
+    for (int c = 0; c < dim; ++c) q[c] = __ldg(fqry + (size_t)qi * dim + c);
+  float bd[kFkMaxK];
+  int bi[kFkMaxK];
+  int cnt = 0;
+  for (int t0 = t_begin; t0 < t_end; t0 += kFkTile) {
+    const int tn = min(kFkTile, t_end - t0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < tn * dim; e += blockDim.x) tile[e] = __ldg(ftgt + (size_t)t0 * dim + e);
+    __syncthreads();
+    if (qi < nq) {
+      for (int t = 0; t < tn; ++t) {
+        const float* f = tile + t * dim;
+        float d = 0.0f;
+        for (int c = 0; c < dim; ++c) { float df = q[c] - f[c]; d += df * df; }
+        if (!isfinite(d)) continue;
+        const int idx = t0 + t;
+        if (cnt == k && !nb_less(d, idx, bd[k - 1], bi[k - 1])) continue;
+        int j = cnt < k ? cnt : k - 1;
+        while (j > 0 && nb_less(d, idx, bd[j - 1], bi[j - 1])) { bd[j] = bd[j - 1]; bi[j] = bi[j - 1]; --j; }
+        bd[j] = d; bi[j] = idx;
+        if (cnt < k) ++cnt;
+      }
+    }
+  }
+  if (qi < nq) {
+    const size_t o = ((size_t)qi * gridDim.y + blockIdx.y) * k;
+    for (int j = 0; j < k; ++j) { part_idx[o + j] = j < cnt ? bi[j] : -1; part_d2[o + j] = j < cnt ? bd[j] : INFINITY; }
+  }
+}
+__global__ void feature_knn_merge_kernel(const int* __restrict__ part_idx, const float* __restrict__ part_d2, int nq,
+                                         int splits, int k, int* __restrict__ out_idx, float* __restrict__ out_d2) {
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= nq) return;
+  float bd[kFkMaxK];
+  int bi[kFkMaxK];
+  int cnt = 0;
+  for (int s = 0; s < splits; ++s)
+    for (int e = 0; e < k; ++e) {
+      const size_t o = ((size_t)qi * splits + s) * k + e;
+      const int idx = part_idx[o];
+      if (idx < 0) break;
+      const float d = part_d2[o];
+      if (cnt == k && !nb_less(d, idx, bd[k - 1], bi[k - 1])) continue;
+      int j = cnt < k ? cnt : k - 1;
+      while (j > 0 && nb_less(d, idx, bd[j - 1], bi[j - 1])) { bd[j] = bd[j - 1]; bi[j] = bi[j - 1]; --j; }
+      bd[j] = d; bi[j] = idx;
+      if (cnt < k) ++cnt;
+    }
+  for (int j = 0; j < k; ++j) {
+    out_idx[(size_t)qi * k + j] = j < cnt ? bi[j] : -1;
+    if (out_d2) out_d2[(size_t)qi * k + j] = j < cnt ? bd[j] : INFINITY;
+  }
+}
+
+// ------------------------------------------------------------------ removeNaNNormalsFromPointCloud ----
+__global__ void finite_normal_flag_kernel(const float4* __restrict__ nrm, int n, int* __restrict__ flags) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 v = __ldg(nrm + i);
+  flags[i] = finite3(v.x, v.y, v.z) ? 1 : 0;
+}
+__global__ void compact_cloud_kernel(const float4* __restrict__ pts, const float4* __restrict__ nrm, int n,
+                                     const int* __restrict__ pos, float4* __restrict__ opts, float4* __restrict__ onrm) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (pos[i + 1] > pos[i]) { opts[pos[i]] = __ldg(pts + i); onrm[pos[i]] = __ldg(nrm + i); }
+}
+
+// ================================================================================================ host ==
+int normals_device(ope_ctx* ctx, ope_cloud* cloud, int k, const float vp[3]) {
+  if (k < 1 || k > 32) return fail(ctx, OPE_ERR_INVALID, "normal estimation k must be in [1, 32]");
+  if (!cloud->normals) OPE_TRY(dalloc(ctx, &cloud->normals, cloud->n));
+  if (cloud->n == 0) return OPE_OK;
+  OPE_TRY(cloud_bbox(ctx, cloud));
+  GridView g;
+  OPE_TRY(cloud_grid(ctx, cloud, knn_cell_size(cloud, k), &g));
+  normals_kernel<<<div_up(cloud->n, 128), 128, 0, ctx->stream>>>(g, cloud->pts, (int)cloud->n, k, vp[0], vp[1], vp[2],
+                                                                 cloud->normals);
+  return check_launch(ctx, "normals_kernel");
+}
+
+int fpfh_device(ope_ctx* ctx, const ope_cloud* cloud, float radius, float** d_fpfh, float** d_spfh_out) {
+  *d_fpfh = nullptr;
+  if (d_spfh_out) *d_spfh_out = nullptr;
+  if (!cloud->normals) return fail(ctx, OPE_ERR_INVALID, "FPFH needs normals (setInputNormals)");
+  const size_t n = cloud->n;
+  float *spfh = nullptr, *fpfh = nullptr;
+  OPE_TRY(dalloc(ctx, &spfh, n * 33));
+  int rc = dalloc(ctx, &fpfh, n * 33);
+  if (rc != OPE_OK) { dfree(ctx, spfh); return rc; }
+  if (n > 0) {
+    GridView g;
+    rc = cloud_grid(ctx, cloud, radius * 0.5f, &g);
+    if (rc == OPE_OK) {
+      const int rings = grid_radius_rings(g, radius);
+      const float r2 = radius * radius;
+      const unsigned blocks = div_up(n, kWarpsPerBlock);
+      spfh_kernel<<<blocks, kWarpsPerBlock * 32, 0, ctx->stream>>>(g, cloud->pts, cloud->normals, (int)n, r2, rings, spfh);
+      rc = check_launch(ctx, "spfh_kernel");
+      if (rc == OPE_OK) {
+        fpfh_kernel<<<blocks, kWarpsPerBlock * 32, 0, ctx->stream>>>(g, cloud->pts, (int)n, r2, rings, spfh, fpfh);
+        rc = check_launch(ctx, "fpfh_kernel");
+      }
+    }
+  }
+  if (rc != OPE_OK) { dfree(ctx, spfh); dfree(ctx, fpfh); return rc; }
+  *d_fpfh = fpfh;
+  if (d_spfh_out) *d_spfh_out = spfh; else dfree(ctx, spfh);
+  return OPE_OK;
+}
+
+int feature_knn_device(ope_ctx* ctx, const float* d_ftgt, size_t nt, const float* d_fqry, size_t nq, int dim, int k,
+                       int* d_idx, float* d_d2) {
+  if (dim < 1 || dim > kFkMaxDim) return fail(ctx, OPE_ERR_INVALID, "feature dimension must be in [1, %d]", kFkMaxDim);
+  if (k < 1 || k > kFkMaxK) return fail(ctx, OPE_ERR_INVALID, "feature k must be in [1, %d]", kFkMaxK);
+  if (nq == 0) return OPE_OK;
+  const unsigned qblocks = div_up(nq, kFkQueries);
+  // enough target splits to give every SM a block, at least one tile each
+  int splits = (int)std::max<size_t>(1, std::min<size_t>((size_t)(2 * ctx->sm_count + qblocks - 1) / qblocks,
+                                                         (nt + kFkTile - 1) / kFkTile));
+  splits = std::min(splits, 1024);
+  int t_per_split = (int)((nt + splits - 1) / std::max(splits, 1));
+  t_per_split = std::max(kFkTile, (t_per_split + kFkTile - 1) / kFkTile * kFkTile);
+  splits = (int)std::max<size_t>(1, (nt + t_per_split - 1) / t_per_split);
+  Scratch<int> pi(ctx);
+  Scratch<float> pd(ctx);
+  OPE_TRY(pi.alloc(nq * splits * k));
+  OPE_TRY(pd.alloc(nq * splits * k));
+  dim3 grid(qblocks, splits);
+  feature_knn_kernel<<<grid, kFkQueries, kFkTile * dim * sizeof(float), ctx->stream>>>(d_ftgt, (int)nt, d_fqry, (int)nq, dim,
+                                                                                        k, t_per_split, pi.p, pd.p);
+  OPE_TRY(check_launch(ctx, "feature_knn_kernel"));
+  feature_knn_merge_kernel<<<div_up(nq, 128), 128, 0, ctx->stream>>>(pi.p, pd.p, (int)nq, splits, k, d_idx, d_d2);
+  return check_launch(ctx, "feature_knn_merge_kernel");
+}
+
+int remove_nan_normals_device(ope_ctx* ctx, ope_cloud** cloud) {
+  ope_cloud* c = *cloud;
+  if (!c->normals || c->n == 0) return OPE_OK;
+  const size_t n = c->n;
+  Scratch<int> flags(ctx);
+  OPE_TRY(flags.alloc(n + 1));
+  OPE_CUDA_TRY(ctx, cudaMemsetAsync(flags.p + n, 0, sizeof(int), ctx->stream));
+  finite_normal_flag_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(c->normals, (int)n, flags.p);
+  OPE_TRY(check_launch(ctx, "finite_normal_flag_kernel"));
+  OPE_TRY(exclusive_scan_i32(ctx, flags.p, n + 1));
+  void* h;
+  OPE_TRY(read_back(ctx, flags.p + n, sizeof(int), &h));
+  const size_t m = (size_t) * (const int*)h;
+  if (m == n) return OPE_OK;
+  ope_cloud* o = nullptr;
+  OPE_TRY(cloud_alloc(ctx, m, true, &o));
+  compact_cloud_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(c->pts, c->normals, (int)n, flags.p, o->pts, o->normals);
+  int rc = check_launch(ctx, "compact_cloud_kernel");
+  if (rc != OPE_OK) { ope_cloud_free(ctx, o); return rc; }
+  ope_cloud_free(ctx, c);
+  *cloud = o;
+  return OPE_OK;
+}
+
+}  // namespace ope
+
+// =========================================================================================== C ABI =====
+using namespace ope;
+
+extern "C" {
+
+int ope_normals_knn(ope_ctx* ctx, ope_cloud* cloud, int k, const float viewpoint[3], float* out4) {
+  if (!ctx || !cloud) return OPE_ERR_INVALID;
+  const float zero[3] = {0, 0, 0};
+  OPE_TRY(normals_device(ctx, cloud, k, viewpoint ? viewpoint : zero));
+  if (out4 && cloud->n)
+    OPE_CUDA_TRY(ctx, cudaMemcpyAsync(out4, cloud->normals, cloud->n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+  OPE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return OPE_OK;
+}
+
+int ope_fpfh(ope_ctx* ctx, const ope_cloud* cloud, float radius, float* out, float* out_spfh) {
+  if (!ctx || !cloud || !out || !(radius > 0)) return OPE_ERR_INVALID;
+  float *f = nullptr, *s = nullptr;
+  OPE_TRY(fpfh_device(ctx, cloud, radius, &f, &s));
+  cudaError_t e = cudaSuccess;
+  if (cloud->n) {
+    e = cudaMemcpyAsync(out, f, cloud->n * 33 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && out_spfh)
+      e = cudaMemcpyAsync(out_spfh, s, cloud->n * 33 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  dfree(ctx, f); dfree(ctx, s);
+  if (e != cudaSuccess) return fail(ctx, OPE_ERR_CUDA, "fpfh download failed: %s", cudaGetErrorString(e));
+  return OPE_OK;
+}
+
+int ope_feature_knn(ope_ctx* ctx, const float* ftgt, size_t nt, const float* fqry, size_t nq, int dim, int k,
+                    int32_t* out_idx, float* out_d2) {
+  if (!ctx || !ftgt || !fqry || !out_idx) return OPE_ERR_INVALID;
+  Scratch<float> dt(ctx), dq(ctx), dd(ctx);
+  Scratch<int> di(ctx);
+  OPE_TRY(dt.alloc(nt * dim)); OPE_TRY(dq.alloc(nq * dim)); OPE_TRY(dd.alloc(nq * k)); OPE_TRY(di.alloc(nq * k));
+  if (nt) OPE_CUDA_TRY(ctx, cudaMemcpyAsync(dt.p, ftgt, nt * dim * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  if (nq) OPE_CUDA_TRY(ctx, cudaMemcpyAsync(dq.p, fqry, nq * dim * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  OPE_TRY(feature_knn_device(ctx, dt.p, nt, dq.p, nq, dim, k, di.p, dd.p));
+  if (nq) {
+    OPE_CUDA_TRY(ctx, cudaMemcpyAsync(out_idx, di.p, nq * k * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_d2) OPE_CUDA_TRY(ctx, cudaMemcpyAsync(out_d2, dd.p, nq * k * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  OPE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return OPE_OK;
+}
+
+}  // extern "C"

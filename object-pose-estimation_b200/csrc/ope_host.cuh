@@ -1,0 +1,158 @@
+// ope_host.cuh — host-side internals of libope_cuda.so: context, device clouds, cached grids, scratch memory.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ope_cuda.h"
+#include "ope_grid.cuh"
+
+struct ope_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool owns_stream = false;
+  int sm_count = 148;
+  int64_t launches = 0;
+  std::string error;
+  void* pinned = nullptr;      // small pinned staging buffer for scalar read-backs
+  size_t pinned_bytes = 0;
+};
+
+// How points are binned into cells: c = (int)floorf((p - o) * inv) - min_b, per axis.
+//  * search grids: o = bbox min, inv = 1/h, min_b = 0
+//  * PCL voxel frames (UniformSampling / VoxelGrid): o = 0, inv = 1/leaf, min_b = floor(min*inv)
+struct Binning {
+  float o[3];
+  float inv[3];
+  int min_b[3];
+  int dim[3];
+};
+
+struct GridEntry {
+  float h = 0;
+  ope::GridView view{};
+  int* cell_start = nullptr;
+  float4* sorted = nullptr;
+  int64_t ncells = 0;
+};
+
+struct ope_cloud {
+  ope_ctx* ctx = nullptr;
+  size_t n = 0;
+  float4* pts = nullptr;       // x, y, z, 1
+  float4* normals = nullptr;   // nx, ny, nz, curvature (optional)
+  bool bbox_valid = false;
+  float bbox[6];               // min xyz, max xyz over finite points
+  int n_finite = 0;
+  std::vector<GridEntry> grids;
+};
+
+namespace ope {
+
+inline int fail(ope_ctx* ctx, int code, const char* fmt, ...) {
+  if (ctx) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    ctx->error = buf;
+  }
+  return code;
+}
+
+#define OPE_CUDA_TRY(ctx, expr)                                                                       \
+  do {                                                                                                \
+    cudaError_t e__ = (expr);                                                                         \
+    if (e__ != cudaSuccess)                                                                           \
+      return ope::fail((ctx), OPE_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+#define OPE_TRY(expr)            \
+  do {                           \
+    int rc__ = (expr);           \
+    if (rc__ != OPE_OK) return rc__; \
+  } while (0)
+
+// stream-ordered scratch allocation (cudaMallocAsync pool, release threshold = keep everything cached)
+template <typename T>
+inline int dalloc(ope_ctx* ctx, T** p, size_t count) {
+  *p = nullptr;
+  if (count == 0) count = 1;
+  OPE_CUDA_TRY(ctx, cudaMallocAsync((void**)p, count * sizeof(T), ctx->stream));
+  return OPE_OK;
+}
+template <typename T>
+inline void dfree(ope_ctx* ctx, T* p) {
+  if (p) cudaFreeAsync((void*)p, ctx->stream);
+}
+// RAII scratch buffer
+template <typename T>
+struct Scratch {
+  ope_ctx* ctx;
+  T* p = nullptr;
+  explicit Scratch(ope_ctx* c) : ctx(c) {}
+  ~Scratch() { dfree(ctx, p); }
+  int alloc(size_t count) { return dalloc(ctx, &p, count); }
+  Scratch(const Scratch&) = delete;
+  Scratch& operator=(const Scratch&) = delete;
+};
+
+inline int check_launch(ope_ctx* ctx, const char* what) {
+  ctx->launches++;
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(ctx, OPE_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+  }
+  return OPE_OK;
+}
+
+// copy `bytes` from device to the pinned staging buffer and wait; returns the host pointer
+inline int read_back(ope_ctx* ctx, const void* dsrc, size_t bytes, void** host) {
+  if (bytes > ctx->pinned_bytes) return fail(ctx, OPE_ERR_INVALID, "read_back larger than staging buffer");
+  OPE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pinned, dsrc, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  OPE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  *host = ctx->pinned;
+  return OPE_OK;
+}
+
+inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// ---- implemented in grid.cu ----
+int cloud_alloc(ope_ctx* ctx, size_t n, bool with_normals, ope_cloud** out);
+int cloud_bbox(ope_ctx* ctx, ope_cloud* c);
+// cached search grid with cell edge ~h (adjusted to respect the cell cap)
+int cloud_grid(ope_ctx* ctx, const ope_cloud* c, float h, GridView* out);
+// suggested cell edge for k-NN queries against this cloud (surface-density heuristic)
+float knn_cell_size(const ope_cloud* c, int k);
+int exclusive_scan_i32(ope_ctx* ctx, int* data, size_t n);
+// build cell_start (ncells+1) and the cell-sorted, index-ordered point array for an arbitrary binning
+int build_cells(ope_ctx* ctx, const float4* pts, size_t n, const Binning& bin, int** cell_start, float4** sorted);
+// device-side versions used by the pipeline
+int uniform_sample_device(ope_ctx* ctx, ope_cloud* cloud, float leaf, int** d_idx, size_t* out_n);
+int gather_cloud(ope_ctx* ctx, const ope_cloud* cloud, const int* d_idx, size_t n, ope_cloud** out);
+
+// ---- features.cu ----
+int normals_device(ope_ctx* ctx, ope_cloud* cloud, int k, const float vp[3]);
+int fpfh_device(ope_ctx* ctx, const ope_cloud* cloud, float radius, float** d_fpfh, float** d_spfh_or_null);
+int feature_knn_device(ope_ctx* ctx, const float* d_ftgt, size_t nt, const float* d_fqry, size_t nq, int dim, int k,
+                       int* d_idx, float* d_d2);
+int remove_nan_normals_device(ope_ctx* ctx, ope_cloud** cloud);
+
+// ---- registration.cu ----
+int transform_device(ope_ctx* ctx, const ope_cloud* in, const Mat4& T, ope_cloud* out);
+int umeyama_device(ope_ctx* ctx, const float4* src, const float4* tgt, const int* d_isrc, const int* d_itgt, size_t n,
+                   float T[16]);
+int fitness_device(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const Mat4& T, double max_range, double* out);
+int icp_device(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const ope_icp_params& prm, const Mat4& guess,
+               ope_reg_result* res, ope_correspondence* out_corr_host, ope_cloud** out_aligned);
+int sacia_device(ope_ctx* ctx, const ope_cloud* src, const float* d_fsrc, const ope_cloud* tgt, const float* d_ftgt,
+                 const ope_sacia_params& prm, const ope_rng_table* table, const float* host_src_xyz3, ope_reg_result* res,
+                 float* out_errors_host);
+
+}  // namespace ope

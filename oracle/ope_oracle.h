@@ -1,0 +1,116 @@
+/* ope_oracle.h — TEST INFRASTRUCTURE: C ABI of the CPU oracle (libope_oracle.so).
+ *
+ * A single-threaded CPU restatement of the reference's registration hot path (SURVEY section 8c,
+ * Appendix A). Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may load it, and only as the checker / timed baseline. The product (libope_cuda.so) never links,
+ * loads or calls it.
+ *
+ * PARITY UNPINNED: the arithmetic of the reference lives in PCL/FLANN/Eigen, none of which exist in
+ * this container, and the reference ships no golden vectors; each function below cites the reference
+ * call site or vendored source it follows and SURVEY Appendix A for the [UPSTREAM] algorithm.
+ *
+ * Conventions: points are float triples at `stride` floats apart (stride >= 3); normals are float
+ * quadruples nx,ny,nz,curvature at stride 4; matrices are 4x4 column-major (Eigen::Matrix4f).
+ */
+#ifndef OPE_ORACLE_H_
+#define OPE_ORACLE_H_
+
+#include "../include/ope_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- search (KdTreeFLANN semantics) ---- */
+/* k-NN of each query in tgt; out_idx/out_d2 are nq*k, padded with -1 / +inf when fewer than k exist.
+ * brute != 0 uses an O(N*M) scan instead of the kd-tree (they must agree). */
+int orc_knn(const float* tgt, size_t nt, size_t tstride, const float* qry, size_t nq, size_t qstride,
+            int k, int brute, int32_t* out_idx, float* out_d2);
+/* radius search, d2 < r*r strict, ascending index. offsets is nq+1; idx/d2 hold up to `capacity`
+ * entries. Returns the total count (which may exceed capacity: call again with a larger buffer). */
+int64_t orc_radius(const float* tgt, size_t nt, size_t tstride, const float* qry, size_t nq, size_t qstride,
+                   float radius, int64_t capacity, int64_t* offsets, int32_t* out_idx, float* out_d2);
+/* feature-space k-NN, L2_Simple over `dim` floats summed left to right (K6). Brute force. */
+int orc_feature_knn(const float* ftgt, size_t nt, const float* fqry, size_t nq, int dim, int k,
+                    int32_t* out_idx, float* out_d2);
+
+/* ---- down-sampling ---- */
+/* pcl::UniformSampling::compute (call site D&L/src/poseestimator.cpp:141-145). Output indices in
+ * ascending voxel-key order. out_idx must hold n entries. */
+int orc_uniform_sample(const float* pts, size_t n, size_t stride, float leaf, int32_t* out_idx, size_t* out_n);
+/* pcl::VoxelGrid::filter (call site D&L/src/processingpcd.cpp:45-59). rgb may be NULL; otherwise
+ * n packed 0x00RRGGBB floats averaged per channel. Outputs hold up to n entries. */
+int orc_voxel_grid(const float* pts, size_t n, size_t stride, const float* rgb, float lx, float ly, float lz,
+                   float* out_xyz /* M*3 */, float* out_rgb /* M or NULL */, size_t* out_n);
+
+/* ---- features ---- */
+/* pcl::NormalEstimation::compute with setKSearch(k) (call sites D&L/src/poseestimator.cpp:151-156,
+ * BM/src/regmeshpcd.cpp:74-90). out is n*4: nx, ny, nz, curvature. */
+int orc_normals_knn(const float* pts, size_t n, size_t stride, int k, const float vp[3], float* out);
+/* pcl::FPFHEstimation::compute with setRadiusSearch(radius) (call site D&L/src/poseestimator.cpp:121-125).
+ * normals n*4; out n*33. */
+int orc_fpfh(const float* pts, size_t n, size_t stride, const float* normals, float radius, float* out);
+/* SPFH pass only (n*33), exposed for stage-wise parity tests. */
+int orc_spfh(const float* pts, size_t n, size_t stride, const float* normals, float radius, float* out);
+
+/* ---- rigid transforms ---- */
+/* TransformationEstimationSVD::estimateRigidTransformation with index lists (NULL = identity correspondences,
+ * D&L/src/poseestimator.cpp:429-435). */
+int orc_umeyama(const float* src, size_t sstride, const float* tgt, size_t tstride, const int32_t* is,
+                const int32_t* it, size_t n, float T[16]);
+/* pcl::transformPointCloud / transformPointCloudWithNormals arithmetic. normals may be NULL. */
+int orc_transform(const float* pts, size_t n, size_t stride, const float* normals, const float T[16],
+                  float* out_pts /* n*3 */, float* out_normals /* n*4 or NULL */);
+
+/* ---- registration ---- */
+/* Registration::getFitnessScore(max_range), VP/impl/registration_mod.hpp:131-165. */
+int orc_fitness(const float* src, size_t ns, size_t sstride, const float* tgt, size_t nt, size_t tstride,
+                const float T[16], double max_range, double* out);
+/* One correspondence-estimation + rejector pass (VP/impl/correspondence_estimation_mod.hpp:127-213,
+ * normal shooting per VP/impl/correspondence_estimation_normal_shooting_weighted.hpp:104-145, rejector chain
+ * VP/impl/icp_mod.hpp:194-208) on clouds as given. out holds ns entries. */
+int orc_correspondences(const float* src, size_t ns, size_t sstride, const float* src_normals,
+                        const float* tgt, size_t nt, size_t tstride, const float* tgt_normals,
+                        const ope_icp_params* prm, ope_correspondence* out, size_t* out_n);
+/* IterativeClosestPoint[WithNormals]::align, VP/impl/registration_mod.hpp:176-219 + VP/impl/icp_mod.hpp:118-272.
+ * Normals may be NULL when the configuration does not need them. out_corr (ns entries) may be NULL. */
+int orc_icp(const float* src, size_t ns, size_t sstride, const float* src_normals,
+            const float* tgt, size_t nt, size_t tstride, const float* tgt_normals,
+            const ope_icp_params* prm, const float guess[16], ope_reg_result* res,
+            ope_correspondence* out_corr);
+/* Draw the libc rand() decisions of a SAC-IA run (selectSamples + the pick in findSimilarFeatures)
+ * WITHOUT reseeding: consumes the process-wide rand() stream exactly as PCL would. samples/picks hold
+ * iterations*nr_samples entries. min_sample_distance is in/out (it is halved after 3*N failed draws). */
+int orc_sacia_draw(const float* src, size_t ns, size_t sstride, int iterations, int nr_samples,
+                   int k_correspondences, float* min_sample_distance, int32_t* samples, int32_t* picks);
+/* SampleConsensusInitialAlignment::align [UPSTREAM ia_ransac.hpp] (call site D&L/src/poseestimator.cpp:50-64).
+ * table == NULL -> decisions are drawn from libc rand() on the fly (same stream as orc_sacia_draw). */
+int orc_sacia(const float* src, size_t ns, size_t sstride, const float* fsrc,
+              const float* tgt, size_t nt, size_t tstride, const float* ftgt,
+              const ope_sacia_params* prm, const ope_rng_table* table, ope_reg_result* res,
+              float* out_errors /* max_iterations floats or NULL */);
+void orc_srand(unsigned seed);
+
+/* ---- PoseEstimator (D&L/src/poseestimator.cpp:16-448) ---- */
+typedef struct orc_pose_estimator orc_pose_estimator;
+orc_pose_estimator* orc_pose_create(const ope_pose_params* prm);
+void orc_pose_destroy(orc_pose_estimator*);
+/* estimateFinalPose(p_sourceCloud, p_targetCloud, fitness, strength), :383-448. `source` is the caller's
+ * in/out cloud (n*3 floats, overwritten with alignedSource like *p_sourceCloud = *alignedSource, :441).
+ * The table, when given, replays the SAC-IA decisions. */
+int orc_pose_estimate_final(orc_pose_estimator*, float* source, size_t ns, const float* target, size_t nt,
+                            size_t tstride, const ope_rng_table* table, ope_pose_result* res);
+/* per-stage wall-clock of the last estimate_final call, seconds:
+ * [0] down-sample [1] normals [2] fpfh [3] sac-ia ("Initial Alignment") [4] icp ("Final Alignment")
+ * [5] fitness [6] dense umeyama + transforms [7] total */
+void orc_pose_stage_seconds(const orc_pose_estimator*, double out[8]);
+
+/* default-initialisers (reference defaults, include/ope_types.h) */
+void orc_icp_params_default(ope_icp_params*);
+void orc_sacia_params_default(ope_sacia_params*);
+void orc_pose_params_default(ope_pose_params*);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

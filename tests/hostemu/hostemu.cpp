@@ -1,0 +1,118 @@
+// tests/hostemu/hostemu.cpp — TEST INFRASTRUCTURE. Compiles the product's OPE_HD device functions
+// (csrc/ope_device.cuh, csrc/ope_grid.cuh) with the HOST compiler so their per-query logic (ring search
+// termination, tie order, eigen33, pair features, SVD) can be checked against the oracle without a GPU.
+// The grid is built serially here with the same binning formula as csrc/grid.cu. Never shipped, never loaded
+// by the product.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+using std::isfinite;
+#include "../../object-pose-estimation_b200/csrc/ope_grid.cuh"
+
+using namespace ope;
+
+namespace {
+struct HostGrid {
+  GridView v;
+  std::vector<int> cell_start;
+  std::vector<float4> sorted;
+};
+
+void build(const float* xyz, int n, float h, HostGrid& g) {
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  int nf = 0;
+  for (int i = 0; i < n; ++i) {
+    const float* p = xyz + 3 * i;
+    if (!finite3(p[0], p[1], p[2])) continue;
+    ++nf;
+    for (int d = 0; d < 3; ++d) { mn[d] = std::min(mn[d], p[d]); mx[d] = std::max(mx[d], p[d]); }
+  }
+  if (nf == 0) { mn[0] = mn[1] = mn[2] = mx[0] = mx[1] = mx[2] = 0; }
+  int dim[3];
+  for (int d = 0; d < 3; ++d) dim[d] = (int)std::floor((double)(mx[d] - mn[d]) / h) + 1;
+  const float inv = 1.0f / h;
+  auto cell = [&](const float* p) {
+    int c[3];
+    for (int d = 0; d < 3; ++d) {
+      c[d] = (int)floorf((p[d] - mn[d]) * inv);
+      c[d] = std::min(std::max(c[d], 0), dim[d] - 1);
+    }
+    return ((int64_t)c[2] * dim[1] + c[1]) * dim[0] + c[0];
+  };
+  int64_t ncells = (int64_t)dim[0] * dim[1] * dim[2];
+  g.cell_start.assign(ncells + 1, 0);
+  for (int i = 0; i < n; ++i) { const float* p = xyz + 3 * i; if (finite3(p[0], p[1], p[2])) g.cell_start[cell(p) + 1]++; }
+  for (int64_t c = 0; c < ncells; ++c) g.cell_start[c + 1] += g.cell_start[c];
+  std::vector<int> cur(g.cell_start.begin(), g.cell_start.end() - 1);
+  g.sorted.resize(nf);
+  for (int i = 0; i < n; ++i) {  // ascending i => index-ordered within a cell
+    const float* p = xyz + 3 * i;
+    if (!finite3(p[0], p[1], p[2])) continue;
+    g.sorted[cur[cell(p)]++] = make_float4(p[0], p[1], p[2], i2f(i));
+  }
+  g.v.ox = mn[0]; g.v.oy = mn[1]; g.v.oz = mn[2]; g.v.h = h; g.v.inv_h = inv;
+  g.v.nx = dim[0]; g.v.ny = dim[1]; g.v.nz = dim[2]; g.v.n = nf;
+  g.v.cell_start = g.cell_start.data(); g.v.pts = g.sorted.data();
+}
+}  // namespace
+
+extern "C" {
+
+int emu_knn(const float* tgt, int nt, const float* qry, int nq, int k, float h, float max_d2, int* out_idx, float* out_d2) {
+  HostGrid g;
+  build(tgt, nt, h, g);
+  for (int i = 0; i < nq; ++i) {
+    const float* q = qry + 3 * i;
+    float bd[32]; int bi[32]; int cnt = 0;
+    if (k == 1) {
+      float d2; int idx = grid_nn1(g.v, q[0], q[1], q[2], max_d2, d2);
+      if (idx >= 0) { bd[0] = d2; bi[0] = idx; cnt = 1; }
+    } else cnt = grid_knn<32>(g.v, q[0], q[1], q[2], k, bd, bi);
+    for (int j = 0; j < k; ++j) { out_idx[i * k + j] = j < cnt ? bi[j] : -1; out_d2[i * k + j] = j < cnt ? bd[j] : INFINITY; }
+  }
+  return 0;
+}
+
+// radius count via the ring visitor
+int emu_radius_count(const float* tgt, int nt, const float* qry, int nq, float radius, float h, int* counts) {
+  HostGrid g;
+  build(tgt, nt, h, g);
+  const int rings = grid_radius_rings(g.v, radius);
+  const float r2 = radius * radius;
+  for (int i = 0; i < nq; ++i) {
+    const float* q = qry + 3 * i;
+    int cnt = 0;
+    int cx = grid_cell_coord(q[0], g.v.ox, g.v.inv_h), cy = grid_cell_coord(q[1], g.v.oy, g.v.inv_h), cz = grid_cell_coord(q[2], g.v.oz, g.v.inv_h);
+    grid_visit_shell(g.v, cx, cy, cz, rings, -1, [&](float px, float py, float pz, int) { if (dist2(q[0], q[1], q[2], px, py, pz) < r2) ++cnt; });
+    counts[i] = cnt;
+  }
+  return 0;
+}
+
+// normal of point q from an explicit neighbour list (indices into pts)
+void emu_normal(const float* pts, const int* nn, int cnt, const float* q, const float* vp, float* out4) {
+  CovAccum acc; acc.reset();
+  for (int j = 0; j < cnt; ++j) acc.add(pts[3 * nn[j]], pts[3 * nn[j] + 1], pts[3 * nn[j] + 2]);
+  normal_from_accum(acc, cnt, q[0], q[1], q[2], vp[0], vp[1], vp[2], out4);
+}
+
+void emu_pair_bins(const float* p1, const float* n1, const float* p2, const float* n2, int* h) {
+  pair_feature_bins(p1[0], p1[1], p1[2], n1, p2[0], p2[1], p2[2], n2, h[0], h[1], h[2]);
+}
+
+void emu_umeyama_small(const float* s, const float* d, int n, float* T16) {
+  Mat4 M; umeyama_small(s, d, n, M); std::memcpy(T16, M.m, 64);
+}
+
+void emu_umeyama_moments(const float* s, const float* d, int n, float* T16) {
+  double acc[16]; for (int i = 0; i < 16; ++i) acc[i] = 0;
+  for (int i = 0; i < n; ++i) {
+    acc[0] += 1; for (int k = 0; k < 3; ++k) { acc[1 + k] += s[3 * i + k]; acc[4 + k] += d[3 * i + k]; }
+    for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) acc[7 + c * 3 + r] += (double)d[3 * i + r] * (double)s[3 * i + c];
+  }
+  Mat4 M; umeyama_from_moments(acc, M); std::memcpy(T16, M.m, 64);
+}
+
+}  // extern "C"
