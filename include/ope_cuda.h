@@ -37,6 +37,9 @@ const char* ope_last_error(const ope_ctx* ctx);
 int ope_ctx_synchronize(ope_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t ope_ctx_launch_count(const ope_ctx* ctx);
+/* device time (ms, CUDA events on the context's stream) of the last launch of the named dominant kernel:
+ * which = 0: icp_kernel (the fused ICP loop), 1: sacia_kernel (hypothesis pool). Negative if it never ran. */
+double ope_ctx_last_kernel_ms(ope_ctx* ctx, int which);
 /* library / build identification: "ope_cuda <version> sm_100a" */
 const char* ope_version(void);
 
@@ -54,6 +57,9 @@ int ope_cloud_download(ope_ctx* ctx, const ope_cloud* cloud, float* xyz, float* 
 int ope_cloud_select(ope_ctx* ctx, const ope_cloud* cloud, const int32_t* idx, size_t n, ope_cloud** out);
 /* pcl::transformPointCloud[WithNormals] -> new cloud (D&L/src/poseestimator.cpp:68,358; VP/impl/icp_mod.hpp:48-115) */
 int ope_cloud_transform(ope_ctx* ctx, const ope_cloud* cloud, const float T[16], ope_cloud** out);
+/* drop the cached search grids of a cloud, so the next call rebuilds its index (what setInputTarget's
+ * target_cloud_updated_ = true does to the kd-tree, VP/impl/registration_mod.hpp:57-67,80-84) */
+int ope_cloud_invalidate(ope_ctx* ctx, ope_cloud* cloud);
 /* attach normals computed by ope_normals_knn to the cloud (pcl::copyPointCloud(normals, pointnormal), :201) */
 int ope_cloud_set_normals(ope_ctx* ctx, ope_cloud* cloud, const float* normals4);
 

@@ -521,7 +521,25 @@ int ope_ctx_create(int device, void* stream, ope_ctx** out) {
     delete ctx;
     return OPE_ERR_CUDA;
   }
+  for (int w = 0; w < 2; ++w)
+    for (int j = 0; j < 2; ++j) cudaEventCreate(&ctx->kev[w][j]);
   *out = ctx;
+  return OPE_OK;
+}
+
+double ope_ctx_last_kernel_ms(ope_ctx* ctx, int which) {
+  if (!ctx || which < 0 || which > 1 || !ctx->kev_valid[which]) return -1.0;
+  float ms = 0;
+  if (cudaEventSynchronize(ctx->kev[which][1]) != cudaSuccess) return -1.0;
+  if (cudaEventElapsedTime(&ms, ctx->kev[which][0], ctx->kev[which][1]) != cudaSuccess) return -1.0;
+  return (double)ms;
+}
+
+int ope_cloud_invalidate(ope_ctx* ctx, ope_cloud* c) {
+  if (!ctx || !c) return OPE_ERR_INVALID;
+  for (auto& g : c->grids) { dfree(ctx, g.cell_start); dfree(ctx, g.sorted); }
+  c->grids.clear();
+  c->bbox_valid = false;
   return OPE_OK;
 }
 
@@ -529,6 +547,8 @@ void ope_ctx_destroy(ope_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  for (int w = 0; w < 2; ++w)
+    for (int j = 0; j < 2; ++j) if (ctx->kev[w][j]) cudaEventDestroy(ctx->kev[w][j]);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -544,7 +564,7 @@ int ope_ctx_synchronize(ope_ctx* ctx) {
 
 int ope_cloud_upload(ope_ctx* ctx, const void* pts, size_t n, size_t stride, size_t offset, const void* normals,
                      size_t nstride, size_t noffset, ope_cloud** out) {
-  if (!ctx || !out || (n > 0 && !pts) || stride < 12) return OPE_ERR_INVALID;
+  if (!ctx || !out || (n > 0 && (!pts || stride < 12))) return OPE_ERR_INVALID;
   if (n > 0x7fffffffull) return fail(ctx, OPE_ERR_INVALID, "cloud too large");
   ope_cloud* c = nullptr;
   OPE_TRY(cloud_alloc(ctx, n, normals != nullptr, &c));

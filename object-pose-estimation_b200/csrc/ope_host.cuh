@@ -20,6 +20,8 @@ struct ope_ctx {
   std::string error;
   void* pinned = nullptr;      // small pinned staging buffer for scalar read-backs
   size_t pinned_bytes = 0;
+  cudaEvent_t kev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [which][begin/end] around the dominant kernels
+  bool kev_valid[2] = {false, false};
 };
 
 // How points are binned into cells: c = (int)floorf((p - o) * inv) - min_b, per axis.

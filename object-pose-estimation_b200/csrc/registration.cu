@@ -362,25 +362,29 @@ struct SaciaDev {
 static constexpr int kSaciaThreads = 256;
 static constexpr int kSaciaMaxSamples = 16;
 
-// one block per hypothesis: 5-point Umeyama (float, sequential like the reference), then every source point's
+// one block per hypothesis: 5-point Umeyama (double moments, as everywhere), then every source point's
 // truncated NN error in parallel, then the float sum in point order by one thread (bit-exact with the reference's
 // serial `error += ...`, so the first-lowest-error hypothesis is the same one).
 __global__ void __launch_bounds__(kSaciaThreads) sacia_kernel(SaciaDev a) {
   __shared__ Mat4 T;
   const int h = a.h_begin + blockIdx.x;
   if (threadIdx.x == 0) {
-    float s[3 * kSaciaMaxSamples], d[3 * kSaciaMaxSamples];
+    double acc[16];
+    for (int i = 0; i < 16; ++i) acc[i] = 0.0;
     for (int j = 0; j < a.nr_samples; ++j) {
       const int si = a.samples[(size_t)h * a.nr_samples + j];
       const int pick = a.picks[(size_t)h * a.nr_samples + j];
       int ti = a.knn_idx[(size_t)si * a.k_corr + pick];
       if (ti < 0) ti = a.knn_idx[(size_t)si * a.k_corr];  // fewer than k target features
       const float4 sp = __ldg(a.src + si), tp = __ldg(a.tgt + ti);
-      s[3 * j] = sp.x; s[3 * j + 1] = sp.y; s[3 * j + 2] = sp.z;
-      d[3 * j] = tp.x; d[3 * j + 1] = tp.y; d[3 * j + 2] = tp.z;
+      const double sv[3] = {sp.x, sp.y, sp.z}, tv[3] = {tp.x, tp.y, tp.z};
+      acc[0] += 1.0;
+      for (int k = 0; k < 3; ++k) { acc[1 + k] += sv[k]; acc[4 + k] += tv[k]; }
+      for (int c = 0; c < 3; ++c)
+        for (int r = 0; r < 3; ++r) acc[7 + c * 3 + r] += tv[r] * sv[c];
     }
     Mat4 M;
-    umeyama_small(s, d, a.nr_samples, M);
+    umeyama_from_moments(acc, M);  // double moments + double SVD, rounded to float once (same as every other Umeyama here)
     T = M;
     for (int i = 0; i < 16; ++i) a.transforms[(size_t)h * 16 + i] = M.m[i];
   }
@@ -544,7 +548,10 @@ int icp_device(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const o
   a.corr_match = match.p; a.corr_d2 = d2.p; a.partials = partials.p; a.result = dres.p;
   if (rc == OPE_OK) {
     void* args[] = {(void*)&a};
+    cudaEventRecord(ctx->kev[0][0], ctx->stream);
     cudaError_t e = cudaLaunchCooperativeKernel((void*)icp_kernel, dim3(blocks), dim3(kIcpThreads), args, 0, ctx->stream);
+    cudaEventRecord(ctx->kev[0][1], ctx->stream);
+    ctx->kev_valid[0] = true;
     if (e != cudaSuccess) rc = fail(ctx, OPE_ERR_CUDA, "cooperative launch of icp_kernel failed: %s", cudaGetErrorString(e));
     else rc = check_launch(ctx, "icp_kernel");
   }
@@ -659,7 +666,10 @@ int sacia_device(ope_ctx* ctx, const ope_cloud* src, const float* d_fsrc, const 
   a.threshold = (float)prm.max_correspondence_distance;
   a.terms = d_terms.p; a.errors = d_errors.p; a.transforms = d_T.p;
   if (nh > 0) {
+    cudaEventRecord(ctx->kev[1][0], ctx->stream);
     sacia_kernel<<<nh, kSaciaThreads, 0, ctx->stream>>>(a);
+    cudaEventRecord(ctx->kev[1][1], ctx->stream);
+    ctx->kev_valid[1] = true;
     OPE_TRY(check_launch(ctx, "sacia_kernel"));
   }
   sacia_select_kernel<<<1, 32, 0, ctx->stream>>>(d_errors.p, d_T.p, h0, h1, d_res.p);

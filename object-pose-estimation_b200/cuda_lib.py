@@ -21,6 +21,7 @@ i64p = C.POINTER(C.c_int64)
 
 EXPORTS = [
     "ope_ctx_create", "ope_ctx_destroy", "ope_last_error", "ope_ctx_synchronize", "ope_ctx_launch_count", "ope_version",
+    "ope_ctx_last_kernel_ms", "ope_cloud_invalidate",
     "ope_cloud_upload", "ope_cloud_free", "ope_cloud_size", "ope_cloud_has_normals", "ope_cloud_download",
     "ope_cloud_select", "ope_cloud_transform", "ope_cloud_set_normals",
     "ope_knn", "ope_knn_cloud", "ope_radius_cloud",
@@ -59,6 +60,7 @@ def lib():
         L.ope_version.restype = C.c_char_p
         L.ope_ctx_launch_count.restype = C.c_int64
         L.ope_cloud_size.restype = C.c_size_t
+        L.ope_ctx_last_kernel_ms.restype = C.c_double
         _LIB = L
     return _LIB
 
@@ -119,9 +121,10 @@ class Cloud:
         return bool(lib().ope_cloud_has_normals(self.h))
 
     def free(self):
-        if self.h:
+        # a cloud must never outlive its context: after Context.close() the device memory is gone with it
+        if self.h and self.ctx.h:
             lib().ope_cloud_free(self.ctx.h, self.h)
-            self.h = None
+        self.h = None
 
     def __del__(self):
         try:
@@ -151,8 +154,15 @@ class Context:
 
     def close(self):
         if self.h:
+            lib().ope_ctx_synchronize(self.h)
             lib().ope_ctx_destroy(self.h)
             self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def _chk(self, rc):
         if rc != 0:
@@ -164,6 +174,13 @@ class Context:
     @property
     def launches(self):
         return int(lib().ope_ctx_launch_count(self.h))
+
+    def last_kernel_ms(self, which=0):
+        """device time of the last icp_kernel (0) / sacia_kernel (1) launch, from CUDA events on the ctx stream"""
+        return float(lib().ope_ctx_last_kernel_ms(self.h, int(which)))
+
+    def invalidate(self, cloud):
+        self._chk(lib().ope_cloud_invalidate(self.h, cloud.h))
 
     # ---- clouds ----
     def upload(self, pts, normals=None):
@@ -339,9 +356,9 @@ class PoseTracker:
         self.h = h
 
     def close(self):
-        if self.h:
+        if self.h and self.ctx.h:
             lib().ope_pose_tracker_destroy(self.h)
-            self.h = None
+        self.h = None
 
     def __del__(self):
         try:

@@ -119,8 +119,9 @@ def apply(T, pts):
 def pose_error(Ta, Tb):
     """(rotation angle in rad, translation distance in m) between two 4x4 poses."""
     Ra, Rb = np.asarray(Ta, float)[:3, :3], np.asarray(Tb, float)[:3, :3]
-    c = (np.trace(Ra.T @ Rb) - 1) / 2
-    return float(np.arccos(np.clip(c, -1, 1))), float(np.linalg.norm(np.asarray(Ta, float)[:3, 3] - np.asarray(Tb, float)[:3, 3]))
+    # ||Ra - Rb||_F = 2*sqrt(2)*sin(angle/2): well conditioned for tiny angles (arccos of the trace is not)
+    s = np.linalg.norm(Ra - Rb) / (2.0 * np.sqrt(2.0))
+    return float(2.0 * np.arcsin(np.clip(s, 0, 1))), float(np.linalg.norm(np.asarray(Ta, float)[:3, 3] - np.asarray(Tb, float)[:3, 3]))
 
 
 # ------------------------------------------------------------------------------------------ scenes ----

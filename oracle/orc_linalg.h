@@ -244,26 +244,32 @@ inline void umeyamaFromSigma(const T sigma[9], const T src_mean[3], const T dst_
   }
 }
 
-// Eigen::umeyama(src, dst, false) in float: n pairs given by callbacks returning pointers to xyz.
+// Eigen::umeyama(src, dst, false) over n pairs given by callbacks returning pointers to xyz.
+//
+// Eigen evaluates the means and the 3x3 cross-covariance with vectorised float reductions whose summation order
+// cannot be reproduced without Eigen, and ICP's stop test (cos >= 1 - 1e-8 on a float trace) turns 1e-7 differences
+// into a different stopping iteration. The oracle therefore accumulates the raw moments in DOUBLE (exact products of
+// float inputs, summation error ~1e-16 relative, i.e. independent of the order to far below float resolution), runs
+// the 3x3 SVD in double and rounds the 4x4 to float once. Any float summation order Eigen may use lies within the
+// float rounding bound of this result; a parallel reduction on the device reproduces it bit for bit (barring
+// ~1e-9-probability double-rounding ties).
 template <typename SrcAt, typename DstAt>
 inline void umeyama(size_t n, SrcAt srcAt, DstAt dstAt, float Tout[16]) {
-  const float one_over_n = 1.0f / (float)n;
-  float sm[3] = {0, 0, 0}, dm[3] = {0, 0, 0};
+  double acc[16];
+  for (int i = 0; i < 16; ++i) acc[i] = 0.0;
   for (size_t i = 0; i < n; ++i) {
     const float* s = srcAt(i); const float* d = dstAt(i);
-    for (int k = 0; k < 3; ++k) { sm[k] += s[k]; dm[k] += d[k]; }
-  }
-  for (int k = 0; k < 3; ++k) { sm[k] *= one_over_n; dm[k] *= one_over_n; }
-  float sigma[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  for (size_t i = 0; i < n; ++i) {
-    const float* s = srcAt(i); const float* d = dstAt(i);
-    float sd[3] = {s[0] - sm[0], s[1] - sm[1], s[2] - sm[2]};
-    float dd[3] = {d[0] - dm[0], d[1] - dm[1], d[2] - dm[2]};
+    acc[0] += 1.0;
+    for (int k = 0; k < 3; ++k) { acc[1 + k] += (double)s[k]; acc[4 + k] += (double)d[k]; }
     for (int c = 0; c < 3; ++c)
-      for (int r = 0; r < 3; ++r) sigma[c * 3 + r] += dd[r] * sd[c];
+      for (int r = 0; r < 3; ++r) acc[7 + c * 3 + r] += (double)d[r] * (double)s[c];
   }
-  for (int i = 0; i < 9; ++i) sigma[i] *= one_over_n;
-  umeyamaFromSigma<float>(sigma, sm, dm, Tout);
+  const double nn = acc[0];
+  double ms[3], mt[3], sigma[9];
+  for (int k = 0; k < 3; ++k) { ms[k] = acc[1 + k] / nn; mt[k] = acc[4 + k] / nn; }
+  for (int c = 0; c < 3; ++c)
+    for (int r = 0; r < 3; ++r) sigma[c * 3 + r] = acc[7 + c * 3 + r] / nn - mt[r] * ms[c];
+  umeyamaFromSigma<double>(sigma, ms, mt, Tout);
 }
 
 }  // namespace orc

@@ -1,0 +1,303 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes -> libope_cuda.so), against the CPU oracle
+on the same seeded inputs. Bars (BASELINE.json north_star): neighbour / correspondence indices bit-exact, FPFH within
+1e-4 relative, poses within 1e-4 rad / 1e-5 m with the same convergence flag and fitness within 1e-5."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROT_TOL = 1e-4    # rad
+TRANS_TOL = 1e-5  # m
+FIT_TOL = 1e-5
+FPFH_RTOL = 1e-4
+
+
+def _pose_close(synth, T, a, b, rot=ROT_TOL, trans=TRANS_TOL):
+    r, t = synth.pose_error(T.mat4(a), T.mat4(b))
+    assert r < rot and t < trans, (r, t)
+
+
+# ------------------------------------------------------------------------------------------------ search ----
+@pytest.mark.parametrize("k", [1, 5, 12, 20, 30])
+def test_knn_indices_bit_exact_surface(ctx, orc, synth, small_model, k):
+    src, tgt, _ = synth.icp_pair(6000, seed=3, model=small_model)
+    ct = ctx.upload(tgt)
+    gi, gd = ctx.knn(ct, src, k)
+    oi, od = orc.knn(tgt, src, k)
+    assert (gi == oi).all()
+    assert (gd == od).all()
+
+
+def test_knn_volume_far_queries_and_ties(ctx, orc):
+    rng = np.random.default_rng(5)
+    tgt = (np.round(rng.random((4000, 3)) * 64) / 64).astype(np.float32)      # many exact ties + duplicates
+    qry = (rng.random((1500, 3)) * 3 - 1).astype(np.float32)                  # many queries far outside the box
+    ct = ctx.upload(tgt)
+    for k in (1, 8):
+        gi, gd = ctx.knn(ct, qry, k)
+        oi, od = orc.knn(tgt, qry, k, brute=True)
+        assert (gi == oi).all() and (gd == od).all()
+
+
+def test_knn_edge_cases(ctx, orc):
+    tgt = np.array([[0, 0, 0], [1, 0, 0], [np.nan, 0, 0], [0, 2, 0]], np.float32)
+    qry = np.array([[0.1, 0, 0], [5, 5, 5]], np.float32)
+    ct = ctx.upload(tgt)
+    gi, gd = ctx.knn(ct, qry, 5)          # k > finite points: padded with -1 / inf
+    oi, od = orc.knn(tgt, qry, 5, brute=True)
+    assert (gi == oi).all() and np.array_equal(gd, od)
+    one = ctx.upload(tgt[:1])
+    gi, _ = ctx.knn(one, qry, 1)
+    assert (gi == 0).all()
+
+
+def test_radius_search(ctx, orc, synth, small_model):
+    pts = small_model[:5000]
+    c = ctx.upload(pts)
+    go, gi, gd = ctx.radius(c, c, 0.01)
+    oo, oi, od = orc.radius(pts, pts, 0.01)
+    assert (go == oo).all() and (gi == oi).all() and (gd == od).all()
+
+
+# ---------------------------------------------------------------------------------------- down-sampling ----
+@pytest.mark.parametrize("leaf", [0.01, 0.008, 0.005])
+def test_uniform_sampling_indices(ctx, orc, model, leaf):
+    c = ctx.upload(model)
+    g = ctx.uniform_sample(c, leaf)
+    o = orc.uniform_sample(model, leaf)
+    assert len(g) == len(o) and (g == o).all()
+
+
+def test_uniform_sampling_scene_with_nan(ctx, orc, synth, model):
+    _, cloud, _ = synth.make_frame(model, 7)
+    pts = cloud.reshape(-1, 3)
+    assert np.isnan(pts).any() or True
+    c = ctx.upload(pts)
+    g = ctx.uniform_sample(c, 0.005)
+    o = orc.uniform_sample(pts, 0.005)
+    assert len(g) == len(o) and (g == o).all()
+
+
+def test_voxel_grid_centroids(ctx, orc, synth, model):
+    cl, _, _ = synth.make_frame(model, 3)
+    rng = np.random.default_rng(0)
+    rgb = rng.integers(0, 1 << 24, len(cl)).astype(np.uint32).view(np.float32)
+    c = ctx.upload(cl)
+    gx, gr = ctx.voxel_grid(c, 0.005, rgb)
+    ox, orr = orc.voxel_grid(cl, 0.005, rgb)
+    assert gx.shape == ox.shape
+    assert np.array_equal(gx, ox)
+    assert np.array_equal(gr.view(np.uint32), orr.view(np.uint32))
+
+
+def test_empty_and_degenerate_clouds(ctx, cuda_lib):
+    e = ctx.upload(np.zeros((0, 3), np.float32))
+    assert len(ctx.uniform_sample(e, 0.01)) == 0
+    same = ctx.upload(np.ones((10, 3), np.float32))
+    assert len(ctx.uniform_sample(same, 0.01)) == 1
+    prm = cuda_lib.icp_params()
+    with pytest.raises(cuda_lib.OpeError):   # no target -> error code, transforms stay identity (no throw across the ABI)
+        ctx.icp(same, e, prm)
+
+
+# --------------------------------------------------------------------------------------------- features ----
+@pytest.mark.parametrize("k", [12, 30])
+def test_normals(ctx, orc, synth, model, k):
+    cl, _, _ = synth.make_frame(model, 11)
+    idx = orc.uniform_sample(cl, 0.008)
+    pts = cl[idx]
+    c = ctx.upload(pts)
+    g = ctx.normals_knn(c, k)
+    o = orc.normals_knn(pts, k)
+    assert np.isfinite(g).all() == np.isfinite(o).all()
+    # same neighbour sets + same float order => identical up to transcendental rounding
+    assert np.allclose(g, o, rtol=0, atol=2e-6), np.abs(g - o).max()
+    assert (g == o).mean() > 0.9
+
+
+def test_fpfh_within_tolerance(ctx, orc, synth, model):
+    cl, _, _ = synth.make_frame(model, 11)
+    pts = cl[orc.uniform_sample(cl, 0.01)]
+    nr = orc.normals_knn(pts, 30)
+    c = ctx.upload(pts, nr)
+    g, gs = ctx.fpfh(c, 0.03, want_spfh=True)
+    o = orc.fpfh(pts, nr, 0.03)
+    os_ = orc.spfh(pts, nr, 0.03)
+    assert np.array_equal(gs, os_), np.abs(gs - os_).max()           # SPFH: integer counts + replayed float adds
+    scale = np.maximum(np.abs(o), 1.0)                                # histograms are percentages (0..100)
+    assert (np.abs(g - o) / scale).max() < FPFH_RTOL
+    sums = g.reshape(len(g), 3, 11).sum(-1)
+    assert np.allclose(sums, 100.0, atol=1e-2)
+
+
+def test_feature_knn_indices(ctx, orc):
+    rng = np.random.default_rng(2)
+    ft = (rng.random((3000, 33)) * 30).astype(np.float32)
+    fq = (rng.random((700, 33)) * 30).astype(np.float32)
+    ft[10] = ft[20]                                                   # exact tie -> smaller index first
+    gi, gd = ctx.feature_knn(ft, fq, 5)
+    oi, od = orc.feature_knn(ft, fq, 5)
+    assert (gi == oi).all() and (gd == od).all()
+
+
+# ------------------------------------------------------------------------------------------ registration ----
+def test_umeyama_dense(ctx, orc, synth, model):
+    rng = np.random.default_rng(4)
+    T = synth.random_pose(rng)
+    moved = synth.apply(T, model)
+    a, b = ctx.upload(model), ctx.upload(moved)
+    g = ctx.umeyama(a, b)
+    r, t = synth.pose_error(g, T)
+    assert r < 1e-5 and t < 1e-5
+    o = orc.umeyama(model, moved)
+    r, t = synth.pose_error(g, o)
+    assert r < ROT_TOL and t < TRANS_TOL
+
+
+def test_fitness(ctx, orc, synth, small_model):
+    src, tgt, T = synth.icp_pair(5000, seed=9, model=small_model)
+    a, b = ctx.upload(src), ctx.upload(tgt)
+    g = ctx.fitness(a, b, T)
+    o = orc.fitness(src, tgt, T)
+    assert abs(g - o) < FIT_TOL * max(1.0, abs(o)) and abs(g - o) / o < 1e-6
+
+
+def test_correspondences_nearest_and_normal_shooting(ctx, orc, synth, cuda_lib, model):
+    T = cuda_lib.T
+    cl, _, _ = synth.make_frame(model, 5)
+    tp = cl[orc.uniform_sample(cl, 0.008)]
+    tn = orc.normals_knn(tp, 30)
+    rng = np.random.default_rng(1)
+    sp = synth.apply(synth.small_pose(rng, 5, 0.01), tp[::2]).astype(np.float32)
+    sn = orc.normals_knn(sp, 30)
+    cs, ct = ctx.upload(sp, sn), ctx.upload(tp, tn)
+    for kw in (dict(max_correspondence_distance=0.01),
+               dict(estimator=T.EST_NORMAL_SHOOTING, k_search=20, rejectors=[(T.REJ_SURFACE_NORMAL, 0.7), (T.REJ_SELF_OCCLUDED_NORMAL, 0.6)])):
+        g = ctx.correspondences(cs, ct, cuda_lib.icp_params(**kw))
+        o = orc.correspondences(sp, tp, orc.icp_params(**kw), sn, tn)
+        assert len(g[0]) == len(o[0]) and len(g[0]) > 10
+        assert (g[0] == o[0]).all() and (g[1] == o[1]).all() and (g[2] == o[2]).all()
+
+
+def test_icp_point_to_point_c2_small(ctx, orc, synth, cuda_lib, small_model):
+    """C2 at a size the oracle finishes in seconds: 50 iterations, max-corr-distance rejection."""
+    T = cuda_lib.T
+    src, tgt, Tgt = synth.icp_pair(8000, seed=2, model=small_model)
+    kw = dict(max_iterations=50, max_correspondence_distance=0.05, transformation_epsilon=1e-8, euclidean_fitness_epsilon=1e-8)
+    cs, ct = ctx.upload(src), ctx.upload(tgt)
+    g, gc = ctx.icp(cs, ct, cuda_lib.icp_params(**kw), want_corr=True)
+    o, oc = orc.icp(src, tgt, orc.icp_params(**kw), want_corr=True)
+    _pose_close(synth, T, g.T, o.T)
+    assert g.converged == o.converged and g.state == o.state and g.iterations == o.iterations
+    assert g.n_correspondences == o.n_correspondences
+    assert (gc[0] == oc[0]).all() and (gc[1] == oc[1]).all()
+    r, t = synth.pose_error(T.mat4(g.T), Tgt)          # and it actually registers the pair (to ICP's noisy local optimum)
+    r0, t0 = synth.pose_error(np.eye(4), Tgt)
+    assert r < 0.5 * r0 and t < 0.2 * t0
+    gf, of = ctx.fitness(cs, ct, T.mat4(g.T)), orc.fitness(src, tgt, T.mat4(o.T))
+    assert abs(gf - of) < FIT_TOL
+
+
+def test_icp_guess_and_aligned_output(ctx, orc, synth, cuda_lib, small_model):
+    T = cuda_lib.T
+    src, tgt, Tgt = synth.icp_pair(3000, seed=4, model=small_model)
+    rng = np.random.default_rng(3)
+    guess = synth.small_pose(rng, 2, 0.005).astype(np.float32)
+    kw = dict(max_iterations=15, max_correspondence_distance=0.05)
+    cs, ct = ctx.upload(src), ctx.upload(tgt)
+    g, aligned = ctx.icp(cs, ct, cuda_lib.icp_params(**kw), guess=guess, want_aligned=True)
+    o = orc.icp(src, tgt, orc.icp_params(**kw), guess=guess)
+    _pose_close(synth, T, g.T, o.T)
+    assert g.iterations == o.iterations and g.state == o.state
+    out = aligned.download()
+    ref = orc.transform(src, T.mat4(g.T))
+    assert np.array_equal(out, ref)
+
+
+def test_icp_with_normals_d_and_l_configuration(ctx, orc, synth, cuda_lib, model):
+    """The reference's fine stage (D&L/src/poseestimator.cpp:310-341): normal shooting k=20, surface-normal 0.7 +
+    self-occluded 0.6 rejectors, SVD, 100 iterations, eps 1e-8, no distance gating."""
+    T = cuda_lib.T
+    cl, _, pose = synth.make_frame(model, 5)
+    rng = np.random.default_rng(8)
+    start = pose @ synth.small_pose(rng, 6, 0.01)
+    sp_full = synth.apply(start, model)
+    sp = sp_full[orc.uniform_sample(sp_full, 0.008)]
+    tp = cl[orc.uniform_sample(cl, 0.008)]
+    sn, tn = orc.normals_knn(sp, 30), orc.normals_knn(tp, 30)
+    kw = dict(max_iterations=100, transformation_epsilon=1e-8, euclidean_fitness_epsilon=1e-8, estimator=T.EST_NORMAL_SHOOTING,
+              k_search=20, rejectors=[(T.REJ_SURFACE_NORMAL, 0.7), (T.REJ_SELF_OCCLUDED_NORMAL, 0.6)], with_normals=1)
+    for variant in (T.ICP_VARIANT_MOD, T.ICP_VARIANT_MODCORR):
+        cs, ct = ctx.upload(sp, sn), ctx.upload(tp, tn)
+        g = ctx.icp(cs, ct, cuda_lib.icp_params(variant=variant, **kw))
+        o = orc.icp(sp, tp, orc.icp_params(variant=variant, **kw), src_normals=sn, tgt_normals=tn)
+        _pose_close(synth, T, g.T, o.T)
+        assert g.converged == o.converged and g.state == o.state
+        assert abs(g.iterations - o.iterations) <= 1 and g.n_correspondences == o.n_correspondences
+        gf, of = ctx.fitness(cs, ct, T.mat4(g.T)), orc.fitness(sp, tp, T.mat4(o.T))
+        assert abs(gf - of) < FIT_TOL
+
+
+def test_icp_no_correspondences(ctx, orc, cuda_lib):
+    rng = np.random.default_rng(0)
+    src = rng.random((200, 3)).astype(np.float32)
+    tgt = src + 100.0
+    kw = dict(max_iterations=5, max_correspondence_distance=0.01)
+    g = ctx.icp(ctx.upload(src), ctx.upload(tgt), cuda_lib.icp_params(**kw))
+    o = orc.icp(src, tgt, orc.icp_params(**kw))
+    assert g.converged == o.converged == 0 and g.state == o.state == cuda_lib.T.CONV_NO_CORRESPONDENCES
+    assert np.array_equal(np.array(list(g.T)), np.array(list(o.T)))
+
+
+def test_sacia_replayed_rng(ctx, orc, synth, cuda_lib, model):
+    """SAC-IA with the same hypothesis sequence replayed: every hypothesis error bit-exact, same winner, same transform."""
+    T = cuda_lib.T
+    cl, _, pose = synth.make_frame(model, 2)
+    sp = model[orc.uniform_sample(model, 0.01)]
+    tp = cl[orc.uniform_sample(cl, 0.01)]
+    sn, tn = orc.normals_knn(sp, 30), orc.normals_knn(tp, 30)
+    sf, tf = orc.fpfh(sp, sn, 0.03), orc.fpfh(tp, tn, 0.03)
+    kw = dict(max_iterations=400, nr_samples=5, k_correspondences=5, min_sample_distance=0.01, max_correspondence_distance=0.05)
+    orc.srand(1)
+    samples, picks = orc.sacia_draw(sp, 400, 5, 5, 0.01)
+    o, oe = orc.sacia(sp, sf, tp, tf, orc.sacia_params(**kw), orc.rng_table(samples, picks), want_errors=True)
+    g, ge = ctx.sacia(ctx.upload(sp), sf, ctx.upload(tp), tf, cuda_lib.sacia_params(**kw), cuda_lib.rng_table(samples, picks),
+                      want_errors=True)
+    assert np.array_equal(ge, oe), np.abs(ge - oe).max()
+    assert g.best_iteration == o.best_iteration and g.best_error == o.best_error
+    assert np.array_equal(np.array(list(g.T)), np.array(list(o.T)))
+    # the product draws the same table from libc rand() as the oracle does
+    orc.srand(1)
+    s2, p2 = cuda_lib.sacia_draw(sp, 400, 5, 5, 0.01)
+    assert np.array_equal(s2, samples) and np.array_equal(p2, picks)
+    # sharded pool: the union of shards reproduces the pool (multi-GPU contract)
+    halves = []
+    for b, e in ((0, 200), (200, 400)):
+        r = ctx.sacia(ctx.upload(sp), sf, ctx.upload(tp), tf, cuda_lib.sacia_params(hypothesis_begin=b, hypothesis_end=e, **kw),
+                      cuda_lib.rng_table(samples, picks))
+        halves.append((np.float32(r.best_error), r.best_iteration))
+    best = min(halves)
+    assert best[1] == o.best_iteration
+
+
+def test_pose_pipeline_matches_oracle(ctx, orc, synth, cuda_lib, model):
+    """DetectAndLocalize frame (C1): full estimateFinalPose, two consecutive frames (coarse+fine, then tracking)."""
+    T = cuda_lib.T
+    cl, _, pose = synth.make_frame(model, 0)
+    otr, gtr = orc.PoseEstimator(), cuda_lib.PoseTracker(ctx)
+    osrc, gsrc = model.copy(), model.copy()
+    for frame in range(2):
+        orc.srand(1)
+        o = otr.estimate_final(osrc, cl)
+        orc.srand(1)
+        g = gtr.estimate_final(gsrc, cl)
+        assert g.ran_coarse == o.ran_coarse
+        assert (g.n_src_coarse, g.n_tgt_coarse, g.n_src_fine, g.n_tgt_fine) == (o.n_src_coarse, o.n_tgt_coarse, o.n_src_fine, o.n_tgt_fine)
+        assert g.sacia_best_iteration == o.sacia_best_iteration
+        _pose_close(synth, T, g.coarse_pose, o.coarse_pose)
+        _pose_close(synth, T, g.fine_pose, o.fine_pose)
+        _pose_close(synth, T, g.final_pose, o.final_pose, rot=2e-4, trans=2e-5)
+        assert g.icp_converged == o.icp_converged and g.icp_state == o.icp_state
+        assert abs(g.fitness - o.fitness) < FIT_TOL
+        assert abs(g.align_strength - o.align_strength) < 1e-3
+        assert np.abs(gsrc - osrc).max() < 1e-4

@@ -1,0 +1,246 @@
+"""CPU tests of the oracle (the checker): every stage against an independent implementation available in this container
+(scipy cKDTree, numpy linalg) or against closed-form ground truth. The reference ships no golden vectors and PCL cannot be
+built here, so this is how the restatement is validated ("parity unpinned")."""
+import numpy as np
+import pytest
+from scipy.spatial import cKDTree
+
+
+def test_knn_kdtree_equals_brute_and_scipy(orc):
+    rng = np.random.default_rng(0)
+    t = rng.random((3000, 3), dtype=np.float32)
+    q = (rng.random((800, 3), dtype=np.float32) * 1.4 - 0.2).astype(np.float32)
+    for k in (1, 5, 20):
+        a = orc.knn(t, q, k)
+        b = orc.knn(t, q, k, brute=True)
+        assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
+        _, i = cKDTree(t.astype(np.float64)).query(q.astype(np.float64), k=k)
+        assert (np.asarray(i).reshape(len(q), k) == a[0]).mean() > 0.999   # float32 vs float64 near-ties only
+
+
+def test_knn_ties_prefer_smaller_index_and_skip_nan(orc):
+    t = np.array([[1, 0, 0], [np.nan, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0]], np.float32)
+    i, d = orc.knn(t, np.zeros((1, 3), np.float32), 4)
+    assert i.tolist() == [[0, 2, 3, 4]] and (d == 1).all()
+    i, d = orc.knn(t, np.zeros((1, 3), np.float32), 6)
+    assert i[0, 4] == -1 and np.isinf(d[0, 4])
+
+
+def test_radius_strict_and_sorted(orc):
+    rng = np.random.default_rng(1)
+    t = rng.random((2000, 3), dtype=np.float32)
+    off, idx, d2 = orc.radius(t, t[:300], 0.1)
+    tree = cKDTree(t.astype(np.float64))
+    for j in range(300):
+        mine = idx[off[j]:off[j + 1]]
+        assert (np.diff(mine) > 0).all()
+        ref = np.array(sorted(tree.query_ball_point(t[j].astype(np.float64), 0.1)))
+        assert len(np.setxor1d(mine, ref)) <= 1          # only points within float rounding of the boundary may differ
+        assert (d2[off[j]:off[j + 1]] < np.float32(0.1) * np.float32(0.1)).all()
+    # strictness: a point exactly at distance r is excluded
+    t2 = np.array([[0, 0, 0], [0.5, 0, 0]], np.float32)
+    off, idx, _ = orc.radius(t2, t2[:1], 0.5)
+    assert idx.tolist() == [0]
+
+
+def test_umeyama_recovers_rigid_transform(orc, synth):
+    rng = np.random.default_rng(2)
+    p = rng.normal(size=(500, 3)).astype(np.float32)
+    for _ in range(5):
+        T = synth.random_pose(rng)
+        q = synth.apply(T, p)
+        r, t = synth.pose_error(orc.umeyama(p, q), T)
+        assert r < 2e-6 and t < 5e-6
+    # index lists + reflection-prone degenerate (planar) set still give a proper rotation
+    flat = p.copy(); flat[:, 2] = 0
+    T = synth.random_pose(rng)
+    M = orc.umeyama(flat, synth.apply(T, flat), np.arange(100), np.arange(100))
+    assert abs(np.linalg.det(M[:3, :3].astype(np.float64)) - 1) < 1e-5
+    r, t = synth.pose_error(M, T)
+    assert r < 1e-5
+
+
+def test_umeyama_matches_numpy_svd(orc):
+    rng = np.random.default_rng(3)
+    s = rng.normal(size=(7, 3)).astype(np.float32)
+    d = rng.normal(size=(7, 3)).astype(np.float32)     # unrelated sets: general covariance
+    M = orc.umeyama(s, d).astype(np.float64)
+    sm, dm = s.mean(0), d.mean(0)
+    sig = (d - dm).T.astype(np.float64) @ (s - sm).astype(np.float64) / 7
+    U, S, Vt = np.linalg.svd(sig)
+    D = np.diag([1, 1, np.sign(np.linalg.det(U) * np.linalg.det(Vt))])
+    R = U @ D @ Vt
+    assert np.abs(M[:3, :3] - R).max() < 1e-5
+    assert np.abs(M[:3, 3] - (dm - R @ sm)).max() < 1e-5
+
+
+def test_uniform_sampling_properties(orc, small_model):
+    leaf = 0.01
+    idx = orc.uniform_sample(small_model, leaf)
+    inv = np.float32(1.0) / np.float32(leaf)
+    ijk = np.floor(small_model * inv).astype(np.int64)
+    keys = {tuple(v) for v in ijk}
+    assert len(idx) == len(keys) == len({tuple(v) for v in ijk[idx]})          # exactly one point per occupied voxel
+    mn = ijk.min(0); dv = ijk.max(0) - mn + 1
+    lin = (ijk[idx] - mn) @ np.array([1, dv[0], dv[0] * dv[1]])
+    assert (np.diff(lin) > 0).all()                                            # canonical order: ascending voxel key
+    # the chosen point minimises ||p - ijk||^2 (the PCL quirk), first index on ties
+    for j in idx[:50]:
+        same = np.nonzero((ijk == ijk[j]).all(1))[0]
+        d = ((small_model[same] - ijk[j].astype(np.float32)) ** 2).sum(1)
+        assert d[list(same).index(j)] <= d.min() * (1 + 1e-6)
+
+
+def test_voxel_grid_centroids(orc, small_model):
+    leaf = 0.01
+    rng = np.random.default_rng(0)
+    rgb = rng.integers(0, 1 << 24, len(small_model)).astype(np.uint32)
+    xyz, col = orc.voxel_grid(small_model, leaf, rgb.view(np.float32))
+    inv = np.float32(1.0) / np.float32(leaf)
+    ijk = np.floor(small_model * inv).astype(np.int64)
+    mn = ijk.min(0); dv = ijk.max(0) - mn + 1
+    lin = (ijk - mn) @ np.array([1, dv[0], dv[0] * dv[1]])
+    order = np.argsort(lin, kind="stable")
+    uniq, start = np.unique(lin[order], return_index=True)
+    assert len(xyz) == len(uniq)
+    ref = np.add.reduceat(small_model[order].astype(np.float64), start) / np.diff(np.append(start, len(order)))[:, None]
+    assert np.abs(xyz - ref).max() < 1e-6
+    r = (col.view(np.uint32) >> 16) & 0xff
+    rr = np.add.reduceat(((rgb[order] >> 16) & 0xff).astype(np.float64), start) / np.diff(np.append(start, len(order)))
+    assert (np.abs(r - np.floor(rr)) <= 1).all()
+    with pytest.raises(RuntimeError):
+        orc.voxel_grid(small_model, 1e-5)       # "Leaf size is too small for the input dataset"
+
+
+def test_normals_on_a_sphere_and_plane(orc):
+    rng = np.random.default_rng(4)
+    v = rng.normal(size=(4000, 3)); v /= np.linalg.norm(v, axis=1, keepdims=True)
+    pts = (v * 0.5 + np.array([0, 0, 2.0])).astype(np.float32)
+    n = orc.normals_knn(pts, 12)
+    radial = (pts - np.array([0, 0, 2.0], np.float32)); radial /= np.linalg.norm(radial, axis=1, keepdims=True)
+    cosang = np.abs((n[:, :3] * radial).sum(1))
+    assert np.median(cosang) > 0.995
+    assert ((n[:, :3] * (-pts)).sum(1) >= 0).all()                     # flipped toward the viewpoint (origin)
+    assert np.allclose(np.linalg.norm(n[:, :3], axis=1), 1, atol=1e-4)
+    plane = np.c_[rng.random((500, 2)), np.full(500, 1.0)].astype(np.float32)
+    npl = orc.normals_knn(plane, 10)
+    assert np.abs(np.abs(npl[:, 2]) - 1).max() < 1e-3 and (npl[:, 3] < 1e-3).all()
+    # numpy cross-check of the eigen decomposition on a generic neighbourhood
+    idx, _ = orc.knn(pts, pts[:20], 12)
+    for j in range(20):
+        nb = pts[idx[j]].astype(np.float64)
+        w, V = np.linalg.eigh(np.cov(nb.T, bias=True))
+        assert abs(abs(V[:, 0] @ n[j, :3]) - 1) < 2e-2               # float32 E[xx]-mu^2 cancellation at z = 2 m
+
+
+def test_fpfh_histogram_invariants(orc, small_model):
+    pts = small_model[orc.uniform_sample(small_model, 0.01)]
+    nr = orc.normals_knn(pts, 30)
+    f = orc.fpfh(pts, nr, 0.03)
+    assert f.shape == (len(pts), 33) and np.isfinite(f).all() and (f >= 0).all()
+    assert np.allclose(f.reshape(len(f), 3, 11).sum(-1), 100, atol=1e-2)
+    s = orc.spfh(pts, nr, 0.03)
+    assert np.allclose(s.reshape(len(s), 3, 11).sum(-1), 100, atol=1e-2)
+    # rigid motion of points + normals leaves the descriptor (nearly) unchanged
+    R = np.array([[0, -1, 0], [1, 0, 0], [0, 0, 1]], np.float32)
+    f2 = orc.fpfh((pts @ R.T + np.float32(0.5)).astype(np.float32), np.c_[nr[:, :3] @ R.T, nr[:, 3]].astype(np.float32), 0.03)
+    assert np.median(np.abs(f - f2).max(1)) < 0.5
+
+
+def test_feature_knn_is_brute_force_l2(orc):
+    rng = np.random.default_rng(5)
+    ft = rng.random((500, 33)).astype(np.float32); fq = rng.random((40, 33)).astype(np.float32)
+    i, d = orc.feature_knn(ft, fq, 5)
+    ref = ((fq[:, None, :].astype(np.float64) - ft[None]) ** 2).sum(-1)
+    assert (np.argsort(ref, 1)[:, :5] == i).all()
+
+
+def test_icp_point_to_point_recovers_pose(orc, synth, small_model):
+    src, tgt, T = synth.icp_pair(4000, seed=1, model=small_model)
+    prm = orc.icp_params(max_iterations=50, max_correspondence_distance=0.05, transformation_epsilon=1e-8,
+                         euclidean_fitness_epsilon=1e-8)
+    res, corr = orc.icp(src, tgt, prm, want_corr=True)
+    M = orc.T.mat4(res.T)
+    r, t = synth.pose_error(M, T)
+    r0, t0 = synth.pose_error(np.eye(4), T)
+    assert r < 0.5 * r0 and t < 0.2 * t0 and res.converged == 1      # noisy, differently sampled, 10 % outliers: local optimum
+    assert res.n_correspondences == len(corr[0]) and (corr[2] <= 0.05 ** 2).all()
+    assert orc.fitness(src, tgt, M) < orc.fitness(src, tgt, np.eye(4))
+    # iteration cap and the convergence state machine
+    res = orc.icp(src, tgt, orc.icp_params(max_iterations=3, max_correspondence_distance=0.05))
+    assert res.iterations == 3 and res.state == orc.T.CONV_ITERATIONS and res.converged == 1
+    res = orc.icp(src, tgt + 100, orc.icp_params(max_iterations=3, max_correspondence_distance=0.05))
+    assert res.converged == 0 and res.state == orc.T.CONV_NO_CORRESPONDENCES and res.iterations == 0
+
+
+def test_icp_normal_shooting_with_rejectors(orc, synth, model):
+    T = orc.T
+    cl, _, pose = synth.make_frame(model, 5)
+    rng = np.random.default_rng(8)
+    start = pose @ synth.small_pose(rng, 6, 0.01)
+    full = synth.apply(start, model)
+    sp = full[orc.uniform_sample(full, 0.008)]; tp = cl[orc.uniform_sample(cl, 0.008)]
+    sn, tn = orc.normals_knn(sp, 30), orc.normals_knn(tp, 30)
+    kw = dict(max_iterations=100, transformation_epsilon=1e-8, euclidean_fitness_epsilon=1e-8, estimator=T.EST_NORMAL_SHOOTING,
+              k_search=20, rejectors=[(T.REJ_SURFACE_NORMAL, 0.7), (T.REJ_SELF_OCCLUDED_NORMAL, 0.6)], with_normals=1)
+    res = orc.icp(sp, tp, orc.icp_params(**kw), src_normals=sn, tgt_normals=tn)
+    M = T.mat4(res.T).astype(np.float64) @ start
+    r, t = synth.pose_error(M, pose)
+    r0, t0 = synth.pose_error(start, pose)
+    assert res.converged == 1 and r < r0 and t < t0                   # partial view, no distance gating: it improves, no more
+
+
+def test_sacia_table_replay_equals_live_rand(orc, synth, model):
+    cl, _, _ = synth.make_frame(model, 2)
+    sp = model[orc.uniform_sample(model, 0.01)]; tp = cl[orc.uniform_sample(cl, 0.01)]
+    sn, tn = orc.normals_knn(sp, 30), orc.normals_knn(tp, 30)
+    sf, tf = orc.fpfh(sp, sn, 0.03), orc.fpfh(tp, tn, 0.03)
+    prm = orc.sacia_params(max_iterations=60, nr_samples=5, k_correspondences=5, min_sample_distance=0.01,
+                           max_correspondence_distance=0.05)
+    orc.srand(1)
+    live = orc.sacia(sp, sf, tp, tf, prm)
+    orc.srand(1)
+    s, p = orc.sacia_draw(sp, 60, 5, 5, 0.01)
+    rep, errs = orc.sacia(sp, sf, tp, tf, prm, orc.rng_table(s, p), want_errors=True)
+    assert list(live.T) == list(rep.T) and live.best_iteration == rep.best_iteration
+    assert rep.best_error == errs.min() and rep.best_iteration == int(np.argmin(errs))
+    d = np.linalg.norm(sp[s][:, :, None] - sp[s][:, None], axis=-1) + np.eye(5) * 10
+    assert (d >= 0.01 - 1e-6).all()                                    # min_sample_distance honoured
+    # shards reproduce the pool
+    prm.hypothesis_begin, prm.hypothesis_end = 30, 60
+    sh = orc.sacia(sp, sf, tp, tf, prm, orc.rng_table(s, p))
+    assert sh.best_iteration == 30 + int(np.argmin(errs[30:]))
+
+
+def test_sacia_recovers_pose_with_consistent_normals(orc, synth, small_model):
+    """On its own terms SAC-IA works: same viewpoint convention on both clouds, no noise."""
+    rng = np.random.default_rng(6)
+    base = small_model[orc.uniform_sample(small_model, 0.01)] + np.float32([0, 0, 1.0])
+    T = synth.small_pose(rng, 40, 0.1)
+    moved = synth.apply(T, base)
+    sn, tn = orc.normals_knn(base, 30, vp=(0, 0, 1)), orc.normals_knn(moved, 30, vp=tuple(synth.apply(T, np.float32([[0, 0, 1]]))[0]))
+    sf, tf = orc.fpfh(base, sn, 0.03), orc.fpfh(moved, tn, 0.03)
+    prm = orc.sacia_params(max_iterations=400, nr_samples=5, k_correspondences=5, min_sample_distance=0.01,
+                           max_correspondence_distance=0.05)
+    orc.srand(1)
+    res = orc.sacia(base, sf, moved, tf, prm)
+    r, t = synth.pose_error(orc.T.mat4(res.T), T)
+    assert r < 0.2 and t < 0.03, (r, t)
+
+
+def test_pose_estimator_state_machine(orc, synth, model):
+    cl, _, pose = synth.make_frame(model, 0)
+    pe = orc.PoseEstimator()
+    src = model.copy()
+    orc.srand(1)
+    a = pe.estimate_final(src, cl)
+    assert a.ran_coarse == 1 and a.n_src_coarse > 500 and a.n_tgt_fine >= 100
+    F, Cc, Fi, Rg = (orc.T.mat4(x).astype(np.float64) for x in (a.final_pose, a.coarse_pose, a.fine_pose, a.rigid_model_pose))
+    assert np.abs(F - Rg @ (Cc @ Fi)).max() < 1e-5                       # finalPose = rigidmodelPose * (coarse * fine)
+    assert np.abs(Rg - np.eye(4)).max() < 1e-4                           # first frame: model -> model
+    assert np.abs(src - synth.apply(Fi @ Cc, model)).max() < 1e-4        # *p_sourceCloud = alignedSource
+    # empty target: identity poses, nothing moves
+    pe2 = orc.PoseEstimator()
+    s2 = model[:1000].copy()
+    b = pe2.estimate_final(s2, np.zeros((0, 3), np.float32))
+    assert b.ran_coarse == 0 and np.array_equal(orc.T.mat4(b.final_pose)[:3, :3].round(5), np.eye(3, dtype=np.float32))
