@@ -6,34 +6,43 @@
 #include <algorithm>
 
 #include "ope_host.cuh"
+#include "ope_octet.cuh"
 
 namespace ope {
 
 // ------------------------------------------------------------------------------------------ normals ----
-// thread per point: exact k-NN on the cloud's own grid (the point itself is neighbour 0), covariance summed
-// sequentially in the sorted neighbour order, eigen33, flip toward the viewpoint.
-__global__ void normals_kernel(GridView g, const float4* __restrict__ pts, int n, int k, float vpx, float vpy, float vpz,
-                               float4* __restrict__ out) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float4 q = __ldg(pts + i);
+// One octet (8 lanes) per point: exact k-NN on the cloud's own grid into the octet's shared list (the point itself is
+// neighbour 0), then lane 0 sums the covariance sequentially in the sorted neighbour order, eigen33, flip
+// toward the viewpoint.
+static constexpr int kNormThreads = 256;
+__global__ void __launch_bounds__(kNormThreads) normals_kernel(GridView g, const float4* __restrict__ pts, int n, int k, float vpx,
+                                                               float vpy, float vpz, float4* __restrict__ out) {
+  __shared__ OctStack stacks[kNormThreads / 8];
+  __shared__ OctKnnList lists[kNormThreads / 8];
+  const Octet o = octet_self();
+  OctStack* st = &stacks[threadIdx.x >> 3];
+  OctKnnList* L = &lists[threadIdx.x >> 3];
+  const int oct_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, n_oct = (gridDim.x * blockDim.x) >> 3;
   const float nan = __int_as_float(0x7fc00000);
-  float r[4] = {nan, nan, nan, nan};
-  if (finite3(q.x, q.y, q.z)) {
-    float bd[32];
-    int bi[32];
-    int cnt = grid_knn<32>(g, q.x, q.y, q.z, k, bd, bi);
-    if (cnt >= 3) {
-      CovAccum acc;
-      acc.reset();
-      for (int j = 0; j < cnt; ++j) {
-        float4 p = __ldg(pts + bi[j]);
-        acc.add(p.x, p.y, p.z);
+  for (int i = oct_id; i < n; i += n_oct) {
+    const float4 q = __ldg(pts + i);
+    const bool ok = finite3(q.x, q.y, q.z);
+    const int cnt = octet_knn(g, st, L, o, ok, q.x, q.y, q.z, k);
+    if (o.sub == 0u) {
+      float r[4] = {nan, nan, nan, nan};
+      if (ok && cnt >= 3) {
+        CovAccum acc;
+        acc.reset();
+        for (int j = 0; j < cnt; ++j) {
+          const float4 p = __ldg(pts + L->i[j]);
+          acc.add(p.x, p.y, p.z);
+        }
+        normal_from_accum(acc, cnt, q.x, q.y, q.z, vpx, vpy, vpz, r);
       }
-      normal_from_accum(acc, cnt, q.x, q.y, q.z, vpx, vpy, vpz, r);
+      out[i] = make_float4(r[0], r[1], r[2], r[3]);
     }
+    __syncwarp(o.mask);
   }
-  out[i] = make_float4(r[0], r[1], r[2], r[3]);
 }
 
 // ------------------------------------------------------------------------------------------- SPFH ------
@@ -44,7 +53,7 @@ __global__ void normals_kernel(GridView g, const float4* __restrict__ pts, int n
 static constexpr int kWarpsPerBlock = 8;
 
 __global__ void spfh_kernel(GridView g, const float4* __restrict__ pts, const float4* __restrict__ nrm, int n, float r2,
-                            int rings, float* __restrict__ spfh) {
+                            float* __restrict__ spfh) {
   __shared__ int hist[kWarpsPerBlock][33];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int p_idx = blockIdx.x * kWarpsPerBlock + warp;
@@ -57,16 +66,10 @@ __global__ void spfh_kernel(GridView g, const float4* __restrict__ pts, const fl
   if (finite3(q.x, q.y, q.z)) {
     const float4 qn4 = __ldg(nrm + p_idx);
     const float qn[3] = {qn4.x, qn4.y, qn4.z};
-    const int cx = grid_cell_coord(q.x, g.ox, g.inv_h), cy = grid_cell_coord(q.y, g.oy, g.inv_h),
-              cz = grid_cell_coord(q.z, g.oz, g.inv_h);
-    const int z0 = max(cz - rings, 0), z1 = min(cz + rings, g.nz - 1);
-    const int y0 = max(cy - rings, 0), y1 = min(cy + rings, g.ny - 1);
-    const int x0 = max(cx - rings, 0), x1 = min(cx + rings, g.nx - 1);
-    if (x0 <= x1)
-      for (int z = z0; z <= z1; ++z)
-        for (int y = y0; y <= y1; ++y) {
-          const int row = (z * g.ny + y) * g.nx;
-          const int b = __ldg(g.cell_start + row + x0), e = __ldg(g.cell_start + row + x1 + 1);
+    // the traversal is warp-uniform (one query per warp); lanes share each leaf range
+    grid_radius_ranges(
+        g, q.x, q.y, q.z, r2, 64,
+        [&](int b, int e) {
           for (int i = b + lane; i < e; i += 32) {
             const float4 c = __ldg(g.pts + i);
             const float d2 = dist2(q.x, q.y, q.z, c.x, c.y, c.z);
@@ -84,7 +87,7 @@ __global__ void spfh_kernel(GridView g, const float4* __restrict__ pts, const fl
               }
             }
           }
-        }
+        });
   }
   for (int o = 16; o > 0; o >>= 1) nb_count += __shfl_xor_sync(0xffffffffu, nb_count, o);
   __syncwarp();
@@ -98,12 +101,12 @@ __global__ void spfh_kernel(GridView g, const float4* __restrict__ pts, const fl
 }
 
 // ------------------------------------------------------------------------------------------- FPFH ------
-// warp per point, lane = histogram bin (lane 0 also carries bin 32). Candidates are examined 32 at a time
-// (one per lane, coalesced float4 loads); the in-radius ones are then consumed in order, each as one
-// coalesced 132-byte read of its SPFH row, weighted by 1/d2 and accumulated in float like the reference
+// warp per point, lane = histogram bin (lane 0 also carries bin 32). Each leaf range is examined 32 candidates at a
+// time (one per lane, coalesced float4 loads); the in-radius ones are then consumed in order, each as one coalesced
+// 132-byte read of its SPFH row, weighted by 1/d2 and accumulated in float like the reference
 // (weightPointSPFHSignature). The three normalisation sums are carried in double.
-__global__ void fpfh_kernel(GridView g, const float4* __restrict__ pts, int n, float r2, int rings,
-                            const float* __restrict__ spfh, float* __restrict__ out) {
+__global__ void fpfh_kernel(GridView g, const float4* __restrict__ pts, int n, float r2, const float* __restrict__ spfh,
+                            float* __restrict__ out) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int p_idx = blockIdx.x * kWarpsPerBlock + warp;
   if (p_idx >= n) return;
@@ -113,16 +116,9 @@ __global__ void fpfh_kernel(GridView g, const float4* __restrict__ pts, int n, f
   const bool ok = finite3(q.x, q.y, q.z);
   int found = 0;
   if (ok) {
-    const int cx = grid_cell_coord(q.x, g.ox, g.inv_h), cy = grid_cell_coord(q.y, g.oy, g.inv_h),
-              cz = grid_cell_coord(q.z, g.oz, g.inv_h);
-    const int z0 = max(cz - rings, 0), z1 = min(cz + rings, g.nz - 1);
-    const int y0 = max(cy - rings, 0), y1 = min(cy + rings, g.ny - 1);
-    const int x0 = max(cx - rings, 0), x1 = min(cx + rings, g.nx - 1);
-    if (x0 <= x1)
-      for (int z = z0; z <= z1; ++z)
-        for (int y = y0; y <= y1; ++y) {
-          const int row = (z * g.ny + y) * g.nx;
-          const int b = __ldg(g.cell_start + row + x0), e = __ldg(g.cell_start + row + x1 + 1);
+    grid_radius_ranges(
+        g, q.x, q.y, q.z, r2, 64,
+        [&](int b, int e) {
           for (int base = b; base < e; base += 32) {
             const int i = base + lane;
             float d2 = FLT_MAX;
@@ -133,7 +129,7 @@ __global__ void fpfh_kernel(GridView g, const float4* __restrict__ pts, int n, f
               j = __float_as_int(c.w);
             }
             const bool inr = d2 < r2;
-            unsigned in_mask = __ballot_sync(0xffffffffu, inr);
+            const unsigned in_mask = __ballot_sync(0xffffffffu, inr);
             found += __popc(in_mask);
             unsigned use_mask = __ballot_sync(0xffffffffu, inr && d2 != 0.0f);
             while (use_mask) {
@@ -153,7 +149,7 @@ __global__ void fpfh_kernel(GridView g, const float4* __restrict__ pts, int n, f
               }
             }
           }
-        }
+        });
   }
   // per-sub-histogram sums: bins 0-10 | 11-21 | 22-32
   const unsigned full = 0xffffffffu;
@@ -272,7 +268,7 @@ int normals_device(ope_ctx* ctx, ope_cloud* cloud, int k, const float vp[3]) {
   OPE_TRY(cloud_bbox(ctx, cloud));
   GridView g;
   OPE_TRY(cloud_grid(ctx, cloud, knn_cell_size(cloud, k), &g));
-  normals_kernel<<<div_up(cloud->n, 128), 128, 0, ctx->stream>>>(g, cloud->pts, (int)cloud->n, k, vp[0], vp[1], vp[2],
+  normals_kernel<<<(unsigned)std::min<size_t>(div_up(cloud->n * 8, kNormThreads), (size_t)ctx->sm_count * 16), kNormThreads, 0, ctx->stream>>>(g, cloud->pts, (int)cloud->n, k, vp[0], vp[1], vp[2],
                                                                  cloud->normals);
   return check_launch(ctx, "normals_kernel");
 }
@@ -290,13 +286,12 @@ int fpfh_device(ope_ctx* ctx, const ope_cloud* cloud, float radius, float** d_fp
     GridView g;
     rc = cloud_grid(ctx, cloud, radius * 0.5f, &g);
     if (rc == OPE_OK) {
-      const int rings = grid_radius_rings(g, radius);
       const float r2 = radius * radius;
       const unsigned blocks = div_up(n, kWarpsPerBlock);
-      spfh_kernel<<<blocks, kWarpsPerBlock * 32, 0, ctx->stream>>>(g, cloud->pts, cloud->normals, (int)n, r2, rings, spfh);
+      spfh_kernel<<<blocks, kWarpsPerBlock * 32, 0, ctx->stream>>>(g, cloud->pts, cloud->normals, (int)n, r2, spfh);
       rc = check_launch(ctx, "spfh_kernel");
       if (rc == OPE_OK) {
-        fpfh_kernel<<<blocks, kWarpsPerBlock * 32, 0, ctx->stream>>>(g, cloud->pts, (int)n, r2, rings, spfh, fpfh);
+        fpfh_kernel<<<blocks, kWarpsPerBlock * 32, 0, ctx->stream>>>(g, cloud->pts, (int)n, r2, spfh, fpfh);
         rc = check_launch(ctx, "fpfh_kernel");
       }
     }

@@ -8,13 +8,12 @@
 #include <cmath>
 
 #include "ope_host.cuh"
+#include "ope_octet.cuh"
 
 namespace ope {
 
 static constexpr int kThreads = 256;
-static constexpr int64_t kMaxSearchCells = (int64_t)1 << 25;  // 128 MiB of cell_start
 static constexpr int64_t kMaxVoxelCells = (int64_t)1 << 28;
-static constexpr int kMaxDim = 4096;
 
 // ============================================================================================ kernels ==
 __device__ __forceinline__ int bin_coord(float v, float o, float inv, int min_b) {
@@ -28,6 +27,7 @@ __device__ __forceinline__ int64_t bin_cell(const Binning& b, float x, float y, 
   cx = min(max(cx, 0), b.dim[0] - 1);
   cy = min(max(cy, 0), b.dim[1] - 1);
   cz = min(max(cz, 0), b.dim[2] - 1);
+  if (b.morton_bits > 0) return (int64_t)morton3((unsigned)cx, (unsigned)cy, (unsigned)cz);
   return ((int64_t)cz * b.dim[1] + cy) * b.dim[0] + cx;
 }
 
@@ -158,57 +158,53 @@ __global__ void cell_sort_kernel(const int* __restrict__ cell_start, int64_t nce
   }
 }
 
-// ---- k-NN / radius query kernels (thread per query) ----
-__global__ void knn_kernel(GridView g, const float4* __restrict__ qry, int nq, int k, int* __restrict__ out_idx,
-                           float* __restrict__ out_d2) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nq) return;
-  float4 q = __ldg(qry + i);
-  float bd[32];
-  int bi[32];
-  int cnt = 0;
-  if (finite3(q.x, q.y, q.z)) {
+// ---- k-NN query kernel: one octet (8 lanes) per query, see ope_octet.cuh ----
+static constexpr int kKnnThreads = 256;
+__global__ void __launch_bounds__(kKnnThreads) knn_kernel(GridView g, const float4* __restrict__ qry, int nq, int k,
+                                                          int* __restrict__ out_idx, float* __restrict__ out_d2) {
+  __shared__ OctStack stacks[kKnnThreads / 8];
+  __shared__ OctKnnList lists[kKnnThreads / 8];
+  const Octet o = octet_self();
+  OctStack* st = &stacks[threadIdx.x >> 3];
+  OctKnnList* L = &lists[threadIdx.x >> 3];
+  const int oct_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, n_oct = (gridDim.x * blockDim.x) >> 3;
+  for (int i = oct_id; i < nq; i += n_oct) {
+    const float4 q = __ldg(qry + i);
+    const bool ok = finite3(q.x, q.y, q.z);
     if (k == 1) {
       float d2;
-      int idx = grid_nn1(g, q.x, q.y, q.z, FLT_MAX, d2);
-      if (idx >= 0) { bd[0] = d2; bi[0] = idx; cnt = 1; }
+      const int idx = octet_nn1(g, st, o, ok, q.x, q.y, q.z, FLT_MAX, d2);
+      if (o.sub == 0u) {
+        out_idx[i] = idx;
+        if (out_d2) out_d2[i] = idx >= 0 ? d2 : INFINITY;
+      }
     } else {
-      cnt = grid_knn<32>(g, q.x, q.y, q.z, k, bd, bi);
+      const int cnt = octet_knn(g, st, L, o, ok, q.x, q.y, q.z, k);
+      for (int j = (int)o.sub; j < k; j += 8) {
+        out_idx[(size_t)i * k + j] = j < cnt ? L->i[j] : -1;
+        if (out_d2) out_d2[(size_t)i * k + j] = j < cnt ? L->d[j] : INFINITY;
+      }
+      __syncwarp(o.mask);
     }
   }
-  for (int j = 0; j < k; ++j) {
-    out_idx[(size_t)i * k + j] = j < cnt ? bi[j] : -1;
-    if (out_d2) out_d2[(size_t)i * k + j] = j < cnt ? bd[j] : INFINITY;
-  }
 }
-__global__ void radius_count_kernel(GridView g, const float4* __restrict__ qry, int nq, float r2, int rings,
-                                    int* __restrict__ counts) {
+__global__ void radius_count_kernel(GridView g, const float4* __restrict__ qry, int nq, float r2, int* __restrict__ counts) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nq) return;
   float4 q = __ldg(qry + i);
   int cnt = 0;
-  if (finite3(q.x, q.y, q.z) && g.n > 0) {
-    int cx = grid_cell_coord(q.x, g.ox, g.inv_h), cy = grid_cell_coord(q.y, g.oy, g.inv_h),
-        cz = grid_cell_coord(q.z, g.oz, g.inv_h);
-    grid_visit_shell(g, cx, cy, cz, rings, -1, [&](float px, float py, float pz, int) {
-      if (dist2(q.x, q.y, q.z, px, py, pz) < r2) ++cnt;
-    });
-  }
+  if (finite3(q.x, q.y, q.z))
+    grid_radius_visit(g, q.x, q.y, q.z, r2, [&](float, float, float, int, float) { ++cnt; });
   counts[i] = cnt;
 }
-__global__ void radius_fill_kernel(GridView g, const float4* __restrict__ qry, int nq, float r2, int rings,
-                                   const int* __restrict__ offsets, int* __restrict__ out_idx, float* __restrict__ out_d2) {
+__global__ void radius_fill_kernel(GridView g, const float4* __restrict__ qry, int nq, float r2, const int* __restrict__ offsets,
+                                   int* __restrict__ out_idx, float* __restrict__ out_d2) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nq) return;
   float4 q = __ldg(qry + i);
-  if (!(finite3(q.x, q.y, q.z) && g.n > 0)) return;
+  if (!finite3(q.x, q.y, q.z)) return;
   int w = offsets[i];
-  int cx = grid_cell_coord(q.x, g.ox, g.inv_h), cy = grid_cell_coord(q.y, g.oy, g.inv_h),
-      cz = grid_cell_coord(q.z, g.oz, g.inv_h);
-  grid_visit_shell(g, cx, cy, cz, rings, -1, [&](float px, float py, float pz, int idx) {
-    float d2 = dist2(q.x, q.y, q.z, px, py, pz);
-    if (d2 < r2) { out_idx[w] = idx; out_d2[w] = d2; ++w; }
-  });
+  grid_radius_visit(g, q.x, q.y, q.z, r2, [&](float, float, float, int idx, float d2) { out_idx[w] = idx; out_d2[w] = d2; ++w; });
 }
 
 // ---- pack / gather / UniformSampling / VoxelGrid ----
@@ -381,38 +377,33 @@ float knn_cell_size(const ope_cloud* c, int k) {
   return h;
 }
 
-int cloud_grid(ope_ctx* ctx, const ope_cloud* cc, float h, GridView* out) {
+// Search grid with cell edge close to h_wanted: 2^bits cells along the longest bbox axis (bits in [1, OPE_MAX_BITS]).
+int cloud_grid(ope_ctx* ctx, const ope_cloud* cc, float h_wanted, GridView* out) {
   ope_cloud* c = const_cast<ope_cloud*>(cc);
-  for (auto& g : c->grids)
-    if (g.h == h) { *out = g.view; return OPE_OK; }
   OPE_TRY(cloud_bbox(ctx, c));
-  float ex[3];
-  for (int d = 0; d < 3; ++d) ex[d] = std::max(c->bbox[3 + d] - c->bbox[d], 0.0f);
-  float hh = h;
-  if (!(hh > 0) || !std::isfinite(hh)) hh = 1.0f;
+  float emax = 0.0f;
+  for (int d = 0; d < 3; ++d) emax = std::max(emax, c->bbox[3 + d] - c->bbox[d]);
+  if (!(emax > 0) || !std::isfinite(emax)) emax = 1.0f;
+  if (!(h_wanted > 0) || !std::isfinite(h_wanted)) h_wanted = emax;
+  int bits = (int)std::ceil(std::log2(std::max(emax / h_wanted, 1.0f)));
+  bits = std::min(std::max(bits, 1), OPE_MAX_BITS);
+  // keep the start array (2^(3*bits) ints) proportionate to the cloud: at most ~64 codes per point, 9 bits only for >1M points
+  while (bits > 1 && ((int64_t)1 << (3 * bits)) > std::max<int64_t>(64 * (int64_t)std::max(c->n_finite, 1), 4096)) --bits;
+  for (auto& g : c->grids)
+    if (g.bits == bits) { *out = g.view; return OPE_OK; }
+  const float hh = emax * (1.0f + 1e-4f) / (float)(1 << bits);
   Binning bin;
-  for (int iter = 0; iter < 64; ++iter) {
-    int64_t total = 1;
-    bool ok = true;
-    for (int d = 0; d < 3; ++d) {
-      double cells = std::floor((double)ex[d] / hh) + 1;
-      if (cells > kMaxDim) ok = false;
-      bin.dim[d] = (int)std::min<double>(cells, kMaxDim);
-      total *= bin.dim[d];
-    }
-    if (ok && total <= kMaxSearchCells) break;
-    hh *= 1.26f;  // ~ cbrt(2)
-  }
-  for (int d = 0; d < 3; ++d) { bin.o[d] = c->bbox[d]; bin.inv[d] = 1.0f / hh; bin.min_b[d] = 0; }
+  for (int d = 0; d < 3; ++d) { bin.o[d] = c->bbox[d]; bin.inv[d] = 1.0f / hh; bin.min_b[d] = 0; bin.dim[d] = 1 << bits; }
+  bin.morton_bits = bits;
   GridEntry g;
-  g.h = h;
-  g.ncells = (int64_t)bin.dim[0] * bin.dim[1] * bin.dim[2];
+  g.bits = bits;
+  g.ncells = (int64_t)1 << (3 * bits);
   OPE_TRY(build_cells(ctx, c->pts, c->n, bin, &g.cell_start, &g.sorted));
   g.view.ox = bin.o[0]; g.view.oy = bin.o[1]; g.view.oz = bin.o[2];
   g.view.h = hh; g.view.inv_h = bin.inv[0];
-  g.view.nx = bin.dim[0]; g.view.ny = bin.dim[1]; g.view.nz = bin.dim[2];
+  g.view.bits = bits;
   g.view.n = c->n_finite;
-  g.view.cell_start = g.cell_start;
+  g.view.start = g.cell_start;
   g.view.pts = g.sorted;
   c->grids.push_back(g);
   *out = g.view;
@@ -446,6 +437,7 @@ static int pcl_voxel_frame(ope_ctx* ctx, ope_cloud* c, const float leaf[3], Binn
     if (dv > 0x7fffffff) return fail(ctx, OPE_ERR_GRID_TOO_LARGE, "voxel grid dimension overflows int32");
     bin->dim[d] = (int)dv;
   }
+  bin->morton_bits = 0;
   *ncells = (int64_t)bin->dim[0] * bin->dim[1] * bin->dim[2];
   if ((double)bin->dim[0] * bin->dim[1] * bin->dim[2] > (double)kMaxVoxelCells)
     return fail(ctx, OPE_ERR_GRID_TOO_LARGE, "leaf size too small for the input: %lld voxels (cap %lld)",
@@ -666,7 +658,7 @@ static int knn_impl(ope_ctx* ctx, const ope_cloud* tgt, const float4* d_qry, siz
   Scratch<float> dd(ctx);
   OPE_TRY(di.alloc(nq * k));
   OPE_TRY(dd.alloc(nq * k));
-  knn_kernel<<<div_up(nq, 128), 128, 0, ctx->stream>>>(g, d_qry, (int)nq, k, di.p, dd.p);
+  knn_kernel<<<(unsigned)std::min<size_t>(div_up(nq * 8, kKnnThreads), (size_t)ctx->sm_count * 16), kKnnThreads, 0, ctx->stream>>>(g, d_qry, (int)nq, k, di.p, dd.p);
   OPE_TRY(check_launch(ctx, "knn_kernel"));
   OPE_CUDA_TRY(ctx, cudaMemcpyAsync(out_idx, di.p, nq * k * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   if (out_d2) OPE_CUDA_TRY(ctx, cudaMemcpyAsync(out_d2, dd.p, nq * k * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
@@ -697,12 +689,11 @@ int ope_radius_cloud(ope_ctx* ctx, const ope_cloud* tgt, const ope_cloud* qry, f
   if (nq == 0) { if (offsets) offsets[0] = 0; return OPE_OK; }
   GridView g;
   OPE_TRY(cloud_grid(ctx, tgt, radius * 0.5f, &g));
-  const int rings = grid_radius_rings(g, radius);
   const float r2 = radius * radius;
   Scratch<int> cnt(ctx);
   OPE_TRY(cnt.alloc(nq + 1));
   OPE_CUDA_TRY(ctx, cudaMemsetAsync(cnt.p + nq, 0, sizeof(int), ctx->stream));
-  radius_count_kernel<<<div_up(nq, 128), 128, 0, ctx->stream>>>(g, qry->pts, (int)nq, r2, rings, cnt.p);
+  radius_count_kernel<<<div_up(nq, 128), 128, 0, ctx->stream>>>(g, qry->pts, (int)nq, r2, cnt.p);
   OPE_TRY(check_launch(ctx, "radius_count_kernel"));
   OPE_TRY(exclusive_scan_i32(ctx, cnt.p, nq + 1));
   std::vector<int> off(nq + 1);
@@ -717,7 +708,7 @@ int ope_radius_cloud(ope_ctx* ctx, const ope_cloud* tgt, const ope_cloud* qry, f
   Scratch<float> dd(ctx);
   OPE_TRY(di.alloc((size_t)*total));
   OPE_TRY(dd.alloc((size_t)*total));
-  radius_fill_kernel<<<div_up(nq, 128), 128, 0, ctx->stream>>>(g, qry->pts, (int)nq, r2, rings, cnt.p, di.p, dd.p);
+  radius_fill_kernel<<<div_up(nq, 128), 128, 0, ctx->stream>>>(g, qry->pts, (int)nq, r2, cnt.p, di.p, dd.p);
   OPE_TRY(check_launch(ctx, "radius_fill_kernel"));
   OPE_CUDA_TRY(ctx, cudaMemcpyAsync(out_idx, di.p, (size_t)*total * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   OPE_CUDA_TRY(ctx, cudaMemcpyAsync(out_d2, dd.p, (size_t)*total * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));

@@ -190,7 +190,7 @@ template <> OPE_HD double t_sqrt<double>(double x) { return sqrt(x); }
 template <typename T> OPE_HD T t_abs(T x) { return x < 0 ? -x : x; }
 template <typename T> struct t_consts;
 template <> struct t_consts<float> {
-  static OPE_HD float jac_eps() { return 1e-7f; }
+  static OPE_HD float jac_eps() { return 4.76837158e-7f; }  // 2^-21: above the float rounding floor of the test
   static OPE_HD float tiny_rel() { return 1e-6f; }
   static OPE_HD float dummy_precision() { return 1e-5f; }
 };
@@ -205,8 +205,8 @@ OPE_HD void svd3(const T Ain[9], T U[9], T S[3], T V[9]) {
   T A[9];
   for (int i = 0; i < 9; ++i) { A[i] = Ain[i]; V[i] = 0; }
   V[0] = V[4] = V[8] = 1;
-  const T eps = t_consts<T>::jac_eps();
-  for (int sweep = 0; sweep < 30; ++sweep) {
+  const T eps2 = t_consts<T>::jac_eps() * t_consts<T>::jac_eps();
+  for (int sweep = 0; sweep < 15; ++sweep) {
     bool rotated = false;
     for (int p = 0; p < 2; ++p)
       for (int q = p + 1; q < 3; ++q) {
@@ -214,7 +214,7 @@ OPE_HD void svd3(const T Ain[9], T U[9], T S[3], T V[9]) {
         T alpha = ap[0] * ap[0] + ap[1] * ap[1] + ap[2] * ap[2];
         T beta = aq[0] * aq[0] + aq[1] * aq[1] + aq[2] * aq[2];
         T gamma = ap[0] * aq[0] + ap[1] * aq[1] + ap[2] * aq[2];
-        if (gamma == 0 || t_abs(gamma) <= eps * t_sqrt<T>(alpha * beta)) continue;
+        if (gamma == 0 || gamma * gamma <= eps2 * (alpha * beta)) continue;  // sqrt-free relative test
         rotated = true;
         T zeta = (beta - alpha) / (2 * gamma);
         T t = (zeta >= 0 ? (T)1 : (T)-1) / (t_abs(zeta) + t_sqrt<T>(1 + zeta * zeta));
@@ -305,14 +305,43 @@ OPE_HD void umeyama_from_sigma(const T sigma[9], const T src_mean[3], const T ds
   }
 }
 
-// Umeyama from raw double moments (ICP / dense model fit): acc = {n, Ss[3], St[3], Sts[9] (t_r*s_c at [c*3+r])}.
+// Umeyama from raw double moments (every Umeyama of the library: SAC-IA's 5 pairs, ICP, the dense model fit):
+// acc = {n, Ss[3], St[3], Sts[9] (t_r*s_c at [c*3+r])}. Means and the cross-covariance are formed in double (the sums
+// are order-independent to ~1e-16, so a parallel reduction and a serial loop agree after rounding), the 3x3 SVD runs in
+// float like Eigen::JacobiSVD<Matrix3f> does in the reference, the translation is closed in double and rounded once.
 OPE_HD void umeyama_from_moments(const double* acc, Mat4& out) {
   const double n = acc[0];
-  double ms[3], mt[3], sigma[9];
+  double ms[3], mt[3];
+  float sigma[9];
   for (int k = 0; k < 3; ++k) { ms[k] = acc[1 + k] / n; mt[k] = acc[4 + k] / n; }
   for (int c = 0; c < 3; ++c)
-    for (int r = 0; r < 3; ++r) sigma[c * 3 + r] = acc[7 + c * 3 + r] / n - mt[r] * ms[c];
-  umeyama_from_sigma<double>(sigma, ms, mt, out);
+    for (int r = 0; r < 3; ++r) sigma[c * 3 + r] = (float)(acc[7 + c * 3 + r] / n - mt[r] * ms[c]);
+  float U[9], S[3], V[9];
+  svd3<float>(sigma, U, S, V);
+  float Sd[3] = {1, 1, 1};
+  if (det3<float>(sigma) < 0) Sd[2] = -1;
+  int rank = 0;
+  for (int i = 0; i < 3; ++i)
+    if (!(t_abs(S[i]) <= t_abs(S[0]) * t_consts<float>::dummy_precision())) ++rank;
+  if (rank == 2) Sd[2] = (det3<float>(U) * det3<float>(V) > 0) ? 1.0f : -1.0f;
+  float R[9];
+  for (int c = 0; c < 3; ++c)
+    for (int r = 0; r < 3; ++r) {
+      float s = U[0 * 3 + r] * Sd[0] * V[0 * 3 + c];
+      s = s + U[1 * 3 + r] * Sd[1] * V[1 * 3 + c];
+      s = s + U[2 * 3 + r] * Sd[2] * V[2 * 3 + c];
+      R[c * 3 + r] = s;
+    }
+  for (int i = 0; i < 16; ++i) out.m[i] = 0.0f;
+  out.m[15] = 1.0f;
+  for (int c = 0; c < 3; ++c)
+    for (int r = 0; r < 3; ++r) out.m[c * 4 + r] = R[c * 3 + r];
+  for (int r = 0; r < 3; ++r) {
+    double rs = (double)R[0 * 3 + r] * ms[0];
+    rs = rs + (double)R[1 * 3 + r] * ms[1];
+    rs = rs + (double)R[2 * 3 + r] * ms[2];
+    out.m[12 + r] = (float)(mt[r] - rs);
+  }
 }
 
 // Eigen::umeyama in float over a handful of pairs, sequential order (SAC-IA: 5 samples). s/d: n*3 arrays.

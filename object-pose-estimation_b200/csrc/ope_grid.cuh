@@ -1,16 +1,21 @@
-// ope_grid.cuh — uniform-grid spatial index replacing pcl::KdTreeFLANN.
+// ope_grid.cuh — voxel-grid spatial index replacing pcl::KdTreeFLANN.
 //
-// Layout in HBM: points of the indexed cloud are counting-sorted by linear cell id (x fastest) into one
-// float4 array {x, y, z, original_index_bits}; within a cell they are ordered by original index, so every
-// traversal below is deterministic. cell_start[c] .. cell_start[c+1] delimits cell c, hence a run of cells
-// x0..x1 of one (y,z) row is ONE contiguous range of float4 — the search loops read rows, not cells:
-// 16-byte coalescable loads, two cell_start look-ups per row.
+// Layout in HBM: the indexed cloud is binned into a 2^bits x 2^bits x 2^bits grid of cubic cells of edge h and
+// counting-sorted by the MORTON code of its cell into one float4 array {x, y, z, original_index_bits}; points of one
+// cell are ordered by original index, so every traversal is deterministic. `start` is the exclusive prefix sum of
+// the per-code counts (2^(3*bits) + 1 int32). Because the order is Morton, every aligned 2^l-cube of cells — every
+// node of the implicit octree over the grid — is ONE contiguous range of float4:
+//     node (level l, code m)  ->  points [ start[m << 3l], start[(m+1) << 3l] )
+// so the tree needs no node storage, empty space is skipped at the coarsest level that is empty, and a leaf is a
+// run of 16-byte loads.
 //
-// Exactness: a query scans the cube of cells with Chebyshev radius r around its own cell; every point
-// outside that cube is farther than r*h*(1 - slack) from the query (the binning function is monotone), so
-// the search stops as soon as the current k-th best distance is inside that bound, and doubles r otherwise.
-// Distances use ope::dist2 (FLANN L2_Simple order, no FMA) and ties break on the smaller original index —
-// the oracle's canonical order — so indices are bit-exact against the CPU restatement.
+// Search = pruned depth-first traversal, nearest child first. A node is skipped when a conservative lower bound of
+// its distance to the query exceeds the current bound (k-th best distance, radius, or the caller's range limit).
+// The bound is evaluated in "cell units" u = (q - o) * inv_h with the same float expression that binned the points,
+// which is monotone, so a point stored in cell c has u_p in [c, c+1) by construction; OPE_CELL_SLACK absorbs the
+// rounding of the subtraction. Distances of points use ope::dist2 (FLANN L2_Simple order, no FMA) and ties break on
+// the smaller original index — the oracle's canonical order — so indices are bit-exact against the CPU restatement
+// for near and far queries alike.
 #pragma once
 #include "ope_device.cuh"
 
@@ -19,10 +24,10 @@ namespace ope {
 struct GridView {
   float ox, oy, oz;   // origin = min corner of the indexed points
   float h, inv_h;     // cell edge
-  int nx, ny, nz;
+  int bits;           // octree depth: 2^bits cells per axis
   int n;              // number of indexed (finite) points
-  const int* cell_start;   // nx*ny*nz + 1
-  const float4* pts;       // n, sorted by cell then original index; .w = original index bits
+  const int* start;   // 2^(3*bits) + 1, indexed by Morton code
+  const float4* pts;  // n, sorted by Morton code then original index; .w = original index bits
 };
 
 #if defined(__CUDACC__) && defined(__CUDA_ARCH__)
@@ -31,90 +36,170 @@ struct GridView {
 #define OPE_LDG(p) (*(p))
 #endif
 
-OPE_HD int grid_cell_coord(float v, float o, float inv_h) { return (int)floorf((v - o) * inv_h); }
-
-// relative slack of the "outside the cube" bound: binning rounding (<= 2.4e-7 cells per cell of offset,
-// dims are capped at 4096) plus margin.
-#define OPE_GRID_SLACK 4e-3f
+#define OPE_CELL_SLACK 4e-4f      // cells: rounding of (p - o) * inv_h on both sides, grids are at most 512 cells wide
+#define OPE_MAX_BITS 9
+#ifndef OPE_NN1_LEAF
+#define OPE_NN1_LEAF 8
+#endif
+#ifndef OPE_COUNT
+#define OPE_COUNT(what)   // tests/hostemu defines this to count node visits / point tests
+#endif
 
 OPE_HD int imin(int a, int b) { return a < b ? a : b; }
 OPE_HD int imax(int a, int b) { return a > b ? a : b; }
-OPE_HD int iabs(int a) { return a < 0 ? -a : a; }
 
-// Visit every indexed point in the cube [c-r, c+r]^3 (clamped to the grid) that is NOT in the cube of
-// radius r_prev (r_prev < 0: nothing excluded). f(px, py, pz, original_index) is called per point.
-template <typename F>
-OPE_HD void grid_visit_shell(const GridView& g, int cx, int cy, int cz, int r, int r_prev, F&& f) {
-  const int z0 = imax(cz - r, 0), z1 = imin(cz + r, g.nz - 1);
-  const int y0 = imax(cy - r, 0), y1 = imin(cy + r, g.ny - 1);
-  const int x0 = imax(cx - r, 0), x1 = imin(cx + r, g.nx - 1);
-  if (x0 > x1) return;
-  for (int z = z0; z <= z1; ++z)
-    for (int y = y0; y <= y1; ++y) {
-      const int row = (z * g.ny + y) * g.nx;
-      const bool inner = r_prev >= 0 && iabs(z - cz) <= r_prev && iabs(y - cy) <= r_prev;
-      // up to two x segments: [x0, min(x1, cx-r_prev-1)] and [max(x0, cx+r_prev+1), x1]; or the full row
-      int segs[4];
-      int nseg = 0;
-      if (!inner) { segs[0] = x0; segs[1] = x1; nseg = 1; }
-      else {
-        int a1 = imin(x1, cx - r_prev - 1);
-        if (x0 <= a1) { segs[0] = x0; segs[1] = a1; nseg = 1; }
-        int b0 = imax(x0, cx + r_prev + 1);
-        if (b0 <= x1) { segs[2 * nseg] = b0; segs[2 * nseg + 1] = x1; ++nseg; }
-      }
-      for (int s = 0; s < nseg; ++s) {
-        const int b = OPE_LDG(g.cell_start + row + segs[2 * s]);
-        const int e = OPE_LDG(g.cell_start + row + segs[2 * s + 1] + 1);
-        for (int i = b; i < e; ++i) {
-          const float4 p = OPE_LDG(g.pts + i);
-          f(p.x, p.y, p.z, f2i(p.w));
+// spread the low 10 bits of v so that there are two zero bits between each
+OPE_HD unsigned part1by2(unsigned v) {
+  v &= 0x000003ffu;
+  v = (v ^ (v << 16)) & 0xff0000ffu;
+  v = (v ^ (v << 8)) & 0x0300f00fu;
+  v = (v ^ (v << 4)) & 0x030c30c3u;
+  v = (v ^ (v << 2)) & 0x09249249u;
+  return v;
+}
+OPE_HD unsigned compact1by2(unsigned v) {
+  v &= 0x09249249u;
+  v = (v ^ (v >> 2)) & 0x030c30c3u;
+  v = (v ^ (v >> 4)) & 0x0300f00fu;
+  v = (v ^ (v >> 8)) & 0xff0000ffu;
+  v = (v ^ (v >> 16)) & 0x000003ffu;
+  return v;
+}
+OPE_HD unsigned morton3(unsigned x, unsigned y, unsigned z) { return part1by2(x) | (part1by2(y) << 1) | (part1by2(z) << 2); }
+
+// cell coordinate of a point along one axis (the binning function; clamped to the grid)
+OPE_HD int grid_cell_coord(float v, float o, float inv_h, int bits) {
+  int c = (int)floorf((v - o) * inv_h);
+  return imin(imax(c, 0), (1 << bits) - 1);
+}
+OPE_HD unsigned grid_cell_code(const GridView& g, float x, float y, float z) {
+  return morton3((unsigned)grid_cell_coord(x, g.ox, g.inv_h, g.bits), (unsigned)grid_cell_coord(y, g.oy, g.inv_h, g.bits),
+                 (unsigned)grid_cell_coord(z, g.oz, g.inv_h, g.bits));
+}
+
+// conservative squared distance (metric units) from the query (cell units ux,uy,uz) to the box of cells
+// [cx*s, (cx+1)*s) x ... ; never larger than the distance to any point stored in that box.
+OPE_HD float oct_box_d2(float ux, float uy, float uz, int cx, int cy, int cz, int s, float h) {
+  const float fs = (float)s;
+  const float lx = (float)cx * fs, ly = (float)cy * fs, lz = (float)cz * fs;
+  float dx = fmaxf(fmaxf(lx - ux, ux - (lx + fs)), 0.0f);
+  float dy = fmaxf(fmaxf(ly - uy, uy - (ly + fs)), 0.0f);
+  float dz = fmaxf(fmaxf(lz - uz, uz - (lz + fs)), 0.0f);
+  dx = fmaxf(dx - OPE_CELL_SLACK, 0.0f);
+  dy = fmaxf(dy - OPE_CELL_SLACK, 0.0f);
+  dz = fmaxf(dz - OPE_CELL_SLACK, 0.0f);
+  const float d = (dx * dx + dy * dy + dz * dz) * (h * h);
+  return d * 0.99999f;
+}
+
+// ---- implicit octree nodes --------------------------------------------------------------------------------
+OPE_HD void oct_node_range(const GridView& g, int level, unsigned code, int& b, int& e) {
+  const int shift = 3 * level;
+  b = OPE_LDG(g.start + ((size_t)code << shift));
+  e = OPE_LDG(g.start + ((size_t)(code + 1u) << shift));
+}
+OPE_HD float oct_node_d2(const GridView& g, float ux, float uy, float uz, int level, unsigned code) {
+  return oct_box_d2(ux, uy, uz, (int)compact1by2(code), (int)compact1by2(code >> 1), (int)compact1by2(code >> 2), 1 << level,
+                    g.h);
+}
+// is the ball (centre u, radius rho, both in cell units) inside the node's box?
+OPE_HD bool oct_ball_inside(float ux, float uy, float uz, float rho, int level, unsigned code) {
+  const float fs = (float)(1 << level);
+  const float lx = (float)compact1by2(code) * fs, ly = (float)compact1by2(code >> 1) * fs, lz = (float)compact1by2(code >> 2) * fs;
+  return ux - rho >= lx && ux + rho <= lx + fs && uy - rho >= ly && uy + rho <= ly + fs && uz - rho >= lz && uz + rho <= lz + fs;
+}
+// smallest ancestor-or-self of (level, code) whose box contains the ball of squared metric radius r2 around the query
+OPE_HD void oct_enclosing(const GridView& g, float ux, float uy, float uz, float r2, int& level, unsigned& code) {
+  if (!(r2 < FLT_MAX)) { code >>= 3 * (g.bits - level); level = g.bits; return; }
+  const float rho = sqrtf(r2) * g.inv_h * 1.0001f + 2.0f * OPE_CELL_SLACK;
+  while (level < g.bits && !oct_ball_inside(ux, uy, uz, rho, level, code)) { code >>= 3; ++level; }
+}
+
+// Stackless pruned depth-first traversal of the subtree rooted at (root_level, root_code), children in Morton order.
+// bound(): current squared-distance bound — nodes whose conservative lower bound EXCEEDS it are skipped (it may shrink
+// while ranges are consumed). range(b, e): consume the points g.pts[b..e) of a node that is a single cell or holds at
+// most `leaf` points. The node (skip_level, skip_code) is not entered (it was consumed by the seed step). The only
+// state is (level, code): no stack, no local memory. Control flow depends only on (g, u, bound()), so a warp that
+// shares one query runs it uniformly.
+template <typename BoundF, typename RangeF>
+OPE_HD void oct_traverse(const GridView& g, float ux, float uy, float uz, int root_level, unsigned root_code, int skip_level,
+                         unsigned skip_code, int leaf, BoundF&& bound, RangeF&& range) {
+  int level = root_level;
+  unsigned code = root_code;
+  for (;;) {
+    bool descend = false;
+    OPE_COUNT(0);
+    if (!(level == skip_level && code == skip_code)) {
+      if (oct_node_d2(g, ux, uy, uz, level, code) <= bound()) {
+        int b, e;
+        oct_node_range(g, level, code, b, e);
+        OPE_COUNT(1);
+        if (e > b) {
+          if (level == 0 || e - b <= leaf) { OPE_COUNT(2); range(b, e); }
+          else descend = true;
         }
       }
     }
+    if (descend) { --level; code <<= 3; continue; }
+    for (;;) {  // next node in depth-first order
+      if (level == root_level) return;
+      if ((code & 7u) != 7u) { ++code; break; }
+      code >>= 3; ++level;
+    }
+  }
 }
 
-// Chebyshev distance (in cells) from the query's (unclamped) cell to the grid box; 0 when inside.
-OPE_HD int grid_outside_cells(const GridView& g, int cx, int cy, int cz) {
-  int d = 0;
-  d = imax(d, imax(-cx, cx - (g.nx - 1)));
-  d = imax(d, imax(-cy, cy - (g.ny - 1)));
-  d = imax(d, imax(-cz, cz - (g.nz - 1)));
-  return d;
-}
-// smallest r whose cube covers the whole grid
-OPE_HD int grid_cover_radius(const GridView& g, int cx, int cy, int cz) {
-  int r = imax(iabs(cx), iabs(g.nx - 1 - cx));
-  r = imax(r, imax(iabs(cy), iabs(g.ny - 1 - cy)));
-  r = imax(r, imax(iabs(cz), iabs(g.nz - 1 - cz)));
-  return r;
+// Greedy seed: walk from the root toward the query, at each level into the nearest child that still holds at least
+// `need` points, and stop at the first node that is a single cell, holds at most `leaf` points, or has no such child.
+// need = 1, leaf >= 1 for nearest-neighbour; need = k, leaf < k for k-NN (then no ancestor of the seed can be a leaf).
+OPE_HD void oct_seed(const GridView& g, float ux, float uy, float uz, int need, int leaf, int& level, unsigned& code, int& b, int& e) {
+  level = g.bits; code = 0u;
+  oct_node_range(g, level, code, b, e);
+  while (level > 0 && e - b > leaf) {
+    const int cl = level - 1;
+    const int shift = 3 * cl;
+    float best_d2 = FLT_MAX;
+    int best_j = -1, bb = 0, be = 0;
+    int prev = OPE_LDG(g.start + ((size_t)(code << 3) << shift));
+    for (unsigned j = 0; j < 8u; ++j) {
+      const unsigned cc = (code << 3) | j;
+      const int nxt = OPE_LDG(g.start + ((size_t)(cc + 1u) << shift));
+      if (nxt - prev >= need) {
+        const float d2 = oct_node_d2(g, ux, uy, uz, cl, cc);
+        if (d2 < best_d2) { best_d2 = d2; best_j = (int)j; bb = prev; be = nxt; }
+      }
+      prev = nxt;
+    }
+    if (best_j < 0) break;
+    level = cl; code = (code << 3) | (unsigned)best_j; b = bb; e = be;
+  }
 }
 
-// Exact nearest neighbour (k = 1). Only neighbours with d2 <= max_d2 matter to the caller: the search may
-// stop once everything unvisited is farther than that (pass FLT_MAX for an unbounded search).
-// Returns original index or -1 (nothing indexed / nothing within the bound visited).
+// Exact nearest neighbour (k = 1). Only neighbours with d2 <= max_d2 matter to the caller (FLT_MAX: unbounded).
+// Returns the original index or -1 (nothing indexed / nothing within the limit).
 OPE_HD int grid_nn1(const GridView& g, float qx, float qy, float qz, float max_d2, float& best_d2) {
   best_d2 = FLT_MAX;
   int best_i = -1;
   if (g.n <= 0) return -1;
-  const int cx = grid_cell_coord(qx, g.ox, g.inv_h), cy = grid_cell_coord(qy, g.oy, g.inv_h),
-            cz = grid_cell_coord(qz, g.oz, g.inv_h);
-  const int cover = grid_cover_radius(g, cx, cy, cz);
-  int r = imax(1, grid_outside_cells(g, cx, cy, cz));
-  int r_prev = -1;
-  for (;;) {
-    grid_visit_shell(g, cx, cy, cz, r, r_prev, [&](float px, float py, float pz, int idx) {
-      float d2 = dist2(qx, qy, qz, px, py, pz);
+  const float ux = (qx - g.ox) * g.inv_h, uy = (qy - g.oy) * g.inv_h, uz = (qz - g.oz) * g.inv_h;
+  auto scan = [&](int b, int e) {
+    for (int i = b; i < e; ++i) {
+      const float4 p = OPE_LDG(g.pts + i);
+      const float d2 = dist2(qx, qy, qz, p.x, p.y, p.z);
+      const int idx = f2i(p.w);
       if (nb_less(d2, idx, best_d2, best_i < 0 ? 0x7fffffff : best_i)) { best_d2 = d2; best_i = idx; }
-    });
-    if (r >= cover) break;
-    float bound = (float)r * g.h * (1.0f - OPE_GRID_SLACK);
-    float bound2 = bound * bound;
-    if (best_i >= 0 && best_d2 <= bound2) break;
-    if (bound2 > max_d2) break;  // anything unvisited is beyond the caller's range
-    r_prev = r;
-    r = imin(r * 2, cover);
-  }
+    }
+  };
+  const int leaf = OPE_NN1_LEAF;
+  int sl, b, e;
+  unsigned sc;
+  oct_seed(g, ux, uy, uz, 1, leaf, sl, sc, b, e);
+  scan(b, e);
+  int rl = sl;
+  unsigned rc = sc;
+  oct_enclosing(g, ux, uy, uz, fminf(best_d2, max_d2), rl, rc);
+  if (!(rl == sl && rc == sc))
+    oct_traverse(g, ux, uy, uz, rl, rc, sl, sc, leaf, [&]() { return fminf(best_d2, max_d2); }, scan);
   return best_i;
 }
 
@@ -124,32 +209,54 @@ OPE_HD int grid_knn(const GridView& g, float qx, float qy, float qz, int k, floa
   if (g.n <= 0 || k <= 0) return 0;
   if (k > g.n) k = g.n;
   int cnt = 0;
-  const int cx = grid_cell_coord(qx, g.ox, g.inv_h), cy = grid_cell_coord(qy, g.oy, g.inv_h),
-            cz = grid_cell_coord(qz, g.oz, g.inv_h);
-  const int cover = grid_cover_radius(g, cx, cy, cz);
-  int r = imax(1, grid_outside_cells(g, cx, cy, cz));
-  int r_prev = -1;
-  for (;;) {
-    grid_visit_shell(g, cx, cy, cz, r, r_prev, [&](float px, float py, float pz, int idx) {
-      float d2 = dist2(qx, qy, qz, px, py, pz);
-      if (cnt == k && !nb_less(d2, idx, bd[k - 1], bi[k - 1])) return;
-      int j = cnt < k ? cnt : k - 1;  // insertion position search from the tail
+  const float ux = (qx - g.ox) * g.inv_h, uy = (qy - g.oy) * g.inv_h, uz = (qz - g.oz) * g.inv_h;
+  auto scan = [&](int b, int e) {
+    for (int i = b; i < e; ++i) {
+      const float4 p = OPE_LDG(g.pts + i);
+      const float d2 = dist2(qx, qy, qz, p.x, p.y, p.z);
+      const int idx = f2i(p.w);
+      if (cnt == k && !nb_less(d2, idx, bd[k - 1], bi[k - 1])) continue;
+      int j = cnt < k ? cnt : k - 1;
       while (j > 0 && nb_less(d2, idx, bd[j - 1], bi[j - 1])) { bd[j] = bd[j - 1]; bi[j] = bi[j - 1]; --j; }
       bd[j] = d2; bi[j] = idx;
       if (cnt < k) ++cnt;
-    });
-    if (r >= cover) break;
-    float bound = (float)r * g.h * (1.0f - OPE_GRID_SLACK);
-    if (cnt == k && bd[k - 1] <= bound * bound) break;
-    r_prev = r;
-    r = imin(r * 2, cover);
-  }
+    }
+  };
+  const int leaf = imin(k - 1, 16);  // < k: the seed node (>= k points) has no ancestor that is consumed whole
+  int sl, b, e;
+  unsigned sc;
+  oct_seed(g, ux, uy, uz, k, leaf, sl, sc, b, e);
+  scan(b, e);
+  int rl = sl;
+  unsigned rc = sc;
+  oct_enclosing(g, ux, uy, uz, cnt == k ? bd[k - 1] : FLT_MAX, rl, rc);
+  if (!(rl == sl && rc == sc))
+    oct_traverse(g, ux, uy, uz, rl, rc, sl, sc, leaf, [&]() { return cnt == k ? bd[k - 1] : FLT_MAX; }, scan);
   return cnt;
 }
 
-// Number of rings that certainly contain every point with distance < radius.
-OPE_HD int grid_radius_rings(const GridView& g, float radius) {
-  return (int)floorf(radius * g.inv_h * (1.0f + OPE_GRID_SLACK)) + 1;
+// Radius traversal: range(b, e) is called for every leaf range that may hold points with d2 <= r2; the caller tests
+// d2 < r2 per point. Starts at the smallest node around the query's own cell that contains the search ball.
+template <typename RangeF>
+OPE_HD void grid_radius_ranges(const GridView& g, float qx, float qy, float qz, float r2, int leaf, RangeF&& range) {
+  if (g.n <= 0) return;
+  const float ux = (qx - g.ox) * g.inv_h, uy = (qy - g.oy) * g.inv_h, uz = (qz - g.oz) * g.inv_h;
+  int rl = 0;
+  unsigned rc = grid_cell_code(g, qx, qy, qz);
+  oct_enclosing(g, ux, uy, uz, r2, rl, rc);
+  oct_traverse(g, ux, uy, uz, rl, rc, -1, 0u, leaf, [&]() { return r2; }, range);
+}
+
+// Every indexed point with d2 < r2 (strict): f(px, py, pz, original_index, d2), in traversal order.
+template <typename F>
+OPE_HD void grid_radius_visit(const GridView& g, float qx, float qy, float qz, float r2, F&& f) {
+  grid_radius_ranges(g, qx, qy, qz, r2, 32, [&](int b, int e) {
+    for (int i = b; i < e; ++i) {
+      const float4 p = OPE_LDG(g.pts + i);
+      const float d2 = dist2(qx, qy, qz, p.x, p.y, p.z);
+      if (d2 < r2) f(p.x, p.y, p.z, f2i(p.w), d2);
+    }
+  });
 }
 
 }  // namespace ope

@@ -32,10 +32,11 @@ struct Binning {
   float inv[3];
   int min_b[3];
   int dim[3];
+  int morton_bits;  // > 0: cells are numbered by the Morton code of (cx,cy,cz) (search grids); 0: x-fastest linear index
 };
 
 struct GridEntry {
-  float h = 0;
+  int bits = 0;
   ope::GridView view{};
   int* cell_start = nullptr;
   float4* sorted = nullptr;

@@ -14,6 +14,7 @@
 #include <cstdlib>
 
 #include "ope_host.cuh"
+#include "ope_octet.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -90,19 +91,24 @@ __global__ void umeyama_final_kernel(const double* __restrict__ partials, int nb
   for (int i = 0; i < 16; ++i) out16[i] = T.m[i];
 }
 
-// fitness: sum of NN-1 squared distances <= max_range of the transformed source (double), plus the count
-__global__ void fitness_kernel(GridView g, const float4* __restrict__ src, int n, Mat4 T, float max_range_f,
-                               double* __restrict__ partials) {
+// fitness: sum of NN-1 squared distances <= max_range of the transformed source (double), plus the count.
+// One octet (8 lanes) per source point.
+__global__ void __launch_bounds__(kRedThreads) fitness_kernel(GridView g, const float4* __restrict__ src, int n, Mat4 T,
+                                                              float max_range_f, double* __restrict__ partials) {
   __shared__ double smem[(kRedThreads / 32) * 2];
+  __shared__ OctStack stacks[kRedThreads / 8];
+  const Octet o = octet_self();
+  OctStack* st = &stacks[threadIdx.x >> 3];
+  const int oct_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, n_oct = (gridDim.x * blockDim.x) >> 3;
   double acc[2] = {0.0, 0.0};
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  for (int i = oct_id; i < n; i += n_oct) {
     const float4 p = __ldg(src + i);
     float x, y, z;
     xform_point(T, p.x, p.y, p.z, x, y, z);
-    if (!finite3(x, y, z)) continue;
+    const bool ok = finite3(x, y, z);
     float d2;
-    int idx = grid_nn1(g, x, y, z, FLT_MAX, d2);
-    if (idx >= 0 && d2 <= max_range_f) { acc[0] += (double)d2; acc[1] += 1.0; }
+    const int idx = octet_nn1(g, st, o, ok, x, y, z, FLT_MAX, d2);
+    if (o.sub == 0u && ok && idx >= 0 && d2 <= max_range_f) { acc[0] += (double)d2; acc[1] += 1.0; }
   }
   block_reduce_store<2>(acc, smem, partials + (size_t)blockIdx.x * 2);
 }
@@ -136,56 +142,69 @@ struct IcpDev {
   float* corr_d2;             // n_src
   double* partials;           // 2 * gridDim * kIcpAcc (double buffered)
   ope_reg_result* result;     // device copy
+  long long* phase_cycles;    // optional (OPE_PROFILE=1): block 0's cycles in [search+reduce, grid barrier, partial sums + SVD, transform]
   Mat4 guess;
 };
 
 static constexpr int kIcpThreads = 256;
 static constexpr int kIcpAcc = 17;  // moments[16] + sum of correspondence distances
 
-// one correspondence for source point i in its CURRENT position; returns match index or -1
-__device__ __forceinline__ int icp_correspond(const IcpDev& a, int i, const float4 p, float& d2_out) {
-  if (!finite3(p.x, p.y, p.z)) return -1;
+// One correspondence for source point i in its CURRENT position p, computed by the octet that owns the point
+// (8 lanes, same arguments). Returns the match index or -1 in every lane.
+__device__ __forceinline__ int icp_correspond(const IcpDev& a, OctStack* st, OctKnnList* L, const Octet& o, int i, const float4 p,
+                                              float& d2_out) {
+  const bool ok = finite3(p.x, p.y, p.z);
   const bool stale = a.variant == OPE_ICP_VARIANT_MODCORR;
   int match = -1;
   float d2 = 0.0f;
   if (a.estimator == OPE_EST_NEAREST) {
-    match = grid_nn1(a.grid, p.x, p.y, p.z, a.max_d2_f, d2);
-    if (match < 0) return -1;
-    if ((double)d2 > a.max_corr_dist * a.max_corr_dist) return -1;
+    match = octet_nn1(a.grid, st, o, ok, p.x, p.y, p.z, a.max_d2_f, d2);
+    if (match >= 0 && (double)d2 > a.max_corr_dist * a.max_corr_dist) match = -1;
   } else {
-    float bd[32];
-    int bi[32];
-    const int cnt = grid_knn<32>(a.grid, p.x, p.y, p.z, a.k_search, bd, bi);
-    if (cnt == 0) return -1;
-    const float4 nr = stale ? __ldg(a.src0_nrm + i) : a.cur_nrm[i];
-    const double N[3] = {nr.x, nr.y, nr.z};
-    double min_dist = DBL_MAX;
-    int min_index = 0;
-    for (int j = 0; j < cnt; ++j) {
-      const float4 t = __ldg(a.tgt_pts + bi[j]);
-      const float px = t.x - p.x, py = t.y - p.y, pz = t.z - p.z;
-      const double V[3] = {px, py, pz};
-      const double C0 = N[1] * V[2] - N[2] * V[1], C1 = N[2] * V[0] - N[0] * V[2], C2 = N[0] * V[1] - N[1] * V[0];
-      const double dist = C0 * C0 + C1 * C1 + C2 * C2;
-      if (dist < min_dist) { min_dist = dist; min_index = j; }
+    const int cnt = octet_knn(a.grid, st, L, o, ok, p.x, p.y, p.z, a.k_search);
+    if (cnt > 0) {
+      // CorrespondenceEstimationNormalShooting: among the k nearest, the one with the smallest squared distance to the
+      // line through p along the source normal (double); the first minimum in list order wins.
+      const float4 nr = stale ? __ldg(a.src0_nrm + i) : a.cur_nrm[i];
+      const double N[3] = {nr.x, nr.y, nr.z};
+      double min_dist = DBL_MAX;
+      int min_index = 0x7fffffff;
+      for (int j = (int)o.sub; j < cnt; j += 8) {
+        const float4 t = __ldg(a.tgt_pts + L->i[j]);
+        const float px = t.x - p.x, py = t.y - p.y, pz = t.z - p.z;
+        const double V[3] = {px, py, pz};
+        const double C0 = N[1] * V[2] - N[2] * V[1], C1 = N[2] * V[0] - N[0] * V[2], C2 = N[0] * V[1] - N[1] * V[0];
+        const double dist = C0 * C0 + C1 * C1 + C2 * C2;
+        if (dist < min_dist) { min_dist = dist; min_index = j; }
+      }
+#pragma unroll
+      for (int s = 1; s < 8; s <<= 1) {
+        const double od = __shfl_xor_sync(o.mask, min_dist, s);
+        const int oi = __shfl_xor_sync(o.mask, min_index, s);
+        if (od < min_dist || (od == min_dist && oi < min_index)) { min_dist = od; min_index = oi; }
+      }
+      if (min_index != 0x7fffffff && !(min_dist > a.max_corr_dist)) {  // sic: squared cross norm vs unsquared threshold
+        match = L->i[min_index];
+        d2 = L->d[min_index];
+      }
     }
-    if (min_dist > a.max_corr_dist) return -1;  // sic: squared cross norm vs unsquared threshold
-    match = bi[min_index];
-    d2 = bd[min_index];
+    __syncwarp(o.mask);  // the list is reused by the octet's next point
   }
-  // rejector chain, VP/impl/icp_mod.hpp:194-208
-  for (int r = 0; r < a.n_rej; ++r) {
-    const float4 sn = stale ? __ldg(a.src0_nrm + i) : a.cur_nrm[i];
-    double score;
-    if (a.rej_kind[r] == OPE_REJ_SURFACE_NORMAL) {
-      const float4 tn = __ldg(a.tgt_nrm + match);
-      score = (double)((sn.x * tn.x) + (sn.y * tn.y) + (sn.z * tn.z));
-    } else {
-      const float4 sp = stale ? __ldg(a.src0_pts + i) : p;
-      const double s = (double)sqrtf(sp.x * sp.x + sp.y * sp.y + sp.z * sp.z);
-      score = (double)((sn.x * (-sp.x / s)) + (sn.y * (-sp.y / s)) + (sn.z * (-sp.z / s)));
+  if (match >= 0) {
+    // rejector chain, VP/impl/icp_mod.hpp:194-208
+    for (int r = 0; r < a.n_rej; ++r) {
+      const float4 sn = stale ? __ldg(a.src0_nrm + i) : a.cur_nrm[i];
+      double score;
+      if (a.rej_kind[r] == OPE_REJ_SURFACE_NORMAL) {
+        const float4 tn = __ldg(a.tgt_nrm + match);
+        score = (double)((sn.x * tn.x) + (sn.y * tn.y) + (sn.z * tn.z));
+      } else {
+        const float4 sp = stale ? __ldg(a.src0_pts + i) : p;
+        const double s = (double)sqrtf(sp.x * sp.x + sp.y * sp.y + sp.z * sp.z);
+        score = (double)((sn.x * (-sp.x / s)) + (sn.y * (-sp.y / s)) + (sn.z * (-sp.z / s)));
+      }
+      if (!(score > a.rej_thr[r])) { match = -1; break; }
     }
-    if (!(score > a.rej_thr[r])) return -1;
   }
   d2_out = d2;
   return match;
@@ -195,14 +214,19 @@ __global__ void __launch_bounds__(kIcpThreads) icp_kernel(IcpDev a) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double smem[(kIcpThreads / 32) * kIcpAcc];
   __shared__ double totals[kIcpAcc];
+  __shared__ OctStack stacks[kIcpThreads / 8];
+  __shared__ OctKnnList lists[kIcpThreads / 8];
+  const Octet o = octet_self();
+  OctStack* st = &stacks[threadIdx.x >> 3];
+  OctKnnList* L = &lists[threadIdx.x >> 3];
+  const int oct_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, n_oct = (gridDim.x * blockDim.x) >> 3;
   __shared__ Mat4 T_inc;
   __shared__ int s_stop;  // 0 continue, 1 stop, 2 stop without a transform (not enough correspondences)
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int nthreads = gridDim.x * blockDim.x;
 
   // input_transformed = guess applied to input (VP/impl/icp_mod.hpp:132-139)
   const bool have_guess = !mat4_is_identity(a.guess);
-  for (int i = tid; i < a.n_src; i += nthreads) {
+  for (int i = oct_id; i < a.n_src; i += n_oct) {
+    if (o.sub != 0u) continue;
     float4 p = __ldg(a.src0_pts + i);
     float4 v = a.src0_nrm ? __ldg(a.src0_nrm + i) : make_float4(0, 0, 0, 0);
     if (have_guess && finite3(p.x, p.y, p.z)) {
@@ -223,15 +247,19 @@ __global__ void __launch_bounds__(kIcpThreads) icp_kernel(IcpDev a) {
   int similar = 0, iterations = 0, state = OPE_CONV_NOT_CONVERGED, converged = 0, n_corr = 0;
   int pass = 0;  // uniform across all threads: selects the partials buffer
 
+  long long t_phase[4] = {0, 0, 0, 0};
+  const bool prof = a.phase_cycles != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
   for (;; ++pass) {
+    long long t0 = prof ? clock64() : 0;
     // ---- phase 1: correspondences + moments ----
     double acc[kIcpAcc];
 #pragma unroll
     for (int k = 0; k < kIcpAcc; ++k) acc[k] = 0.0;
-    for (int i = tid; i < a.n_src; i += nthreads) {
+    for (int i = oct_id; i < a.n_src; i += n_oct) {  // one octet (8 lanes) per source point
       const float4 p = a.cur_pts[i];
       float d2 = 0.0f;
-      const int m = icp_correspond(a, i, p, d2);
+      const int m = icp_correspond(a, st, L, o, i, p, d2);
+      if (o.sub != 0u) continue;  // lane 0 of the octet records and accumulates
       a.corr_match[i] = m;
       a.corr_d2[i] = d2;
       if (m >= 0) {
@@ -250,7 +278,9 @@ __global__ void __launch_bounds__(kIcpThreads) icp_kernel(IcpDev a) {
     double* my_partials = a.partials + ((size_t)(pass & 1) * gridDim.x + blockIdx.x) * kIcpAcc;
     block_reduce_store<kIcpAcc>(acc, smem, my_partials);
     __threadfence();
+    if (prof) { const long long t1 = clock64(); t_phase[0] += t1 - t0; t0 = t1; }
     grid.sync();
+    if (prof) { const long long t1 = clock64(); t_phase[1] += t1 - t0; t0 = t1; }
     // ---- phase 2: every block reduces all partials in the same order ----
     if (threadIdx.x < kIcpAcc) {
       const double* base = a.partials + (size_t)(pass & 1) * gridDim.x * kIcpAcc;
@@ -300,11 +330,14 @@ __global__ void __launch_bounds__(kIcpThreads) icp_kernel(IcpDev a) {
       s_stop = stop;
     }
     __syncthreads();
+    if (prof) { const long long t1 = clock64(); t_phase[2] += t1 - t0; t0 = t1; }
     // ---- phase 3: transformCloud(input_transformed, transformation_), own points only ----
     const int stop = s_stop;
     if (stop != 2) {
       const Mat4 T = T_inc;
-      for (int i = tid; i < a.n_src; i += nthreads) {
+      // the octet that searches point i is also the one that moves it (lane 0): no cross-block hazard on cur_pts
+      for (int i = oct_id; i < a.n_src; i += n_oct) {
+        if (o.sub != 0u) continue;
         float4 p = a.cur_pts[i];
         if (!finite3(p.x, p.y, p.z)) continue;
         float x, y, z;
@@ -321,8 +354,10 @@ __global__ void __launch_bounds__(kIcpThreads) icp_kernel(IcpDev a) {
         }
       }
     }
+    if (prof) { const long long t1 = clock64(); t_phase[3] += t1 - t0; }
     if (stop) break;
   }
+  if (prof) for (int i = 0; i < 4; ++i) a.phase_cycles[i] = t_phase[i];
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     ope_reg_result r;
     for (int i = 0; i < 16; ++i) r.T[i] = final_t.m[i];
@@ -332,14 +367,20 @@ __global__ void __launch_bounds__(kIcpThreads) icp_kernel(IcpDev a) {
   }
 }
 
-// one estimation + rejection pass (no loop), thread per source point
-__global__ void correspond_once_kernel(IcpDev a) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.n_src) return;
-  const float4 p = a.cur_pts[i];
-  float d2 = 0.0f;
-  a.corr_match[i] = icp_correspond(a, i, p, d2);
-  a.corr_d2[i] = d2;
+// one estimation + rejection pass (no loop), one octet per source point
+__global__ void __launch_bounds__(kIcpThreads) correspond_once_kernel(IcpDev a) {
+  __shared__ OctStack stacks[kIcpThreads / 8];
+  __shared__ OctKnnList lists[kIcpThreads / 8];
+  const Octet o = octet_self();
+  OctStack* st = &stacks[threadIdx.x >> 3];
+  OctKnnList* L = &lists[threadIdx.x >> 3];
+  const int oct_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, n_oct = (gridDim.x * blockDim.x) >> 3;
+  for (int i = oct_id; i < a.n_src; i += n_oct) {
+    const float4 p = a.cur_pts[i];
+    float d2 = 0.0f;
+    const int m = icp_correspond(a, st, L, o, i, p, d2);
+    if (o.sub == 0u) { a.corr_match[i] = m; a.corr_d2[i] = d2; }
+  }
 }
 
 // ============================================================================================ SAC-IA ====
@@ -367,6 +408,7 @@ static constexpr int kSaciaMaxSamples = 16;
 // serial `error += ...`, so the first-lowest-error hypothesis is the same one).
 __global__ void __launch_bounds__(kSaciaThreads) sacia_kernel(SaciaDev a) {
   __shared__ Mat4 T;
+  __shared__ OctStack stacks[kSaciaThreads / 8];
   const int h = a.h_begin + blockIdx.x;
   if (threadIdx.x == 0) {
     double acc[16];
@@ -391,17 +433,16 @@ __global__ void __launch_bounds__(kSaciaThreads) sacia_kernel(SaciaDev a) {
   __syncthreads();
   const Mat4 M = T;
   float* terms = a.terms + (size_t)blockIdx.x * a.ns;
-  for (int i = threadIdx.x; i < a.ns; i += blockDim.x) {
+  const Octet o = octet_self();
+  OctStack* st = &stacks[threadIdx.x >> 3];
+  for (int i = threadIdx.x >> 3; i < a.ns; i += kSaciaThreads / 8) {  // one octet per source point
     const float4 p = __ldg(a.src + i);
     float x, y, z;
     xform_point(M, p.x, p.y, p.z, x, y, z);
-    float term = 1.0f;
-    if (finite3(x, y, z)) {
-      float d2;
-      const int idx = grid_nn1(a.grid, x, y, z, a.threshold, d2);
-      if (idx >= 0 && d2 <= a.threshold) term = d2 / a.threshold;
-    }
-    terms[i] = term;
+    const bool ok = finite3(x, y, z);
+    float d2;
+    const int idx = octet_nn1(a.grid, st, o, ok, x, y, z, a.threshold, d2);
+    if (o.sub == 0u) terms[i] = (ok && idx >= 0 && d2 <= a.threshold) ? d2 / a.threshold : 1.0f;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -457,7 +498,7 @@ int fitness_device(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, con
   OPE_TRY(cloud_bbox(ctx, const_cast<ope_cloud*>(tgt)));
   GridView g;
   OPE_TRY(cloud_grid(ctx, tgt, knn_cell_size(tgt, 1), &g));
-  const int nb = (int)std::min<size_t>(std::max<size_t>(1, (src->n + kRedThreads - 1) / kRedThreads), (size_t)ctx->sm_count * 8);
+  const int nb = (int)std::min<size_t>(std::max<size_t>(1, (src->n * 8 + kRedThreads - 1) / kRedThreads), (size_t)ctx->sm_count * 4);
   Scratch<double> partials(ctx), fin(ctx);
   OPE_TRY(partials.alloc((size_t)nb * 2));
   OPE_TRY(fin.alloc(2));
@@ -542,9 +583,12 @@ int icp_device(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const o
   if (rc == OPE_OK) {
     if (per_sm < 1) rc = fail(ctx, OPE_ERR_CUDA, "icp_kernel cannot be resident");
     const int max_blocks = per_sm * ctx->sm_count;
-    blocks = (int)std::min<size_t>(std::max<size_t>(1, (n + kIcpThreads - 1) / kIcpThreads), (size_t)max_blocks);
+    blocks = (int)std::min<size_t>(std::max<size_t>(1, (n * 8 + kIcpThreads - 1) / kIcpThreads), (size_t)max_blocks);
   }
   if (rc == OPE_OK) rc = partials.alloc((size_t)2 * blocks * kIcpAcc);
+  Scratch<long long> phases(ctx);
+  const bool profile = std::getenv("OPE_PROFILE") != nullptr;
+  if (rc == OPE_OK && profile) { rc = phases.alloc(4); a.phase_cycles = phases.p; }
   a.corr_match = match.p; a.corr_d2 = d2.p; a.partials = partials.p; a.result = dres.p;
   if (rc == OPE_OK) {
     void* args[] = {(void*)&a};
@@ -559,6 +603,15 @@ int icp_device(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const o
     void* h;
     rc = read_back(ctx, dres.p, sizeof(ope_reg_result), &h);
     if (rc == OPE_OK) std::memcpy(res, h, sizeof(ope_reg_result));
+  }
+  if (rc == OPE_OK && profile) {
+    void* h;
+    if (read_back(ctx, phases.p, 4 * sizeof(long long), &h) == OPE_OK) {
+      const long long* c = (const long long*)h;
+      fprintf(stderr, "[ope profile] icp_kernel blocks=%d block0 cycles: search+reduce %lld | grid barrier %lld | partials+svd %lld | transform %lld (per iteration: %.0f %.0f %.0f %.0f)\n",
+              blocks, c[0], c[1], c[2], c[3], (double)c[0] / std::max(res->iterations, 1), (double)c[1] / std::max(res->iterations, 1),
+              (double)c[2] / std::max(res->iterations, 1), (double)c[3] / std::max(res->iterations, 1));
+    }
   }
   if (rc == OPE_OK && out_corr_host && n > 0) {
     std::vector<int> hm(n);
@@ -782,7 +835,7 @@ int ope_correspondences(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt
   Scratch<float> d2(ctx);
   OPE_TRY(match.alloc(n)); OPE_TRY(d2.alloc(n));
   a.corr_match = match.p; a.corr_d2 = d2.p;
-  correspond_once_kernel<<<div_up(n, 128), 128, 0, ctx->stream>>>(a);
+  correspond_once_kernel<<<(unsigned)std::min<size_t>(div_up(n * 8, kIcpThreads), (size_t)ctx->sm_count * 8), kIcpThreads, 0, ctx->stream>>>(a);
   OPE_TRY(check_launch(ctx, "correspond_once_kernel"));
   std::vector<int> hm(n);
   std::vector<float> hd(n);

@@ -141,8 +141,9 @@ inline void svd3(const T Ain[9], T U[9], T S[3], T V[9]) {
   T A[9];
   for (int i = 0; i < 9; ++i) { A[i] = Ain[i]; V[i] = 0; }
   V[0] = V[4] = V[8] = 1;
-  const T eps = std::is_same<T, float>::value ? (T)1e-7 : (T)1e-15;
-  for (int sweep = 0; sweep < 30; ++sweep) {
+  const T eps = std::is_same<T, float>::value ? (T)4.76837158e-7 /* 2^-21 */ : (T)1e-15;
+  const T eps2 = eps * eps;
+  for (int sweep = 0; sweep < 15; ++sweep) {
     bool rotated = false;
     for (int p = 0; p < 2; ++p)
       for (int q = p + 1; q < 3; ++q) {
@@ -150,7 +151,7 @@ inline void svd3(const T Ain[9], T U[9], T S[3], T V[9]) {
         T alpha = ap[0] * ap[0] + ap[1] * ap[1] + ap[2] * ap[2];
         T beta = aq[0] * aq[0] + aq[1] * aq[1] + aq[2] * aq[2];
         T gamma = ap[0] * aq[0] + ap[1] * aq[1] + ap[2] * aq[2];
-        if (gamma == 0 || std::fabs(gamma) <= eps * std::sqrt(alpha * beta)) continue;
+        if (gamma == 0 || gamma * gamma <= eps2 * (alpha * beta)) continue;  // sqrt-free relative test
         rotated = true;
         T zeta = (beta - alpha) / (2 * gamma);
         T t = (zeta >= 0 ? (T)1 : (T)-1) / (std::fabs(zeta) + std::sqrt(1 + zeta * zeta));
@@ -249,10 +250,11 @@ inline void umeyamaFromSigma(const T sigma[9], const T src_mean[3], const T dst_
 // Eigen evaluates the means and the 3x3 cross-covariance with vectorised float reductions whose summation order
 // cannot be reproduced without Eigen, and ICP's stop test (cos >= 1 - 1e-8 on a float trace) turns 1e-7 differences
 // into a different stopping iteration. The oracle therefore accumulates the raw moments in DOUBLE (exact products of
-// float inputs, summation error ~1e-16 relative, i.e. independent of the order to far below float resolution), runs
-// the 3x3 SVD in double and rounds the 4x4 to float once. Any float summation order Eigen may use lies within the
-// float rounding bound of this result; a parallel reduction on the device reproduces it bit for bit (barring
-// ~1e-9-probability double-rounding ties).
+// float inputs, summation error ~1e-16 relative, i.e. independent of the order to far below float resolution) and
+// rounds the 3x3 cross-covariance to float; any float summation order Eigen may use lies within the float rounding
+// bound of that matrix. From there on it is float like the reference: Jacobi SVD of the float matrix, R = U S V^T in
+// float; the translation mu_dst - R mu_src is closed in double and rounded once. A parallel reduction on the device
+// reproduces this bit for bit (barring ~1e-9-probability double-rounding ties).
 template <typename SrcAt, typename DstAt>
 inline void umeyama(size_t n, SrcAt srcAt, DstAt dstAt, float Tout[16]) {
   double acc[16];
@@ -265,11 +267,37 @@ inline void umeyama(size_t n, SrcAt srcAt, DstAt dstAt, float Tout[16]) {
       for (int r = 0; r < 3; ++r) acc[7 + c * 3 + r] += (double)d[r] * (double)s[c];
   }
   const double nn = acc[0];
-  double ms[3], mt[3], sigma[9];
+  double ms[3], mt[3];
+  float sigma[9];
   for (int k = 0; k < 3; ++k) { ms[k] = acc[1 + k] / nn; mt[k] = acc[4 + k] / nn; }
   for (int c = 0; c < 3; ++c)
-    for (int r = 0; r < 3; ++r) sigma[c * 3 + r] = acc[7 + c * 3 + r] / nn - mt[r] * ms[c];
-  umeyamaFromSigma<double>(sigma, ms, mt, Tout);
+    for (int r = 0; r < 3; ++r) sigma[c * 3 + r] = (float)(acc[7 + c * 3 + r] / nn - mt[r] * ms[c]);
+  float U[9], S[3], V[9];
+  svd3<float>(sigma, U, S, V);
+  float Sd[3] = {1, 1, 1};
+  if (det3<float>(sigma) < 0) Sd[2] = -1;
+  int rank = 0;
+  for (int i = 0; i < 3; ++i)
+    if (!(std::fabs(S[i]) <= std::fabs(S[0]) * 1e-5f)) ++rank;  // NumTraits<float>::dummy_precision
+  if (rank == 2) Sd[2] = (det3<float>(U) * det3<float>(V) > 0) ? 1.0f : -1.0f;
+  float R[9];
+  for (int c = 0; c < 3; ++c)
+    for (int r = 0; r < 3; ++r) {
+      float s = U[0 * 3 + r] * Sd[0] * V[0 * 3 + c];
+      s = s + U[1 * 3 + r] * Sd[1] * V[1 * 3 + c];
+      s = s + U[2 * 3 + r] * Sd[2] * V[2 * 3 + c];
+      R[c * 3 + r] = s;
+    }
+  for (int i = 0; i < 16; ++i) Tout[i] = 0.0f;
+  Tout[15] = 1.0f;
+  for (int c = 0; c < 3; ++c)
+    for (int r = 0; r < 3; ++r) Tout[c * 4 + r] = R[c * 3 + r];
+  for (int r = 0; r < 3; ++r) {
+    double rs = (double)R[0 * 3 + r] * ms[0];
+    rs = rs + (double)R[1 * 3 + r] * ms[1];
+    rs = rs + (double)R[2 * 3 + r] * ms[2];
+    Tout[12 + r] = (float)(mt[r] - rs);
+  }
 }
 
 }  // namespace orc

@@ -9,6 +9,8 @@
 #include <cstring>
 #include <vector>
 using std::isfinite;
+static long g_counts[4] = {0, 0, 0, 0};
+#define OPE_COUNT(what) (g_counts[what]++)
 #include "../../object-pose-estimation_b200/csrc/ope_grid.cuh"
 
 using namespace ope;
@@ -20,7 +22,7 @@ struct HostGrid {
   std::vector<float4> sorted;
 };
 
-void build(const float* xyz, int n, float h, HostGrid& g) {
+void build(const float* xyz, int n, float h_wanted, HostGrid& g) {
   float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   int nf = 0;
   for (int i = 0; i < n; ++i) {
@@ -30,35 +32,30 @@ void build(const float* xyz, int n, float h, HostGrid& g) {
     for (int d = 0; d < 3; ++d) { mn[d] = std::min(mn[d], p[d]); mx[d] = std::max(mx[d], p[d]); }
   }
   if (nf == 0) { mn[0] = mn[1] = mn[2] = mx[0] = mx[1] = mx[2] = 0; }
-  int dim[3];
-  for (int d = 0; d < 3; ++d) dim[d] = (int)std::floor((double)(mx[d] - mn[d]) / h) + 1;
-  const float inv = 1.0f / h;
-  auto cell = [&](const float* p) {
-    int c[3];
-    for (int d = 0; d < 3; ++d) {
-      c[d] = (int)floorf((p[d] - mn[d]) * inv);
-      c[d] = std::min(std::max(c[d], 0), dim[d] - 1);
-    }
-    return ((int64_t)c[2] * dim[1] + c[1]) * dim[0] + c[0];
-  };
-  int64_t ncells = (int64_t)dim[0] * dim[1] * dim[2];
-  g.cell_start.assign(ncells + 1, 0);
-  for (int i = 0; i < n; ++i) { const float* p = xyz + 3 * i; if (finite3(p[0], p[1], p[2])) g.cell_start[cell(p) + 1]++; }
-  for (int64_t c = 0; c < ncells; ++c) g.cell_start[c + 1] += g.cell_start[c];
+  float emax = std::max(mx[0] - mn[0], std::max(mx[1] - mn[1], mx[2] - mn[2]));
+  if (!(emax > 0)) emax = 1.0f;
+  int bits = (int)std::ceil(std::log2(std::max(emax / h_wanted, 1.0f)));
+  bits = std::min(std::max(bits, 1), 8);
+  const float hh = emax * (1.0f + 1e-4f) / (float)(1 << bits);
+  const float inv = 1.0f / hh;
+  g.v.ox = mn[0]; g.v.oy = mn[1]; g.v.oz = mn[2]; g.v.h = hh; g.v.inv_h = inv; g.v.bits = bits; g.v.n = nf;
+  const size_t ncodes = (size_t)1 << (3 * bits);
+  g.cell_start.assign(ncodes + 1, 0);
+  for (int i = 0; i < n; ++i) { const float* p = xyz + 3 * i; if (finite3(p[0], p[1], p[2])) g.cell_start[grid_cell_code(g.v, p[0], p[1], p[2]) + 1]++; }
+  for (size_t c = 0; c < ncodes; ++c) g.cell_start[c + 1] += g.cell_start[c];
   std::vector<int> cur(g.cell_start.begin(), g.cell_start.end() - 1);
   g.sorted.resize(nf);
   for (int i = 0; i < n; ++i) {  // ascending i => index-ordered within a cell
     const float* p = xyz + 3 * i;
     if (!finite3(p[0], p[1], p[2])) continue;
-    g.sorted[cur[cell(p)]++] = make_float4(p[0], p[1], p[2], i2f(i));
+    g.sorted[cur[grid_cell_code(g.v, p[0], p[1], p[2])]++] = make_float4(p[0], p[1], p[2], i2f(i));
   }
-  g.v.ox = mn[0]; g.v.oy = mn[1]; g.v.oz = mn[2]; g.v.h = h; g.v.inv_h = inv;
-  g.v.nx = dim[0]; g.v.ny = dim[1]; g.v.nz = dim[2]; g.v.n = nf;
-  g.v.cell_start = g.cell_start.data(); g.v.pts = g.sorted.data();
+  g.v.start = g.cell_start.data(); g.v.pts = g.sorted.data();
 }
 }  // namespace
 
 extern "C" {
+void emu_counts(long* out, int reset) { for (int i = 0; i < 4; ++i) { out[i] = g_counts[i]; if (reset) g_counts[i] = 0; } }
 
 int emu_knn(const float* tgt, int nt, const float* qry, int nq, int k, float h, float max_d2, int* out_idx, float* out_d2) {
   HostGrid g;
@@ -75,17 +72,15 @@ int emu_knn(const float* tgt, int nt, const float* qry, int nq, int k, float h, 
   return 0;
 }
 
-// radius count via the ring visitor
+// radius count via the pruned traversal
 int emu_radius_count(const float* tgt, int nt, const float* qry, int nq, float radius, float h, int* counts) {
   HostGrid g;
   build(tgt, nt, h, g);
-  const int rings = grid_radius_rings(g.v, radius);
   const float r2 = radius * radius;
   for (int i = 0; i < nq; ++i) {
     const float* q = qry + 3 * i;
     int cnt = 0;
-    int cx = grid_cell_coord(q[0], g.v.ox, g.v.inv_h), cy = grid_cell_coord(q[1], g.v.oy, g.v.inv_h), cz = grid_cell_coord(q[2], g.v.oz, g.v.inv_h);
-    grid_visit_shell(g.v, cx, cy, cz, rings, -1, [&](float px, float py, float pz, int) { if (dist2(q[0], q[1], q[2], px, py, pz) < r2) ++cnt; });
+    grid_radius_visit(g.v, q[0], q[1], q[2], r2, [&](float, float, float, int, float) { ++cnt; });
     counts[i] = cnt;
   }
   return 0;
