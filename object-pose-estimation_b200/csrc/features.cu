@@ -11,37 +11,35 @@
 namespace ope {
 
 // ------------------------------------------------------------------------------------------ normals ----
-// One octet (8 lanes) per point: exact k-NN on the cloud's own grid into the octet's shared list (the point itself is
-// neighbour 0), then lane 0 sums the covariance sequentially in the sorted neighbour order, eigen33, flip
-// toward the viewpoint.
+// One warp per point: exact k-NN on the cloud's own grid into the warp's register list (the point itself is neighbour 0),
+// the neighbours' coordinates are fetched one per lane, then the covariance is summed sequentially in the sorted
+// neighbour order from shuffles, eigen33, flip toward the viewpoint.
 static constexpr int kNormThreads = 256;
 __global__ void __launch_bounds__(kNormThreads) normals_kernel(GridView g, const float4* __restrict__ pts, int n, int k, float vpx,
                                                                float vpy, float vpz, float4* __restrict__ out) {
-  __shared__ OctStack stacks[kNormThreads / 8];
-  __shared__ OctKnnList lists[kNormThreads / 8];
-  const Octet o = octet_self();
-  OctStack* st = &stacks[threadIdx.x >> 3];
-  OctKnnList* L = &lists[threadIdx.x >> 3];
-  const int oct_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, n_oct = (gridDim.x * blockDim.x) >> 3;
+  __shared__ OctStack stacks[kNormThreads / 32];
+  OctStack* st = &stacks[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
   const float nan = __int_as_float(0x7fc00000);
-  for (int i = oct_id; i < n; i += n_oct) {
+  for (int i = wid; i < n; i += n_warps) {
     const float4 q = __ldg(pts + i);
     const bool ok = finite3(q.x, q.y, q.z);
-    const int cnt = octet_knn(g, st, L, o, ok, q.x, q.y, q.z, k);
-    if (o.sub == 0u) {
-      float r[4] = {nan, nan, nan, nan};
-      if (ok && cnt >= 3) {
-        CovAccum acc;
-        acc.reset();
-        for (int j = 0; j < cnt; ++j) {
-          const float4 p = __ldg(pts + L->i[j]);
-          acc.add(p.x, p.y, p.z);
-        }
-        normal_from_accum(acc, cnt, q.x, q.y, q.z, vpx, vpy, vpz, r);
-      }
-      out[i] = make_float4(r[0], r[1], r[2], r[3]);
+    float ld;
+    int li;
+    const int cnt = warp_knn(g, st, ok, q.x, q.y, q.z, k, FLT_MAX, ld, li);
+    float4 p = make_float4(0, 0, 0, 0);
+    if (lane < cnt) p = __ldg(pts + li);
+    float r[4] = {nan, nan, nan, nan};
+    if (ok && cnt >= 3) {
+      CovAccum acc;
+      acc.reset();
+      for (int j = 0; j < cnt; ++j)   // every lane sums the same sequence: uniform, no divergence
+        acc.add(__shfl_sync(0xffffffffu, p.x, j), __shfl_sync(0xffffffffu, p.y, j), __shfl_sync(0xffffffffu, p.z, j));
+      normal_from_accum(acc, cnt, q.x, q.y, q.z, vpx, vpy, vpz, r);
     }
-    __syncwarp(o.mask);
+    if (lane == 0) out[i] = make_float4(r[0], r[1], r[2], r[3]);
+    __syncwarp();
   }
 }
 
@@ -268,7 +266,7 @@ int normals_device(ope_ctx* ctx, ope_cloud* cloud, int k, const float vp[3]) {
   OPE_TRY(cloud_bbox(ctx, cloud));
   GridView g;
   OPE_TRY(cloud_grid(ctx, cloud, knn_cell_size(cloud, k), &g));
-  normals_kernel<<<(unsigned)std::min<size_t>(div_up(cloud->n * 8, kNormThreads), (size_t)ctx->sm_count * 16), kNormThreads, 0, ctx->stream>>>(g, cloud->pts, (int)cloud->n, k, vp[0], vp[1], vp[2],
+  normals_kernel<<<(unsigned)std::min<size_t>(div_up(cloud->n * 32, kNormThreads), (size_t)ctx->sm_count * 8), kNormThreads, 0, ctx->stream>>>(g, cloud->pts, (int)cloud->n, k, vp[0], vp[1], vp[2],
                                                                  cloud->normals);
   return check_launch(ctx, "normals_kernel");
 }

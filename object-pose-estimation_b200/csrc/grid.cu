@@ -158,34 +158,42 @@ __global__ void cell_sort_kernel(const int* __restrict__ cell_start, int64_t nce
   }
 }
 
-// ---- k-NN query kernel: one octet (8 lanes) per query, see ope_octet.cuh ----
+// ---- k-NN query kernels (ope_octet.cuh): k = 1 one query per thread (block_nn1), k > 1 one query per warp (warp_knn) ----
 static constexpr int kKnnThreads = 256;
+__global__ void __launch_bounds__(kKnnThreads) nn1_kernel(GridView g, const float4* __restrict__ qry, int nq,
+                                                          int* __restrict__ out_idx, float* __restrict__ out_d2) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Nn1Smem<kKnnThreads>* nn = reinterpret_cast<Nn1Smem<kKnnThreads>*>(smem_raw);
+  for (int base = blockIdx.x * kKnnThreads; base < nq; base += gridDim.x * kKnnThreads) {
+    const int i = base + (int)threadIdx.x;
+    float4 q = make_float4(0, 0, 0, 0);
+    if (i < nq) q = __ldg(qry + i);
+    const bool ok = i < nq && finite3(q.x, q.y, q.z);
+    float d2;
+    const int idx = block_nn1<kKnnThreads>(g, nn, ok, q.x, q.y, q.z, FLT_MAX, -1, nullptr, d2);
+    if (i < nq) {
+      out_idx[i] = ok ? idx : -1;
+      if (out_d2) out_d2[i] = (ok && idx >= 0) ? d2 : INFINITY;
+    }
+  }
+}
 __global__ void __launch_bounds__(kKnnThreads) knn_kernel(GridView g, const float4* __restrict__ qry, int nq, int k,
                                                           int* __restrict__ out_idx, float* __restrict__ out_d2) {
-  __shared__ OctStack stacks[kKnnThreads / 8];
-  __shared__ OctKnnList lists[kKnnThreads / 8];
-  const Octet o = octet_self();
-  OctStack* st = &stacks[threadIdx.x >> 3];
-  OctKnnList* L = &lists[threadIdx.x >> 3];
-  const int oct_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, n_oct = (gridDim.x * blockDim.x) >> 3;
-  for (int i = oct_id; i < nq; i += n_oct) {
+  __shared__ OctStack stacks[kKnnThreads / 32];
+  OctStack* st = &stacks[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = wid; i < nq; i += n_warps) {
     const float4 q = __ldg(qry + i);
     const bool ok = finite3(q.x, q.y, q.z);
-    if (k == 1) {
-      float d2;
-      const int idx = octet_nn1(g, st, o, ok, q.x, q.y, q.z, FLT_MAX, d2);
-      if (o.sub == 0u) {
-        out_idx[i] = idx;
-        if (out_d2) out_d2[i] = idx >= 0 ? d2 : INFINITY;
-      }
-    } else {
-      const int cnt = octet_knn(g, st, L, o, ok, q.x, q.y, q.z, k);
-      for (int j = (int)o.sub; j < k; j += 8) {
-        out_idx[(size_t)i * k + j] = j < cnt ? L->i[j] : -1;
-        if (out_d2) out_d2[(size_t)i * k + j] = j < cnt ? L->d[j] : INFINITY;
-      }
-      __syncwarp(o.mask);
+    float ld;
+    int li;
+    const int cnt = warp_knn(g, st, ok, q.x, q.y, q.z, k, FLT_MAX, ld, li);
+    if (lane < k) {
+      out_idx[(size_t)i * k + lane] = lane < cnt ? li : -1;
+      if (out_d2) out_d2[(size_t)i * k + lane] = lane < cnt ? ld : INFINITY;
     }
+    __syncwarp();
   }
 }
 __global__ void radius_count_kernel(GridView g, const float4* __restrict__ qry, int nq, float r2, int* __restrict__ counts) {
@@ -542,6 +550,7 @@ void ope_ctx_destroy(ope_ctx* ctx) {
   for (int w = 0; w < 2; ++w)
     for (int j = 0; j < 2; ++j) if (ctx->kev[w][j]) cudaEventDestroy(ctx->kev[w][j]);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->stage) cudaFreeHost(ctx->stage);
   if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -561,13 +570,12 @@ int ope_cloud_upload(ope_ctx* ctx, const void* pts, size_t n, size_t stride, siz
   ope_cloud* c = nullptr;
   OPE_TRY(cloud_alloc(ctx, n, normals != nullptr, &c));
   if (n > 0) {
-    // pack to float4 in pinned memory, one async copy each
-    float4* hp = nullptr;
+    // pack to float4 in the context's pinned staging arena, one async copy each
+    void* stage = nullptr;
     const size_t bytes = n * sizeof(float4) * (normals ? 2 : 1);
-    if (cudaHostAlloc((void**)&hp, bytes, cudaHostAllocDefault) != cudaSuccess) {
-      ope_cloud_free(ctx, c);
-      return fail(ctx, OPE_ERR_CUDA, "pinned staging allocation failed");
-    }
+    int rc = stage_reserve(ctx, bytes, &stage);
+    if (rc != OPE_OK) { ope_cloud_free(ctx, c); return rc; }
+    float4* hp = (float4*)stage;
     const char* b = (const char*)pts + offset;
     for (size_t i = 0; i < n; ++i) {
       float v[3];
@@ -586,7 +594,6 @@ int ope_cloud_upload(ope_ctx* ctx, const void* pts, size_t n, size_t stride, siz
       e = cudaMemcpyAsync(c->normals, hn, n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFreeHost(hp);
     if (e != cudaSuccess) {
       ope_cloud_free(ctx, c);
       return fail(ctx, OPE_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e));
@@ -612,16 +619,19 @@ int ope_cloud_has_normals(const ope_cloud* c) { return c && c->normals ? 1 : 0; 
 int ope_cloud_download(ope_ctx* ctx, const ope_cloud* c, float* xyz, float* normals4) {
   if (!ctx || !c) return OPE_ERR_INVALID;
   if (c->n == 0) return OPE_OK;
-  std::vector<float4> h(c->n);
+  void* stage = nullptr;
+  OPE_TRY(stage_reserve(ctx, c->n * sizeof(float4), &stage));
+  const float4* h = (const float4*)stage;
   if (xyz) {
-    OPE_CUDA_TRY(ctx, cudaMemcpyAsync(h.data(), c->pts, c->n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    OPE_CUDA_TRY(ctx, cudaMemcpyAsync(stage, c->pts, c->n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
     OPE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     for (size_t i = 0; i < c->n; ++i) { xyz[3 * i] = h[i].x; xyz[3 * i + 1] = h[i].y; xyz[3 * i + 2] = h[i].z; }
   }
   if (normals4) {
     if (!c->normals) return fail(ctx, OPE_ERR_INVALID, "cloud has no normals");
-    OPE_CUDA_TRY(ctx, cudaMemcpyAsync(normals4, c->normals, c->n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    OPE_CUDA_TRY(ctx, cudaMemcpyAsync(stage, c->normals, c->n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
     OPE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    std::memcpy(normals4, stage, c->n * sizeof(float4));
   }
   return OPE_OK;
 }
@@ -658,8 +668,17 @@ static int knn_impl(ope_ctx* ctx, const ope_cloud* tgt, const float4* d_qry, siz
   Scratch<float> dd(ctx);
   OPE_TRY(di.alloc(nq * k));
   OPE_TRY(dd.alloc(nq * k));
-  knn_kernel<<<(unsigned)std::min<size_t>(div_up(nq * 8, kKnnThreads), (size_t)ctx->sm_count * 16), kKnnThreads, 0, ctx->stream>>>(g, d_qry, (int)nq, k, di.p, dd.p);
-  OPE_TRY(check_launch(ctx, "knn_kernel"));
+  if (k == 1) {
+    OPE_CUDA_TRY(ctx, cudaFuncSetAttribute((const void*)nn1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sizeof(Nn1Smem<kKnnThreads>)));
+    nn1_kernel<<<(unsigned)std::min<size_t>(div_up(nq, kKnnThreads), (size_t)ctx->sm_count * 4), kKnnThreads,
+                 sizeof(Nn1Smem<kKnnThreads>), ctx->stream>>>(g, d_qry, (int)nq, di.p, dd.p);
+    OPE_TRY(check_launch(ctx, "nn1_kernel"));
+  } else {
+    knn_kernel<<<(unsigned)std::min<size_t>(div_up(nq * 32, kKnnThreads), (size_t)ctx->sm_count * 8), kKnnThreads, 0,
+                 ctx->stream>>>(g, d_qry, (int)nq, k, di.p, dd.p);
+    OPE_TRY(check_launch(ctx, "knn_kernel"));
+  }
   OPE_CUDA_TRY(ctx, cudaMemcpyAsync(out_idx, di.p, nq * k * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   if (out_d2) OPE_CUDA_TRY(ctx, cudaMemcpyAsync(out_d2, dd.p, nq * k * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   OPE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));

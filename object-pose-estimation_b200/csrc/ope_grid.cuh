@@ -102,19 +102,6 @@ OPE_HD float oct_node_d2(const GridView& g, float ux, float uy, float uz, int le
   return oct_box_d2(ux, uy, uz, (int)compact1by2(code), (int)compact1by2(code >> 1), (int)compact1by2(code >> 2), 1 << level,
                     g.h);
 }
-// is the ball (centre u, radius rho, both in cell units) inside the node's box?
-OPE_HD bool oct_ball_inside(float ux, float uy, float uz, float rho, int level, unsigned code) {
-  const float fs = (float)(1 << level);
-  const float lx = (float)compact1by2(code) * fs, ly = (float)compact1by2(code >> 1) * fs, lz = (float)compact1by2(code >> 2) * fs;
-  return ux - rho >= lx && ux + rho <= lx + fs && uy - rho >= ly && uy + rho <= ly + fs && uz - rho >= lz && uz + rho <= lz + fs;
-}
-// smallest ancestor-or-self of (level, code) whose box contains the ball of squared metric radius r2 around the query
-OPE_HD void oct_enclosing(const GridView& g, float ux, float uy, float uz, float r2, int& level, unsigned& code) {
-  if (!(r2 < FLT_MAX)) { code >>= 3 * (g.bits - level); level = g.bits; return; }
-  const float rho = sqrtf(r2) * g.inv_h * 1.0001f + 2.0f * OPE_CELL_SLACK;
-  while (level < g.bits && !oct_ball_inside(ux, uy, uz, rho, level, code)) { code >>= 3; ++level; }
-}
-
 // Stackless pruned depth-first traversal of the subtree rooted at (root_level, root_code), children in Morton order.
 // bound(): current squared-distance bound — nodes whose conservative lower bound EXCEEDS it are skipped (it may shrink
 // while ranges are consumed). range(b, e): consume the points g.pts[b..e) of a node that is a single cell or holds at
@@ -175,11 +162,165 @@ OPE_HD void oct_seed(const GridView& g, float ux, float uy, float uz, int need, 
   }
 }
 
+// ---- ball -> nodes --------------------------------------------------------------------------------------------
+// The cells that can hold a point within squared metric distance r2 of the query, expressed as at most 2x2x2 nodes of
+// the SMALLEST level L at which the ball's cell range spans at most two nodes per axis. Unlike one enclosing ancestor
+// (which degenerates to the root whenever the ball straddles a high-level boundary) this start set is always local:
+// near queries get <= 8 single cells, far ones <= 8 coarse nodes that the pruned traversal then descends.
+struct BallNodes {
+  int L;        // node level
+  int nlo[3];   // node coordinates (level L) of the low corner
+  int span[3];  // 0 or 1 extra node along each axis
+  bool hit;     // false: the ball misses the grid entirely
+};
+OPE_HD BallNodes ball_nodes(const GridView& g, float ux, float uy, float uz, float r2) {
+  BallNodes B;
+  B.hit = true;
+  if (!(r2 < FLT_MAX)) {
+    B.L = g.bits;
+    for (int d = 0; d < 3; ++d) { B.nlo[d] = 0; B.span[d] = 0; }
+    return B;
+  }
+  const float fm = (float)((1 << g.bits) - 1);
+  const float rho = sqrtf(r2) * g.inv_h * 1.0001f + 2.0f * OPE_CELL_SLACK;
+  const float u[3] = {ux, uy, uz};
+  int lo[3], hi[3];
+  for (int d = 0; d < 3; ++d) {
+    const float a = floorf(u[d] - rho), b = floorf(u[d] + rho);
+    if (b < 0.0f || a > fm) B.hit = false;
+    lo[d] = (int)fminf(fmaxf(a, 0.0f), fm);
+    hi[d] = (int)fminf(fmaxf(b, 0.0f), fm);
+  }
+  int L = 0;
+  while (L < g.bits && (((hi[0] >> L) - (lo[0] >> L)) > 1 || ((hi[1] >> L) - (lo[1] >> L)) > 1 || ((hi[2] >> L) - (lo[2] >> L)) > 1)) ++L;
+  B.L = L;
+  for (int d = 0; d < 3; ++d) { B.nlo[d] = lo[d] >> L; B.span[d] = (hi[d] >> L) - (lo[d] >> L); }
+  return B;
+}
+// j-th node (j in 0..7: bit 0 = x, bit 1 = y, bit 2 = z) of the ball's start set; false when it does not exist
+OPE_HD bool ball_node(const BallNodes& B, int j, unsigned& code) {
+  const int dx = j & 1, dy = (j >> 1) & 1, dz = j >> 2;
+  if (!B.hit || dx > B.span[0] || dy > B.span[1] || dz > B.span[2]) return false;
+  code = morton3((unsigned)(B.nlo[0] + dx), (unsigned)(B.nlo[1] + dy), (unsigned)(B.nlo[2] + dz));
+  return true;
+}
+
+// Seed for an unseeded nearest-neighbour query: climb from the query's own (clamped) cell to the first non-empty
+// ancestor, descend greedily toward the query while the node is large, scan what is left. Cheap for queries near the
+// indexed surface (one or two levels), bounded by 2*bits node visits for far ones.
+#ifndef OPE_PROBE_LEAF
+#define OPE_PROBE_LEAF 8
+#endif
+template <typename ScanF>
+OPE_HD void nn1_probe(const GridView& g, float qx, float qy, float qz, float ux, float uy, float uz, ScanF&& scan) {
+  unsigned code = grid_cell_code(g, qx, qy, qz);
+  int level = 0, b, e;
+  for (;;) {
+    oct_node_range(g, level, code, b, e);
+    OPE_COUNT(1);
+    if (e > b || level == g.bits) break;
+    code >>= 3; ++level;
+  }
+  while (level > 0 && e - b > OPE_PROBE_LEAF) {
+    const int cl = level - 1;
+    const int shift = 3 * cl;
+    float best_d2 = FLT_MAX;
+    int best_j = -1, bb = 0, be = 0;
+    int prev = OPE_LDG(g.start + ((size_t)(code << 3) << shift));
+    for (unsigned j = 0; j < 8u; ++j) {
+      const unsigned cc = (code << 3) | j;
+      const int nxt = OPE_LDG(g.start + ((size_t)(cc + 1u) << shift));
+      if (nxt > prev) {
+        const float d2 = oct_node_d2(g, ux, uy, uz, cl, cc);
+        if (d2 < best_d2) { best_d2 = d2; best_j = (int)j; bb = prev; be = nxt; }
+      }
+      prev = nxt;
+    }
+    OPE_COUNT(1);
+    level = cl; code = (code << 3) | (unsigned)best_j; b = bb; e = be;
+  }
+  scan(b, imin(e, b + 4 * OPE_PROBE_LEAF));  // a seed only: any point is a valid upper bound
+}
+
+// Fast path: the whole candidate set of the current bound, when it is at most `fast_max` points in <= 8 nodes, is
+// scanned directly (16 independent `start` loads, then runs of 16-byte point loads). Returns false — nothing scanned —
+// when the set is larger; the caller then runs a pruned traversal (thread-level below, 8 lanes per query on the device).
+#ifndef OPE_NN1_FAST_MAX
+#define OPE_NN1_FAST_MAX 96
+#endif
+OPE_HD bool nn1_fast(const GridView& g, float qx, float qy, float qz, float ux, float uy, float uz, float max_d2, float& best_d2,
+                     int& best_i) {
+  const BallNodes B = ball_nodes(g, ux, uy, uz, fminf(best_d2, max_d2));
+  if (!B.hit) return true;
+  const int sh = 3 * B.L;
+  int nb[8], ne[8];
+  unsigned nc[8];
+  int total = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    nb[j] = ne[j] = 0; nc[j] = 0u;
+    if (ball_node(B, j, nc[j])) {
+      nb[j] = OPE_LDG(g.start + ((size_t)nc[j] << sh));
+      ne[j] = OPE_LDG(g.start + ((size_t)(nc[j] + 1u) << sh));
+      OPE_COUNT(1);
+    }
+    total += ne[j] - nb[j];
+  }
+  if (total > OPE_NN1_FAST_MAX) return false;
+  // First two points of every node: 16 predicated, mutually independent 16-byte loads in straight-line code (one L2
+  // round trip for the common case of a handful of points per cell), pruned against the bound the query arrived with.
+  const float bound0 = fminf(best_d2, max_d2);
+  float4 pa[8], pb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (ne[j] > nb[j] && oct_node_d2(g, ux, uy, uz, B.L, nc[j]) > bound0) ne[j] = nb[j];  // node outside the ball
+    pa[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    pb[j] = pa[j];
+    if (ne[j] - nb[j] > 0) pa[j] = OPE_LDG(g.pts + nb[j]);
+    if (ne[j] - nb[j] > 1) pb[j] = OPE_LDG(g.pts + nb[j] + 1);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (ne[j] - nb[j] > 0) {
+      OPE_COUNT(2);
+      const float d2 = dist2(qx, qy, qz, pa[j].x, pa[j].y, pa[j].z);
+      const int idx = f2i(pa[j].w);
+      if (nb_less(d2, idx, best_d2, best_i)) { best_d2 = d2; best_i = idx; }
+    }
+    if (ne[j] - nb[j] > 1) {
+      const float d2 = dist2(qx, qy, qz, pb[j].x, pb[j].y, pb[j].z);
+      const int idx = f2i(pb[j].w);
+      if (nb_less(d2, idx, best_d2, best_i)) { best_d2 = d2; best_i = idx; }
+    }
+  }
+  // the rest (cells with more than two points), two loads in flight
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    for (int i = nb[j] + 2; i < ne[j]; i += 2) {
+      const float4 p0 = OPE_LDG(g.pts + i);
+      const bool two = i + 1 < ne[j];
+      const float4 p1 = two ? OPE_LDG(g.pts + i + 1) : p0;
+      float d2 = dist2(qx, qy, qz, p0.x, p0.y, p0.z);
+      int idx = f2i(p0.w);
+      if (nb_less(d2, idx, best_d2, best_i)) { best_d2 = d2; best_i = idx; }
+      if (two) {
+        d2 = dist2(qx, qy, qz, p1.x, p1.y, p1.z);
+        idx = f2i(p1.w);
+        if (nb_less(d2, idx, best_d2, best_i)) { best_d2 = d2; best_i = idx; }
+      }
+    }
+  }
+  return true;
+}
+
 // Exact nearest neighbour (k = 1). Only neighbours with d2 <= max_d2 matter to the caller (FLT_MAX: unbounded).
-// Returns the original index or -1 (nothing indexed / nothing within the limit).
-OPE_HD int grid_nn1(const GridView& g, float qx, float qy, float qz, float max_d2, float& best_d2) {
+// seed_idx >= 0 names an indexed point (coordinates seed_pts[seed_idx], original order) used as the initial bound — e.g.
+// the previous ICP iteration's match; the result is the same exact nearest neighbour either way.
+// Returns the original index or -1 (nothing indexed); the caller rejects best_d2 > max_d2.
+OPE_HD int grid_nn1(const GridView& g, float qx, float qy, float qz, float max_d2, float& best_d2, int seed_idx = -1,
+                    const float4* seed_pts = nullptr) {
   best_d2 = FLT_MAX;
-  int best_i = -1;
+  int best_i = 0x7fffffff;
   if (g.n <= 0) return -1;
   const float ux = (qx - g.ox) * g.inv_h, uy = (qy - g.oy) * g.inv_h, uz = (qz - g.oz) * g.inv_h;
   auto scan = [&](int b, int e) {
@@ -187,20 +328,23 @@ OPE_HD int grid_nn1(const GridView& g, float qx, float qy, float qz, float max_d
       const float4 p = OPE_LDG(g.pts + i);
       const float d2 = dist2(qx, qy, qz, p.x, p.y, p.z);
       const int idx = f2i(p.w);
-      if (nb_less(d2, idx, best_d2, best_i < 0 ? 0x7fffffff : best_i)) { best_d2 = d2; best_i = idx; }
+      if (nb_less(d2, idx, best_d2, best_i)) { best_d2 = d2; best_i = idx; }
     }
   };
-  const int leaf = OPE_NN1_LEAF;
-  int sl, b, e;
-  unsigned sc;
-  oct_seed(g, ux, uy, uz, 1, leaf, sl, sc, b, e);
-  scan(b, e);
-  int rl = sl;
-  unsigned rc = sc;
-  oct_enclosing(g, ux, uy, uz, fminf(best_d2, max_d2), rl, rc);
-  if (!(rl == sl && rc == sc))
-    oct_traverse(g, ux, uy, uz, rl, rc, sl, sc, leaf, [&]() { return fminf(best_d2, max_d2); }, scan);
-  return best_i;
+  if (seed_idx >= 0 && seed_pts) {
+    const float4 s = OPE_LDG(seed_pts + seed_idx);
+    if (finite3(s.x, s.y, s.z)) { best_d2 = dist2(qx, qy, qz, s.x, s.y, s.z); best_i = seed_idx; }
+  }
+  if (best_i == 0x7fffffff) nn1_probe(g, qx, qy, qz, ux, uy, uz, scan);
+  if (!nn1_fast(g, qx, qy, qz, ux, uy, uz, max_d2, best_d2, best_i)) {
+    const BallNodes B = ball_nodes(g, ux, uy, uz, fminf(best_d2, max_d2));
+    for (int j = 0; j < 8; ++j) {
+      unsigned code;
+      if (!ball_node(B, j, code)) continue;
+      oct_traverse(g, ux, uy, uz, B.L, code, -1, 0u, OPE_NN1_LEAF, [&]() { return fminf(best_d2, max_d2); }, scan);
+    }
+  }
+  return best_i == 0x7fffffff ? -1 : best_i;
 }
 
 // Exact k nearest (k <= KMAX), ascending (d2, index) into bd/bi. Returns the count found (min(k, n)).
@@ -227,24 +371,28 @@ OPE_HD int grid_knn(const GridView& g, float qx, float qy, float qz, int k, floa
   unsigned sc;
   oct_seed(g, ux, uy, uz, k, leaf, sl, sc, b, e);
   scan(b, e);
-  int rl = sl;
-  unsigned rc = sc;
-  oct_enclosing(g, ux, uy, uz, cnt == k ? bd[k - 1] : FLT_MAX, rl, rc);
-  if (!(rl == sl && rc == sc))
-    oct_traverse(g, ux, uy, uz, rl, rc, sl, sc, leaf, [&]() { return cnt == k ? bd[k - 1] : FLT_MAX; }, scan);
+  const BallNodes B = ball_nodes(g, ux, uy, uz, cnt == k ? bd[k - 1] : FLT_MAX);
+  for (int j = 0; j < 8; ++j) {
+    unsigned code;
+    if (!ball_node(B, j, code)) continue;
+    if (B.L <= sl && (code >> (3 * (sl - B.L))) == sc) continue;  // inside the seed node: already consumed
+    oct_traverse(g, ux, uy, uz, B.L, code, sl, sc, leaf, [&]() { return cnt == k ? bd[k - 1] : FLT_MAX; }, scan);
+  }
   return cnt;
 }
 
 // Radius traversal: range(b, e) is called for every leaf range that may hold points with d2 <= r2; the caller tests
-// d2 < r2 per point. Starts at the smallest node around the query's own cell that contains the search ball.
+// d2 < r2 per point. Starts from the ball's <= 8 start nodes (ball_nodes), each traversed with pruning.
 template <typename RangeF>
 OPE_HD void grid_radius_ranges(const GridView& g, float qx, float qy, float qz, float r2, int leaf, RangeF&& range) {
   if (g.n <= 0) return;
   const float ux = (qx - g.ox) * g.inv_h, uy = (qy - g.oy) * g.inv_h, uz = (qz - g.oz) * g.inv_h;
-  int rl = 0;
-  unsigned rc = grid_cell_code(g, qx, qy, qz);
-  oct_enclosing(g, ux, uy, uz, r2, rl, rc);
-  oct_traverse(g, ux, uy, uz, rl, rc, -1, 0u, leaf, [&]() { return r2; }, range);
+  const BallNodes B = ball_nodes(g, ux, uy, uz, r2);
+  for (int j = 0; j < 8; ++j) {
+    unsigned code;
+    if (!ball_node(B, j, code)) continue;
+    oct_traverse(g, ux, uy, uz, B.L, code, -1, 0u, leaf, [&]() { return r2; }, range);
+  }
 }
 
 // Every indexed point with d2 < r2 (strict): f(px, py, pz, original_index, d2), in traversal order.

@@ -20,6 +20,8 @@ struct ope_ctx {
   std::string error;
   void* pinned = nullptr;      // small pinned staging buffer for scalar read-backs
   size_t pinned_bytes = 0;
+  void* stage = nullptr;       // grow-only pinned staging arena for cloud uploads / downloads (host <-> device at PCIe speed)
+  size_t stage_bytes = 0;
   cudaEvent_t kev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [which][begin/end] around the dominant kernels
   bool kev_valid[2] = {false, false};
 };
@@ -125,6 +127,22 @@ inline int read_back(ope_ctx* ctx, const void* dsrc, size_t bytes, void** host) 
 }
 
 inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// pinned staging arena of at least `bytes` (grow-only; the previous contents are not preserved)
+inline int stage_reserve(ope_ctx* ctx, size_t bytes, void** out) {
+  if (bytes > ctx->stage_bytes) {
+    if (ctx->stage) cudaFreeHost(ctx->stage);
+    ctx->stage = nullptr; ctx->stage_bytes = 0;
+    size_t want = bytes + bytes / 4 + (1 << 16);
+    if (cudaHostAlloc(&ctx->stage, want, cudaHostAllocDefault) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(ctx, OPE_ERR_CUDA, "pinned staging allocation of %zu bytes failed", want);
+    }
+    ctx->stage_bytes = want;
+  }
+  *out = ctx->stage;
+  return OPE_OK;
+}
 
 // ---- implemented in grid.cu ----
 int cloud_alloc(ope_ctx* ctx, size_t n, bool with_normals, ope_cloud** out);

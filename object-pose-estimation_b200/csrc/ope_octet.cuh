@@ -1,25 +1,30 @@
-// ope_octet.cuh — cooperative nearest-neighbour search: EIGHT LANES PER QUERY over the implicit octree of ope_grid.cuh.
+// ope_octet.cuh — device-side cooperative search over the implicit octree of ope_grid.cuh.
 //
-// Why octets. One query per thread leaves a B200 mostly empty at the reference's cloud sizes (50 000 queries = 16 % of
-// the resident-thread capacity) and walks the tree with data-dependent loops that serialise inside a warp (ncu on the
-// thread-per-query version: ~1/13 SIMT efficiency, barrier stalls behind the slowest lane). An octet matches the
-// octree's arity: at an internal node lane j tests child j (one 4-byte `start` load + one box distance per lane, the
-// sibling's load gives the range end by shuffle), at a leaf the lanes test eight points per step (16-byte loads of
-// consecutive float4). There is no divergence inside an octet, the dependent-load chain per query shrinks from ~100
-// node visits to ~20 steps, and there are 8x more threads to hide L2 latency with.
+// Three building blocks, all exact (bit-identical to ope::grid_nn1 / ope::grid_knn: same float distances, same
+// (d2, index) tie order, the same conservative bounds):
 //
-// Traversal is depth-first with the nearest child on top of a per-octet stack in shared memory (64 entries x 16 B:
-// node, lower bound, point range), pruned against the octet-wide current bound; entries are re-checked when popped.
-// All warp primitives are scoped to the octet's own 8-lane mask, so the four octets of a warp are independent.
-// Results are bit-identical to ope::grid_nn1 / ope::grid_knn (same exact distances, same (d2, index) tie order, the
-// same conservative bounds), which the host-compiled tests check against the CPU oracle.
+//  block_nn1   nearest neighbour, one query per THREAD. Each thread seeds its bound (the caller's previous match, or
+//              nn1_probe) and tries ope::nn1_fast: the <= 8 cells/nodes the bound's ball touches, 16 independent `start`
+//              loads and a few 16-byte point loads — two dependent L2 round trips. Queries whose candidate set is too large
+//              (far from the indexed surface) are compacted into a shared-memory list and finished one per WARP with
+//              large leaves (few dependent steps, wide pipelined point scans), so that a few slow queries never hold 31
+//              finished lanes hostage.
+//  coop_nn1    the pruned traversal with G lanes per query: at an internal node lane j tests child j (one 4-byte
+//              `start` load + one box distance per lane, the sibling's load gives the range end by shuffle), at a leaf the
+//              lanes test eight points per step. Starts from the ball's start nodes (ope::ball_nodes), nearest on top of a
+//              small per-octet stack in shared memory.
+//  warp_knn    exact k nearest (k <= 32), one query per WARP, the sorted result list held one entry per lane in
+//              REGISTERS (insertion = ballot + shfl_up, no shared memory), leaves scanned 32 points per step, internal
+//              nodes expanded by lanes 0..7.
 #pragma once
 #include "ope_grid.cuh"
 
 namespace ope {
 
-static constexpr int kOctStack = 64;   // >= 7 * OPE_MAX_BITS + 1
-static constexpr int kOctLeaf = 32;    // nodes with at most this many points are scanned, 8 points per step
+static constexpr int kOctStack = 72;   // >= 8 + 7 * OPE_MAX_BITS: initial push of <= 8 nodes, +7 net per expansion
+static constexpr int kOctLeaf = 32;    // octet: nodes with at most this many points are scanned, 8 points per step
+static constexpr int kWarpLeaf = 64;   // warp k-NN: ... 32 points per step
+static constexpr int kFarLeaf = 256;   // deferred nearest-neighbour queries (a warp each): few dependent steps, wide scans
 
 struct __align__(16) OctEntry {
   unsigned node;  // level << 27 | code
@@ -28,166 +33,240 @@ struct __align__(16) OctEntry {
 };
 struct OctStack { OctEntry s[kOctStack]; };
 
-// top-k list of one octet (k <= 32), ascending (d2, index), in shared memory
-struct OctKnnList { float d[32]; int i[32]; };
-
-struct Octet {
-  unsigned sub;    // lane within the octet, 0..7
-  unsigned obase;  // first lane of the octet within the warp: 0, 8, 16, 24
-  unsigned mask;   // the octet's lanes
+// A cooperative group of G lanes inside a warp (G = 8: octet, G = 32: warp)
+template <int G>
+struct Coop {
+  unsigned sub;    // lane within the group
+  unsigned gbase;  // first lane of the group within the warp
+  unsigned mask;   // the group's lanes
+  __device__ __forceinline__ Coop() {
+    const unsigned lane = threadIdx.x & 31u;
+    sub = lane & (unsigned)(G - 1);
+    gbase = lane & ~(unsigned)(G - 1);
+    mask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << gbase);
+  }
 };
-__device__ __forceinline__ Octet octet_self() {
-  Octet o;
-  const unsigned lane = threadIdx.x & 31u;
-  o.sub = lane & 7u; o.obase = lane & 24u; o.mask = 0xffu << o.obase;
-  return o;
-}
-__device__ __forceinline__ float octet_min(const Octet& o, float v) {
-  v = fminf(v, __shfl_xor_sync(o.mask, v, 1));
-  v = fminf(v, __shfl_xor_sync(o.mask, v, 2));
-  v = fminf(v, __shfl_xor_sync(o.mask, v, 4));
-  return v;
-}
-__device__ __forceinline__ int octet_sum(const Octet& o, int v) {
-  v += __shfl_xor_sync(o.mask, v, 1);
-  v += __shfl_xor_sync(o.mask, v, 2);
-  v += __shfl_xor_sync(o.mask, v, 4);
+using Octet = Coop<8>;
+
+template <int G>
+__device__ __forceinline__ float coop_min(const Coop<G>& o, float v) {
+#pragma unroll
+  for (int s = 1; s < G; s <<= 1) v = fminf(v, __shfl_xor_sync(o.mask, v, s));
   return v;
 }
 
-__device__ __forceinline__ void octet_push_root(const GridView& g, OctStack* st, const Octet& o, float ux, float uy, float uz) {
-  if (o.sub == 0u) {
-    OctEntry en;
-    en.node = (unsigned)g.bits << 27; en.d2 = oct_box_d2(ux, uy, uz, 0, 0, 0, 1 << g.bits, g.h); en.b = 0; en.e = g.n;
-    st->s[0] = en;
-  }
-  __syncwarp(o.mask);
-}
-
-// Expand an internal node: lane `sub` owns child `sub`; children that are non-empty and within `bound` are pushed,
-// the nearest one on top. `split` is octet-uniform. Returns the number pushed (octet-uniform).
-__device__ __forceinline__ int octet_expand(const GridView& g, OctStack* st, const Octet& o, int sp, bool split, unsigned node, int e,
-                                            float ux, float uy, float uz, float bound) {
-  const int level = (int)(node >> 27);
-  const unsigned code = node & 0x07ffffffu;
-  const int cl = level - 1;
-  const unsigned cc = (code << 3) | o.sub;
-  int cb = 0;
-  if (split) cb = __ldg(g.start + ((size_t)cc << (3 * cl)));
-  const int nb = __shfl_down_sync(o.mask, cb, 1, 8);
-  const int ce = (o.sub == 7u) ? e : nb;
-  float cd2 = FLT_MAX;
-  bool pass = false;
-  if (split && ce > cb) {
-    cd2 = oct_node_d2(g, ux, uy, uz, cl, cc);
-    pass = cd2 <= bound;
-  }
-  const unsigned om = (__ballot_sync(o.mask, pass) >> o.obase) & 0xffu;
+// Push the group's candidate nodes (lane j < 8 offers one when `pass`): all passing ones go on the stack, the nearest
+// (ties: lower lane) on top. Returns the number pushed (group-uniform). Lanes >= 8 must call with pass = false.
+template <int G>
+__device__ __forceinline__ int coop_push(OctStack* st, const Coop<G>& o, int sp, bool pass, unsigned node, float d2, int b, int e) {
+  const unsigned om = (__ballot_sync(o.mask, pass) >> o.gbase) & 0xffu;
   const int npass = __popc(om);
-  // nearest passing child (ties: lower child index) goes on top of the stack
-  float md = pass ? cd2 : FLT_MAX;
+  if (npass == 0) return 0;
+  float md = pass ? d2 : FLT_MAX;
   unsigned mi = o.sub;
 #pragma unroll
-  for (int s = 1; s < 8; s <<= 1) {
+  for (int s = 1; s < 8; s <<= 1) {   // the 8 offering lanes are an aligned group of 8: xor stays inside it
     const float od = __shfl_xor_sync(o.mask, md, s);
     const unsigned oi = __shfl_xor_sync(o.mask, mi, s);
     if (od < md || (od == md && oi < mi)) { md = od; mi = oi; }
   }
+  if (G > 8) mi = __shfl_sync(o.mask, mi, 0);  // lanes >= 8 of a warp-sized group take lane 0's view
   if (pass) {
     const unsigned others = om & ~(1u << mi);
     const int pos = (o.sub == mi) ? sp + npass - 1 : sp + __popc(others & ((1u << o.sub) - 1u));
     OctEntry en;
-    en.node = ((unsigned)cl << 27) | cc; en.d2 = cd2; en.b = cb; en.e = ce;
+    en.node = node; en.d2 = d2; en.b = b; en.e = e;
     st->s[pos] = en;
   }
   __syncwarp(o.mask);
   return npass;
 }
 
-// Exact nearest neighbour for the octet's query. The 8 lanes of the octet must call this together with the same
-// arguments; `active` false = no query. Returns the original index or -1, and its squared distance, in every lane.
-__device__ __forceinline__ int octet_nn1(const GridView& g, OctStack* st, const Octet& o, bool active, float qx, float qy, float qz,
-                                         float max_d2, float& out_d2) {
+// Start set of a (seeded) search: the ball's <= 8 nodes, lane j < 8 owns node j.
+template <int G>
+__device__ __forceinline__ int coop_push_ball(const GridView& g, OctStack* st, const Coop<G>& o, bool active, float ux, float uy,
+                                              float uz, float bound) {
+  bool pass = false;
+  unsigned node = 0u;
+  float d2 = FLT_MAX;
+  int b = 0, e = 0;
+  if (active && o.sub < 8u) {
+    const BallNodes B = ball_nodes(g, ux, uy, uz, bound);
+    unsigned code;
+    if (ball_node(B, (int)o.sub, code)) {
+      oct_node_range(g, B.L, code, b, e);
+      if (e > b) {
+        d2 = oct_node_d2(g, ux, uy, uz, B.L, code);
+        pass = d2 <= bound;
+        node = ((unsigned)B.L << 27) | code;
+      }
+    }
+  }
+  return coop_push(st, o, 0, pass, node, d2, b, e);
+}
+
+// Expand an internal node: lane j < 8 owns child j; children that are non-empty and within `bound` are pushed.
+// `split` is group-uniform.
+template <int G>
+__device__ __forceinline__ int coop_expand(const GridView& g, OctStack* st, const Coop<G>& o, int sp, bool split, unsigned node, int e,
+                                           float ux, float uy, float uz, float bound) {
+  const int level = (int)(node >> 27);
+  const unsigned code = node & 0x07ffffffu;
+  const int cl = level - 1;
+  const unsigned cc = (code << 3) | (o.sub & 7u);
+  const bool mine = split && o.sub < 8u;
+  int cb = 0;
+  if (mine) cb = __ldg(g.start + ((size_t)cc << (3 * cl)));
+  const int nb = __shfl_down_sync(o.mask, cb, 1, 8);
+  const int ce = (o.sub == 7u) ? e : nb;
+  float cd2 = FLT_MAX;
+  bool pass = false;
+  if (mine && ce > cb) {
+    cd2 = oct_node_d2(g, ux, uy, uz, cl, cc);
+    pass = cd2 <= bound;
+  }
+  return coop_push(st, o, sp, pass, ((unsigned)cl << 27) | cc, cd2, cb, ce);
+}
+
+// Exact nearest neighbour for the group's query (G lanes: 8 or 32), starting from (best_d2, best_i) — a valid candidate
+// or (FLT_MAX, INT_MAX). Nodes holding at most LEAF points are scanned G points per step (independent 16-byte loads),
+// larger ones are expanded. The lanes must call this together with the same arguments. Returns the index (INT_MAX: none)
+// and distance in every lane.
+template <int G, int LEAF>
+__device__ __forceinline__ int coop_nn1(const GridView& g, OctStack* st, const Coop<G>& o, bool active, float qx, float qy, float qz,
+                                        float max_d2, float& best_d2, int best_i) {
   const float ux = (qx - g.ox) * g.inv_h, uy = (qy - g.oy) * g.inv_h, uz = (qz - g.oz) * g.inv_h;
-  float best_d2 = FLT_MAX;
-  int best_i = 0x7fffffff;
-  int sp = 0;
-  if (active && g.n > 0) { octet_push_root(g, st, o, ux, uy, uz); sp = 1; }
+  int sp = coop_push_ball(g, st, o, active && g.n > 0, ux, uy, uz, fminf(best_d2, max_d2));
   while (sp > 0) {
     --sp;
     const OctEntry en = st->s[sp];
     __syncwarp(o.mask);  // every lane holds the popped entry before its slot can be overwritten
-    const float bound = fminf(octet_min(o, best_d2), max_d2);
+    const float bound = fminf(coop_min(o, best_d2), max_d2);
     const bool live = en.d2 <= bound;
     const int level = (int)(en.node >> 27);
-    const bool leaf = level == 0 || en.e - en.b <= kOctLeaf;
+    const bool leaf = level == 0 || en.e - en.b <= LEAF;
     if (live && leaf) {
-      for (int i = en.b + (int)o.sub; i < en.e; i += 8) {
+#pragma unroll 4
+      for (int i = en.b + (int)o.sub; i < en.e; i += G) {
         const float4 p = __ldg(g.pts + i);
         const float d2 = dist2(qx, qy, qz, p.x, p.y, p.z);
         const int idx = __float_as_int(p.w);
         if (nb_less(d2, idx, best_d2, best_i)) { best_d2 = d2; best_i = idx; }
       }
     }
-    sp += octet_expand(g, st, o, sp, live && !leaf, en.node, en.e, ux, uy, uz, bound);
+    sp += coop_expand(g, st, o, sp, live && !leaf, en.node, en.e, ux, uy, uz, bound);
   }
 #pragma unroll
-  for (int s = 1; s < 8; s <<= 1) {
+  for (int s = 1; s < G; s <<= 1) {
     const float od = __shfl_xor_sync(o.mask, best_d2, s);
     const int oi = __shfl_xor_sync(o.mask, best_i, s);
     if (nb_less(od, oi, best_d2, best_i)) { best_d2 = od; best_i = oi; }
   }
-  out_d2 = best_d2;
+  return best_i;
+}
+
+// ---- block_nn1 ----------------------------------------------------------------------------------------------
+// Shared-memory workspace of one block of T threads (T a multiple of 32): deferred-query list, per-thread result
+// slots, one stack per octet of the first kNn1Octets*8 threads.
+template <int T>
+struct Nn1Smem {
+  static constexpr int kGroups = T / 32;   // deferred queries are finished one per warp
+  int n_def;
+  float4 def_q[T];   // x, y, z, seed d2
+  int def_seed[T];   // seed index (INT_MAX: none)
+  int def_tid[T];
+  int res_i[T];
+  float res_d[T];
+  OctStack stacks[kGroups];
+};
+
+// One query per thread (active = false: none). seed_idx >= 0: index of an indexed point (seed_pts, original order) used
+// as the initial bound. Returns the exact nearest neighbour's original index or -1 (nothing indexed) and its squared
+// distance; only neighbours with d2 <= max_d2 matter (the caller rejects larger results). Contains __syncthreads():
+// every thread of the block must call it.
+template <int T>
+__device__ __forceinline__ int block_nn1(const GridView& g, Nn1Smem<T>* sm, bool active, float qx, float qy, float qz, float max_d2,
+                                         int seed_idx, const float4* __restrict__ seed_pts, float& d2_out,
+                                         long long* prof = nullptr /* thread 0: [0] fast-phase cycles [1] deferred-phase cycles [2] deferred count */) {
+  if (threadIdx.x == 0) sm->n_def = 0;
+  __syncthreads();
+  const long long pt0 = prof ? clock64() : 0;
+  float best_d2 = FLT_MAX;
+  int best_i = 0x7fffffff;
+  bool deferred = false;
+  active = active && g.n > 0;
+  if (active) {
+    const float ux = (qx - g.ox) * g.inv_h, uy = (qy - g.oy) * g.inv_h, uz = (qz - g.oz) * g.inv_h;
+    if (seed_idx >= 0) {
+      const float4 s = __ldg(seed_pts + seed_idx);
+      best_d2 = dist2(qx, qy, qz, s.x, s.y, s.z);
+      best_i = seed_idx;
+    } else {
+      nn1_probe(g, qx, qy, qz, ux, uy, uz, [&](int b, int e) {
+        for (int i = b; i < e; ++i) {
+          const float4 p = __ldg(g.pts + i);
+          const float d2 = dist2(qx, qy, qz, p.x, p.y, p.z);
+          const int idx = __float_as_int(p.w);
+          if (nb_less(d2, idx, best_d2, best_i)) { best_d2 = d2; best_i = idx; }
+        }
+      });
+    }
+    if (!nn1_fast(g, qx, qy, qz, ux, uy, uz, max_d2, best_d2, best_i)) {
+      deferred = true;
+      const int slot = atomicAdd(&sm->n_def, 1);
+      sm->def_q[slot] = make_float4(qx, qy, qz, best_d2);
+      sm->def_seed[slot] = best_i;
+      sm->def_tid[slot] = (int)threadIdx.x;
+    }
+  }
+  __syncthreads();
+  const int n_def = sm->n_def;
+  const long long pt1 = prof ? clock64() : 0;
+  if (n_def > 0) {
+    const Coop<32> o;
+    OctStack* st = &sm->stacks[threadIdx.x >> 5];
+    for (int d = (int)(threadIdx.x >> 5); d < n_def; d += Nn1Smem<T>::kGroups) {
+      const float4 q = sm->def_q[d];
+      float bd = q.w;
+      const int bi = coop_nn1<32, kFarLeaf>(g, st, o, true, q.x, q.y, q.z, max_d2, bd, sm->def_seed[d]);
+      if (o.sub == 0u) { const int t = sm->def_tid[d]; sm->res_i[t] = bi; sm->res_d[t] = bd; }
+    }
+  }
+  __syncthreads();
+  if (prof) { const long long pt2 = clock64(); prof[0] += pt1 - pt0; prof[1] += pt2 - pt1; prof[2] += n_def; }
+  if (deferred) { best_i = sm->res_i[threadIdx.x]; best_d2 = sm->res_d[threadIdx.x]; }
+  d2_out = best_d2;
   return best_i == 0x7fffffff ? -1 : best_i;
 }
 
-// Insert (d2, idx) into the octet's sorted list (cnt entries, capacity k <= 32) when `doit`; the eight lanes move four
-// slots each. All arguments octet-uniform; executed by all 8 lanes; returns the new count.
-__device__ __forceinline__ int octet_list_insert(OctKnnList* L, const Octet& o, int cnt, int k, float d2, int idx, bool doit) {
-  int less = 0;
-  float od[4];
-  int oi[4];
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int s = (int)o.sub + 8 * r;
-    od[r] = FLT_MAX; oi[r] = 0x7fffffff;
-    if (doit && s < cnt) { od[r] = L->d[s]; oi[r] = L->i[s]; if (nb_less(od[r], oi[r], d2, idx)) ++less; }
-  }
-  const int p = octet_sum(o, less);  // entries that sort before the new one
-  const int ncnt = !doit ? cnt : (cnt < k ? cnt + 1 : k);
-  __syncwarp(o.mask);  // all old values are in registers
-  if (doit) {
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int s = (int)o.sub + 8 * r;
-      if (s < cnt && s >= p && s + 1 < ncnt) { L->d[s + 1] = od[r]; L->i[s + 1] = oi[r]; }
-    }
-    if (o.sub == 0u && p < ncnt) { L->d[p] = d2; L->i[p] = idx; }
-  }
-  __syncwarp(o.mask);
-  return ncnt;
-}
-
-// Exact k nearest (k <= 32) for the octet's query into the octet's shared list, ascending (d2, index).
-// Returns the count (min(k, n)), identical in every lane of the octet.
-__device__ __forceinline__ int octet_knn(const GridView& g, OctStack* st, OctKnnList* L, const Octet& o, bool active, float qx,
-                                         float qy, float qz, int k) {
+// ---- warp_knn -----------------------------------------------------------------------------------------------
+// Exact k nearest (k <= 32) for the warp's query. Result: lane j < count holds the j-th nearest (ld, li), ascending
+// (d2, index); other lanes hold (FLT_MAX, INT_MAX). `init_bound`: only neighbours with d2 <= init_bound are wanted (an
+// upper bound of the k-th distance, e.g. from the previous ICP iteration's list; FLT_MAX: none). All 32 lanes call
+// with the same arguments. Returns the count (min(k, n) when init_bound is FLT_MAX).
+__device__ __forceinline__ int warp_knn(const GridView& g, OctStack* st, bool active, float qx, float qy, float qz, int k,
+                                        float init_bound, float& ld, int& li) {
+  const Coop<32> o;
+  const unsigned full = 0xffffffffu;
   const float ux = (qx - g.ox) * g.inv_h, uy = (qy - g.oy) * g.inv_h, uz = (qz - g.oz) * g.inv_h;
   if (k > g.n) k = g.n;
+  ld = FLT_MAX; li = 0x7fffffff;
   int cnt = 0;
-  int sp = 0;
-  if (active && g.n > 0 && k > 0) { octet_push_root(g, st, o, ux, uy, uz); sp = 1; }
+  if (!(active && g.n > 0 && k > 0)) return 0;
+  const unsigned kmask = k >= 32 ? full : ((1u << k) - 1u);
+  float kth_d = FLT_MAX;   // current k-th entry (valid when cnt == k)
+  int kth_i = 0x7fffffff;
+  int sp = coop_push_ball(g, st, o, true, ux, uy, uz, init_bound);
   while (sp > 0) {
     --sp;
     const OctEntry en = st->s[sp];
-    __syncwarp(o.mask);
-    float bound = (cnt == k) ? L->d[k - 1] : FLT_MAX;
+    __syncwarp();
+    float bound = (cnt == k) ? fminf(kth_d, init_bound) : init_bound;
     const bool live = en.d2 <= bound;
     const int level = (int)(en.node >> 27);
-    const bool leaf = level == 0 || en.e - en.b <= kOctLeaf;
+    const bool leaf = level == 0 || en.e - en.b <= kWarpLeaf;
     if (live && leaf) {
-      // eight candidates per step; the ones that beat the current k-th are inserted one at a time, in lane order
-      for (int base = en.b; base < en.e; base += 8) {
+      for (int base = en.b; base < en.e; base += 32) {
         const int i = base + (int)o.sub;
         float d2 = FLT_MAX;
         int idx = 0x7fffffff;
@@ -196,21 +275,29 @@ __device__ __forceinline__ int octet_knn(const GridView& g, OctStack* st, OctKnn
           d2 = dist2(qx, qy, qz, p.x, p.y, p.z);
           idx = __float_as_int(p.w);
         }
-        const bool cand = idx != 0x7fffffff && (cnt < k || nb_less(d2, idx, L->d[k - 1], L->i[k - 1]));
-        unsigned cm = (__ballot_sync(o.mask, cand) >> o.obase) & 0xffu;
+        const bool cand = idx != 0x7fffffff && d2 <= init_bound && (cnt < k || nb_less(d2, idx, kth_d, kth_i));
+        unsigned cm = __ballot_sync(full, cand);
         while (cm != 0u) {
           const int src = __ffs(cm) - 1;
           cm &= cm - 1u;
-          const float cd = __shfl_sync(o.mask, d2, src, 8);
-          const int ci = __shfl_sync(o.mask, idx, src, 8);
-          const bool still = cnt < k || nb_less(cd, ci, L->d[k - 1], L->i[k - 1]);
-          cnt = octet_list_insert(L, o, cnt, k, cd, ci, still);
+          const float cd = __shfl_sync(full, d2, src);
+          const int ci = __shfl_sync(full, idx, src);
+          if (cnt < k || nb_less(cd, ci, kth_d, kth_i)) {   // warp-uniform
+            const int pos = __popc(__ballot_sync(full, nb_less(ld, li, cd, ci)) & kmask);
+            const float ud = __shfl_up_sync(full, ld, 1);
+            const int ui = __shfl_up_sync(full, li, 1);
+            if ((int)o.sub > pos) { ld = ud; li = ui; }
+            else if ((int)o.sub == pos) { ld = cd; li = ci; }
+            if (cnt < k) ++cnt;
+            if (cnt == k) { kth_d = __shfl_sync(full, ld, k - 1); kth_i = __shfl_sync(full, li, k - 1); }
+          }
         }
       }
-      bound = (cnt == k) ? L->d[k - 1] : FLT_MAX;
+      bound = (cnt == k) ? fminf(kth_d, init_bound) : init_bound;
     }
-    sp += octet_expand(g, st, o, sp, live && !leaf, en.node, en.e, ux, uy, uz, bound);
+    sp += coop_expand(g, st, o, sp, live && !leaf, en.node, en.e, ux, uy, uz, bound);
   }
+  if ((int)o.sub >= cnt) { ld = FLT_MAX; li = 0x7fffffff; }
   return cnt;
 }
 

@@ -92,31 +92,37 @@ __global__ void umeyama_final_kernel(const double* __restrict__ partials, int nb
 }
 
 // fitness: sum of NN-1 squared distances <= max_range of the transformed source (double), plus the count.
-// One octet (8 lanes) per source point.
-__global__ void __launch_bounds__(kRedThreads) fitness_kernel(GridView g, const float4* __restrict__ src, int n, Mat4 T,
-                                                              float max_range_f, double* __restrict__ partials) {
-  __shared__ double smem[(kRedThreads / 32) * 2];
-  __shared__ OctStack stacks[kRedThreads / 8];
-  const Octet o = octet_self();
-  OctStack* st = &stacks[threadIdx.x >> 3];
-  const int oct_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, n_oct = (gridDim.x * blockDim.x) >> 3;
+// One query per thread through block_nn1 (fast path per thread, far queries finished by octets).
+static constexpr int kNnThreads = 256;
+__global__ void __launch_bounds__(kNnThreads) fitness_kernel(GridView g, const float4* __restrict__ src, int n, Mat4 T,
+                                                             float max_range_f, double* __restrict__ partials) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Nn1Smem<kNnThreads>* nn = reinterpret_cast<Nn1Smem<kNnThreads>*>(smem_raw);
+  __shared__ double smem[(kNnThreads / 32) * 2];
   double acc[2] = {0.0, 0.0};
-  for (int i = oct_id; i < n; i += n_oct) {
-    const float4 p = __ldg(src + i);
-    float x, y, z;
-    xform_point(T, p.x, p.y, p.z, x, y, z);
-    const bool ok = finite3(x, y, z);
+  for (int base = blockIdx.x * kNnThreads; base < n; base += gridDim.x * kNnThreads) {
+    const int i = base + (int)threadIdx.x;
+    float x = 0, y = 0, z = 0;
+    bool ok = false;
+    if (i < n) {
+      const float4 p = __ldg(src + i);
+      xform_point(T, p.x, p.y, p.z, x, y, z);
+      ok = finite3(x, y, z);
+    }
     float d2;
-    const int idx = octet_nn1(g, st, o, ok, x, y, z, FLT_MAX, d2);
-    if (o.sub == 0u && ok && idx >= 0 && d2 <= max_range_f) { acc[0] += (double)d2; acc[1] += 1.0; }
+    const int idx = block_nn1<kNnThreads>(g, nn, ok, x, y, z, FLT_MAX, -1, nullptr, d2);
+    if (ok && idx >= 0 && d2 <= max_range_f) { acc[0] += (double)d2; acc[1] += 1.0; }
   }
   block_reduce_store<2>(acc, smem, partials + (size_t)blockIdx.x * 2);
 }
 __global__ void sum_partials_kernel(const double* __restrict__ partials, int nblocks, int nacc, double* __restrict__ out) {
-  if (blockIdx.x != 0 || threadIdx.x >= nacc) return;
+  // one warp per accumulator, lanes stride over the blocks, fixed shuffle tree
+  const int a = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (blockIdx.x != 0 || a >= nacc) return;
   double s = 0.0;
-  for (int b = 0; b < nblocks; ++b) s += partials[(size_t)b * nacc + threadIdx.x];
-  out[threadIdx.x] = s;
+  for (int b = lane; b < nblocks; b += 32) s += partials[(size_t)b * nacc + a];
+  s = warp_sum_d(s);
+  if (lane == 0) out[a] = s;
 }
 
 // =============================================================================================== ICP ====
@@ -137,96 +143,182 @@ struct IcpDev {
   float max_d2_f;             // squared, clamped to FLT_MAX (nearest estimator search bound)
   double rot_thr, trans_thr, rel_mse_thr, abs_mse_thr;
   int max_similar, fail_after_max;
-  // outputs
+  // outputs / state
   int* corr_match;            // n_src, -1 = no correspondence this iteration
   float* corr_d2;             // n_src
+  int* seed;                  // nearest: n_src, last exact neighbour (seed of the next iteration's search), -1 = none
+                              // normal shooting: n_src * k_search, last k-NN list (bounds the next search), -1 = none
   double* partials;           // 2 * gridDim * kIcpAcc (double buffered)
+  unsigned* barrier;          // monotonic arrival counter of the grid barrier (zeroed by the host)
   ope_reg_result* result;     // device copy
   long long* phase_cycles;    // optional (OPE_PROFILE=1): block 0's cycles in [search+reduce, grid barrier, partial sums + SVD, transform]
   Mat4 guess;
 };
 
-static constexpr int kIcpThreads = 256;
+static constexpr int kIcpThreads = 512;
+static constexpr int kIcpWarps = kIcpThreads / 32;
 static constexpr int kIcpAcc = 17;  // moments[16] + sum of correspondence distances
 
-// One correspondence for source point i in its CURRENT position p, computed by the octet that owns the point
-// (8 lanes, same arguments). Returns the match index or -1 in every lane.
-__device__ __forceinline__ int icp_correspond(const IcpDev& a, OctStack* st, OctKnnList* L, const Octet& o, int i, const float4 p,
-                                              float& d2_out) {
-  const bool ok = finite3(p.x, p.y, p.z);
-  const bool stale = a.variant == OPE_ICP_VARIANT_MODCORR;
-  int match = -1;
-  float d2 = 0.0f;
-  if (a.estimator == OPE_EST_NEAREST) {
-    match = octet_nn1(a.grid, st, o, ok, p.x, p.y, p.z, a.max_d2_f, d2);
-    if (match >= 0 && (double)d2 > a.max_corr_dist * a.max_corr_dist) match = -1;
-  } else {
-    const int cnt = octet_knn(a.grid, st, L, o, ok, p.x, p.y, p.z, a.k_search);
-    if (cnt > 0) {
-      // CorrespondenceEstimationNormalShooting: among the k nearest, the one with the smallest squared distance to the
-      // line through p along the source normal (double); the first minimum in list order wins.
-      const float4 nr = stale ? __ldg(a.src0_nrm + i) : a.cur_nrm[i];
-      const double N[3] = {nr.x, nr.y, nr.z};
-      double min_dist = DBL_MAX;
-      int min_index = 0x7fffffff;
-      for (int j = (int)o.sub; j < cnt; j += 8) {
-        const float4 t = __ldg(a.tgt_pts + L->i[j]);
-        const float px = t.x - p.x, py = t.y - p.y, pz = t.z - p.z;
-        const double V[3] = {px, py, pz};
-        const double C0 = N[1] * V[2] - N[2] * V[1], C1 = N[2] * V[0] - N[0] * V[2], C2 = N[0] * V[1] - N[1] * V[0];
-        const double dist = C0 * C0 + C1 * C1 + C2 * C2;
-        if (dist < min_dist) { min_dist = dist; min_index = j; }
-      }
+struct IcpSmem {
+  union {
+    Nn1Smem<kIcpThreads> nn;      // nearest estimator
+    OctStack wstack[kIcpWarps];   // normal shooting: one traversal stack per warp
+  } u;
+  double red[kIcpWarps][kIcpAcc];
+  double totals[kIcpAcc];
+  Mat4 T_inc;
+  int stop;  // 0 continue, 1 stop, 2 stop without a transform (not enough correspondences)
+};
+
+// ---- grid barrier: monotonic counter, release on arrival, acquire on the spin (cooperative launch => co-resident) ----
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while (v < target);
+  }
+  __syncthreads();
+}
+
+// Sum v[0..15] over the 32 lanes with 16 double shuffles instead of 80: at every level a lane keeps half of its
+// values and hands the other half to its partner. Afterwards lane l holds the warp total of slot
+// ((l>>4)&1)*8 + ((l>>3)&1)*4 + ((l>>2)&1)*2 + ((l>>1)&1) (both lanes of a pair hold the same one). Fixed shape.
+__device__ __forceinline__ double warp_reduce16(const double* v, int lane, int& slot) {
+  double w8[8], w4[4], w2[2], w1;
+  const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2;
 #pragma unroll
-      for (int s = 1; s < 8; s <<= 1) {
-        const double od = __shfl_xor_sync(o.mask, min_dist, s);
-        const int oi = __shfl_xor_sync(o.mask, min_index, s);
-        if (od < min_dist || (od == min_dist && oi < min_index)) { min_dist = od; min_index = oi; }
-      }
-      if (min_index != 0x7fffffff && !(min_dist > a.max_corr_dist)) {  // sic: squared cross norm vs unsquared threshold
-        match = L->i[min_index];
-        d2 = L->d[min_index];
-      }
-    }
-    __syncwarp(o.mask);  // the list is reused by the octet's next point
+  for (int j = 0; j < 8; ++j) {
+    const double keep = b16 ? v[j + 8] : v[j], give = b16 ? v[j] : v[j + 8];
+    w8[j] = keep + __shfl_xor_sync(0xffffffffu, give, 16);
   }
-  if (match >= 0) {
-    // rejector chain, VP/impl/icp_mod.hpp:194-208
-    for (int r = 0; r < a.n_rej; ++r) {
-      const float4 sn = stale ? __ldg(a.src0_nrm + i) : a.cur_nrm[i];
-      double score;
-      if (a.rej_kind[r] == OPE_REJ_SURFACE_NORMAL) {
-        const float4 tn = __ldg(a.tgt_nrm + match);
-        score = (double)((sn.x * tn.x) + (sn.y * tn.y) + (sn.z * tn.z));
-      } else {
-        const float4 sp = stale ? __ldg(a.src0_pts + i) : p;
-        const double s = (double)sqrtf(sp.x * sp.x + sp.y * sp.y + sp.z * sp.z);
-        score = (double)((sn.x * (-sp.x / s)) + (sn.y * (-sp.y / s)) + (sn.z * (-sp.z / s)));
-      }
-      if (!(score > a.rej_thr[r])) { match = -1; break; }
-    }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const double keep = b8 ? w8[j + 4] : w8[j], give = b8 ? w8[j] : w8[j + 4];
+    w4[j] = keep + __shfl_xor_sync(0xffffffffu, give, 8);
   }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const double keep = b4 ? w4[j + 2] : w4[j], give = b4 ? w4[j] : w4[j + 2];
+    w2[j] = keep + __shfl_xor_sync(0xffffffffu, give, 4);
+  }
+  {
+    const double keep = b2 ? w2[1] : w2[0], give = b2 ? w2[0] : w2[1];
+    w1 = keep + __shfl_xor_sync(0xffffffffu, give, 2);
+  }
+  w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+  slot = (b16 ? 8 : 0) + (b8 ? 4 : 0) + (b4 ? 2 : 0) + (b2 ? 1 : 0);
+  return w1;
+}
+
+// rejector chain for one candidate correspondence (VP/impl/icp_mod.hpp:194-208); returns the match or -1
+__device__ __forceinline__ int icp_reject(const IcpDev& a, int i, const float4 p, int match) {
+  const bool stale = a.variant == OPE_ICP_VARIANT_MODCORR;
+  for (int r = 0; r < a.n_rej && match >= 0; ++r) {
+    const float4 sn = stale ? __ldg(a.src0_nrm + i) : a.cur_nrm[i];
+    double score;
+    if (a.rej_kind[r] == OPE_REJ_SURFACE_NORMAL) {
+      const float4 tn = __ldg(a.tgt_nrm + match);
+      score = (double)((sn.x * tn.x) + (sn.y * tn.y) + (sn.z * tn.z));
+    } else {
+      const float4 sp = stale ? __ldg(a.src0_pts + i) : p;
+      const double s = (double)sqrtf(sp.x * sp.x + sp.y * sp.y + sp.z * sp.z);
+      score = (double)((sn.x * (-sp.x / s)) + (sn.y * (-sp.y / s)) + (sn.z * (-sp.z / s)));
+    }
+    if (!(score > a.rej_thr[r])) match = -1;
+  }
+  return match;
+}
+
+// CorrespondenceEstimation (nearest): one source point per THREAD, block-uniform call (block_nn1 synchronises).
+__device__ __forceinline__ int icp_correspond_nearest(const IcpDev& a, Nn1Smem<kIcpThreads>* nn, int i, bool in_range, const float4 p,
+                                                      bool use_seed, float& d2_out, long long* prof = nullptr) {
+  const bool ok = in_range && finite3(p.x, p.y, p.z);
+  const int sd = (use_seed && in_range) ? a.seed[i] : -1;
+  float d2 = 0.0f;
+  int match = block_nn1<kIcpThreads>(a.grid, nn, ok, p.x, p.y, p.z, a.max_d2_f, sd, a.tgt_pts, d2, prof);
+  if (!in_range) return -1;
+  a.seed[i] = match;
+  if (match >= 0 && (double)d2 > a.max_corr_dist * a.max_corr_dist) match = -1;
+  if (match >= 0) match = icp_reject(a, i, p, match);
   d2_out = d2;
   return match;
 }
 
-__global__ void __launch_bounds__(kIcpThreads) icp_kernel(IcpDev a) {
-  cg::grid_group grid = cg::this_grid();
-  __shared__ double smem[(kIcpThreads / 32) * kIcpAcc];
-  __shared__ double totals[kIcpAcc];
-  __shared__ OctStack stacks[kIcpThreads / 8];
-  __shared__ OctKnnList lists[kIcpThreads / 8];
-  const Octet o = octet_self();
-  OctStack* st = &stacks[threadIdx.x >> 3];
-  OctKnnList* L = &lists[threadIdx.x >> 3];
-  const int oct_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, n_oct = (gridDim.x * blockDim.x) >> 3;
-  __shared__ Mat4 T_inc;
-  __shared__ int s_stop;  // 0 continue, 1 stop, 2 stop without a transform (not enough correspondences)
+// CorrespondenceEstimationNormalShooting: one source point per WARP. Among the k nearest, the one with the smallest
+// squared distance to the line through p along the source normal (double); the first minimum in list order wins.
+__device__ __forceinline__ int icp_correspond_shooting(const IcpDev& a, OctStack* st, int i, const float4 p, bool use_seed,
+                                                       float& d2_out) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const bool ok = finite3(p.x, p.y, p.z);
+  const bool stale = a.variant == OPE_ICP_VARIANT_MODCORR;
+  const int k = a.k_search < a.grid.n ? a.k_search : a.grid.n;
+  // the previous iteration's k neighbours bound this iteration's k-th distance
+  float bound = FLT_MAX;
+  if (use_seed && ok) {
+    int pj = -1;
+    if (lane < k) pj = a.seed[(size_t)i * a.k_search + lane];
+    float d = 0.0f;
+    if (pj >= 0) { const float4 t = __ldg(a.tgt_pts + pj); d = dist2(p.x, p.y, p.z, t.x, t.y, t.z); }
+    const bool all_valid = __ballot_sync(full, lane >= k || pj >= 0) == full;
+    for (int o = 16; o > 0; o >>= 1) d = fmaxf(d, __shfl_xor_sync(full, d, o));
+    if (all_valid) bound = d;
+  }
+  float ld;
+  int li;
+  const int cnt = warp_knn(a.grid, st, ok, p.x, p.y, p.z, a.k_search, bound, ld, li);
+  if (lane < a.k_search) a.seed[(size_t)i * a.k_search + lane] = (lane < cnt) ? li : -1;
+  int match = -1;
+  float d2 = 0.0f;
+  if (cnt > 0) {
+    const float4 nr = stale ? __ldg(a.src0_nrm + i) : a.cur_nrm[i];
+    const double N[3] = {nr.x, nr.y, nr.z};
+    double dist = DBL_MAX;
+    int jdx = 0x7fffffff;
+    if (lane < cnt) {
+      const float4 t = __ldg(a.tgt_pts + li);
+      const float px = t.x - p.x, py = t.y - p.y, pz = t.z - p.z;
+      const double V[3] = {px, py, pz};
+      const double C0 = N[1] * V[2] - N[2] * V[1], C1 = N[2] * V[0] - N[0] * V[2], C2 = N[0] * V[1] - N[1] * V[0];
+      dist = C0 * C0 + C1 * C1 + C2 * C2;
+      jdx = lane;
+      if (!(dist < DBL_MAX)) { dist = DBL_MAX; jdx = 0x7fffffff; }  // NaN / inf never win (`dist < min_dist` in the reference)
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const double od = __shfl_xor_sync(full, dist, o);
+      const int oj = __shfl_xor_sync(full, jdx, o);
+      if (od < dist || (od == dist && oj < jdx)) { dist = od; jdx = oj; }
+    }
+    // the reference starts from min_index = 0: with no finite candidate it still reports neighbour 0 unless rejected below
+    const int pick = jdx == 0x7fffffff ? 0 : jdx;
+    const double min_dist = jdx == 0x7fffffff ? DBL_MAX : dist;
+    if (!(min_dist > a.max_corr_dist)) {  // sic: squared cross norm vs unsquared threshold
+      match = __shfl_sync(full, li, pick);
+      d2 = __shfl_sync(full, ld, pick);
+    }
+  }
+  if (match >= 0) match = icp_reject(a, i, p, match);
+  d2_out = d2;
+  return match;
+}
+
+__global__ void __launch_bounds__(kIcpThreads, 1) icp_kernel(IcpDev a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  IcpSmem* sm = reinterpret_cast<IcpSmem*>(smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gwarp = blockIdx.x * kIcpWarps + warp, n_gwarps = gridDim.x * kIcpWarps;
+  const bool shooting = a.estimator == OPE_EST_NORMAL_SHOOTING;
+
+  // nearest mode: block b owns the contiguous slice [lo, hi) of the source, one point per thread per round
+  const int chunk = (a.n_src + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int lo = min(a.n_src, (int)blockIdx.x * chunk), hi = min(a.n_src, lo + chunk);
 
   // input_transformed = guess applied to input (VP/impl/icp_mod.hpp:132-139)
   const bool have_guess = !mat4_is_identity(a.guess);
-  for (int i = oct_id; i < a.n_src; i += n_oct) {
-    if (o.sub != 0u) continue;
+  for (int i = blockIdx.x * kIcpThreads + threadIdx.x; i < a.n_src; i += gridDim.x * kIcpThreads) {
     float4 p = __ldg(a.src0_pts + i);
     float4 v = a.src0_nrm ? __ldg(a.src0_nrm + i) : make_float4(0, 0, 0, 0);
     if (have_guess && finite3(p.x, p.y, p.z)) {
@@ -241,6 +333,11 @@ __global__ void __launch_bounds__(kIcpThreads) icp_kernel(IcpDev a) {
     a.cur_pts[i] = p;
     if (a.cur_nrm) a.cur_nrm[i] = v;
   }
+  // The initialisation above is grid-strided; the iterations use their own ownership maps (nearest: the block's slice,
+  // shooting: warp gwarp owns points gwarp + j*n_gwarps), so the first iteration is preceded by a grid barrier.
+  unsigned bar_target = gridDim.x;
+  grid_barrier(a.barrier, bar_target);
+
   // per-block replicated state (identical in every block: same inputs, same order of operations)
   Mat4 final_t = a.guess;
   double prev_mse = DBL_MAX, cur_mse = DBL_MAX;
@@ -248,57 +345,102 @@ __global__ void __launch_bounds__(kIcpThreads) icp_kernel(IcpDev a) {
   int pass = 0;  // uniform across all threads: selects the partials buffer
 
   long long t_phase[4] = {0, 0, 0, 0};
+  long long t_nn[3] = {0, 0, 0};
   const bool prof = a.phase_cycles != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
   for (;; ++pass) {
     long long t0 = prof ? clock64() : 0;
     // ---- phase 1: correspondences + moments ----
-    double acc[kIcpAcc];
+    for (int e = lane; e < kIcpAcc; e += 32) sm->red[warp][e] = 0.0;
+    __syncwarp();
+    if (!shooting) {
+      for (int base = lo; base < hi; base += kIcpThreads) {
+        const int i = base + (int)threadIdx.x;
+        const bool in_range = i < hi;
+        float4 p = make_float4(0, 0, 0, 0);
+        if (in_range) p = a.cur_pts[i];
+        float d2 = 0.0f;
+        const int m = icp_correspond_nearest(a, &sm->u.nn, i, in_range, p, pass > 0, d2, prof ? t_nn : nullptr);
+        if (in_range) { a.corr_match[i] = m; a.corr_d2[i] = d2; }
+        double v[16];
 #pragma unroll
-    for (int k = 0; k < kIcpAcc; ++k) acc[k] = 0.0;
-    for (int i = oct_id; i < a.n_src; i += n_oct) {  // one octet (8 lanes) per source point
-      const float4 p = a.cur_pts[i];
-      float d2 = 0.0f;
-      const int m = icp_correspond(a, st, L, o, i, p, d2);
-      if (o.sub != 0u) continue;  // lane 0 of the octet records and accumulates
-      a.corr_match[i] = m;
-      a.corr_d2[i] = d2;
-      if (m >= 0) {
-        const float4 t = __ldg(a.tgt_pts + m);
-        acc[0] += 1.0;
-        acc[1] += p.x; acc[2] += p.y; acc[3] += p.z;
-        acc[4] += t.x; acc[5] += t.y; acc[6] += t.z;
-        const double sv[3] = {p.x, p.y, p.z}, tv[3] = {t.x, t.y, t.z};
+        for (int e = 0; e < 16; ++e) v[e] = 0.0;
+        double dsum = 0.0;
+        if (m >= 0) {
+          const float4 t = __ldg(a.tgt_pts + m);
+          v[0] = 1.0;
+          v[1] = p.x; v[2] = p.y; v[3] = p.z;
+          v[4] = t.x; v[5] = t.y; v[6] = t.z;
+          const double sv[3] = {p.x, p.y, p.z}, tv[3] = {t.x, t.y, t.z};
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
+          for (int c = 0; c < 3; ++c)
 #pragma unroll
-          for (int r = 0; r < 3; ++r) acc[7 + c * 3 + r] += tv[r] * sv[c];
-        acc[16] += (double)d2;
+            for (int r = 0; r < 3; ++r) v[7 + c * 3 + r] = tv[r] * sv[c];
+          dsum = (double)d2;
+        }
+        if (__ballot_sync(0xffffffffu, m >= 0) != 0u) {  // warp-uniform
+          int slot;
+          const double w = warp_reduce16(v, lane, slot);
+          dsum = warp_sum_d(dsum);
+          if ((lane & 1) == 0) sm->red[warp][slot] += w;
+          if (lane == 1) sm->red[warp][16] += dsum;
+          __syncwarp();
+        }
+      }
+    } else {
+      OctStack* st = &sm->u.wstack[warp];
+      for (int i = gwarp; i < a.n_src; i += n_gwarps) {  // one warp per source point
+        const float4 p = a.cur_pts[i];
+        float d2 = 0.0f;
+        const int m = icp_correspond_shooting(a, st, i, p, pass > 0, d2);
+        if (lane == 0) { a.corr_match[i] = m; a.corr_d2[i] = d2; }
+        if (m >= 0 && lane < kIcpAcc) {   // lane e computes term e of the 17 moments
+          const float4 t = __ldg(a.tgt_pts + m);
+          double term;
+          if (lane == 0) term = 1.0;
+          else if (lane < 4) term = lane == 1 ? p.x : (lane == 2 ? p.y : p.z);
+          else if (lane < 7) term = lane == 4 ? t.x : (lane == 5 ? t.y : t.z);
+          else if (lane < 16) {
+            const int c = (lane - 7) / 3, r = (lane - 7) % 3;
+            const double sv = c == 0 ? p.x : (c == 1 ? p.y : p.z);
+            const double tv = r == 0 ? t.x : (r == 1 ? t.y : t.z);
+            term = tv * sv;
+          } else term = (double)d2;
+          sm->red[warp][lane] += term;
+        }
+        __syncwarp();
       }
     }
+    __syncthreads();
     double* my_partials = a.partials + ((size_t)(pass & 1) * gridDim.x + blockIdx.x) * kIcpAcc;
-    block_reduce_store<kIcpAcc>(acc, smem, my_partials);
-    __threadfence();
-    if (prof) { const long long t1 = clock64(); t_phase[0] += t1 - t0; t0 = t1; }
-    grid.sync();
-    if (prof) { const long long t1 = clock64(); t_phase[1] += t1 - t0; t0 = t1; }
-    // ---- phase 2: every block reduces all partials in the same order ----
     if (threadIdx.x < kIcpAcc) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < kIcpWarps; ++w) s += sm->red[w][threadIdx.x];
+      my_partials[threadIdx.x] = s;
+    }
+    if (prof) { const long long t1 = clock64(); t_phase[0] += t1 - t0; t0 = t1; }
+    bar_target += gridDim.x;
+    grid_barrier(a.barrier, bar_target);
+    if (prof) { const long long t1 = clock64(); t_phase[1] += t1 - t0; t0 = t1; }
+    // ---- phase 2: every block reduces all partials in the same order (warp per accumulator, lanes over blocks) ----
+    for (int e = warp; e < kIcpAcc; e += kIcpWarps) {
       const double* base = a.partials + (size_t)(pass & 1) * gridDim.x * kIcpAcc;
       double s = 0.0;
-      for (int b = 0; b < (int)gridDim.x; ++b) s += __ldcg(base + (size_t)b * kIcpAcc + threadIdx.x);
-      totals[threadIdx.x] = s;
+      for (int b = lane; b < (int)gridDim.x; b += 32) s += __ldcg(base + (size_t)b * kIcpAcc + e);
+      s = warp_sum_d(s);
+      if (lane == 0) sm->totals[e] = s;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
       int stop = 0;
-      n_corr = (int)totals[0];
+      n_corr = (int)sm->totals[0];
       if (n_corr < a.min_corr) {
         state = OPE_CONV_NO_CORRESPONDENCES; converged = 0; stop = 2;  // VP/impl/icp_mod.hpp:232-240
-        T_inc = mat4_identity();
+        sm->T_inc = mat4_identity();
       } else {
         Mat4 T;
-        umeyama_from_moments(totals, T);
-        T_inc = T;
+        umeyama_from_moments(sm->totals, T);
+        sm->T_inc = T;
         final_t = mat4_mul(T, final_t);
         ++iterations;
         // DefaultConvergenceCriteria::hasConverged
@@ -313,7 +455,7 @@ __global__ void __launch_bounds__(kIcpThreads) icp_kernel(IcpDev a) {
           int hit = 0, hit_state = 0;
           if (cos_angle >= a.rot_thr && translation_sqr <= a.trans_thr) { hit = 1; hit_state = OPE_CONV_TRANSFORM; }
           else {
-            cur_mse = totals[16] / (double)n_corr;
+            cur_mse = sm->totals[16] / (double)n_corr;
             if (fabs(cur_mse - prev_mse) < a.abs_mse_thr) { hit = 1; hit_state = OPE_CONV_ABS_MSE; }
             else if (fabs(cur_mse - prev_mse) / prev_mse < a.rel_mse_thr) { hit = 1; hit_state = OPE_CONV_REL_MSE; }
             else prev_mse = cur_mse;
@@ -327,37 +469,59 @@ __global__ void __launch_bounds__(kIcpThreads) icp_kernel(IcpDev a) {
         if (a.force_all && iterations < a.max_iterations) conv = 0;
         if (conv) stop = 1;
       }
-      s_stop = stop;
+      sm->stop = stop;
     }
     __syncthreads();
     if (prof) { const long long t1 = clock64(); t_phase[2] += t1 - t0; t0 = t1; }
     // ---- phase 3: transformCloud(input_transformed, transformation_), own points only ----
-    const int stop = s_stop;
+    const int stop = sm->stop;
     if (stop != 2) {
-      const Mat4 T = T_inc;
-      // the octet that searches point i is also the one that moves it (lane 0): no cross-block hazard on cur_pts
-      for (int i = oct_id; i < a.n_src; i += n_oct) {
-        if (o.sub != 0u) continue;
-        float4 p = a.cur_pts[i];
-        if (!finite3(p.x, p.y, p.z)) continue;
-        float x, y, z;
-        xform_point(T, p.x, p.y, p.z, x, y, z);
-        p.x = x; p.y = y; p.z = z;
-        a.cur_pts[i] = p;
-        if (a.cur_nrm) {
-          float4 v = a.cur_nrm[i];
-          if (finite3(v.x, v.y, v.z)) {
-            xform_normal(T, v.x, v.y, v.z, x, y, z);
-            v.x = x; v.y = y; v.z = z;
-            a.cur_nrm[i] = v;
+      const Mat4 T = sm->T_inc;
+      // the thread / warp that searches point i is also the one that moves it: no cross-block hazard on cur_pts
+      if (!shooting) {
+        for (int i = lo + (int)threadIdx.x; i < hi; i += kIcpThreads) {
+          float4 p = a.cur_pts[i];
+          if (!finite3(p.x, p.y, p.z)) continue;
+          float x, y, z;
+          xform_point(T, p.x, p.y, p.z, x, y, z);
+          p.x = x; p.y = y; p.z = z;
+          a.cur_pts[i] = p;
+          if (a.cur_nrm) {
+            float4 v = a.cur_nrm[i];
+            if (finite3(v.x, v.y, v.z)) {
+              xform_normal(T, v.x, v.y, v.z, x, y, z);
+              v.x = x; v.y = y; v.z = z;
+              a.cur_nrm[i] = v;
+            }
+          }
+        }
+      } else if (lane == 0) {
+        for (int i = gwarp; i < a.n_src; i += n_gwarps) {
+          float4 p = a.cur_pts[i];
+          if (!finite3(p.x, p.y, p.z)) continue;
+          float x, y, z;
+          xform_point(T, p.x, p.y, p.z, x, y, z);
+          p.x = x; p.y = y; p.z = z;
+          a.cur_pts[i] = p;
+          if (a.cur_nrm) {
+            float4 v = a.cur_nrm[i];
+            if (finite3(v.x, v.y, v.z)) {
+              xform_normal(T, v.x, v.y, v.z, x, y, z);
+              v.x = x; v.y = y; v.z = z;
+              a.cur_nrm[i] = v;
+            }
           }
         }
       }
+      __syncwarp();
     }
     if (prof) { const long long t1 = clock64(); t_phase[3] += t1 - t0; }
     if (stop) break;
   }
-  if (prof) for (int i = 0; i < 4; ++i) a.phase_cycles[i] = t_phase[i];
+  if (prof) {
+    for (int i = 0; i < 4; ++i) a.phase_cycles[i] = t_phase[i];
+    for (int i = 0; i < 3; ++i) a.phase_cycles[4 + i] = t_nn[i];
+  }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     ope_reg_result r;
     for (int i = 0; i < 16; ++i) r.T[i] = final_t.m[i];
@@ -367,19 +531,30 @@ __global__ void __launch_bounds__(kIcpThreads) icp_kernel(IcpDev a) {
   }
 }
 
-// one estimation + rejection pass (no loop), one octet per source point
-__global__ void __launch_bounds__(kIcpThreads) correspond_once_kernel(IcpDev a) {
-  __shared__ OctStack stacks[kIcpThreads / 8];
-  __shared__ OctKnnList lists[kIcpThreads / 8];
-  const Octet o = octet_self();
-  OctStack* st = &stacks[threadIdx.x >> 3];
-  OctKnnList* L = &lists[threadIdx.x >> 3];
-  const int oct_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, n_oct = (gridDim.x * blockDim.x) >> 3;
-  for (int i = oct_id; i < a.n_src; i += n_oct) {
-    const float4 p = a.cur_pts[i];
-    float d2 = 0.0f;
-    const int m = icp_correspond(a, st, L, o, i, p, d2);
-    if (o.sub == 0u) { a.corr_match[i] = m; a.corr_d2[i] = d2; }
+// one estimation + rejection pass (no loop) on the clouds as given
+__global__ void __launch_bounds__(kIcpThreads, 1) correspond_once_kernel(IcpDev a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  IcpSmem* sm = reinterpret_cast<IcpSmem*>(smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (a.estimator != OPE_EST_NORMAL_SHOOTING) {
+    for (int base = blockIdx.x * kIcpThreads; base < a.n_src; base += gridDim.x * kIcpThreads) {
+      const int i = base + (int)threadIdx.x;
+      const bool in_range = i < a.n_src;
+      float4 p = make_float4(0, 0, 0, 0);
+      if (in_range) p = a.cur_pts[i];
+      float d2 = 0.0f;
+      const int m = icp_correspond_nearest(a, &sm->u.nn, i, in_range, p, false, d2);
+      if (in_range) { a.corr_match[i] = m; a.corr_d2[i] = d2; }
+    }
+  } else {
+    OctStack* st = &sm->u.wstack[warp];
+    for (int i = blockIdx.x * kIcpWarps + warp; i < a.n_src; i += gridDim.x * kIcpWarps) {
+      const float4 p = a.cur_pts[i];
+      float d2 = 0.0f;
+      const int m = icp_correspond_shooting(a, st, i, p, false, d2);
+      if (lane == 0) { a.corr_match[i] = m; a.corr_d2[i] = d2; }
+      __syncwarp();
+    }
   }
 }
 
@@ -404,11 +579,12 @@ static constexpr int kSaciaThreads = 256;
 static constexpr int kSaciaMaxSamples = 16;
 
 // one block per hypothesis: 5-point Umeyama (double moments, as everywhere), then every source point's
-// truncated NN error in parallel, then the float sum in point order by one thread (bit-exact with the reference's
-// serial `error += ...`, so the first-lowest-error hypothesis is the same one).
+// truncated NN error in parallel (one point per thread, block_nn1), then the float sum in point order by one thread
+// (bit-exact with the reference's serial `error += ...`, so the first-lowest-error hypothesis is the same one).
 __global__ void __launch_bounds__(kSaciaThreads) sacia_kernel(SaciaDev a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Nn1Smem<kSaciaThreads>* nn = reinterpret_cast<Nn1Smem<kSaciaThreads>*>(smem_raw);
   __shared__ Mat4 T;
-  __shared__ OctStack stacks[kSaciaThreads / 8];
   const int h = a.h_begin + blockIdx.x;
   if (threadIdx.x == 0) {
     double acc[16];
@@ -426,23 +602,25 @@ __global__ void __launch_bounds__(kSaciaThreads) sacia_kernel(SaciaDev a) {
         for (int r = 0; r < 3; ++r) acc[7 + c * 3 + r] += tv[r] * sv[c];
     }
     Mat4 M;
-    umeyama_from_moments(acc, M);  // double moments + double SVD, rounded to float once (same as every other Umeyama here)
+    umeyama_from_moments(acc, M);
     T = M;
     for (int i = 0; i < 16; ++i) a.transforms[(size_t)h * 16 + i] = M.m[i];
   }
   __syncthreads();
   const Mat4 M = T;
   float* terms = a.terms + (size_t)blockIdx.x * a.ns;
-  const Octet o = octet_self();
-  OctStack* st = &stacks[threadIdx.x >> 3];
-  for (int i = threadIdx.x >> 3; i < a.ns; i += kSaciaThreads / 8) {  // one octet per source point
-    const float4 p = __ldg(a.src + i);
-    float x, y, z;
-    xform_point(M, p.x, p.y, p.z, x, y, z);
-    const bool ok = finite3(x, y, z);
+  for (int base = 0; base < a.ns; base += kSaciaThreads) {
+    const int i = base + (int)threadIdx.x;
+    float x = 0, y = 0, z = 0;
+    bool ok = false;
+    if (i < a.ns) {
+      const float4 p = __ldg(a.src + i);
+      xform_point(M, p.x, p.y, p.z, x, y, z);
+      ok = finite3(x, y, z);
+    }
     float d2;
-    const int idx = octet_nn1(a.grid, st, o, ok, x, y, z, a.threshold, d2);
-    if (o.sub == 0u) terms[i] = (ok && idx >= 0 && d2 <= a.threshold) ? d2 / a.threshold : 1.0f;
+    const int idx = block_nn1<kSaciaThreads>(a.grid, nn, ok, x, y, z, a.threshold, -1, nullptr, d2);
+    if (i < a.ns) terms[i] = (ok && idx >= 0 && d2 <= a.threshold) ? d2 / a.threshold : 1.0f;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -469,6 +647,12 @@ __global__ void sacia_select_kernel(const float* __restrict__ errors, const floa
 }
 
 // ================================================================================================ host ==
+// opt a kernel in to `bytes` of dynamic shared memory (B200: up to 227 KB per block)
+static int dyn_smem(ope_ctx* ctx, const void* fn, size_t bytes) {
+  OPE_CUDA_TRY(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return OPE_OK;
+}
+
 int transform_device(ope_ctx* ctx, const ope_cloud* in, const Mat4& T, ope_cloud* out) {
   if (in->n == 0) return OPE_OK;
   transform_kernel<<<div_up(in->n, 256), 256, 0, ctx->stream>>>(in->pts, in->normals, (int)in->n, T, out->pts, out->normals);
@@ -498,14 +682,15 @@ int fitness_device(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, con
   OPE_TRY(cloud_bbox(ctx, const_cast<ope_cloud*>(tgt)));
   GridView g;
   OPE_TRY(cloud_grid(ctx, tgt, knn_cell_size(tgt, 1), &g));
-  const int nb = (int)std::min<size_t>(std::max<size_t>(1, (src->n * 8 + kRedThreads - 1) / kRedThreads), (size_t)ctx->sm_count * 4);
+  const int nb = (int)std::min<size_t>(std::max<size_t>(1, (src->n + kNnThreads - 1) / kNnThreads), (size_t)ctx->sm_count * 4);
   Scratch<double> partials(ctx), fin(ctx);
   OPE_TRY(partials.alloc((size_t)nb * 2));
   OPE_TRY(fin.alloc(2));
   const float mr = max_range >= (double)FLT_MAX ? FLT_MAX : (float)max_range;
-  fitness_kernel<<<nb, kRedThreads, 0, ctx->stream>>>(g, src->pts, (int)src->n, T, mr, partials.p);
+  OPE_TRY(dyn_smem(ctx, (const void*)fitness_kernel, sizeof(Nn1Smem<kNnThreads>)));
+  fitness_kernel<<<nb, kNnThreads, sizeof(Nn1Smem<kNnThreads>), ctx->stream>>>(g, src->pts, (int)src->n, T, mr, partials.p);
   OPE_TRY(check_launch(ctx, "fitness_kernel"));
-  sum_partials_kernel<<<1, 32, 0, ctx->stream>>>(partials.p, nb, 2, fin.p);
+  sum_partials_kernel<<<1, 64, 0, ctx->stream>>>(partials.p, nb, 2, fin.p);
   OPE_TRY(check_launch(ctx, "sum_partials_kernel"));
   void* h;
   OPE_TRY(read_back(ctx, fin.p, 2 * sizeof(double), &h));
@@ -568,32 +753,39 @@ int icp_device(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const o
   ope_cloud* work = nullptr;
   OPE_TRY(cloud_alloc(ctx, n, src->normals != nullptr, &work));
   a.cur_pts = work->pts; a.cur_nrm = work->normals;
-  Scratch<int> match(ctx);
+  Scratch<int> match(ctx), seed(ctx);
   Scratch<float> d2(ctx);
   Scratch<double> partials(ctx);
+  Scratch<unsigned> bar(ctx);
   Scratch<ope_reg_result> dres(ctx);
+  const bool shooting = prm.estimator == OPE_EST_NORMAL_SHOOTING;
   int rc = match.alloc(n);
   if (rc == OPE_OK) rc = d2.alloc(n);
+  if (rc == OPE_OK) rc = seed.alloc(shooting ? n * (size_t)prm.k_search : n);
   if (rc == OPE_OK) rc = dres.alloc(1);
-  // cooperative grid: enough threads for one point each, capped by co-residency
+  if (rc == OPE_OK) rc = bar.alloc(1);
+  if (rc == OPE_OK && cudaMemsetAsync(bar.p, 0, sizeof(unsigned), ctx->stream) != cudaSuccess) rc = fail(ctx, OPE_ERR_CUDA, "memset failed");
+  if (rc == OPE_OK) rc = dyn_smem(ctx, (const void*)icp_kernel, sizeof(IcpSmem));
+  // cooperative grid: one point per thread (nearest) / per warp (normal shooting), capped by co-residency
   int per_sm = 0;
-  if (rc == OPE_OK && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, icp_kernel, kIcpThreads, 0) != cudaSuccess)
+  if (rc == OPE_OK && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, icp_kernel, kIcpThreads, sizeof(IcpSmem)) != cudaSuccess)
     rc = fail(ctx, OPE_ERR_CUDA, "occupancy query failed");
   int blocks = 1;
   if (rc == OPE_OK) {
     if (per_sm < 1) rc = fail(ctx, OPE_ERR_CUDA, "icp_kernel cannot be resident");
     const int max_blocks = per_sm * ctx->sm_count;
-    blocks = (int)std::min<size_t>(std::max<size_t>(1, (n * 8 + kIcpThreads - 1) / kIcpThreads), (size_t)max_blocks);
+    const size_t want = shooting ? (n + kIcpWarps - 1) / kIcpWarps : (n + 127) / 128;
+    blocks = (int)std::min<size_t>(std::max<size_t>(1, want), (size_t)max_blocks);
   }
   if (rc == OPE_OK) rc = partials.alloc((size_t)2 * blocks * kIcpAcc);
   Scratch<long long> phases(ctx);
   const bool profile = std::getenv("OPE_PROFILE") != nullptr;
-  if (rc == OPE_OK && profile) { rc = phases.alloc(4); a.phase_cycles = phases.p; }
-  a.corr_match = match.p; a.corr_d2 = d2.p; a.partials = partials.p; a.result = dres.p;
+  if (rc == OPE_OK && profile) { rc = phases.alloc(8); a.phase_cycles = phases.p; }
+  a.corr_match = match.p; a.corr_d2 = d2.p; a.seed = seed.p; a.partials = partials.p; a.barrier = bar.p; a.result = dres.p;
   if (rc == OPE_OK) {
     void* args[] = {(void*)&a};
     cudaEventRecord(ctx->kev[0][0], ctx->stream);
-    cudaError_t e = cudaLaunchCooperativeKernel((void*)icp_kernel, dim3(blocks), dim3(kIcpThreads), args, 0, ctx->stream);
+    cudaError_t e = cudaLaunchCooperativeKernel((void*)icp_kernel, dim3(blocks), dim3(kIcpThreads), args, sizeof(IcpSmem), ctx->stream);
     cudaEventRecord(ctx->kev[0][1], ctx->stream);
     ctx->kev_valid[0] = true;
     if (e != cudaSuccess) rc = fail(ctx, OPE_ERR_CUDA, "cooperative launch of icp_kernel failed: %s", cudaGetErrorString(e));
@@ -606,8 +798,10 @@ int icp_device(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const o
   }
   if (rc == OPE_OK && profile) {
     void* h;
-    if (read_back(ctx, phases.p, 4 * sizeof(long long), &h) == OPE_OK) {
+    if (read_back(ctx, phases.p, 8 * sizeof(long long), &h) == OPE_OK) {
       const long long* c = (const long long*)h;
+      fprintf(stderr, "[ope profile] block_nn1 block0 per iteration: fast phase %.0f cycles | deferred phase %.0f cycles | deferred queries %.1f\n",
+              (double)c[4] / std::max(res->iterations, 1), (double)c[5] / std::max(res->iterations, 1), (double)c[6] / std::max(res->iterations, 1));
       fprintf(stderr, "[ope profile] icp_kernel blocks=%d block0 cycles: search+reduce %lld | grid barrier %lld | partials+svd %lld | transform %lld (per iteration: %.0f %.0f %.0f %.0f)\n",
               blocks, c[0], c[1], c[2], c[3], (double)c[0] / std::max(res->iterations, 1), (double)c[1] / std::max(res->iterations, 1),
               (double)c[2] / std::max(res->iterations, 1), (double)c[3] / std::max(res->iterations, 1));
@@ -720,7 +914,8 @@ int sacia_device(ope_ctx* ctx, const ope_cloud* src, const float* d_fsrc, const 
   a.terms = d_terms.p; a.errors = d_errors.p; a.transforms = d_T.p;
   if (nh > 0) {
     cudaEventRecord(ctx->kev[1][0], ctx->stream);
-    sacia_kernel<<<nh, kSaciaThreads, 0, ctx->stream>>>(a);
+    OPE_TRY(dyn_smem(ctx, (const void*)sacia_kernel, sizeof(Nn1Smem<kSaciaThreads>)));
+    sacia_kernel<<<nh, kSaciaThreads, sizeof(Nn1Smem<kSaciaThreads>), ctx->stream>>>(a);
     cudaEventRecord(ctx->kev[1][1], ctx->stream);
     ctx->kev_valid[1] = true;
     OPE_TRY(check_launch(ctx, "sacia_kernel"));
@@ -831,11 +1026,15 @@ int ope_correspondences(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt
   a.variant = OPE_ICP_VARIANT_MOD;
   a.cur_pts = src->pts; a.cur_nrm = src->normals;
   const size_t n = src->n;
-  Scratch<int> match(ctx);
+  Scratch<int> match(ctx), seed(ctx);
   Scratch<float> d2(ctx);
+  const bool shooting = prm->estimator == OPE_EST_NORMAL_SHOOTING;
   OPE_TRY(match.alloc(n)); OPE_TRY(d2.alloc(n));
-  a.corr_match = match.p; a.corr_d2 = d2.p;
-  correspond_once_kernel<<<(unsigned)std::min<size_t>(div_up(n * 8, kIcpThreads), (size_t)ctx->sm_count * 8), kIcpThreads, 0, ctx->stream>>>(a);
+  OPE_TRY(seed.alloc(shooting ? n * (size_t)prm->k_search : n));
+  a.corr_match = match.p; a.corr_d2 = d2.p; a.seed = seed.p;
+  OPE_TRY(dyn_smem(ctx, (const void*)correspond_once_kernel, sizeof(IcpSmem)));
+  const size_t want = shooting ? div_up(n, kIcpWarps) : div_up(n, kIcpThreads);
+  correspond_once_kernel<<<(unsigned)std::min<size_t>(want, (size_t)ctx->sm_count * 4), kIcpThreads, sizeof(IcpSmem), ctx->stream>>>(a);
   OPE_TRY(check_launch(ctx, "correspond_once_kernel"));
   std::vector<int> hm(n);
   std::vector<float> hd(n);

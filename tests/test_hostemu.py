@@ -54,6 +54,22 @@ def test_grid_nn1_bounded_search(emu, orc, synth, small_model):
     assert ((a[0][~inside, 0] == -1) | (a[1][~inside, 0] > lim)).all()
 
 
+@pytest.mark.parametrize("h", [0.0015, 0.004, 0.03])
+def test_grid_nn1_seed_independent(emu, orc, synth, small_model, h):
+    """the seeded search (previous ICP match as the initial bound) returns the same exact neighbour as the unseeded one"""
+    src, tgt, _ = synth.icp_pair(4000, 2, small_model)
+    rng = np.random.default_rng(3)
+    ref_i, ref_d = orc.knn(tgt, src, 1, brute=True)
+    t = np.ascontiguousarray(tgt, np.float32); q = np.ascontiguousarray(src, np.float32)
+    for seeds in (ref_i[:, 0].copy(), rng.integers(0, len(tgt), len(src)).astype(np.int32),
+                  np.where(rng.random(len(src)) < 0.5, -1, rng.integers(0, len(tgt), len(src))).astype(np.int32)):
+        seeds = np.ascontiguousarray(seeds, np.int32)
+        idx = np.empty(len(q), np.int32); d2 = np.empty(len(q), np.float32)
+        emu.emu_nn1_seeded(t.ctypes.data_as(f32p), len(t), q.ctypes.data_as(f32p), len(q), seeds.ctypes.data_as(i32p),
+                           C.c_float(h), C.c_float(3.0e38), idx.ctypes.data_as(i32p), d2.ctypes.data_as(f32p))
+        assert (idx == ref_i[:, 0]).all() and (d2 == ref_d[:, 0]).all()
+
+
 def test_grid_radius_counts(emu, orc, synth, small_model):
     src, tgt, _ = synth.icp_pair(3000, 0, small_model)
     cnt = np.empty(len(src), np.int32)
