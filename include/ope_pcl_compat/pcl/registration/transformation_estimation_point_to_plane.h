@@ -1,0 +1,4 @@
+// <pcl/registration/transformation_estimation_point_to_plane.h> forwarded to the B200 shim (include/ope_pcl/registration.h); see INTEGRATION.md.
+#pragma once
+#include "../pcl_config.h"
+#include "../../../ope_pcl/registration.h"

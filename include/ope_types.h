@@ -1,5 +1,5 @@
 /* ope_types.h — plain-C parameter and result records shared by the CUDA library
- * (include/ope_cuda.h) and by the CPU oracle (oracle/ope_oracle.h).
+ * (include/ope_cuda.h) and by the CPU checker used in tests (it includes this header; the product never includes it).
  *
  * Every default below is the default of the reference class it configures; the
  * citation is relative to /root/reference (D&L = DetectAndLocalize, BM = BuildModel,

@@ -209,10 +209,11 @@ def icp_pair(n=50000, seed=0, model=None, max_deg=10.0, max_t=0.02, sigma=0.001,
     return np.ascontiguousarray(src, np.float32), np.ascontiguousarray(tgt, np.float32), T
 
 
-def turntable_views(model, n_views=36, z=0.8, seed=0):
-    """C4: n_views object-only views at 360/n_views degree steps, each in its own camera frame."""
+def turntable_views(model, n_views=36, z=0.8, seed=0, first=None):
+    """C4: n_views object-only views at 360/n_views degree steps, each in its own camera frame (`first`: render only
+    the first that many)."""
     out = []
-    for i in range(n_views):
+    for i in range(n_views if first is None else min(first, n_views)):
         rng = rng_for(seed * 1000 + i, stream=4)
         T = np.eye(4)
         T[:3, :3] = rotation_about([0, 1, 0], 2 * np.pi * i / n_views) @ rotation_about([1, 0, 0], np.deg2rad(-60))
