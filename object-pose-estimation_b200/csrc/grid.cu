@@ -418,6 +418,12 @@ int cloud_grid(ope_ctx* ctx, const ope_cloud* cc, float h_wanted, GridView* out)
   return OPE_OK;
 }
 
+int cloud_any_grid(ope_ctx* ctx, const ope_cloud* c, GridView* out) {
+  if (!c->grids.empty()) { *out = c->grids.front().view; return OPE_OK; }
+  OPE_TRY(cloud_bbox(ctx, const_cast<ope_cloud*>(c)));
+  return cloud_grid(ctx, c, knn_cell_size(c, 1), out);
+}
+
 int gather_cloud(ope_ctx* ctx, const ope_cloud* cloud, const int* d_idx, size_t n, ope_cloud** out) {
   ope_cloud* o = nullptr;
   OPE_TRY(cloud_alloc(ctx, n, cloud->normals != nullptr, &o));

@@ -309,13 +309,9 @@ OPE_HD void umeyama_from_sigma(const T sigma[9], const T src_mean[3], const T ds
 // acc = {n, Ss[3], St[3], Sts[9] (t_r*s_c at [c*3+r])}. Means and the cross-covariance are formed in double (the sums
 // are order-independent to ~1e-16, so a parallel reduction and a serial loop agree after rounding), the 3x3 SVD runs in
 // float like Eigen::JacobiSVD<Matrix3f> does in the reference, the translation is closed in double and rounded once.
-OPE_HD void umeyama_from_moments(const double* acc, Mat4& out) {
-  const double n = acc[0];
-  double ms[3], mt[3];
-  float sigma[9];
-  for (int k = 0; k < 3; ++k) { ms[k] = acc[1 + k] / n; mt[k] = acc[4 + k] / n; }
-  for (int c = 0; c < 3; ++c)
-    for (int r = 0; r < 3; ++r) sigma[c * 3 + r] = (float)(acc[7 + c * 3 + r] / n - mt[r] * ms[c]);
+// The part after the means and the float cross-covariance are known (split out so that a kernel can form them with one
+// division per lane instead of fifteen in a row; the arithmetic is identical).
+OPE_HD void umeyama_from_sigma_means(const float sigma[9], const double ms[3], const double mt[3], Mat4& out) {
   float U[9], S[3], V[9];
   svd3<float>(sigma, U, S, V);
   float Sd[3] = {1, 1, 1};
@@ -342,6 +338,15 @@ OPE_HD void umeyama_from_moments(const double* acc, Mat4& out) {
     rs = rs + (double)R[2 * 3 + r] * ms[2];
     out.m[12 + r] = (float)(mt[r] - rs);
   }
+}
+OPE_HD void umeyama_from_moments(const double* acc, Mat4& out) {
+  const double n = acc[0];
+  double ms[3], mt[3];
+  float sigma[9];
+  for (int k = 0; k < 3; ++k) { ms[k] = acc[1 + k] / n; mt[k] = acc[4 + k] / n; }
+  for (int c = 0; c < 3; ++c)
+    for (int r = 0; r < 3; ++r) sigma[c * 3 + r] = (float)(acc[7 + c * 3 + r] / n - mt[r] * ms[c]);
+  umeyama_from_sigma_means(sigma, ms, mt, out);
 }
 
 // Eigen::umeyama in float over a handful of pairs, sequential order (SAC-IA: 5 samples). s/d: n*3 arrays.

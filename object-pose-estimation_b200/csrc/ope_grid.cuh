@@ -204,6 +204,10 @@ OPE_HD bool ball_node(const BallNodes& B, int j, unsigned& code) {
   code = morton3((unsigned)(B.nlo[0] + dx), (unsigned)(B.nlo[1] + dy), (unsigned)(B.nlo[2] + dz));
   return true;
 }
+// conservative squared distance to the j-th start node, from its coordinates (no Morton decode)
+OPE_HD float ball_node_d2(const GridView& g, const BallNodes& B, int j, float ux, float uy, float uz) {
+  return oct_box_d2(ux, uy, uz, B.nlo[0] + (j & 1), B.nlo[1] + ((j >> 1) & 1), B.nlo[2] + (j >> 2), 1 << B.L, g.h);
+}
 
 // Seed for an unseeded nearest-neighbour query: climb from the query's own (clamped) cell to the first non-empty
 // ancestor, descend greedily toward the query while the node is large, scan what is left. Cheap for queries near the
@@ -242,15 +246,45 @@ OPE_HD void nn1_probe(const GridView& g, float qx, float qy, float qz, float ux,
   scan(b, imin(e, b + 4 * OPE_PROBE_LEAF));  // a seed only: any point is a valid upper bound
 }
 
-// Fast path: the whole candidate set of the current bound, when it is at most `fast_max` points in <= 8 nodes, is
+// ---- nearest neighbour with a certificate --------------------------------------------------------------------
+// State of one query: the best candidate (d1, i1) in the canonical (d2, index) order and s2, the smallest squared
+// distance seen among the OTHER points. A search that examines every point within the scan radius
+//     r_s = min(sqrt(d1), sqrt(max_d2)) + gap
+// ends with the exact nearest neighbour and with the certificate radius R^2 = min(s2, r_s^2): every indexed point other
+// than i1 is at least R away. A caller that later moves the query by delta may keep i1 without searching as long as
+// d(q', x_i1) + delta < R - delta (triangle inequality) — this is how the ICP loop skips most searches once the
+// increments become small, while staying exact. gap = 0 reproduces the plain search.
+struct Nn1State {
+  float d1;  // best squared distance (FLT_MAX: none)
+  int i1;    // its original index (0x7fffffff: none)
+  float s2;  // smallest squared distance among the other points examined (FLT_MAX: none)
+};
+OPE_HD void nn1_offer(Nn1State& st, float d2, int idx) {
+  if (idx == st.i1) return;  // the seed is met again during the scan
+  if (nb_less(d2, idx, st.d1, st.i1)) { st.s2 = st.d1; st.d1 = d2; st.i1 = idx; }
+  else st.s2 = fminf(st.s2, d2);
+}
+// squared scan radius for the current best (slightly inflated so that rounding can only enlarge the scanned set)
+OPE_HD float nn1_scan_r2(float d1, float max_d2, float gap) {
+  const float m = fminf(d1, max_d2);
+  if (!(m < FLT_MAX)) return FLT_MAX;
+  if (gap <= 0.0f) return m;
+  const float r = sqrtf(m) + gap;
+  return r * r * 1.000001f;
+}
+
+// Fast path: the whole candidate set of the scan radius, when it is at most OPE_NN1_FAST_MAX points in <= 8 nodes, is
 // scanned directly (16 independent `start` loads, then runs of 16-byte point loads). Returns false — nothing scanned —
-// when the set is larger; the caller then runs a pruned traversal (thread-level below, 8 lanes per query on the device).
+// when the set is larger; the caller then runs a pruned traversal (thread-level below, a warp per query on the device).
+// On success *r2_out is the squared radius within which every point has been examined.
 #ifndef OPE_NN1_FAST_MAX
 #define OPE_NN1_FAST_MAX 96
 #endif
-OPE_HD bool nn1_fast(const GridView& g, float qx, float qy, float qz, float ux, float uy, float uz, float max_d2, float& best_d2,
-                     int& best_i) {
-  const BallNodes B = ball_nodes(g, ux, uy, uz, fminf(best_d2, max_d2));
+OPE_HD bool nn1_fast(const GridView& g, float qx, float qy, float qz, float ux, float uy, float uz, float max_d2, float gap,
+                     Nn1State& st, float* r2_out) {
+  const float bound0 = nn1_scan_r2(st.d1, max_d2, gap);
+  if (r2_out) *r2_out = bound0;
+  const BallNodes B = ball_nodes(g, ux, uy, uz, bound0);
   if (!B.hit) return true;
   const int sh = 3 * B.L;
   int nb[8], ne[8];
@@ -268,12 +302,11 @@ OPE_HD bool nn1_fast(const GridView& g, float qx, float qy, float qz, float ux, 
   }
   if (total > OPE_NN1_FAST_MAX) return false;
   // First two points of every node: 16 predicated, mutually independent 16-byte loads in straight-line code (one L2
-  // round trip for the common case of a handful of points per cell), pruned against the bound the query arrived with.
-  const float bound0 = fminf(best_d2, max_d2);
+  // round trip for the common case of a handful of points per cell), pruned against the radius the query arrived with.
   float4 pa[8], pb[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    if (ne[j] > nb[j] && oct_node_d2(g, ux, uy, uz, B.L, nc[j]) > bound0) ne[j] = nb[j];  // node outside the ball
+    if (ne[j] > nb[j] && ball_node_d2(g, B, j, ux, uy, uz) > bound0) ne[j] = nb[j];  // node outside the ball
     pa[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     pb[j] = pa[j];
     if (ne[j] - nb[j] > 0) pa[j] = OPE_LDG(g.pts + nb[j]);
@@ -281,17 +314,8 @@ OPE_HD bool nn1_fast(const GridView& g, float qx, float qy, float qz, float ux, 
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    if (ne[j] - nb[j] > 0) {
-      OPE_COUNT(2);
-      const float d2 = dist2(qx, qy, qz, pa[j].x, pa[j].y, pa[j].z);
-      const int idx = f2i(pa[j].w);
-      if (nb_less(d2, idx, best_d2, best_i)) { best_d2 = d2; best_i = idx; }
-    }
-    if (ne[j] - nb[j] > 1) {
-      const float d2 = dist2(qx, qy, qz, pb[j].x, pb[j].y, pb[j].z);
-      const int idx = f2i(pb[j].w);
-      if (nb_less(d2, idx, best_d2, best_i)) { best_d2 = d2; best_i = idx; }
-    }
+    if (ne[j] - nb[j] > 0) { OPE_COUNT(2); nn1_offer(st, dist2(qx, qy, qz, pa[j].x, pa[j].y, pa[j].z), f2i(pa[j].w)); }
+    if (ne[j] - nb[j] > 1) nn1_offer(st, dist2(qx, qy, qz, pb[j].x, pb[j].y, pb[j].z), f2i(pb[j].w));
   }
   // the rest (cells with more than two points), two loads in flight
 #pragma unroll
@@ -300,17 +324,20 @@ OPE_HD bool nn1_fast(const GridView& g, float qx, float qy, float qz, float ux, 
       const float4 p0 = OPE_LDG(g.pts + i);
       const bool two = i + 1 < ne[j];
       const float4 p1 = two ? OPE_LDG(g.pts + i + 1) : p0;
-      float d2 = dist2(qx, qy, qz, p0.x, p0.y, p0.z);
-      int idx = f2i(p0.w);
-      if (nb_less(d2, idx, best_d2, best_i)) { best_d2 = d2; best_i = idx; }
-      if (two) {
-        d2 = dist2(qx, qy, qz, p1.x, p1.y, p1.z);
-        idx = f2i(p1.w);
-        if (nb_less(d2, idx, best_d2, best_i)) { best_d2 = d2; best_i = idx; }
-      }
+      nn1_offer(st, dist2(qx, qy, qz, p0.x, p0.y, p0.z), f2i(p0.w));
+      if (two) nn1_offer(st, dist2(qx, qy, qz, p1.x, p1.y, p1.z), f2i(p1.w));
     }
   }
   return true;
+}
+// plain form (no certificate)
+OPE_HD bool nn1_fast(const GridView& g, float qx, float qy, float qz, float ux, float uy, float uz, float max_d2, float& best_d2,
+                     int& best_i) {
+  Nn1State st;
+  st.d1 = best_d2; st.i1 = best_i; st.s2 = FLT_MAX;
+  const bool done = nn1_fast(g, qx, qy, qz, ux, uy, uz, max_d2, 0.0f, st, nullptr);
+  best_d2 = st.d1; best_i = st.i1;
+  return done;
 }
 
 // Exact nearest neighbour (k = 1). Only neighbours with d2 <= max_d2 matter to the caller (FLT_MAX: unbounded).
@@ -318,33 +345,38 @@ OPE_HD bool nn1_fast(const GridView& g, float qx, float qy, float qz, float ux, 
 // the previous ICP iteration's match; the result is the same exact nearest neighbour either way.
 // Returns the original index or -1 (nothing indexed); the caller rejects best_d2 > max_d2.
 OPE_HD int grid_nn1(const GridView& g, float qx, float qy, float qz, float max_d2, float& best_d2, int seed_idx = -1,
-                    const float4* seed_pts = nullptr) {
+                    const float4* seed_pts = nullptr, float gap = 0.0f, float* cert_r2 = nullptr) {
   best_d2 = FLT_MAX;
-  int best_i = 0x7fffffff;
+  if (cert_r2) *cert_r2 = 0.0f;
+  Nn1State st;
+  st.d1 = FLT_MAX; st.i1 = 0x7fffffff; st.s2 = FLT_MAX;
   if (g.n <= 0) return -1;
   const float ux = (qx - g.ox) * g.inv_h, uy = (qy - g.oy) * g.inv_h, uz = (qz - g.oz) * g.inv_h;
   auto scan = [&](int b, int e) {
     for (int i = b; i < e; ++i) {
       const float4 p = OPE_LDG(g.pts + i);
-      const float d2 = dist2(qx, qy, qz, p.x, p.y, p.z);
-      const int idx = f2i(p.w);
-      if (nb_less(d2, idx, best_d2, best_i)) { best_d2 = d2; best_i = idx; }
+      nn1_offer(st, dist2(qx, qy, qz, p.x, p.y, p.z), f2i(p.w));
     }
   };
   if (seed_idx >= 0 && seed_pts) {
     const float4 s = OPE_LDG(seed_pts + seed_idx);
-    if (finite3(s.x, s.y, s.z)) { best_d2 = dist2(qx, qy, qz, s.x, s.y, s.z); best_i = seed_idx; }
+    if (finite3(s.x, s.y, s.z)) { st.d1 = dist2(qx, qy, qz, s.x, s.y, s.z); st.i1 = seed_idx; }
   }
-  if (best_i == 0x7fffffff) nn1_probe(g, qx, qy, qz, ux, uy, uz, scan);
-  if (!nn1_fast(g, qx, qy, qz, ux, uy, uz, max_d2, best_d2, best_i)) {
-    const BallNodes B = ball_nodes(g, ux, uy, uz, fminf(best_d2, max_d2));
+  if (st.i1 == 0x7fffffff) nn1_probe(g, qx, qy, qz, ux, uy, uz, scan);
+  st.s2 = FLT_MAX;  // the probe is only a seed: the search below establishes the second-best distance
+  float r2 = 0.0f;
+  if (!nn1_fast(g, qx, qy, qz, ux, uy, uz, max_d2, gap, st, &r2)) {
+    const BallNodes B = ball_nodes(g, ux, uy, uz, nn1_scan_r2(st.d1, max_d2, gap));
     for (int j = 0; j < 8; ++j) {
       unsigned code;
       if (!ball_node(B, j, code)) continue;
-      oct_traverse(g, ux, uy, uz, B.L, code, -1, 0u, OPE_NN1_LEAF, [&]() { return fminf(best_d2, max_d2); }, scan);
+      oct_traverse(g, ux, uy, uz, B.L, code, -1, 0u, OPE_NN1_LEAF, [&]() { return nn1_scan_r2(st.d1, max_d2, gap); }, scan);
     }
+    r2 = nn1_scan_r2(st.d1, max_d2, gap);
   }
-  return best_i == 0x7fffffff ? -1 : best_i;
+  best_d2 = st.d1;
+  if (cert_r2) *cert_r2 = fminf(st.s2, r2);  // every indexed point other than the result is at least sqrt(this) away
+  return st.i1 == 0x7fffffff ? -1 : st.i1;
 }
 
 // Exact k nearest (k <= KMAX), ascending (d2, index) into bd/bi. Returns the count found (min(k, n)).

@@ -149,6 +149,9 @@ int cloud_alloc(ope_ctx* ctx, size_t n, bool with_normals, ope_cloud** out);
 int cloud_bbox(ope_ctx* ctx, ope_cloud* c);
 // cached search grid with cell edge ~h (adjusted to respect the cell cap)
 int cloud_grid(ope_ctx* ctx, const ope_cloud* c, float h, GridView* out);
+// any cached search grid of the cloud (builds the default nearest-neighbour grid when there is none): used for the
+// Morton work order of a source cloud
+int cloud_any_grid(ope_ctx* ctx, const ope_cloud* c, GridView* out);
 // suggested cell edge for k-NN queries against this cloud (surface-density heuristic)
 float knn_cell_size(const ope_cloud* c, int k);
 int exclusive_scan_i32(ope_ctx* ctx, int* data, size_t n);

@@ -128,20 +128,22 @@ __device__ __forceinline__ int coop_expand(const GridView& g, OctStack* st, cons
   return coop_push(st, o, sp, pass, ((unsigned)cl << 27) | cc, cd2, cb, ce);
 }
 
-// Exact nearest neighbour for the group's query (G lanes: 8 or 32), starting from (best_d2, best_i) — a valid candidate
-// or (FLT_MAX, INT_MAX). Nodes holding at most LEAF points are scanned G points per step (independent 16-byte loads),
-// larger ones are expanded. The lanes must call this together with the same arguments. Returns the index (INT_MAX: none)
-// and distance in every lane.
+// Exact nearest neighbour for the group's query (G lanes: 8 or 32), starting from st (a valid candidate or none).
+// Nodes holding at most LEAF points are scanned G points per step (independent 16-byte loads), larger ones are expanded;
+// everything within the scan radius nn1_scan_r2(best, max_d2, gap) is examined, so on return st holds the exact
+// neighbour, the second-best distance, and *r2_out the squared radius the certificate may rely on (ope_grid.cuh).
+// The lanes must call this together with the same arguments; every lane returns the same state.
 template <int G, int LEAF>
-__device__ __forceinline__ int coop_nn1(const GridView& g, OctStack* st, const Coop<G>& o, bool active, float qx, float qy, float qz,
-                                        float max_d2, float& best_d2, int best_i) {
+__device__ __forceinline__ void coop_nn1(const GridView& g, OctStack* st_mem, const Coop<G>& o, bool active, float qx, float qy, float qz,
+                                         float max_d2, float gap, Nn1State& st, float* r2_out) {
   const float ux = (qx - g.ox) * g.inv_h, uy = (qy - g.oy) * g.inv_h, uz = (qz - g.oz) * g.inv_h;
-  int sp = coop_push_ball(g, st, o, active && g.n > 0, ux, uy, uz, fminf(best_d2, max_d2));
+  float bound = nn1_scan_r2(st.d1, max_d2, gap);
+  int sp = coop_push_ball(g, st_mem, o, active && g.n > 0, ux, uy, uz, bound);
   while (sp > 0) {
     --sp;
-    const OctEntry en = st->s[sp];
+    const OctEntry en = st_mem->s[sp];
     __syncwarp(o.mask);  // every lane holds the popped entry before its slot can be overwritten
-    const float bound = fminf(coop_min(o, best_d2), max_d2);
+    bound = nn1_scan_r2(coop_min(o, st.d1), max_d2, gap);
     const bool live = en.d2 <= bound;
     const int level = (int)(en.node >> 27);
     const bool leaf = level == 0 || en.e - en.b <= LEAF;
@@ -149,20 +151,176 @@ __device__ __forceinline__ int coop_nn1(const GridView& g, OctStack* st, const C
 #pragma unroll 4
       for (int i = en.b + (int)o.sub; i < en.e; i += G) {
         const float4 p = __ldg(g.pts + i);
-        const float d2 = dist2(qx, qy, qz, p.x, p.y, p.z);
-        const int idx = __float_as_int(p.w);
-        if (nb_less(d2, idx, best_d2, best_i)) { best_d2 = d2; best_i = idx; }
+        nn1_offer(st, dist2(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w));
       }
     }
-    sp += coop_expand(g, st, o, sp, live && !leaf, en.node, en.e, ux, uy, uz, bound);
+    sp += coop_expand(g, st_mem, o, sp, live && !leaf, en.node, en.e, ux, uy, uz, bound);
   }
+  // merge the lanes' states: best of the bests; second = the smallest of every lane's second and of the displaced bests
+  float d1 = st.d1;
+  int i1 = st.i1;
 #pragma unroll
   for (int s = 1; s < G; s <<= 1) {
-    const float od = __shfl_xor_sync(o.mask, best_d2, s);
-    const int oi = __shfl_xor_sync(o.mask, best_i, s);
-    if (nb_less(od, oi, best_d2, best_i)) { best_d2 = od; best_i = oi; }
+    const float od = __shfl_xor_sync(o.mask, d1, s);
+    const int oi = __shfl_xor_sync(o.mask, i1, s);
+    if (nb_less(od, oi, d1, i1)) { d1 = od; i1 = oi; }
   }
-  return best_i;
+  float s2 = st.s2;
+  if (st.i1 != i1) s2 = fminf(s2, st.d1);
+  s2 = coop_min(o, s2);
+  st.d1 = d1; st.i1 = i1; st.s2 = s2;
+  if (r2_out) *r2_out = nn1_scan_r2(d1, max_d2, gap);
+}
+// plain form (no certificate): returns the index (INT_MAX: none), distance in best_d2
+template <int G, int LEAF>
+__device__ __forceinline__ int coop_nn1(const GridView& g, OctStack* st_mem, const Coop<G>& o, bool active, float qx, float qy, float qz,
+                                        float max_d2, float& best_d2, int best_i) {
+  Nn1State st;
+  st.d1 = best_d2; st.i1 = best_i; st.s2 = FLT_MAX;
+  coop_nn1<G, LEAF>(g, st_mem, o, active, qx, qy, qz, max_d2, 0.0f, st, nullptr);
+  best_d2 = st.d1;
+  return st.i1;
+}
+
+// ---- far queries: directory in shared memory, leaves collected then scanned wide ------------------------------
+// A far query's traversal is a chain of dependent steps; with the `start` look-ups going to L2 (~300 cycles), a
+// 5-shuffle bound update and a nearest-first argmin per step it costs ~850 cycles a step (ncu, profiles/). Here
+//  * the upper levels of the implicit octree (levels >= dl: at most 4097 `start` entries, 16 KB) are cached in SHARED
+//    memory once per persistent kernel, and nodes at level dl are never split, so the traversal itself touches no
+//    global memory;
+//  * leaves are only COLLECTED during the traversal and then scanned in batches (8 independent 16-byte loads per lane
+//    in flight), the bound being refreshed per batch instead of per node;
+//  * the nearest-first ordering of children is kept only for unseeded queries (ORDERED), whose bound must shrink.
+static constexpr int kDirMaxLevels = 4;                       // directory covers the top 4 levels below the root
+static constexpr int kDirEntries = (1 << (3 * kDirMaxLevels)) + 1;
+static constexpr int kLeafCap = 96;                           // collected leaf ranges per warp
+static constexpr int kFlushPts = 2048;                        // ... or this many points: scan, refresh the bound
+
+struct FarDir {
+  const int* sdir;  // shared memory: sdir[c] = start[c << (3 * dl)], c in [0, 2^(3 * (bits - dl))]
+  int dl;           // lowest level the directory resolves
+};
+struct LeafList { int2 r[kLeafCap]; };
+
+__device__ __forceinline__ int far_dir_level(const GridView& g) { return g.bits > kDirMaxLevels ? g.bits - kDirMaxLevels : 0; }
+// block-cooperative load of the directory (call once, followed by __syncthreads)
+__device__ __forceinline__ void far_dir_load(const GridView& g, int* sdir) {
+  const int dl = far_dir_level(g);
+  const int n = (1 << (3 * (g.bits - dl))) + 1;
+  for (int c = threadIdx.x; c < n; c += blockDim.x) sdir[c] = g.n > 0 ? __ldg(g.start + ((size_t)c << (3 * dl))) : 0;
+}
+__device__ __forceinline__ void far_node_range(const GridView& g, const FarDir& D, int level, unsigned code, int& b, int& e) {
+  if (level >= D.dl) {
+    const int sh = 3 * (level - D.dl);
+    b = D.sdir[(size_t)code << sh];
+    e = D.sdir[(size_t)(code + 1u) << sh];
+  } else {
+    oct_node_range(g, level, code, b, e);
+  }
+}
+
+// Exact nearest neighbour + certificate for the WARP's query (all 32 lanes, same arguments, same `st` on entry).
+template <bool ORDERED>
+__device__ __forceinline__ void warp_nn1_far(const GridView& g, const FarDir& D, OctStack* stk, LeafList* LL, float qx, float qy, float qz,
+                                             float max_d2, float gap, Nn1State& st, float* r2_out) {
+  const Coop<32> o;
+  const unsigned full = 0xffffffffu;
+  const int lane = (int)o.sub;
+  const float ux = (qx - g.ox) * g.inv_h, uy = (qy - g.oy) * g.inv_h, uz = (qz - g.oz) * g.inv_h;
+  float bound = nn1_scan_r2(st.d1, max_d2, gap);
+  int sp = 0, nleaf = 0, leafpts = 0;
+  // start set: the ball's <= 8 nodes
+  {
+    bool pass = false;
+    unsigned node = 0u;
+    float d2 = FLT_MAX;
+    int b = 0, e = 0;
+    if (g.n > 0 && lane < 8) {
+      const BallNodes B = ball_nodes(g, ux, uy, uz, bound);
+      unsigned code;
+      if (ball_node(B, lane, code)) {
+        far_node_range(g, D, B.L, code, b, e);
+        if (e > b) {
+          d2 = ball_node_d2(g, B, lane, ux, uy, uz);
+          pass = d2 <= bound;
+          node = ((unsigned)B.L << 27) | code;
+        }
+      }
+    }
+    sp = coop_push(stk, o, 0, pass, node, d2, b, e);
+  }
+  auto flush = [&]() {
+    for (int r = 0; r < nleaf; ++r) {
+      const int2 be = LL->r[r];
+      for (int i0 = be.x + lane; i0 < be.y; i0 += 32 * 8) {
+        float4 p[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const int i = i0 + 32 * k; p[k] = (i < be.y) ? __ldg(g.pts + i) : make_float4(0, 0, 0, 0); }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (i0 + 32 * k < be.y) nn1_offer(st, dist2(qx, qy, qz, p[k].x, p[k].y, p[k].z), __float_as_int(p[k].w));
+      }
+    }
+    nleaf = 0; leafpts = 0;
+    __syncwarp();
+    bound = nn1_scan_r2(coop_min(o, st.d1), max_d2, gap);
+  };
+  for (;;) {
+    if (sp == 0) { if (nleaf > 0) flush(); break; }
+    if (nleaf == kLeafCap || leafpts >= kFlushPts) flush();
+    --sp;
+    const OctEntry en = stk->s[sp];
+    __syncwarp();
+    if (!(en.d2 <= bound)) continue;
+    const int level = (int)(en.node >> 27);
+    const int cnt = en.e - en.b;
+    if (level <= D.dl || cnt <= kFarLeaf) {
+      if (lane == 0) LL->r[nleaf] = make_int2(en.b, en.e);
+      ++nleaf; leafpts += cnt;
+      if (ORDERED && nleaf == 1 && sp > 0) flush();  // unseeded: the first (nearest) leaf tightens the bound for everything else
+      continue;
+    }
+    // expand: lanes 0..7 own the children (level - 1 >= dl: resolved from shared memory)
+    const unsigned code = en.node & 0x07ffffffu;
+    const int cl = level - 1;
+    const unsigned cc = (code << 3) | ((unsigned)lane & 7u);
+    int cb = 0;
+    if (lane < 8) cb = D.sdir[(size_t)cc << (3 * (cl - D.dl))];
+    const int nb = __shfl_down_sync(full, cb, 1, 8);
+    const int ce = (lane == 7) ? en.e : nb;
+    float cd2 = FLT_MAX;
+    bool pass = false;
+    if (lane < 8 && ce > cb) {
+      cd2 = oct_node_d2(g, ux, uy, uz, cl, cc);
+      pass = cd2 <= bound;
+    }
+    if (ORDERED) {
+      sp += coop_push(stk, o, sp, pass, ((unsigned)cl << 27) | cc, cd2, cb, ce);
+    } else {
+      const unsigned om = __ballot_sync(full, pass) & 0xffu;
+      if (pass) {
+        OctEntry ne;
+        ne.node = ((unsigned)cl << 27) | cc; ne.d2 = cd2; ne.b = cb; ne.e = ce;
+        stk->s[sp + __popc(om & ((1u << lane) - 1u))] = ne;
+      }
+      sp += __popc(om);
+      __syncwarp();
+    }
+  }
+  // merge the lanes' states
+  float d1 = st.d1;
+  int i1 = st.i1;
+#pragma unroll
+  for (int s = 1; s < 32; s <<= 1) {
+    const float od = __shfl_xor_sync(full, d1, s);
+    const int oi = __shfl_xor_sync(full, i1, s);
+    if (nb_less(od, oi, d1, i1)) { d1 = od; i1 = oi; }
+  }
+  float s2 = st.s2;
+  if (st.i1 != i1) s2 = fminf(s2, st.d1);
+  s2 = coop_min(o, s2);
+  st.d1 = d1; st.i1 = i1; st.s2 = s2;
+  if (r2_out) *r2_out = nn1_scan_r2(d1, max_d2, gap);
 }
 
 // ---- block_nn1 ----------------------------------------------------------------------------------------------

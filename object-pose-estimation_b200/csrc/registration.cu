@@ -126,15 +126,32 @@ __global__ void sum_partials_kernel(const double* __restrict__ partials, int nbl
 }
 
 // =============================================================================================== ICP ====
+// Work layout. The source is processed in the Morton order of its own cached grid (spatially coherent neighbours
+// sit in the same warp: their searches touch the same cells, so the divergent 4- and 16-byte loads coalesce and hit
+// L1); `cur_pts[s].w` carries the ORIGINAL index, which is what every caller-visible array is indexed by.
+//
+//  nearest estimator — two grid barriers per iteration:
+//    A  one source point per THREAD: seed the bound with the previous iteration's exact neighbour, ope::nn1_fast; the
+//       queries whose candidate set is too large (far from the target surface) are compacted — deterministically —
+//       into the block's segment of a grid-wide queue;                                                  [barrier 1]
+//    B  ALL warps of the grid drain the queue round-robin, one far query per WARP (coop_nn1, large leaves), so the
+//       blocks that happened to own many far points do not hold the others at the barrier;              [barrier 2]
+//    C  every block reduces the per-block double moments in the same order, warp 0 forms the means and the float
+//       cross-covariance with one division per lane, lane 0 runs the 3x3 Jacobi SVD (Umeyama) and the convergence
+//       test, then the block transforms its own slice of the source in place.
+//  normal shooting — one barrier per iteration: one source point per WARP (warp_knn bounded by the previous iteration's
+//       k-th distance), each warp owns a contiguous run of points and transforms it with all its lanes.
 struct IcpDev {
   GridView grid;
   const float4* tgt_pts;      // original order (match index -> point)
   const float4* tgt_nrm;      // original order or null
-  const float4* src0_pts;     // untouched input (variant MODCORR reads stale normals/points from here)
+  const float4* src0_pts;     // untouched input, original order (variant MODCORR reads stale normals/points from here)
   const float4* src0_nrm;
-  float4* cur_pts;            // working copy, transformed in place every iteration
+  const float4* src_sorted;   // finite source points in Morton order of the source's own grid, .w = original index
+  int n_src;                  // points in the source cloud
+  int n_work;                 // finite points = entries of src_sorted / cur_*
+  float4* cur_pts;            // working copy (sorted order), transformed in place every iteration, .w = original index
   float4* cur_nrm;
-  int n_src;
   // parameters
   int max_iterations, min_corr, estimator, k_search, n_rej, transformation, variant, force_all;
   int rej_kind[OPE_MAX_REJECTORS];
@@ -144,28 +161,39 @@ struct IcpDev {
   double rot_thr, trans_thr, rel_mse_thr, abs_mse_thr;
   int max_similar, fail_after_max;
   // outputs / state
-  int* corr_match;            // n_src, -1 = no correspondence this iteration
+  int* corr_match;            // n_src by ORIGINAL index, -1 = no correspondence this iteration (pre-filled by the host)
   float* corr_d2;             // n_src
-  int* seed;                  // nearest: n_src, last exact neighbour (seed of the next iteration's search), -1 = none
-                              // normal shooting: n_src * k_search, last k-NN list (bounds the next search), -1 = none
+  int* seed;                  // nearest: n_work (sorted position) last exact neighbour, -1 = none
+                              // normal shooting: n_work * k_search, last k-NN list, -1 = none
+  float4* ref;                // nearest: n_work certificates {query position when issued, R}: every target point other than
+                              // seed[s] is at least R away from that position (R <= 0: none)
+  float cert_gap;             // how far beyond the neighbour a search looks so that R exceeds the neighbour's distance
+  float4* def_q;              // far-query queue: x, y, z, seed d2          (block b's segment starts at its slice)
+  int4* def_m;                //                  sorted position, seed index, original index, 0
+  int* def_count;             // per block
+  int* def_head;              // claim counters of the far queue, one per iteration parity (zeroed by the host / by block 0)
   double* partials;           // 2 * gridDim * kIcpAcc (double buffered)
   unsigned* barrier;          // monotonic arrival counter of the grid barrier (zeroed by the host)
   ope_reg_result* result;     // device copy
-  long long* phase_cycles;    // optional (OPE_PROFILE=1): block 0's cycles in [search+reduce, grid barrier, partial sums + SVD, transform]
+  long long* phase_cycles;    // optional (OPE_PROFILE=1): block 0's cycles per phase
   Mat4 guess;
 };
 
 static constexpr int kIcpThreads = 512;
 static constexpr int kIcpWarps = kIcpThreads / 32;
 static constexpr int kIcpAcc = 17;  // moments[16] + sum of correspondence distances
+static constexpr int kIcpMaxBlocks = 1024;
 
 struct IcpSmem {
-  union {
-    Nn1Smem<kIcpThreads> nn;      // nearest estimator
-    OctStack wstack[kIcpWarps];   // normal shooting: one traversal stack per warp
-  } u;
+  OctStack wstack[kIcpWarps];   // one traversal stack per warp (far queries / k-NN)
+  LeafList leaves[kIcpWarps];   // collected leaf ranges of the warp's far query
+  int dir[kDirEntries];         // upper levels of the target's implicit octree (warp_nn1_far)
+  Nn1Smem<kIcpThreads> nn;      // only the one-pass kernel uses the block-local variant
   double red[kIcpWarps][kIcpAcc];
   double totals[kIcpAcc];
+  int prefix[kIcpMaxBlocks];    // inclusive prefix of the blocks' far-query counts
+  int warp_cnt[kIcpWarps];
+  int n_def;
   Mat4 T_inc;
   int stop;  // 0 continue, 1 stop, 2 stop without a transform (not enough correspondences)
 };
@@ -213,43 +241,51 @@ __device__ __forceinline__ double warp_reduce16(const double* v, int lane, int& 
   return w1;
 }
 
-// rejector chain for one candidate correspondence (VP/impl/icp_mod.hpp:194-208); returns the match or -1
-__device__ __forceinline__ int icp_reject(const IcpDev& a, int i, const float4 p, int match) {
+// term e (0..16) of the moments of one correspondence (p -> t, squared distance d2)
+__device__ __forceinline__ double moment_term(int e, const float4 p, const float4 t, float d2) {
+  if (e == 0) return 1.0;
+  if (e < 4) return e == 1 ? (double)p.x : (e == 2 ? (double)p.y : (double)p.z);
+  if (e < 7) return e == 4 ? (double)t.x : (e == 5 ? (double)t.y : (double)t.z);
+  if (e < 16) {
+    const int c = (e - 7) / 3, r = (e - 7) % 3;
+    const double sv = c == 0 ? p.x : (c == 1 ? p.y : p.z);
+    const double tv = r == 0 ? t.x : (r == 1 ? t.y : t.z);
+    return tv * sv;
+  }
+  return (double)d2;
+}
+
+// rejector chain for one candidate correspondence (VP/impl/icp_mod.hpp:194-208); s = position in cur_*, orig = original
+// index. Returns the match or -1.
+__device__ __forceinline__ int icp_reject(const IcpDev& a, int s, int orig, const float4 p, int match) {
   const bool stale = a.variant == OPE_ICP_VARIANT_MODCORR;
   for (int r = 0; r < a.n_rej && match >= 0; ++r) {
-    const float4 sn = stale ? __ldg(a.src0_nrm + i) : a.cur_nrm[i];
+    const float4 sn = stale ? __ldg(a.src0_nrm + orig) : a.cur_nrm[s];
     double score;
     if (a.rej_kind[r] == OPE_REJ_SURFACE_NORMAL) {
       const float4 tn = __ldg(a.tgt_nrm + match);
       score = (double)((sn.x * tn.x) + (sn.y * tn.y) + (sn.z * tn.z));
     } else {
-      const float4 sp = stale ? __ldg(a.src0_pts + i) : p;
-      const double s = (double)sqrtf(sp.x * sp.x + sp.y * sp.y + sp.z * sp.z);
-      score = (double)((sn.x * (-sp.x / s)) + (sn.y * (-sp.y / s)) + (sn.z * (-sp.z / s)));
+      const float4 sp = stale ? __ldg(a.src0_pts + orig) : p;
+      const double sl = (double)sqrtf(sp.x * sp.x + sp.y * sp.y + sp.z * sp.z);
+      score = (double)((sn.x * (-sp.x / sl)) + (sn.y * (-sp.y / sl)) + (sn.z * (-sp.z / sl)));
     }
     if (!(score > a.rej_thr[r])) match = -1;
   }
   return match;
 }
 
-// CorrespondenceEstimation (nearest): one source point per THREAD, block-uniform call (block_nn1 synchronises).
-__device__ __forceinline__ int icp_correspond_nearest(const IcpDev& a, Nn1Smem<kIcpThreads>* nn, int i, bool in_range, const float4 p,
-                                                      bool use_seed, float& d2_out, long long* prof = nullptr) {
-  const bool ok = in_range && finite3(p.x, p.y, p.z);
-  const int sd = (use_seed && in_range) ? a.seed[i] : -1;
-  float d2 = 0.0f;
-  int match = block_nn1<kIcpThreads>(a.grid, nn, ok, p.x, p.y, p.z, a.max_d2_f, sd, a.tgt_pts, d2, prof);
-  if (!in_range) return -1;
-  a.seed[i] = match;
+// exact neighbour -> correspondence: distance gate (VP/impl/correspondence_estimation_mod.hpp:171) + rejector chain
+__device__ __forceinline__ int icp_gate(const IcpDev& a, int s, int orig, const float4 p, int nn, float d2) {
+  int match = nn;
   if (match >= 0 && (double)d2 > a.max_corr_dist * a.max_corr_dist) match = -1;
-  if (match >= 0) match = icp_reject(a, i, p, match);
-  d2_out = d2;
+  if (match >= 0) match = icp_reject(a, s, orig, p, match);
   return match;
 }
 
 // CorrespondenceEstimationNormalShooting: one source point per WARP. Among the k nearest, the one with the smallest
 // squared distance to the line through p along the source normal (double); the first minimum in list order wins.
-__device__ __forceinline__ int icp_correspond_shooting(const IcpDev& a, OctStack* st, int i, const float4 p, bool use_seed,
+__device__ __forceinline__ int icp_correspond_shooting(const IcpDev& a, OctStack* st, int s, int orig, const float4 p, bool use_seed,
                                                        float& d2_out) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -260,7 +296,7 @@ __device__ __forceinline__ int icp_correspond_shooting(const IcpDev& a, OctStack
   float bound = FLT_MAX;
   if (use_seed && ok) {
     int pj = -1;
-    if (lane < k) pj = a.seed[(size_t)i * a.k_search + lane];
+    if (lane < k) pj = a.seed[(size_t)s * a.k_search + lane];
     float d = 0.0f;
     if (pj >= 0) { const float4 t = __ldg(a.tgt_pts + pj); d = dist2(p.x, p.y, p.z, t.x, t.y, t.z); }
     const bool all_valid = __ballot_sync(full, lane >= k || pj >= 0) == full;
@@ -270,11 +306,11 @@ __device__ __forceinline__ int icp_correspond_shooting(const IcpDev& a, OctStack
   float ld;
   int li;
   const int cnt = warp_knn(a.grid, st, ok, p.x, p.y, p.z, a.k_search, bound, ld, li);
-  if (lane < a.k_search) a.seed[(size_t)i * a.k_search + lane] = (lane < cnt) ? li : -1;
+  if (a.seed && lane < a.k_search) a.seed[(size_t)s * a.k_search + lane] = (lane < cnt) ? li : -1;
   int match = -1;
   float d2 = 0.0f;
   if (cnt > 0) {
-    const float4 nr = stale ? __ldg(a.src0_nrm + i) : a.cur_nrm[i];
+    const float4 nr = stale ? __ldg(a.src0_nrm + orig) : a.cur_nrm[s];
     const double N[3] = {nr.x, nr.y, nr.z};
     double dist = DBL_MAX;
     int jdx = 0x7fffffff;
@@ -300,9 +336,27 @@ __device__ __forceinline__ int icp_correspond_shooting(const IcpDev& a, OctStack
       d2 = __shfl_sync(full, ld, pick);
     }
   }
-  if (match >= 0) match = icp_reject(a, i, p, match);
+  if (match >= 0) match = icp_reject(a, s, orig, p, match);
   d2_out = d2;
   return match;
+}
+
+// in-place rigid transform of cur_pts[s] / cur_nrm[s]
+__device__ __forceinline__ void icp_move(const IcpDev& a, const Mat4& T, int s) {
+  float4 p = a.cur_pts[s];
+  if (!finite3(p.x, p.y, p.z)) return;
+  float x, y, z;
+  xform_point(T, p.x, p.y, p.z, x, y, z);
+  p.x = x; p.y = y; p.z = z;
+  a.cur_pts[s] = p;
+  if (a.cur_nrm) {
+    float4 v = a.cur_nrm[s];
+    if (finite3(v.x, v.y, v.z)) {
+      xform_normal(T, v.x, v.y, v.z, x, y, z);
+      v.x = x; v.y = y; v.z = z;
+      a.cur_nrm[s] = v;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(kIcpThreads, 1) icp_kernel(IcpDev a) {
@@ -311,17 +365,21 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_kernel(IcpDev a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gwarp = blockIdx.x * kIcpWarps + warp, n_gwarps = gridDim.x * kIcpWarps;
   const bool shooting = a.estimator == OPE_EST_NORMAL_SHOOTING;
+  OctStack* st = &sm->wstack[warp];
 
-  // nearest mode: block b owns the contiguous slice [lo, hi) of the source, one point per thread per round
-  const int chunk = (a.n_src + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int lo = min(a.n_src, (int)blockIdx.x * chunk), hi = min(a.n_src, lo + chunk);
+  // nearest: block b owns the slice [lo, hi) of the sorted source; shooting: warp gw owns [wlo, whi)
+  const int chunk = (a.n_work + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int lo = min(a.n_work, (int)blockIdx.x * chunk), hi = min(a.n_work, lo + chunk);
+  const int wchunk = (a.n_work + n_gwarps - 1) / n_gwarps;
+  const int wlo = min(a.n_work, gwarp * wchunk), whi = min(a.n_work, wlo + wchunk);
 
-  // input_transformed = guess applied to input (VP/impl/icp_mod.hpp:132-139)
+  // input_transformed = guess applied to input (VP/impl/icp_mod.hpp:132-139), in sorted order
   const bool have_guess = !mat4_is_identity(a.guess);
-  for (int i = blockIdx.x * kIcpThreads + threadIdx.x; i < a.n_src; i += gridDim.x * kIcpThreads) {
-    float4 p = __ldg(a.src0_pts + i);
-    float4 v = a.src0_nrm ? __ldg(a.src0_nrm + i) : make_float4(0, 0, 0, 0);
-    if (have_guess && finite3(p.x, p.y, p.z)) {
+  for (int s = blockIdx.x * kIcpThreads + threadIdx.x; s < a.n_work; s += gridDim.x * kIcpThreads) {
+    float4 p = __ldg(a.src_sorted + s);
+    const int orig = __float_as_int(p.w);
+    float4 v = a.src0_nrm ? __ldg(a.src0_nrm + orig) : make_float4(0, 0, 0, 0);
+    if (have_guess) {
       float x, y, z;
       xform_point(a.guess, p.x, p.y, p.z, x, y, z);
       p.x = x; p.y = y; p.z = z;
@@ -330,11 +388,13 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_kernel(IcpDev a) {
         v.x = x; v.y = y; v.z = z;
       }
     }
-    a.cur_pts[i] = p;
-    if (a.cur_nrm) a.cur_nrm[i] = v;
+    a.cur_pts[s] = p;
+    if (a.cur_nrm) a.cur_nrm[s] = v;
   }
-  // The initialisation above is grid-strided; the iterations use their own ownership maps (nearest: the block's slice,
-  // shooting: warp gwarp owns points gwarp + j*n_gwarps), so the first iteration is preceded by a grid barrier.
+  far_dir_load(a.grid, sm->dir);
+  FarDir fdir;
+  fdir.sdir = sm->dir; fdir.dl = far_dir_level(a.grid);
+  // the initialisation above is grid-strided, the iterations use their own ownership maps: one barrier in between
   unsigned bar_target = gridDim.x;
   grid_barrier(a.barrier, bar_target);
 
@@ -344,183 +404,318 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_kernel(IcpDev a) {
   int similar = 0, iterations = 0, state = OPE_CONV_NOT_CONVERGED, converged = 0, n_corr = 0;
   int pass = 0;  // uniform across all threads: selects the partials buffer
 
-  long long t_phase[4] = {0, 0, 0, 0};
-  long long t_nn[3] = {0, 0, 0};
+  long long t_phase[7] = {0, 0, 0, 0, 0, 0, 0};
+  long long t_prev[7] = {0, 0, 0, 0, 0, 0, 0};
+  const bool prof_any = a.phase_cycles != nullptr;
+  long long n_far = 0;
   const bool prof = a.phase_cycles != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
   for (;; ++pass) {
     long long t0 = prof ? clock64() : 0;
-    // ---- phase 1: correspondences + moments ----
     for (int e = lane; e < kIcpAcc; e += 32) sm->red[warp][e] = 0.0;
-    __syncwarp();
+    if (threadIdx.x == 0) sm->n_def = 0;
+    __syncthreads();
     if (!shooting) {
+      // ---- phase A: thread per point, fast path; far queries go to the grid-wide queue ----
       for (int base = lo; base < hi; base += kIcpThreads) {
-        const int i = base + (int)threadIdx.x;
-        const bool in_range = i < hi;
+        const int s = base + (int)threadIdx.x;
+        const bool in_range = s < hi;
         float4 p = make_float4(0, 0, 0, 0);
-        if (in_range) p = a.cur_pts[i];
+        int sd = -1;
+        if (in_range) { p = a.cur_pts[s]; if (pass > 0) sd = __ldcg(a.seed + s); }  // seed/ref may have been written by another SM
+        const int orig = __float_as_int(p.w);
+        const bool ok = in_range && a.grid.n > 0 && finite3(p.x, p.y, p.z);
+        Nn1State nst;
+        nst.d1 = FLT_MAX; nst.i1 = 0x7fffffff; nst.s2 = FLT_MAX;
+        bool far = false, certified = false;
+        if (ok) {
+          const float ux = (p.x - a.grid.ox) * a.grid.inv_h, uy = (p.y - a.grid.oy) * a.grid.inv_h, uz = (p.z - a.grid.oz) * a.grid.inv_h;
+          if (sd >= 0) {
+            const float4 t = __ldg(a.tgt_pts + sd);
+            nst.d1 = dist2(p.x, p.y, p.z, t.x, t.y, t.z);
+            nst.i1 = sd;
+            // certificate of an earlier iteration: every other target point was at least R from the position rf; the point
+            // has moved by delta since, so they are at least R - delta away now. If the old neighbour is strictly closer
+            // than that (with a margin far above float rounding) it is still THE nearest neighbour: no search.
+            const float4 rf = __ldcg(a.ref + s);
+            if (rf.w > 0.0f) {
+              const float delta = sqrtf(dist2(p.x, p.y, p.z, rf.x, rf.y, rf.z));
+              const float d1n = sqrtf(nst.d1);
+              certified = (d1n + 2.0f * delta) * 1.00001f + 2e-6f < rf.w;
+              // range certificate: the old neighbour and everything else are still beyond the correspondence limit, so the
+              // point has no correspondence whatever its exact neighbour is (the gate below rejects d2 > max^2)
+              if (!certified && a.max_d2_f < FLT_MAX) {
+                const float lim = sqrtf(a.max_d2_f) * 1.00001f + 2e-6f;
+                certified = d1n > lim && rf.w - delta > lim;
+              }
+            }
+          } else {
+            nn1_probe(a.grid, p.x, p.y, p.z, ux, uy, uz, [&](int b, int e) {
+              for (int i = b; i < e; ++i) {
+                const float4 c = __ldg(a.grid.pts + i);
+                nn1_offer(nst, dist2(p.x, p.y, p.z, c.x, c.y, c.z), __float_as_int(c.w));
+              }
+            });
+            nst.s2 = FLT_MAX;  // the probe only seeds the bound
+          }
+          if (!certified) {
+            float r2 = 0.0f;
+            far = !nn1_fast(a.grid, p.x, p.y, p.z, ux, uy, uz, a.max_d2_f, a.cert_gap, nst, &r2);
+            if (!far) a.ref[s] = make_float4(p.x, p.y, p.z, sqrtf(fminf(nst.s2, r2)));
+          }
+        }
+        const float best_d2 = nst.d1;
+        const int best_i = nst.i1;
+        // deterministic compaction of the far queries into this block's queue segment [lo + n_def, ...)
+        const unsigned fm = __ballot_sync(0xffffffffu, far);
+        if (lane == 0) sm->warp_cnt[warp] = __popc(fm);
+        __syncthreads();
+        int before = sm->n_def;
+        for (int w = 0; w < warp; ++w) before += sm->warp_cnt[w];
+        if (far) {
+          const int slot = lo + before + __popc(fm & ((1u << lane) - 1u));
+          a.def_q[slot] = make_float4(p.x, p.y, p.z, best_d2);
+          a.def_m[slot] = make_int4(s, best_i, orig, 0);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          int tot = sm->n_def;
+          for (int w = 0; w < kIcpWarps; ++w) tot += sm->warp_cnt[w];
+          sm->n_def = tot;
+        }
+        // finish the near queries: gate, rejectors, outputs, moments
+        int m = -1;
         float d2 = 0.0f;
-        const int m = icp_correspond_nearest(a, &sm->u.nn, i, in_range, p, pass > 0, d2, prof ? t_nn : nullptr);
-        if (in_range) { a.corr_match[i] = m; a.corr_d2[i] = d2; }
-        double v[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] = 0.0;
-        double dsum = 0.0;
-        if (m >= 0) {
-          const float4 t = __ldg(a.tgt_pts + m);
-          v[0] = 1.0;
-          v[1] = p.x; v[2] = p.y; v[3] = p.z;
-          v[4] = t.x; v[5] = t.y; v[6] = t.z;
-          const double sv[3] = {p.x, p.y, p.z}, tv[3] = {t.x, t.y, t.z};
-#pragma unroll
-          for (int c = 0; c < 3; ++c)
-#pragma unroll
-            for (int r = 0; r < 3; ++r) v[7 + c * 3 + r] = tv[r] * sv[c];
-          dsum = (double)d2;
+        if (ok && !far) {
+          const int nn = best_i == 0x7fffffff ? -1 : best_i;
+          a.seed[s] = nn;
+          d2 = best_d2;
+          m = icp_gate(a, s, orig, p, nn, d2);
+          a.corr_match[orig] = m;
+          a.corr_d2[orig] = d2;
+        } else if (in_range && !far) {
+          a.seed[s] = -1;
+          a.corr_match[orig] = -1;
         }
         if (__ballot_sync(0xffffffffu, m >= 0) != 0u) {  // warp-uniform
+          double v[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = 0.0;
+          double dsum = 0.0;
+          if (m >= 0) {
+            const float4 t = __ldg(a.tgt_pts + m);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = moment_term(e, p, t, d2);
+            dsum = (double)d2;
+          }
           int slot;
           const double w = warp_reduce16(v, lane, slot);
           dsum = warp_sum_d(dsum);
           if ((lane & 1) == 0) sm->red[warp][slot] += w;
           if (lane == 1) sm->red[warp][16] += dsum;
-          __syncwarp();
+        }
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) a.def_count[blockIdx.x] = sm->n_def;
+      if (prof) { const long long t1 = clock64(); t_phase[0] += t1 - t0; t0 = t1; n_far += sm->n_def; }
+      bar_target += gridDim.x;
+      grid_barrier(a.barrier, bar_target);
+      if (prof) { const long long t1 = clock64(); t_phase[1] += t1 - t0; t0 = t1; }
+      // ---- phase B: all warps of the grid drain the queue, one far query per warp ----
+      if (warp == 0) {  // inclusive prefix of the per-block counts (gridDim <= kIcpMaxBlocks)
+        int run = 0;
+        for (int b0 = 0; b0 < (int)gridDim.x; b0 += 32) {
+          const int b = b0 + lane;
+          int c = b < (int)gridDim.x ? __ldcg(a.def_count + b) : 0;
+          for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, c, o); if (lane >= o) c += t; }
+          if (b < (int)gridDim.x) sm->prefix[b] = run + c;
+          run += __shfl_sync(0xffffffffu, c, 31);
         }
       }
-    } else {
-      OctStack* st = &sm->u.wstack[warp];
-      for (int i = gwarp; i < a.n_src; i += n_gwarps) {  // one warp per source point
-        const float4 p = a.cur_pts[i];
-        float d2 = 0.0f;
-        const int m = icp_correspond_shooting(a, st, i, p, pass > 0, d2);
-        if (lane == 0) { a.corr_match[i] = m; a.corr_d2[i] = d2; }
-        if (m >= 0 && lane < kIcpAcc) {   // lane e computes term e of the 17 moments
-          const float4 t = __ldg(a.tgt_pts + m);
-          double term;
-          if (lane == 0) term = 1.0;
-          else if (lane < 4) term = lane == 1 ? p.x : (lane == 2 ? p.y : p.z);
-          else if (lane < 7) term = lane == 4 ? t.x : (lane == 5 ? t.y : t.z);
-          else if (lane < 16) {
-            const int c = (lane - 7) / 3, r = (lane - 7) % 3;
-            const double sv = c == 0 ? p.x : (c == 1 ? p.y : p.z);
-            const double tv = r == 0 ? t.x : (r == 1 ? t.y : t.z);
-            term = tv * sv;
-          } else term = (double)d2;
-          sm->red[warp][lane] += term;
+      __syncthreads();
+      const int total = sm->prefix[gridDim.x - 1];
+      int* head = a.def_head + (pass & 1);
+      if (blockIdx.x == 0 && threadIdx.x == 0) a.def_head[(pass + 1) & 1] = 0;  // nobody touches the other counter before barrier 3
+      for (;;) {  // warps claim far queries one at a time: whoever is free takes the next (results do not depend on who)
+        int e = 0;
+        if (lane == 0) e = atomicAdd(head, 1);
+        e = __shfl_sync(0xffffffffu, e, 0);
+        if (e >= total) break;
+        int bl = 0, br = (int)gridDim.x - 1;  // first block whose inclusive prefix exceeds e
+        while (bl < br) { const int mid = (bl + br) >> 1; if (sm->prefix[mid] > e) br = mid; else bl = mid + 1; }
+        const int j = e - (bl > 0 ? sm->prefix[bl - 1] : 0);
+        const int slot = min(a.n_work, bl * chunk) + j;
+        const float4 q = __ldcg(a.def_q + slot);
+        const int4 qm = __ldcg(a.def_m + slot);
+        Nn1State nst;
+        nst.d1 = q.w; nst.i1 = qm.y; nst.s2 = FLT_MAX;
+        float r2 = 0.0f;
+        const long long q0 = prof_any ? clock64() : 0;
+        if (pass == 0) warp_nn1_far<true>(a.grid, fdir, st, &sm->leaves[warp], q.x, q.y, q.z, a.max_d2_f, a.cert_gap, nst, &r2);
+        else warp_nn1_far<false>(a.grid, fdir, st, &sm->leaves[warp], q.x, q.y, q.z, a.max_d2_f, a.cert_gap, nst, &r2);
+        if (prof_any && lane == 0 && pass < 64) {
+          atomicMax((unsigned long long*)(a.phase_cycles + 16 + pass * 8 + 7), (unsigned long long)(clock64() - q0));
+          atomicAdd((unsigned long long*)(a.phase_cycles + 16 + 64 * 8 + pass), 1ull);
+        }
+        const float bd = nst.d1;
+        const int nn = nst.i1 == 0x7fffffff ? -1 : nst.i1;
+        const float4 p = make_float4(q.x, q.y, q.z, 0.0f);
+        const int m = icp_gate(a, qm.x, qm.z, p, nn, bd);  // warp-uniform
+        if (lane == 0) {
+          a.seed[qm.x] = nn; a.corr_match[qm.z] = m; a.corr_d2[qm.z] = bd;
+          a.ref[qm.x] = make_float4(q.x, q.y, q.z, sqrtf(fminf(nst.s2, r2)));
         }
         __syncwarp();
       }
+      if (prof) { const long long t1 = clock64(); t_phase[2] += t1 - t0; t0 = t1; }
+      bar_target += gridDim.x;
+      grid_barrier(a.barrier, bar_target);
+      if (prof) { const long long t1 = clock64(); t_phase[3] += t1 - t0; t0 = t1; }
+      // ---- the moments of this block's own far queries, in queue order (deterministic whoever searched them) ----
+      {
+        const int n_def = sm->n_def;
+        for (int base = 0; base < n_def; base += kIcpThreads) {
+          const int j = base + (int)threadIdx.x;
+          int m = -1;
+          float d2 = 0.0f;
+          float4 p = make_float4(0, 0, 0, 0);
+          if (j < n_def) {
+            p = a.def_q[lo + j];
+            const int4 qm = a.def_m[lo + j];
+            m = __ldcg(a.corr_match + qm.z);
+            d2 = __ldcg(a.corr_d2 + qm.z);
+          }
+          if (__ballot_sync(0xffffffffu, m >= 0) != 0u) {
+            double v[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = 0.0;
+            double dsum = 0.0;
+            if (m >= 0) {
+              const float4 t = __ldg(a.tgt_pts + m);
+#pragma unroll
+              for (int e = 0; e < 16; ++e) v[e] = moment_term(e, p, t, d2);
+              dsum = (double)d2;
+            }
+            int slot;
+            const double w = warp_reduce16(v, lane, slot);
+            dsum = warp_sum_d(dsum);
+            if ((lane & 1) == 0) sm->red[warp][slot] += w;
+            if (lane == 1) sm->red[warp][16] += dsum;
+          }
+        }
+      }
+      if (prof) { const long long t1 = clock64(); t_phase[4] += t1 - t0; t0 = t1; }
+    } else {
+      for (int s = wlo; s < whi; ++s) {  // one warp per source point
+        const float4 p = a.cur_pts[s];
+        const int orig = __float_as_int(p.w);
+        float d2 = 0.0f;
+        const int m = icp_correspond_shooting(a, st, s, orig, p, pass > 0, d2);
+        if (lane == 0) { a.corr_match[orig] = m; a.corr_d2[orig] = d2; }
+        if (m >= 0 && lane < kIcpAcc) {
+          const float4 t = __ldg(a.tgt_pts + m);
+          sm->red[warp][lane] += moment_term(lane, p, t, d2);
+        }
+        __syncwarp();
+      }
+      if (prof) { const long long t1 = clock64(); t_phase[0] += t1 - t0; t0 = t1; }
     }
     __syncthreads();
     double* my_partials = a.partials + ((size_t)(pass & 1) * gridDim.x + blockIdx.x) * kIcpAcc;
     if (threadIdx.x < kIcpAcc) {
-      double s = 0.0;
+      double sum = 0.0;
 #pragma unroll
-      for (int w = 0; w < kIcpWarps; ++w) s += sm->red[w][threadIdx.x];
-      my_partials[threadIdx.x] = s;
+      for (int w = 0; w < kIcpWarps; ++w) sum += sm->red[w][threadIdx.x];
+      my_partials[threadIdx.x] = sum;
     }
-    if (prof) { const long long t1 = clock64(); t_phase[0] += t1 - t0; t0 = t1; }
     bar_target += gridDim.x;
     grid_barrier(a.barrier, bar_target);
-    if (prof) { const long long t1 = clock64(); t_phase[1] += t1 - t0; t0 = t1; }
-    // ---- phase 2: every block reduces all partials in the same order (warp per accumulator, lanes over blocks) ----
+    if (prof) { const long long t1 = clock64(); t_phase[4] += t1 - t0; t0 = t1; }
+    // ---- phase C: every block reduces all partials in the same order (warp per accumulator, lanes over blocks) ----
     for (int e = warp; e < kIcpAcc; e += kIcpWarps) {
       const double* base = a.partials + (size_t)(pass & 1) * gridDim.x * kIcpAcc;
-      double s = 0.0;
-      for (int b = lane; b < (int)gridDim.x; b += 32) s += __ldcg(base + (size_t)b * kIcpAcc + e);
-      s = warp_sum_d(s);
-      if (lane == 0) sm->totals[e] = s;
+      double sum = 0.0;
+      for (int b = lane; b < (int)gridDim.x; b += 32) sum += __ldcg(base + (size_t)b * kIcpAcc + e);
+      sum = warp_sum_d(sum);
+      if (lane == 0) sm->totals[e] = sum;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (warp == 0) {
       int stop = 0;
       n_corr = (int)sm->totals[0];
       if (n_corr < a.min_corr) {
         state = OPE_CONV_NO_CORRESPONDENCES; converged = 0; stop = 2;  // VP/impl/icp_mod.hpp:232-240
-        sm->T_inc = mat4_identity();
+        if (lane == 0) sm->T_inc = mat4_identity();
       } else {
-        Mat4 T;
-        umeyama_from_moments(sm->totals, T);
-        sm->T_inc = T;
-        final_t = mat4_mul(T, final_t);
-        ++iterations;
-        // DefaultConvergenceCriteria::hasConverged
-        state = OPE_CONV_NOT_CONVERGED;
-        int conv = 0;
-        if (iterations >= a.max_iterations) {
-          if (!a.fail_after_max) { state = OPE_CONV_ITERATIONS; conv = 1; }
-          else { conv = 0; stop = 1; }
-        } else {
-          const double cos_angle = 0.5 * (double)(T(0, 0) + T(1, 1) + T(2, 2) - 1);
-          const double translation_sqr = (double)(T(0, 3) * T(0, 3) + T(1, 3) * T(1, 3) + T(2, 3) * T(2, 3));
-          int hit = 0, hit_state = 0;
-          if (cos_angle >= a.rot_thr && translation_sqr <= a.trans_thr) { hit = 1; hit_state = OPE_CONV_TRANSFORM; }
-          else {
-            cur_mse = sm->totals[16] / (double)n_corr;
-            if (fabs(cur_mse - prev_mse) < a.abs_mse_thr) { hit = 1; hit_state = OPE_CONV_ABS_MSE; }
-            else if (fabs(cur_mse - prev_mse) / prev_mse < a.rel_mse_thr) { hit = 1; hit_state = OPE_CONV_REL_MSE; }
-            else prev_mse = cur_mse;
-          }
-          if (hit) {
-            if (similar < a.max_similar) ++similar;
-            else { similar = 0; state = hit_state; conv = 1; }
-          }
+        // Umeyama prelude, one division per lane (same arithmetic as ope::umeyama_from_moments)
+        const double n = sm->totals[0];
+        double mean = 0.0;
+        if (lane < 6) mean = sm->totals[1 + lane] / n;  // lanes 0-2: source mean, 3-5: target mean
+        double ms[3], mt[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { ms[k] = __shfl_sync(0xffffffffu, mean, k); mt[k] = __shfl_sync(0xffffffffu, mean, 3 + k); }
+        float sg = 0.0f;
+        if (lane < 9) {
+          const int c = lane / 3, r = lane % 3;
+          const double msc = c == 0 ? ms[0] : (c == 1 ? ms[1] : ms[2]);
+          const double mtr = r == 0 ? mt[0] : (r == 1 ? mt[1] : mt[2]);
+          sg = (float)(sm->totals[7 + lane] / n - mtr * msc);
         }
-        converged = conv;
-        if (a.force_all && iterations < a.max_iterations) conv = 0;
-        if (conv) stop = 1;
+        float sigma[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) sigma[k] = __shfl_sync(0xffffffffu, sg, k);
+        if (lane == 0) {
+          Mat4 T;
+          umeyama_from_sigma_means(sigma, ms, mt, T);
+          sm->T_inc = T;
+          final_t = mat4_mul(T, final_t);
+          ++iterations;
+          // DefaultConvergenceCriteria::hasConverged
+          state = OPE_CONV_NOT_CONVERGED;
+          int conv = 0;
+          if (iterations >= a.max_iterations) {
+            if (!a.fail_after_max) { state = OPE_CONV_ITERATIONS; conv = 1; }
+            else { conv = 0; stop = 1; }
+          } else {
+            const double cos_angle = 0.5 * (double)(T(0, 0) + T(1, 1) + T(2, 2) - 1);
+            const double translation_sqr = (double)(T(0, 3) * T(0, 3) + T(1, 3) * T(1, 3) + T(2, 3) * T(2, 3));
+            int hit = 0, hit_state = 0;
+            if (cos_angle >= a.rot_thr && translation_sqr <= a.trans_thr) { hit = 1; hit_state = OPE_CONV_TRANSFORM; }
+            else {
+              cur_mse = sm->totals[16] / (double)n_corr;
+              if (fabs(cur_mse - prev_mse) < a.abs_mse_thr) { hit = 1; hit_state = OPE_CONV_ABS_MSE; }
+              else if (fabs(cur_mse - prev_mse) / prev_mse < a.rel_mse_thr) { hit = 1; hit_state = OPE_CONV_REL_MSE; }
+              else prev_mse = cur_mse;
+            }
+            if (hit) {
+              if (similar < a.max_similar) ++similar;
+              else { similar = 0; state = hit_state; conv = 1; }
+            }
+          }
+          converged = conv;
+          if (a.force_all && iterations < a.max_iterations) conv = 0;
+          if (conv) stop = 1;
+        }
       }
-      sm->stop = stop;
+      if (lane == 0) sm->stop = stop;
     }
     __syncthreads();
-    if (prof) { const long long t1 = clock64(); t_phase[2] += t1 - t0; t0 = t1; }
-    // ---- phase 3: transformCloud(input_transformed, transformation_), own points only ----
+    if (prof) { const long long t1 = clock64(); t_phase[5] += t1 - t0; t0 = t1; }
+    // ---- transformCloud(input_transformed, transformation_), own points only ----
     const int stop = sm->stop;
     if (stop != 2) {
       const Mat4 T = sm->T_inc;
-      // the thread / warp that searches point i is also the one that moves it: no cross-block hazard on cur_pts
-      if (!shooting) {
-        for (int i = lo + (int)threadIdx.x; i < hi; i += kIcpThreads) {
-          float4 p = a.cur_pts[i];
-          if (!finite3(p.x, p.y, p.z)) continue;
-          float x, y, z;
-          xform_point(T, p.x, p.y, p.z, x, y, z);
-          p.x = x; p.y = y; p.z = z;
-          a.cur_pts[i] = p;
-          if (a.cur_nrm) {
-            float4 v = a.cur_nrm[i];
-            if (finite3(v.x, v.y, v.z)) {
-              xform_normal(T, v.x, v.y, v.z, x, y, z);
-              v.x = x; v.y = y; v.z = z;
-              a.cur_nrm[i] = v;
-            }
-          }
-        }
-      } else if (lane == 0) {
-        for (int i = gwarp; i < a.n_src; i += n_gwarps) {
-          float4 p = a.cur_pts[i];
-          if (!finite3(p.x, p.y, p.z)) continue;
-          float x, y, z;
-          xform_point(T, p.x, p.y, p.z, x, y, z);
-          p.x = x; p.y = y; p.z = z;
-          a.cur_pts[i] = p;
-          if (a.cur_nrm) {
-            float4 v = a.cur_nrm[i];
-            if (finite3(v.x, v.y, v.z)) {
-              xform_normal(T, v.x, v.y, v.z, x, y, z);
-              v.x = x; v.y = y; v.z = z;
-              a.cur_nrm[i] = v;
-            }
-          }
-        }
-      }
-      __syncwarp();
+      if (!shooting) { for (int s = lo + (int)threadIdx.x; s < hi; s += kIcpThreads) icp_move(a, T, s); }
+      else { for (int s = wlo + lane; s < whi; s += 32) icp_move(a, T, s); __syncwarp(); }
     }
-    if (prof) { const long long t1 = clock64(); t_phase[3] += t1 - t0; }
+    if (prof) {
+      const long long t1 = clock64(); t_phase[6] += t1 - t0;
+      if (pass < 64) for (int k = 0; k < 7; ++k) { a.phase_cycles[16 + pass * 8 + k] = t_phase[k] - t_prev[k]; t_prev[k] = t_phase[k]; }
+    }
     if (stop) break;
   }
   if (prof) {
-    for (int i = 0; i < 4; ++i) a.phase_cycles[i] = t_phase[i];
-    for (int i = 0; i < 3; ++i) a.phase_cycles[4 + i] = t_nn[i];
+    for (int i = 0; i < 7; ++i) a.phase_cycles[i] = t_phase[i];
+    a.phase_cycles[7] = n_far;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     ope_reg_result r;
@@ -531,7 +726,7 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_kernel(IcpDev a) {
   }
 }
 
-// one estimation + rejection pass (no loop) on the clouds as given
+// one estimation + rejection pass (no loop) on the clouds as given (cur_* = the caller's clouds, original order)
 __global__ void __launch_bounds__(kIcpThreads, 1) correspond_once_kernel(IcpDev a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   IcpSmem* sm = reinterpret_cast<IcpSmem*>(smem_raw);
@@ -542,16 +737,20 @@ __global__ void __launch_bounds__(kIcpThreads, 1) correspond_once_kernel(IcpDev 
       const bool in_range = i < a.n_src;
       float4 p = make_float4(0, 0, 0, 0);
       if (in_range) p = a.cur_pts[i];
+      const bool ok = in_range && finite3(p.x, p.y, p.z);
       float d2 = 0.0f;
-      const int m = icp_correspond_nearest(a, &sm->u.nn, i, in_range, p, false, d2);
-      if (in_range) { a.corr_match[i] = m; a.corr_d2[i] = d2; }
+      const int nn = block_nn1<kIcpThreads>(a.grid, &sm->nn, ok, p.x, p.y, p.z, a.max_d2_f, -1, nullptr, d2);
+      if (in_range) {
+        const int m = ok ? icp_gate(a, i, i, p, nn, d2) : -1;
+        a.corr_match[i] = m; a.corr_d2[i] = d2;
+      }
     }
   } else {
-    OctStack* st = &sm->u.wstack[warp];
+    OctStack* st = &sm->wstack[warp];
     for (int i = blockIdx.x * kIcpWarps + warp; i < a.n_src; i += gridDim.x * kIcpWarps) {
       const float4 p = a.cur_pts[i];
       float d2 = 0.0f;
-      const int m = icp_correspond_shooting(a, st, i, p, false, d2);
+      const int m = icp_correspond_shooting(a, st, i, i, p, false, d2);
       if (lane == 0) { a.corr_match[i] = m; a.corr_d2[i] = d2; }
       __syncwarp();
     }
@@ -750,21 +949,36 @@ int icp_device(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const o
   OPE_TRY(icp_fill(ctx, src, tgt, prm, &a));
   a.guess = guess;
   const size_t n = src->n;
+  // the source in Morton order of its own (cached) grid: spatially coherent work order, finite points only
+  GridView gsrc;
+  std::memset(&gsrc, 0, sizeof(gsrc));
+  if (n > 0) OPE_TRY(cloud_any_grid(ctx, src, &gsrc));
+  a.src_sorted = gsrc.pts;
+  a.n_work = gsrc.n;
+  const size_t nw = (size_t)a.n_work;
   ope_cloud* work = nullptr;
-  OPE_TRY(cloud_alloc(ctx, n, src->normals != nullptr, &work));
+  OPE_TRY(cloud_alloc(ctx, std::max<size_t>(n, 1), src->normals != nullptr, &work));
+  work->n = n;
   a.cur_pts = work->pts; a.cur_nrm = work->normals;
-  Scratch<int> match(ctx), seed(ctx);
+  Scratch<int> match(ctx), seed(ctx), dcount(ctx), dhead(ctx);
   Scratch<float> d2(ctx);
+  Scratch<float4> defq(ctx), refs(ctx);
+  Scratch<int4> defm(ctx);
   Scratch<double> partials(ctx);
   Scratch<unsigned> bar(ctx);
   Scratch<ope_reg_result> dres(ctx);
   const bool shooting = prm.estimator == OPE_EST_NORMAL_SHOOTING;
   int rc = match.alloc(n);
   if (rc == OPE_OK) rc = d2.alloc(n);
-  if (rc == OPE_OK) rc = seed.alloc(shooting ? n * (size_t)prm.k_search : n);
+  if (rc == OPE_OK) rc = seed.alloc(shooting ? nw * (size_t)prm.k_search : nw);
+  if (rc == OPE_OK && !shooting) rc = defq.alloc(nw);
+  if (rc == OPE_OK && !shooting) rc = defm.alloc(nw);
+  if (rc == OPE_OK && !shooting) rc = refs.alloc(nw);
   if (rc == OPE_OK) rc = dres.alloc(1);
   if (rc == OPE_OK) rc = bar.alloc(1);
   if (rc == OPE_OK && cudaMemsetAsync(bar.p, 0, sizeof(unsigned), ctx->stream) != cudaSuccess) rc = fail(ctx, OPE_ERR_CUDA, "memset failed");
+  if (rc == OPE_OK && n > 0 && cudaMemsetAsync(match.p, 0xff, n * sizeof(int), ctx->stream) != cudaSuccess) rc = fail(ctx, OPE_ERR_CUDA, "memset failed");
+  if (rc == OPE_OK && n > 0 && cudaMemsetAsync(d2.p, 0, n * sizeof(float), ctx->stream) != cudaSuccess) rc = fail(ctx, OPE_ERR_CUDA, "memset failed");
   if (rc == OPE_OK) rc = dyn_smem(ctx, (const void*)icp_kernel, sizeof(IcpSmem));
   // cooperative grid: one point per thread (nearest) / per warp (normal shooting), capped by co-residency
   int per_sm = 0;
@@ -773,15 +987,28 @@ int icp_device(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const o
   int blocks = 1;
   if (rc == OPE_OK) {
     if (per_sm < 1) rc = fail(ctx, OPE_ERR_CUDA, "icp_kernel cannot be resident");
-    const int max_blocks = per_sm * ctx->sm_count;
-    const size_t want = shooting ? (n + kIcpWarps - 1) / kIcpWarps : (n + 127) / 128;
+    const int max_blocks = std::min(per_sm * ctx->sm_count, kIcpMaxBlocks);
+    const size_t want = shooting ? (nw + kIcpWarps - 1) / kIcpWarps : (nw + 127) / 128;
     blocks = (int)std::min<size_t>(std::max<size_t>(1, want), (size_t)max_blocks);
   }
   if (rc == OPE_OK) rc = partials.alloc((size_t)2 * blocks * kIcpAcc);
+  if (rc == OPE_OK) rc = dcount.alloc(blocks);
+  if (rc == OPE_OK) rc = dhead.alloc(2);
+  if (rc == OPE_OK && cudaMemsetAsync(dhead.p, 0, 2 * sizeof(int), ctx->stream) != cudaSuccess) rc = fail(ctx, OPE_ERR_CUDA, "memset failed");
   Scratch<long long> phases(ctx);
   const bool profile = std::getenv("OPE_PROFILE") != nullptr;
-  if (rc == OPE_OK && profile) { rc = phases.alloc(8); a.phase_cycles = phases.p; }
-  a.corr_match = match.p; a.corr_d2 = d2.p; a.seed = seed.p; a.partials = partials.p; a.barrier = bar.p; a.result = dres.p;
+  const size_t n_prof = 16 + 64 * 8 + 64;
+  if (rc == OPE_OK && profile) {
+    rc = phases.alloc(n_prof); a.phase_cycles = phases.p;
+    if (rc == OPE_OK) cudaMemsetAsync(phases.p, 0, n_prof * sizeof(long long), ctx->stream);
+  }
+  a.corr_match = match.p; a.corr_d2 = d2.p; a.seed = seed.p; a.def_q = defq.p; a.def_m = defm.p; a.def_count = dcount.p;
+  a.ref = refs.p; a.def_head = dhead.p;
+  {
+    const char* g = std::getenv("OPE_ICP_CERT_GAP");  // in target-grid cells; 0 disables the certificates (every query searches)
+    a.cert_gap = (g ? (float)std::atof(g) : 0.5f) * a.grid.h;
+  }
+  a.partials = partials.p; a.barrier = bar.p; a.result = dres.p;
   if (rc == OPE_OK) {
     void* args[] = {(void*)&a};
     cudaEventRecord(ctx->kev[0][0], ctx->stream);
@@ -798,13 +1025,20 @@ int icp_device(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const o
   }
   if (rc == OPE_OK && profile) {
     void* h;
-    if (read_back(ctx, phases.p, 8 * sizeof(long long), &h) == OPE_OK) {
+    if (read_back(ctx, phases.p, n_prof * sizeof(long long), &h) == OPE_OK) {
       const long long* c = (const long long*)h;
-      fprintf(stderr, "[ope profile] block_nn1 block0 per iteration: fast phase %.0f cycles | deferred phase %.0f cycles | deferred queries %.1f\n",
-              (double)c[4] / std::max(res->iterations, 1), (double)c[5] / std::max(res->iterations, 1), (double)c[6] / std::max(res->iterations, 1));
-      fprintf(stderr, "[ope profile] icp_kernel blocks=%d block0 cycles: search+reduce %lld | grid barrier %lld | partials+svd %lld | transform %lld (per iteration: %.0f %.0f %.0f %.0f)\n",
-              blocks, c[0], c[1], c[2], c[3], (double)c[0] / std::max(res->iterations, 1), (double)c[1] / std::max(res->iterations, 1),
-              (double)c[2] / std::max(res->iterations, 1), (double)c[3] / std::max(res->iterations, 1));
+      const double it = std::max(res->iterations, 1);
+      if (std::getenv("OPE_PROFILE_ITER")) {
+        fprintf(stderr, "[ope profile] per iteration (block 0 cycles): A | bar1 | B | bar2 | far-moments+bar3 | C | xform | slowest far query (grid) | far queries (grid)\n");
+        for (int p = 0; p < std::min(res->iterations, 64); ++p) {
+          const long long* r = c + 16 + p * 8;
+          fprintf(stderr, "  it %2d: %7lld %7lld %7lld %7lld %7lld %7lld %6lld | %8lld | %6lld\n", p, r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7],
+                  c[16 + 64 * 8 + p]);
+        }
+      }
+      fprintf(stderr, "[ope profile] icp_kernel blocks=%d, block 0 cycles per iteration: A fast path %.0f | barrier1 %.0f | B far queue %.0f | "
+              "barrier2 %.0f | far moments + barrier3 %.0f | C partials+svd %.0f | transform %.0f | far queries of block 0: %.1f\n",
+              blocks, c[0] / it, c[1] / it, c[2] / it, c[3] / it, c[4] / it, c[5] / it, c[6] / it, c[7] / it);
     }
   }
   if (rc == OPE_OK && out_corr_host && n > 0) {

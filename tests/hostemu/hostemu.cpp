@@ -88,6 +88,22 @@ int emu_nn1_seeded(const float* tgt, int nt, const float* qry, int nq, const int
   return 0;
 }
 
+// nearest neighbour + certificate radius (gap > 0): out_r2[i] = squared distance below which no OTHER point exists
+int emu_nn1_cert(const float* tgt, int nt, const float* qry, int nq, const int* seeds, float h, float max_d2, float gap, int* out_idx,
+                 float* out_d2, float* out_r2) {
+  HostGrid g;
+  build(tgt, nt, h, g);
+  std::vector<float4> orig(nt);
+  for (int i = 0; i < nt; ++i) orig[i] = make_float4(tgt[3 * i], tgt[3 * i + 1], tgt[3 * i + 2], 1.0f);
+  for (int i = 0; i < nq; ++i) {
+    const float* q = qry + 3 * i;
+    float d2, r2;
+    const int idx = grid_nn1(g.v, q[0], q[1], q[2], max_d2, d2, seeds ? seeds[i] : -1, orig.data(), gap, &r2);
+    out_idx[i] = idx; out_d2[i] = idx >= 0 ? d2 : INFINITY; out_r2[i] = r2;
+  }
+  return 0;
+}
+
 // radius count via the pruned traversal
 int emu_radius_count(const float* tgt, int nt, const float* qry, int nq, float radius, float h, int* counts) {
   HostGrid g;

@@ -70,6 +70,32 @@ def test_grid_nn1_seed_independent(emu, orc, synth, small_model, h):
         assert (idx == ref_i[:, 0]).all() and (d2 == ref_d[:, 0]).all()
 
 
+@pytest.mark.parametrize("h,gap", [(0.0015, 0.0008), (0.004, 0.002), (0.004, 0.0)])
+def test_grid_nn1_certificate_radius(emu, orc, synth, small_model, h, gap):
+    """the certificate of the ICP loop: after a search with a gap, no point other than the result lies within sqrt(r2), the
+    result itself is the exact neighbour, and r2 reaches at least (d1 + gap)^2 unless a second point is closer than that"""
+    src, tgt, _ = synth.icp_pair(3000, 5, small_model)
+    t = np.ascontiguousarray(tgt, np.float32); q = np.ascontiguousarray(src, np.float32)
+    lim = np.float32(0.05) ** 2
+    idx = np.empty(len(q), np.int32); d2 = np.empty(len(q), np.float32); r2 = np.empty(len(q), np.float32)
+    emu.emu_nn1_cert(t.ctypes.data_as(f32p), len(t), q.ctypes.data_as(f32p), len(q), None, C.c_float(h), C.c_float(float(lim)),
+                     C.c_float(gap), idx.ctypes.data_as(i32p), d2.ctypes.data_as(f32p), r2.ctypes.data_as(f32p))
+    ri, rd = orc.knn(tgt, src, 2, brute=True)
+    inside = rd[:, 0] <= lim
+    assert (idx[inside] == ri[inside, 0]).all() and (d2[inside] == rd[inside, 0]).all()
+    # nothing else within the certified radius: the true second-nearest distance is >= r2
+    assert (rd[inside, 1] >= r2[inside]).all()
+    # and the radius is not vacuous: at least min(second distance, (min(d1, dmax) + gap)^2) (more when the seed was farther)
+    want = np.minimum(rd[:, 1].astype(np.float64), (np.sqrt(np.minimum(rd[:, 0], lim).astype(np.float64)) + gap) ** 2)
+    assert (r2[inside] >= want[inside] * (1 - 1e-4)).all()
+    # queries with nothing inside the limit: everything is at least sqrt(r2) away and r2 covers the limit plus the gap
+    out = ~inside
+    # beyond the limit the returned index is only a candidate (the caller rejects it), but the radius must still hold for
+    # every OTHER point: the nearest point that is not the returned one is at least sqrt(r2) away
+    other = np.where(idx == ri[:, 0], rd[:, 1], rd[:, 0])
+    assert (other[out] >= r2[out] * (1 - 1e-6)).all()
+
+
 def test_grid_radius_counts(emu, orc, synth, small_model):
     src, tgt, _ = synth.icp_pair(3000, 0, small_model)
     cnt = np.empty(len(src), np.int32)
