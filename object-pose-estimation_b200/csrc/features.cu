@@ -184,13 +184,15 @@ static constexpr int kFkMaxDim = 64;
 static constexpr int kFkMaxK = 16;
 
 __global__ void feature_knn_kernel(const float* __restrict__ ftgt, int nt, const float* __restrict__ fqry, int nq, int dim,
-                                   int k, int t_per_split, int* __restrict__ part_idx, float* __restrict__ part_d2) {
+                                   int k, int t_per_split, const int* __restrict__ qlist, int* __restrict__ part_idx,
+                                   float* __restrict__ part_d2) {
   extern __shared__ float tile[];  // kFkTile * dim
-  const int qi = blockIdx.x * kFkQueries + threadIdx.x;
+  const int qi = blockIdx.x * kFkQueries + threadIdx.x;   // position in the work list (nq entries)
+  const int qsrc = (qi < nq && qlist) ? qlist[qi] : qi;    // row of fqry
   const int t_begin = blockIdx.y * t_per_split, t_end = min(nt, t_begin + t_per_split);
   float q[kFkMaxDim];
   if (qi < nq)
-    for (int c = 0; c < dim; ++c) q[c] = __ldg(fqry + (size_t)qi * dim + c);
+    for (int c = 0; c < dim; ++c) q[c] = __ldg(fqry + (size_t)qsrc * dim + c);
   float bd[kFkMaxK];
   int bi[kFkMaxK];
   int cnt = 0;
@@ -220,9 +222,11 @@ __global__ void feature_knn_kernel(const float* __restrict__ ftgt, int nt, const
   }
 }
 __global__ void feature_knn_merge_kernel(const int* __restrict__ part_idx, const float* __restrict__ part_d2, int nq,
-                                         int splits, int k, int* __restrict__ out_idx, float* __restrict__ out_d2) {
+                                         int splits, int k, const int* __restrict__ qlist, int* __restrict__ out_idx,
+                                         float* __restrict__ out_d2) {
   const int qi = blockIdx.x * blockDim.x + threadIdx.x;
   if (qi >= nq) return;
+  const int qdst = qlist ? qlist[qi] : qi;
   float bd[kFkMaxK];
   int bi[kFkMaxK];
   int cnt = 0;
@@ -239,8 +243,8 @@ __global__ void feature_knn_merge_kernel(const int* __restrict__ part_idx, const
       if (cnt < k) ++cnt;
     }
   for (int j = 0; j < k; ++j) {
-    out_idx[(size_t)qi * k + j] = j < cnt ? bi[j] : -1;
-    if (out_d2) out_d2[(size_t)qi * k + j] = j < cnt ? bd[j] : INFINITY;
+    out_idx[(size_t)qdst * k + j] = j < cnt ? bi[j] : -1;
+    if (out_d2) out_d2[(size_t)qdst * k + j] = j < cnt ? bd[j] : INFINITY;
   }
 }
 
@@ -300,10 +304,11 @@ int fpfh_device(ope_ctx* ctx, const ope_cloud* cloud, float radius, float** d_fp
   return OPE_OK;
 }
 
-int feature_knn_device(ope_ctx* ctx, const float* d_ftgt, size_t nt, const float* d_fqry, size_t nq, int dim, int k,
-                       int* d_idx, float* d_d2) {
+int feature_knn_exact_device(ope_ctx* ctx, const float* d_ftgt, size_t nt, const float* d_fqry, size_t nq_all, int dim, int k,
+                             const int* d_qlist, size_t n_list, int* d_idx, float* d_d2) {
   if (dim < 1 || dim > kFkMaxDim) return fail(ctx, OPE_ERR_INVALID, "feature dimension must be in [1, %d]", kFkMaxDim);
   if (k < 1 || k > kFkMaxK) return fail(ctx, OPE_ERR_INVALID, "feature k must be in [1, %d]", kFkMaxK);
+  const size_t nq = d_qlist ? n_list : nq_all;
   if (nq == 0) return OPE_OK;
   const unsigned qblocks = div_up(nq, kFkQueries);
   // enough target splits to give every SM a block, at least one tile each
@@ -319,10 +324,21 @@ int feature_knn_device(ope_ctx* ctx, const float* d_ftgt, size_t nt, const float
   OPE_TRY(pd.alloc(nq * splits * k));
   dim3 grid(qblocks, splits);
   feature_knn_kernel<<<grid, kFkQueries, kFkTile * dim * sizeof(float), ctx->stream>>>(d_ftgt, (int)nt, d_fqry, (int)nq, dim,
-                                                                                        k, t_per_split, pi.p, pd.p);
+                                                                                        k, t_per_split, d_qlist, pi.p, pd.p);
   OPE_TRY(check_launch(ctx, "feature_knn_kernel"));
-  feature_knn_merge_kernel<<<div_up(nq, 128), 128, 0, ctx->stream>>>(pi.p, pd.p, (int)nq, splits, k, d_idx, d_d2);
+  feature_knn_merge_kernel<<<div_up(nq, 128), 128, 0, ctx->stream>>>(pi.p, pd.p, (int)nq, splits, k, d_qlist, d_idx, d_d2);
   return check_launch(ctx, "feature_knn_merge_kernel");
+}
+
+// tensor-core path (featgemm.cu) when the problem is large enough to pay for it, exact float32 kernel otherwise; both give
+// the same indices and distances (the GEMM only nominates, the ranking is always the exact float32 one)
+int feature_knn_device(ope_ctx* ctx, const float* d_ftgt, size_t nt, const float* d_fqry, size_t nq, int dim, int k,
+                       int* d_idx, float* d_d2) {
+  if (dim < 1 || dim > kFkMaxDim) return fail(ctx, OPE_ERR_INVALID, "feature dimension must be in [1, %d]", kFkMaxDim);
+  if (k < 1 || k > kFkMaxK) return fail(ctx, OPE_ERR_INVALID, "feature k must be in [1, %d]", kFkMaxK);
+  if (nq == 0) return OPE_OK;
+  if (feature_knn_gemm_applicable(nt, nq, dim, k)) return feature_knn_gemm_device(ctx, d_ftgt, nt, d_fqry, nq, dim, k, d_idx, d_d2, nullptr);
+  return feature_knn_exact_device(ctx, d_ftgt, nt, d_fqry, nq, dim, k, nullptr, 0, d_idx, d_d2);
 }
 
 int remove_nan_normals_device(ope_ctx* ctx, ope_cloud** cloud) {

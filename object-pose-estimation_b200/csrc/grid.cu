@@ -527,14 +527,14 @@ int ope_ctx_create(int device, void* stream, ope_ctx** out) {
     delete ctx;
     return OPE_ERR_CUDA;
   }
-  for (int w = 0; w < 2; ++w)
+  for (int w = 0; w < 3; ++w)
     for (int j = 0; j < 2; ++j) cudaEventCreate(&ctx->kev[w][j]);
   *out = ctx;
   return OPE_OK;
 }
 
 double ope_ctx_last_kernel_ms(ope_ctx* ctx, int which) {
-  if (!ctx || which < 0 || which > 1 || !ctx->kev_valid[which]) return -1.0;
+  if (!ctx || which < 0 || which > 2 || !ctx->kev_valid[which]) return -1.0;
   float ms = 0;
   if (cudaEventSynchronize(ctx->kev[which][1]) != cudaSuccess) return -1.0;
   if (cudaEventElapsedTime(&ms, ctx->kev[which][0], ctx->kev[which][1]) != cudaSuccess) return -1.0;
@@ -553,7 +553,7 @@ void ope_ctx_destroy(ope_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (int w = 0; w < 2; ++w)
+  for (int w = 0; w < 3; ++w)
     for (int j = 0; j < 2; ++j) if (ctx->kev[w][j]) cudaEventDestroy(ctx->kev[w][j]);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->stage) cudaFreeHost(ctx->stage);
@@ -563,6 +563,12 @@ void ope_ctx_destroy(ope_ctx* ctx) {
 
 const char* ope_last_error(const ope_ctx* ctx) { return ctx ? ctx->error.c_str() : "no context"; }
 int64_t ope_ctx_launch_count(const ope_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int ope_ctx_feature_knn_stats(const ope_ctx* ctx, int64_t* gemm_queries, int64_t* fallbacks) {
+  if (!ctx) return OPE_ERR_INVALID;
+  if (gemm_queries) *gemm_queries = ctx->feature_knn_gemm_queries;
+  if (fallbacks) *fallbacks = ctx->feature_knn_fallbacks;
+  return OPE_OK;
+}
 int ope_ctx_synchronize(ope_ctx* ctx) {
   if (!ctx) return OPE_ERR_INVALID;
   OPE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));

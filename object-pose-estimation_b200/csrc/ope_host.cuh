@@ -22,8 +22,10 @@ struct ope_ctx {
   size_t pinned_bytes = 0;
   void* stage = nullptr;       // grow-only pinned staging arena for cloud uploads / downloads (host <-> device at PCIe speed)
   size_t stage_bytes = 0;
-  cudaEvent_t kev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [which][begin/end] around the dominant kernels
-  bool kev_valid[2] = {false, false};
+  cudaEvent_t kev[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};  // [which][begin/end] around the dominant kernels
+  bool kev_valid[3] = {false, false, false};
+  int64_t feature_knn_gemm_queries = 0;  // queries answered through the tcgen05 distance GEMM ...
+  int64_t feature_knn_fallbacks = 0;     // ... of which the exact kernel had to re-answer (candidate set not provably complete)
 };
 
 // How points are binned into cells: c = (int)floorf((p - o) * inv) - min_b, per axis.
@@ -166,6 +168,13 @@ int normals_device(ope_ctx* ctx, ope_cloud* cloud, int k, const float vp[3]);
 int fpfh_device(ope_ctx* ctx, const ope_cloud* cloud, float radius, float** d_fpfh, float** d_spfh_or_null);
 int feature_knn_device(ope_ctx* ctx, const float* d_ftgt, size_t nt, const float* d_fqry, size_t nq, int dim, int k,
                        int* d_idx, float* d_d2);
+// exact float32 kernel; d_qlist (n_list entries) restricts it to those queries, nullptr = all nq
+int feature_knn_exact_device(ope_ctx* ctx, const float* d_ftgt, size_t nt, const float* d_fqry, size_t nq, int dim, int k,
+                             const int* d_qlist, size_t n_list, int* d_idx, float* d_d2);
+// ---- featgemm.cu: tcgen05 / TMA distance GEMM + exact re-rank ----
+bool feature_knn_gemm_applicable(size_t nt, size_t nq, int dim, int k);
+int feature_knn_gemm_device(ope_ctx* ctx, const float* d_ftgt, size_t nt, const float* d_fqry, size_t nq, int dim, int k, int* d_idx,
+                            float* d_d2, int* n_fallback);
 int remove_nan_normals_device(ope_ctx* ctx, ope_cloud** cloud);
 
 // ---- registration.cu ----

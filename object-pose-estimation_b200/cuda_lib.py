@@ -21,7 +21,7 @@ i64p = C.POINTER(C.c_int64)
 
 EXPORTS = [
     "ope_ctx_create", "ope_ctx_destroy", "ope_last_error", "ope_ctx_synchronize", "ope_ctx_launch_count", "ope_version",
-    "ope_ctx_last_kernel_ms", "ope_cloud_invalidate",
+    "ope_ctx_last_kernel_ms", "ope_cloud_invalidate", "ope_ctx_feature_knn_stats",
     "ope_cloud_upload", "ope_cloud_free", "ope_cloud_size", "ope_cloud_has_normals", "ope_cloud_download",
     "ope_cloud_select", "ope_cloud_transform", "ope_cloud_set_normals",
     "ope_knn", "ope_knn_cloud", "ope_radius_cloud",
@@ -178,6 +178,12 @@ class Context:
     def last_kernel_ms(self, which=0):
         """device time of the last icp_kernel (0) / sacia_kernel (1) launch, from CUDA events on the ctx stream"""
         return float(lib().ope_ctx_last_kernel_ms(self.h, int(which)))
+
+    def feature_knn_stats(self):
+        """(queries answered through the tcgen05 distance GEMM, queries the exact kernel re-answered)"""
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._chk(lib().ope_ctx_feature_knn_stats(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def invalidate(self, cloud):
         self._chk(lib().ope_cloud_invalidate(self.h, cloud.h))

@@ -301,3 +301,32 @@ def test_pose_pipeline_matches_oracle(ctx, orc, synth, cuda_lib, model):
         assert abs(g.fitness - o.fitness) < FIT_TOL
         assert abs(g.align_strength - o.align_strength) < 1e-3
         assert np.abs(gsrc - osrc).max() < 1e-4
+
+
+# ------------------------------------------------------------------------------ tcgen05 feature-distance GEMM ----
+@pytest.mark.parametrize("nq,nt", [(300, 700), (1000, 1500), (2500, 20000)])
+def test_feature_knn_gemm_path_is_bit_identical_to_the_exact_kernel(ctx, orc, nq, nt, monkeypatch):
+    """K6 through the tensor cores: the GEMM only nominates candidates, the ranking is the exact float32 one, so indices AND
+    distances must equal the exact kernel's / the oracle's bit for bit — on FPFH-like histograms (many near ties), with NaN
+    rows, and on clustered data where the completeness proof must sometimes fall back to the exact kernel."""
+    rng = np.random.default_rng(nq + nt)
+    ft = rng.gamma(0.6, 8.0, size=(nt, 33)).astype(np.float32)
+    ft = (100.0 * ft / ft.reshape(nt, 3, 11).sum(2).repeat(11, 1)).astype(np.float32)   # three sub-histograms summing to 100
+    fq = ft[rng.integers(0, nt, nq)] + rng.normal(0, 0.5, size=(nq, 33)).astype(np.float32)
+    fq[::17] = ft[rng.integers(0, nt, len(fq[::17]))]            # exact duplicates of targets: zero distances, index ties
+    ft[5] = np.nan
+    fq[3] = np.nan
+    ft[100:140] = ft[100]                                        # 40 identical targets: a plateau wider than the candidate list
+    monkeypatch.setenv("OPE_FEATURE_KNN", "exact")
+    ei, ed = ctx.feature_knn(ft, fq, 5)
+    monkeypatch.setenv("OPE_FEATURE_KNN", "gemm")
+    g0, f0 = ctx.feature_knn_stats()
+    gi, gd = ctx.feature_knn(ft, fq, 5)
+    g1, f1 = ctx.feature_knn_stats()
+    assert g1 - g0 == nq                                          # the tensor-core path really ran
+    assert np.array_equal(gi, ei) and np.array_equal(gd, ed)
+    oi, od = orc.feature_knn(ft[:2000], fq[:200], 5)
+    if nt <= 2000:
+        assert np.array_equal(gi[:200], oi) and np.array_equal(gd[:200], od)
+    assert f1 - f0 < nq // 2, "the completeness proof should rarely need the exact kernel"
+    assert ctx.last_kernel_ms(2) > 0
