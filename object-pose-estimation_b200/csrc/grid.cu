@@ -68,16 +68,26 @@ __global__ void bbox_partial_kernel(const float4* __restrict__ pts, int n, float
   }
 }
 __global__ void bbox_final_kernel(const float* __restrict__ partials, int nblocks, float* __restrict__ out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  // one warp: lanes stride over the per-block partials, shuffle tree
+  const int lane = threadIdx.x;
   float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   int cnt = 0;
-  for (int b = 0; b < nblocks; ++b) {
+  for (int b = lane; b < nblocks; b += 32) {
     const float* p = partials + 8 * b;
     for (int d = 0; d < 3; ++d) { mn[d] = fminf(mn[d], p[d]); mx[d] = fmaxf(mx[d], p[3 + d]); }
     cnt += __float_as_int(p[6]);
   }
-  for (int d = 0; d < 3; ++d) { out[d] = mn[d]; out[3 + d] = mx[d]; }
-  out[6] = __int_as_float(cnt);
+  for (int o = 16; o > 0; o >>= 1) {
+    for (int d = 0; d < 3; ++d) {
+      mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+      mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+    }
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if (lane == 0) {
+    for (int d = 0; d < 3; ++d) { out[d] = mn[d]; out[3 + d] = mx[d]; }
+    out[6] = __int_as_float(cnt);
+  }
 }
 
 // ---- exclusive scan (int32), 2048 items per block ----

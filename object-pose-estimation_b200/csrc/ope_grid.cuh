@@ -281,9 +281,11 @@ OPE_HD float nn1_scan_r2(float d1, float max_d2, float gap) {
 #define OPE_NN1_FAST_MAX 96
 #endif
 OPE_HD bool nn1_fast(const GridView& g, float qx, float qy, float qz, float ux, float uy, float uz, float max_d2, float gap,
-                     Nn1State& st, float* r2_out) {
+                     Nn1State& st, float* r2_out, int* total_out = nullptr, unsigned* node_mask_out = nullptr) {
   const float bound0 = nn1_scan_r2(st.d1, max_d2, gap);
   if (r2_out) *r2_out = bound0;
+  if (total_out) *total_out = 0;
+  if (node_mask_out) *node_mask_out = 0u;
   const BallNodes B = ball_nodes(g, ux, uy, uz, bound0);
   if (!B.hit) return true;
   const int sh = 3 * B.L;
@@ -299,6 +301,13 @@ OPE_HD bool nn1_fast(const GridView& g, float qx, float qy, float qz, float ux, 
       OPE_COUNT(1);
     }
     total += ne[j] - nb[j];
+  }
+  if (total_out) *total_out = total;
+  if (node_mask_out) {
+    unsigned m = 0u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m |= (ne[j] > nb[j]) ? (1u << j) : 0u;
+    *node_mask_out = m;
   }
   if (total > OPE_NN1_FAST_MAX) return false;
   // First two points of every node: 16 predicated, mutually independent 16-byte loads in straight-line code (one L2
@@ -330,6 +339,29 @@ OPE_HD bool nn1_fast(const GridView& g, float qx, float qy, float qz, float ux, 
   }
   return true;
 }
+// Medium queries: pruned, stackless depth-first traversal of the ball's start nodes by ONE thread (every thread of a warp
+// runs its own; the work is a few dozen node visits and a hundred point tests). On return st is exact and *r2_out is the
+// squared radius the certificate may rely on.
+#ifndef OPE_NN1_DFS_LEAF
+#define OPE_NN1_DFS_LEAF 12
+#endif
+OPE_HD void nn1_thread_dfs(const GridView& g, float qx, float qy, float qz, float ux, float uy, float uz, float max_d2, float gap,
+                           Nn1State& st, float* r2_out) {
+  const BallNodes B = ball_nodes(g, ux, uy, uz, nn1_scan_r2(st.d1, max_d2, gap));
+  for (int j = 0; j < 8; ++j) {
+    unsigned code;
+    if (!ball_node(B, j, code)) continue;
+    oct_traverse(g, ux, uy, uz, B.L, code, -1, 0u, OPE_NN1_DFS_LEAF, [&]() { return nn1_scan_r2(st.d1, max_d2, gap); },
+                 [&](int b, int e) {
+                   for (int i = b; i < e; ++i) {
+                     const float4 p = OPE_LDG(g.pts + i);
+                     nn1_offer(st, dist2(qx, qy, qz, p.x, p.y, p.z), f2i(p.w));
+                   }
+                 });
+  }
+  if (r2_out) *r2_out = nn1_scan_r2(st.d1, max_d2, gap);
+}
+
 // plain form (no certificate)
 OPE_HD bool nn1_fast(const GridView& g, float qx, float qy, float qz, float ux, float uy, float uz, float max_d2, float& best_d2,
                      int& best_i) {
@@ -365,15 +397,7 @@ OPE_HD int grid_nn1(const GridView& g, float qx, float qy, float qz, float max_d
   if (st.i1 == 0x7fffffff) nn1_probe(g, qx, qy, qz, ux, uy, uz, scan);
   st.s2 = FLT_MAX;  // the probe is only a seed: the search below establishes the second-best distance
   float r2 = 0.0f;
-  if (!nn1_fast(g, qx, qy, qz, ux, uy, uz, max_d2, gap, st, &r2)) {
-    const BallNodes B = ball_nodes(g, ux, uy, uz, nn1_scan_r2(st.d1, max_d2, gap));
-    for (int j = 0; j < 8; ++j) {
-      unsigned code;
-      if (!ball_node(B, j, code)) continue;
-      oct_traverse(g, ux, uy, uz, B.L, code, -1, 0u, OPE_NN1_LEAF, [&]() { return nn1_scan_r2(st.d1, max_d2, gap); }, scan);
-    }
-    r2 = nn1_scan_r2(st.d1, max_d2, gap);
-  }
+  if (!nn1_fast(g, qx, qy, qz, ux, uy, uz, max_d2, gap, st, &r2)) nn1_thread_dfs(g, qx, qy, qz, ux, uy, uz, max_d2, gap, st, &r2);
   best_d2 = st.d1;
   if (cert_r2) *cert_r2 = fminf(st.s2, r2);  // every indexed point other than the result is at least sqrt(this) away
   return st.i1 == 0x7fffffff ? -1 : st.i1;

@@ -200,7 +200,7 @@ struct FarDir {
   const int* sdir;  // shared memory: sdir[c] = start[c << (3 * dl)], c in [0, 2^(3 * (bits - dl))]
   int dl;           // lowest level the directory resolves
 };
-struct LeafList { int2 r[kLeafCap]; };
+struct LeafList { int2 r[kLeafCap]; };   // point ranges [x, y) of the collected leaves
 
 __device__ __forceinline__ int far_dir_level(const GridView& g) { return g.bits > kDirMaxLevels ? g.bits - kDirMaxLevels : 0; }
 // block-cooperative load of the directory (call once, followed by __syncthreads)
@@ -219,12 +219,14 @@ __device__ __forceinline__ void far_node_range(const GridView& g, const FarDir& 
   }
 }
 
-// Exact nearest neighbour + certificate for the WARP's query (all 32 lanes, same arguments, same `st` on entry).
-template <bool ORDERED>
-__device__ __forceinline__ void warp_nn1_far(const GridView& g, const FarDir& D, OctStack* stk, LeafList* LL, float qx, float qy, float qz,
-                                             float max_d2, float gap, Nn1State& st, float* r2_out) {
-  const Coop<32> o;
-  const unsigned full = 0xffffffffu;
+// Exact nearest neighbour + certificate for the GROUP's query (G = 8 or 32 lanes, same arguments, same `st` on entry).
+// Leaves are collected during the traversal and scanned in batches, the bound being refreshed per batch.
+template <int G, bool ORDERED>
+__device__ __forceinline__ void coop_nn1_far(const GridView& g, const FarDir& D, OctStack* stk, LeafList* LL, float qx, float qy, float qz,
+                                             float max_d2, float gap, Nn1State& st, float* r2_out,
+                                             unsigned long long* counters = nullptr /* [pops, leaves, points, flushes] */,
+                                             int only_node = -1 /* >= 0: search only that start node (a split query) */) {
+  const Coop<G> o;
   const int lane = (int)o.sub;
   const float ux = (qx - g.ox) * g.inv_h, uy = (qy - g.oy) * g.inv_h, uz = (qz - g.oz) * g.inv_h;
   float bound = nn1_scan_r2(st.d1, max_d2, gap);
@@ -235,7 +237,7 @@ __device__ __forceinline__ void warp_nn1_far(const GridView& g, const FarDir& D,
     unsigned node = 0u;
     float d2 = FLT_MAX;
     int b = 0, e = 0;
-    if (g.n > 0 && lane < 8) {
+    if (g.n > 0 && lane < 8 && (only_node < 0 || lane == only_node)) {
       const BallNodes B = ball_nodes(g, ux, uy, uz, bound);
       unsigned code;
       if (ball_node(B, lane, code)) {
@@ -249,20 +251,23 @@ __device__ __forceinline__ void warp_nn1_far(const GridView& g, const FarDir& D,
     }
     sp = coop_push(stk, o, 0, pass, node, d2, b, e);
   }
+  // every collected leaf is scanned with up to 8 loads per lane in flight (measured: flattening the leaves into one index
+  // space costs more in look-ups than it saves in round trips)
   auto flush = [&]() {
     for (int r = 0; r < nleaf; ++r) {
       const int2 be = LL->r[r];
-      for (int i0 = be.x + lane; i0 < be.y; i0 += 32 * 8) {
+      for (int i0 = be.x + lane; i0 < be.y; i0 += G * 8) {
         float4 p[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { const int i = i0 + 32 * k; p[k] = (i < be.y) ? __ldg(g.pts + i) : make_float4(0, 0, 0, 0); }
+        for (int k = 0; k < 8; ++k) { const int i = i0 + G * k; p[k] = (i < be.y) ? __ldg(g.pts + i) : make_float4(0, 0, 0, 0); }
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          if (i0 + 32 * k < be.y) nn1_offer(st, dist2(qx, qy, qz, p[k].x, p[k].y, p[k].z), __float_as_int(p[k].w));
+          if (i0 + G * k < be.y) nn1_offer(st, dist2(qx, qy, qz, p[k].x, p[k].y, p[k].z), __float_as_int(p[k].w));
       }
     }
+    if (counters && lane == 0) { atomicAdd(counters + 1, (unsigned long long)nleaf); atomicAdd(counters + 2, (unsigned long long)leafpts); atomicAdd(counters + 3, 1ull); }
     nleaf = 0; leafpts = 0;
-    __syncwarp();
+    __syncwarp(o.mask);
     bound = nn1_scan_r2(coop_min(o, st.d1), max_d2, gap);
   };
   for (;;) {
@@ -270,12 +275,14 @@ __device__ __forceinline__ void warp_nn1_far(const GridView& g, const FarDir& D,
     if (nleaf == kLeafCap || leafpts >= kFlushPts) flush();
     --sp;
     const OctEntry en = stk->s[sp];
-    __syncwarp();
+    __syncwarp(o.mask);
+    if (counters && lane == 0) atomicAdd(counters, 1ull);
     if (!(en.d2 <= bound)) continue;
     const int level = (int)(en.node >> 27);
     const int cnt = en.e - en.b;
     if (level <= D.dl || cnt <= kFarLeaf) {
       if (lane == 0) LL->r[nleaf] = make_int2(en.b, en.e);
+      __syncwarp(o.mask);
       ++nleaf; leafpts += cnt;
       if (ORDERED && nleaf == 1 && sp > 0) flush();  // unseeded: the first (nearest) leaf tightens the bound for everything else
       continue;
@@ -286,7 +293,7 @@ __device__ __forceinline__ void warp_nn1_far(const GridView& g, const FarDir& D,
     const unsigned cc = (code << 3) | ((unsigned)lane & 7u);
     int cb = 0;
     if (lane < 8) cb = D.sdir[(size_t)cc << (3 * (cl - D.dl))];
-    const int nb = __shfl_down_sync(full, cb, 1, 8);
+    const int nb = __shfl_down_sync(o.mask, cb, 1, 8);
     const int ce = (lane == 7) ? en.e : nb;
     float cd2 = FLT_MAX;
     bool pass = false;
@@ -297,23 +304,23 @@ __device__ __forceinline__ void warp_nn1_far(const GridView& g, const FarDir& D,
     if (ORDERED) {
       sp += coop_push(stk, o, sp, pass, ((unsigned)cl << 27) | cc, cd2, cb, ce);
     } else {
-      const unsigned om = __ballot_sync(full, pass) & 0xffu;
+      const unsigned om = (__ballot_sync(o.mask, pass) >> o.gbase) & 0xffu;
       if (pass) {
         OctEntry ne;
         ne.node = ((unsigned)cl << 27) | cc; ne.d2 = cd2; ne.b = cb; ne.e = ce;
         stk->s[sp + __popc(om & ((1u << lane) - 1u))] = ne;
       }
       sp += __popc(om);
-      __syncwarp();
+      __syncwarp(o.mask);
     }
   }
   // merge the lanes' states
   float d1 = st.d1;
   int i1 = st.i1;
 #pragma unroll
-  for (int s = 1; s < 32; s <<= 1) {
-    const float od = __shfl_xor_sync(full, d1, s);
-    const int oi = __shfl_xor_sync(full, i1, s);
+  for (int s = 1; s < G; s <<= 1) {
+    const float od = __shfl_xor_sync(o.mask, d1, s);
+    const int oi = __shfl_xor_sync(o.mask, i1, s);
     if (nb_less(od, oi, d1, i1)) { d1 = od; i1 = oi; }
   }
   float s2 = st.s2;

@@ -80,15 +80,22 @@ __global__ void moments_kernel(const float4* __restrict__ src, const float4* __r
   }
   block_reduce_store<kMomentAcc>(acc, smem, partials + (size_t)blockIdx.x * kMomentAcc);
 }
+// one warp per accumulator (lanes stride over the blocks, fixed shuffle tree), then one thread runs the 3x3 Umeyama
 __global__ void umeyama_final_kernel(const double* __restrict__ partials, int nblocks, float* __restrict__ out16) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double acc[kMomentAcc];
-  for (int a = 0; a < kMomentAcc; ++a) acc[a] = 0.0;
-  for (int b = 0; b < nblocks; ++b)
-    for (int a = 0; a < kMomentAcc; ++a) acc[a] += partials[(size_t)b * kMomentAcc + a];
-  Mat4 T;
-  umeyama_from_moments(acc, T);
-  for (int i = 0; i < 16; ++i) out16[i] = T.m[i];
+  __shared__ double acc[kMomentAcc];
+  const int a = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (a < kMomentAcc) {
+    double s = 0.0;
+    for (int b = lane; b < nblocks; b += 32) s += partials[(size_t)b * kMomentAcc + a];
+    s = warp_sum_d(s);
+    if (lane == 0) acc[a] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Mat4 T;
+    umeyama_from_moments(acc, T);
+    for (int i = 0; i < 16; ++i) out16[i] = T.m[i];
+  }
 }
 
 // fitness: sum of NN-1 squared distances <= max_range of the transformed source (double), plus the count.
@@ -168,10 +175,15 @@ struct IcpDev {
   float4* ref;                // nearest: n_work certificates {query position when issued, R}: every target point other than
                               // seed[s] is at least R away from that position (R <= 0: none)
   float cert_gap;             // how far beyond the neighbour a search looks so that R exceeds the neighbour's distance
+  int dfs_max;                // candidate-set size up to which a thread finishes its own query (above: the warp queue)
+  int split_min;              // far queries with more candidate points than this are split by start node
+  int small_max;              // unused (an octet queue for small far queries was measured on C2 and lost: the octets of one warp
+                              // diverge — every query has its own control flow — and serialise; every far query gets a warp)
   float4* def_q;              // far-query queue: x, y, z, seed d2          (block b's segment starts at its slice)
-  int4* def_m;                //                  sorted position, seed index, original index, 0
-  int* def_count;             // per block
-  int* def_head;              // claim counters of the far queue, one per iteration parity (zeroed by the host / by block 0)
+  int4* def_m;                //                  sorted position, seed index, original index, start node (-1: all)
+  float4* def_res;            // result of a queue entry: d1, i1 (bits), s2, r2
+  int* def_count;             // [2][gridDim]: per block, small then large
+  int* def_head;              // [2 parities][2 kinds] claim counters of the far queues (zeroed by the host / by block 0)
   double* partials;           // 2 * gridDim * kIcpAcc (double buffered)
   unsigned* barrier;          // monotonic arrival counter of the grid barrier (zeroed by the host)
   ope_reg_result* result;     // device copy
@@ -183,17 +195,19 @@ static constexpr int kIcpThreads = 512;
 static constexpr int kIcpWarps = kIcpThreads / 32;
 static constexpr int kIcpAcc = 17;  // moments[16] + sum of correspondence distances
 static constexpr int kIcpMaxBlocks = 1024;
+static constexpr int kIcpSplitMin = 6144;   // far queries with more candidate points than this are split by start node (<= 8 entries)
+
 
 struct IcpSmem {
   OctStack wstack[kIcpWarps];   // one traversal stack per warp (far queries / k-NN)
   LeafList leaves[kIcpWarps];   // collected leaf ranges of the warp's far query
-  int dir[kDirEntries];         // upper levels of the target's implicit octree (warp_nn1_far)
+  int dir[kDirEntries];         // upper levels of the target's implicit octree (coop_nn1_far)
   Nn1Smem<kIcpThreads> nn;      // only the one-pass kernel uses the block-local variant
   double red[kIcpWarps][kIcpAcc];
   double totals[kIcpAcc];
-  int prefix[kIcpMaxBlocks];    // inclusive prefix of the blocks' far-query counts
-  int warp_cnt[kIcpWarps];
-  int n_def;
+  int prefix[2][kIcpMaxBlocks]; // inclusive prefixes of the blocks' far-query counts: [0] small (octets), [1] large (warps)
+  int warp_cnt[2][kIcpWarps];
+  int n_def[2];
   Mat4 T_inc;
   int stop;  // 0 continue, 1 stop, 2 stop without a transform (not enough correspondences)
 };
@@ -412,7 +426,7 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_kernel(IcpDev a) {
   for (;; ++pass) {
     long long t0 = prof ? clock64() : 0;
     for (int e = lane; e < kIcpAcc; e += 32) sm->red[warp][e] = 0.0;
-    if (threadIdx.x == 0) sm->n_def = 0;
+    if (threadIdx.x < 2) sm->n_def[threadIdx.x] = 0;
     __syncthreads();
     if (!shooting) {
       // ---- phase A: thread per point, fast path; far queries go to the grid-wide queue ----
@@ -427,6 +441,8 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_kernel(IcpDev a) {
         Nn1State nst;
         nst.d1 = FLT_MAX; nst.i1 = 0x7fffffff; nst.s2 = FLT_MAX;
         bool far = false, certified = false;
+        int total = 0;  // candidate points in the start nodes of an uncertified query
+        unsigned node_mask = 0u;
         if (ok) {
           const float ux = (p.x - a.grid.ox) * a.grid.inv_h, uy = (p.y - a.grid.oy) * a.grid.inv_h, uz = (p.z - a.grid.oz) * a.grid.inv_h;
           if (sd >= 0) {
@@ -458,30 +474,49 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_kernel(IcpDev a) {
             nst.s2 = FLT_MAX;  // the probe only seeds the bound
           }
           if (!certified) {
+            // three tiers by the size of the candidate set: direct scan (<= 96 points), this thread's own pruned traversal
+            // (<= dfs_max points in the ball's start nodes: every thread works in parallel), the grid-wide warp queue
             float r2 = 0.0f;
-            far = !nn1_fast(a.grid, p.x, p.y, p.z, ux, uy, uz, a.max_d2_f, a.cert_gap, nst, &r2);
+            far = !nn1_fast(a.grid, p.x, p.y, p.z, ux, uy, uz, a.max_d2_f, a.cert_gap, nst, &r2, &total, &node_mask);
+            if (far && total <= a.dfs_max) {
+              nn1_thread_dfs(a.grid, p.x, p.y, p.z, ux, uy, uz, a.max_d2_f, a.cert_gap, nst, &r2);
+              far = false;
+            }
             if (!far) a.ref[s] = make_float4(p.x, p.y, p.z, sqrtf(fminf(nst.s2, r2)));
           }
         }
         const float best_d2 = nst.d1;
         const int best_i = nst.i1;
-        // deterministic compaction of the far queries into this block's queue segment [lo + n_def, ...)
-        const unsigned fm = __ballot_sync(0xffffffffu, far);
-        if (lane == 0) sm->warp_cnt[warp] = __popc(fm);
-        __syncthreads();
-        int before = sm->n_def;
-        for (int w = 0; w < warp; ++w) before += sm->warp_cnt[w];
-        if (far) {
-          const int slot = lo + before + __popc(fm & ((1u << lane) - 1u));
-          a.def_q[slot] = make_float4(p.x, p.y, p.z, best_d2);
-          a.def_m[slot] = make_int4(s, best_i, orig, 0);
+        // Deterministic compaction of the far queries into this block's queue segment (filled from the back). A query whose
+        // candidate set is huge (e.g. a point near the axis of a cylinder: thousands of near-equidistant neighbours, all of
+        // which an exact search must test) is split into one entry per non-empty start node, so that up to eight warps of
+        // the grid share it; the entries of one query are adjacent and are merged by the owner after barrier 2.
+        int nsub = far ? ((total > a.split_min) ? __popc(node_mask) : 1) : 0;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+          int incl = nsub;
+          for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+          if (lane == 31) sm->warp_cnt[1][warp] = incl;
+          __syncthreads();
+          int before = sm->n_def[1], block_total = sm->n_def[1];
+          for (int w = 0; w < kIcpWarps; ++w) { if (w < warp) before += sm->warp_cnt[1][w]; block_total += sm->warp_cnt[1][w]; }
+          __syncthreads();
+          if (block_total > hi - lo) { nsub = nsub > 1 ? 1 : nsub; continue; }  // no room for the split entries: one entry per query
+          before += incl - nsub;
+          if (far) {
+            int k = 0;
+            for (int j = 0; j < 8; ++j) {
+              if (nsub > 1 && !((node_mask >> j) & 1u)) continue;
+              if (nsub == 1 && j > 0) break;
+              const int slot = hi - 1 - (before + k);
+              a.def_q[slot] = make_float4(p.x, p.y, p.z, nst.d1);
+              a.def_m[slot] = make_int4(s, nst.i1, orig, nsub > 1 ? j : -1);
+              ++k;
+            }
+          }
+          if (threadIdx.x == 0) sm->n_def[1] = block_total;
+          break;
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-          int tot = sm->n_def;
-          for (int w = 0; w < kIcpWarps; ++w) tot += sm->warp_cnt[w];
-          sm->n_def = tot;
-        }
         // finish the near queries: gate, rejectors, outputs, moments
         int m = -1;
         float d2 = 0.0f;
@@ -515,74 +550,95 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_kernel(IcpDev a) {
         }
         __syncthreads();
       }
-      if (threadIdx.x == 0) a.def_count[blockIdx.x] = sm->n_def;
-      if (prof) { const long long t1 = clock64(); t_phase[0] += t1 - t0; t0 = t1; n_far += sm->n_def; }
+      if (threadIdx.x < 2) a.def_count[threadIdx.x * gridDim.x + blockIdx.x] = sm->n_def[threadIdx.x];
+      if (prof) { const long long t1 = clock64(); t_phase[0] += t1 - t0; t0 = t1; n_far += sm->n_def[0] + sm->n_def[1]; }
       bar_target += gridDim.x;
       grid_barrier(a.barrier, bar_target);
       if (prof) { const long long t1 = clock64(); t_phase[1] += t1 - t0; t0 = t1; }
       // ---- phase B: all warps of the grid drain the queue, one far query per warp ----
-      if (warp == 0) {  // inclusive prefix of the per-block counts (gridDim <= kIcpMaxBlocks)
+      if (warp < 2) {  // inclusive prefixes of the per-block counts (gridDim <= kIcpMaxBlocks): warp 0 small, warp 1 large
         int run = 0;
         for (int b0 = 0; b0 < (int)gridDim.x; b0 += 32) {
           const int b = b0 + lane;
-          int c = b < (int)gridDim.x ? __ldcg(a.def_count + b) : 0;
+          int c = b < (int)gridDim.x ? __ldcg(a.def_count + warp * gridDim.x + b) : 0;
           for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, c, o); if (lane >= o) c += t; }
-          if (b < (int)gridDim.x) sm->prefix[b] = run + c;
+          if (b < (int)gridDim.x) sm->prefix[warp][b] = run + c;
           run += __shfl_sync(0xffffffffu, c, 31);
         }
       }
       __syncthreads();
-      const int total = sm->prefix[gridDim.x - 1];
-      int* head = a.def_head + (pass & 1);
-      if (blockIdx.x == 0 && threadIdx.x == 0) a.def_head[(pass + 1) & 1] = 0;  // nobody touches the other counter before barrier 3
-      for (;;) {  // warps claim far queries one at a time: whoever is free takes the next (results do not depend on who)
-        int e = 0;
-        if (lane == 0) e = atomicAdd(head, 1);
-        e = __shfl_sync(0xffffffffu, e, 0);
-        if (e >= total) break;
-        int bl = 0, br = (int)gridDim.x - 1;  // first block whose inclusive prefix exceeds e
-        while (bl < br) { const int mid = (bl + br) >> 1; if (sm->prefix[mid] > e) br = mid; else bl = mid + 1; }
-        const int j = e - (bl > 0 ? sm->prefix[bl - 1] : 0);
-        const int slot = min(a.n_work, bl * chunk) + j;
-        const float4 q = __ldcg(a.def_q + slot);
-        const int4 qm = __ldcg(a.def_m + slot);
-        Nn1State nst;
-        nst.d1 = q.w; nst.i1 = qm.y; nst.s2 = FLT_MAX;
-        float r2 = 0.0f;
-        const long long q0 = prof_any ? clock64() : 0;
-        if (pass == 0) warp_nn1_far<true>(a.grid, fdir, st, &sm->leaves[warp], q.x, q.y, q.z, a.max_d2_f, a.cert_gap, nst, &r2);
-        else warp_nn1_far<false>(a.grid, fdir, st, &sm->leaves[warp], q.x, q.y, q.z, a.max_d2_f, a.cert_gap, nst, &r2);
-        if (prof_any && lane == 0 && pass < 64) {
-          atomicMax((unsigned long long*)(a.phase_cycles + 16 + pass * 8 + 7), (unsigned long long)(clock64() - q0));
-          atomicAdd((unsigned long long*)(a.phase_cycles + 16 + 64 * 8 + pass), 1ull);
+      if (blockIdx.x == 0 && threadIdx.x < 2) a.def_head[((pass + 1) & 1) * 2 + threadIdx.x] = 0;  // nobody touches the other parity before barrier 3
+      // Groups claim far queries one at a time — whoever is free takes the next; a result does not depend on who computed
+      // it. Large queries first, one per WARP; then the small ones, one per OCTET (64 dependent chains in flight per SM).
+      {
+        const int total_l = sm->prefix[1][gridDim.x - 1];
+        int* head = a.def_head + (pass & 1) * 2 + 1;
+        OctStack* stw = &sm->wstack[warp];
+        LeafList* llw = &sm->leaves[warp];
+        for (;;) {
+          int e = 0;
+          if (lane == 0) e = atomicAdd(head, 1);
+          e = __shfl_sync(0xffffffffu, e, 0);
+          if (e >= total_l) break;
+          int bl = 0, br = (int)gridDim.x - 1;  // first block whose inclusive prefix exceeds e
+          while (bl < br) { const int mid = (bl + br) >> 1; if (sm->prefix[1][mid] > e) br = mid; else bl = mid + 1; }
+          const int j = e - (bl > 0 ? sm->prefix[1][bl - 1] : 0);
+          const int slot = min(a.n_work, min(a.n_work, bl * chunk) + chunk) - 1 - j;
+          const float4 q = __ldcg(a.def_q + slot);
+          const int4 qm = __ldcg(a.def_m + slot);
+          Nn1State nst;
+          nst.d1 = q.w; nst.i1 = qm.y; nst.s2 = FLT_MAX;
+          float r2 = 0.0f;
+          const long long q0 = prof_any ? clock64() : 0;
+          unsigned long long* cnt = (prof_any && pass < 64) ? (unsigned long long*)(a.phase_cycles + 16 + 64 * 8 + 64 + pass * 4) : nullptr;
+          if (pass == 0) coop_nn1_far<32, true>(a.grid, fdir, stw, llw, q.x, q.y, q.z, a.max_d2_f, a.cert_gap, nst, &r2, cnt, qm.w);
+          else coop_nn1_far<32, false>(a.grid, fdir, stw, llw, q.x, q.y, q.z, a.max_d2_f, a.cert_gap, nst, &r2, cnt, qm.w);
+          if (prof_any && lane == 0 && pass < 64) {
+            atomicMax((unsigned long long*)(a.phase_cycles + 16 + pass * 8 + 7), (unsigned long long)(clock64() - q0));
+            atomicAdd((unsigned long long*)(a.phase_cycles + 16 + 64 * 8 + pass), 1ull);
+          }
+          if (lane == 0) a.def_res[slot] = make_float4(nst.d1, __int_as_float(nst.i1), nst.s2, r2);
+          __syncwarp();
         }
-        const float bd = nst.d1;
-        const int nn = nst.i1 == 0x7fffffff ? -1 : nst.i1;
-        const float4 p = make_float4(q.x, q.y, q.z, 0.0f);
-        const int m = icp_gate(a, qm.x, qm.z, p, nn, bd);  // warp-uniform
-        if (lane == 0) {
-          a.seed[qm.x] = nn; a.corr_match[qm.z] = m; a.corr_d2[qm.z] = bd;
-          a.ref[qm.x] = make_float4(q.x, q.y, q.z, sqrtf(fminf(nst.s2, r2)));
-        }
-        __syncwarp();
       }
       if (prof) { const long long t1 = clock64(); t_phase[2] += t1 - t0; t0 = t1; }
       bar_target += gridDim.x;
       grid_barrier(a.barrier, bar_target);
       if (prof) { const long long t1 = clock64(); t_phase[3] += t1 - t0; t0 = t1; }
-      // ---- the moments of this block's own far queries, in queue order (deterministic whoever searched them) ----
+      // ---- this block's own far queries, in queue order (deterministic whoever searched them): merge the entries of a
+      //      split query, gate, write neighbour / certificate / correspondence, accumulate the moments ----
       {
-        const int n_def = sm->n_def;
+        const int n_def = sm->n_def[1];
         for (int base = 0; base < n_def; base += kIcpThreads) {
           const int j = base + (int)threadIdx.x;
           int m = -1;
           float d2 = 0.0f;
           float4 p = make_float4(0, 0, 0, 0);
           if (j < n_def) {
-            p = a.def_q[lo + j];
-            const int4 qm = a.def_m[lo + j];
-            m = __ldcg(a.corr_match + qm.z);
-            d2 = __ldcg(a.corr_d2 + qm.z);
+            const int qslot = hi - 1 - j;
+            const int4 qm = a.def_m[qslot];
+            const bool first = j == 0 || a.def_m[qslot + 1].x != qm.x;   // entries of one query are adjacent
+            if (first) {
+              p = a.def_q[qslot];
+              Nn1State nst;
+              nst.d1 = FLT_MAX; nst.i1 = 0x7fffffff; nst.s2 = FLT_MAX;
+              float r2 = FLT_MAX;
+              for (int k = 0; k < 8 && j + k < n_def; ++k) {
+                if (k > 0 && a.def_m[qslot - k].x != qm.x) break;
+                const float4 r = __ldcg(a.def_res + (qslot - k));
+                const float rd1 = r.x, rs2 = r.z;
+                const int ri1 = __float_as_int(r.y);
+                r2 = fminf(r2, r.w);
+                if (ri1 == nst.i1) { nst.s2 = fminf(nst.s2, rs2); continue; }   // the shared seed survived in several entries
+                if (nb_less(rd1, ri1, nst.d1, nst.i1)) { nst.s2 = fminf(fminf(nst.s2, rs2), nst.d1); nst.d1 = rd1; nst.i1 = ri1; }
+                else nst.s2 = fminf(fminf(nst.s2, rs2), rd1);
+              }
+              const int nn = nst.i1 == 0x7fffffff ? -1 : nst.i1;
+              d2 = nst.d1;
+              m = icp_gate(a, qm.x, qm.z, p, nn, d2);
+              a.seed[qm.x] = nn; a.corr_match[qm.z] = m; a.corr_d2[qm.z] = d2;
+              a.ref[qm.x] = make_float4(p.x, p.y, p.z, sqrtf(fminf(nst.s2, r2)));
+            }
           }
           if (__ballot_sync(0xffffffffu, m >= 0) != 0u) {
             double v[16];
@@ -867,7 +923,7 @@ int umeyama_device(ope_ctx* ctx, const float4* src, const float4* tgt, const int
   OPE_TRY(out.alloc(16));
   moments_kernel<<<nb, kRedThreads, 0, ctx->stream>>>(src, tgt, d_isrc, d_itgt, (int)n, partials.p);
   OPE_TRY(check_launch(ctx, "moments_kernel"));
-  umeyama_final_kernel<<<1, 32, 0, ctx->stream>>>(partials.p, nb, out.p);
+  umeyama_final_kernel<<<1, 32 * kMomentAcc, 0, ctx->stream>>>(partials.p, nb, out.p);
   OPE_TRY(check_launch(ctx, "umeyama_final_kernel"));
   void* h;
   OPE_TRY(read_back(ctx, out.p, 16 * sizeof(float), &h));
@@ -962,7 +1018,7 @@ int icp_device(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const o
   a.cur_pts = work->pts; a.cur_nrm = work->normals;
   Scratch<int> match(ctx), seed(ctx), dcount(ctx), dhead(ctx);
   Scratch<float> d2(ctx);
-  Scratch<float4> defq(ctx), refs(ctx);
+  Scratch<float4> defq(ctx), refs(ctx), defres(ctx);
   Scratch<int4> defm(ctx);
   Scratch<double> partials(ctx);
   Scratch<unsigned> bar(ctx);
@@ -974,6 +1030,7 @@ int icp_device(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const o
   if (rc == OPE_OK && !shooting) rc = defq.alloc(nw);
   if (rc == OPE_OK && !shooting) rc = defm.alloc(nw);
   if (rc == OPE_OK && !shooting) rc = refs.alloc(nw);
+  if (rc == OPE_OK && !shooting) rc = defres.alloc(nw);
   if (rc == OPE_OK) rc = dres.alloc(1);
   if (rc == OPE_OK) rc = bar.alloc(1);
   if (rc == OPE_OK && cudaMemsetAsync(bar.p, 0, sizeof(unsigned), ctx->stream) != cudaSuccess) rc = fail(ctx, OPE_ERR_CUDA, "memset failed");
@@ -992,21 +1049,27 @@ int icp_device(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const o
     blocks = (int)std::min<size_t>(std::max<size_t>(1, want), (size_t)max_blocks);
   }
   if (rc == OPE_OK) rc = partials.alloc((size_t)2 * blocks * kIcpAcc);
-  if (rc == OPE_OK) rc = dcount.alloc(blocks);
-  if (rc == OPE_OK) rc = dhead.alloc(2);
-  if (rc == OPE_OK && cudaMemsetAsync(dhead.p, 0, 2 * sizeof(int), ctx->stream) != cudaSuccess) rc = fail(ctx, OPE_ERR_CUDA, "memset failed");
+  if (rc == OPE_OK) rc = dcount.alloc((size_t)2 * blocks);
+  if (rc == OPE_OK) rc = dhead.alloc(4);
+  if (rc == OPE_OK && cudaMemsetAsync(dhead.p, 0, 4 * sizeof(int), ctx->stream) != cudaSuccess) rc = fail(ctx, OPE_ERR_CUDA, "memset failed");
   Scratch<long long> phases(ctx);
   const bool profile = std::getenv("OPE_PROFILE") != nullptr;
-  const size_t n_prof = 16 + 64 * 8 + 64;
+  const size_t n_prof = 16 + 64 * 8 + 64 + 64 * 4;
   if (rc == OPE_OK && profile) {
     rc = phases.alloc(n_prof); a.phase_cycles = phases.p;
     if (rc == OPE_OK) cudaMemsetAsync(phases.p, 0, n_prof * sizeof(long long), ctx->stream);
   }
   a.corr_match = match.p; a.corr_d2 = d2.p; a.seed = seed.p; a.def_q = defq.p; a.def_m = defm.p; a.def_count = dcount.p;
-  a.ref = refs.p; a.def_head = dhead.p;
+  a.ref = refs.p; a.def_head = dhead.p; a.def_res = defres.p;
   {
     const char* g = std::getenv("OPE_ICP_CERT_GAP");  // in target-grid cells; 0 disables the certificates (every query searches)
     a.cert_gap = (g ? (float)std::atof(g) : 0.5f) * a.grid.h;
+    const char* d = std::getenv("OPE_ICP_DFS_MAX");
+    a.dfs_max = d ? std::atoi(d) : 0;   // measured: a single thread's traversal is a long dependent chain; the warp queue wins
+    const char* sp_ = std::getenv("OPE_ICP_SPLIT_MIN");
+    a.split_min = sp_ ? std::atoi(sp_) : kIcpSplitMin;
+    const char* sm_ = std::getenv("OPE_ICP_SMALL_MAX");
+    a.small_max = sm_ ? std::atoi(sm_) : 0;
   }
   a.partials = partials.p; a.barrier = bar.p; a.result = dres.p;
   if (rc == OPE_OK) {
@@ -1032,8 +1095,10 @@ int icp_device(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const o
         fprintf(stderr, "[ope profile] per iteration (block 0 cycles): A | bar1 | B | bar2 | far-moments+bar3 | C | xform | slowest far query (grid) | far queries (grid)\n");
         for (int p = 0; p < std::min(res->iterations, 64); ++p) {
           const long long* r = c + 16 + p * 8;
-          fprintf(stderr, "  it %2d: %7lld %7lld %7lld %7lld %7lld %7lld %6lld | %8lld | %6lld\n", p, r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7],
-                  c[16 + 64 * 8 + p]);
+          const long long* k = c + 16 + 64 * 8 + 64 + p * 4;
+          const double nq = (double)std::max<long long>(c[16 + 64 * 8 + p], 1);
+          fprintf(stderr, "  it %2d: %7lld %7lld %7lld %7lld %7lld %7lld %6lld | %8lld | %6lld | per far query: %.1f pops %.1f leaves %.0f points %.1f flushes\n",
+                  p, r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], c[16 + 64 * 8 + p], k[0] / nq, k[1] / nq, k[2] / nq, k[3] / nq);
         }
       }
       fprintf(stderr, "[ope profile] icp_kernel blocks=%d, block 0 cycles per iteration: A fast path %.0f | barrier1 %.0f | B far queue %.0f | "
