@@ -466,4 +466,50 @@ __device__ __forceinline__ int warp_knn(const GridView& g, OctStack* st, bool ac
   return cnt;
 }
 
+// ---- warp_knn_smem ------------------------------------------------------------------------------------------
+// Exact k nearest (k <= 32) of the warp's query among nt target points held in SHARED memory in their original order
+// (small targets: a sampled cluster is ~1 500 points = 24 KB). No index and no dependent loads: 32 points per step,
+// the same register list and (d2, index) order as warp_knn, so the results are identical. n_finite = number of finite
+// target points (k is clamped to it, like KdTreeFLANN does).
+__device__ __forceinline__ int warp_knn_smem(const float4* tg, int nt, int n_finite, bool active, float qx, float qy, float qz, int k,
+                                             float init_bound, float& ld, int& li) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  if (k > n_finite) k = n_finite;
+  ld = FLT_MAX; li = 0x7fffffff;
+  int cnt = 0;
+  if (!(active && k > 0)) return 0;
+  const unsigned kmask = k >= 32 ? full : ((1u << k) - 1u);
+  float kth_d = FLT_MAX;
+  int kth_i = 0x7fffffff;
+  for (int base = 0; base < nt; base += 32) {
+    const int j = base + lane;
+    float d2 = FLT_MAX;
+    int idx = 0x7fffffff;
+    if (j < nt) {
+      const float4 t = tg[j];
+      if (finite3(t.x, t.y, t.z)) { d2 = dist2(qx, qy, qz, t.x, t.y, t.z); idx = j; }
+    }
+    const bool cand = idx != 0x7fffffff && d2 <= init_bound && (cnt < k || nb_less(d2, idx, kth_d, kth_i));
+    unsigned cm = __ballot_sync(full, cand);
+    while (cm != 0u) {
+      const int src = __ffs(cm) - 1;
+      cm &= cm - 1u;
+      const float cd = __shfl_sync(full, d2, src);
+      const int ci = __shfl_sync(full, idx, src);
+      if (cnt < k || nb_less(cd, ci, kth_d, kth_i)) {   // warp-uniform
+        const int pos = __popc(__ballot_sync(full, nb_less(ld, li, cd, ci)) & kmask);
+        const float ud = __shfl_up_sync(full, ld, 1);
+        const int ui = __shfl_up_sync(full, li, 1);
+        if (lane > pos) { ld = ud; li = ui; }
+        else if (lane == pos) { ld = cd; li = ci; }
+        if (cnt < k) ++cnt;
+        if (cnt == k) { kth_d = __shfl_sync(full, ld, k - 1); kth_i = __shfl_sync(full, li, k - 1); }
+      }
+    }
+  }
+  if (lane >= cnt) { ld = FLT_MAX; li = 0x7fffffff; }
+  return cnt;
+}
+
 }  // namespace ope

@@ -176,6 +176,8 @@ struct IcpDev {
                               // seed[s] is at least R away from that position (R <= 0: none)
   float cert_gap;             // how far beyond the neighbour a search looks so that R exceeds the neighbour's distance
   int dfs_max;                // candidate-set size up to which a thread finishes its own query (above: the warp queue)
+  int tgt_in_smem;            // normal shooting against a small target: the target lives in shared memory (warp_knn_smem)
+  int n_tgt;                  // points in the target cloud
   int split_min;              // far queries with more candidate points than this are split by start node
   int small_max;              // unused (an octet queue for small far queries was measured on C2 and lost: the octets of one warp
                               // diverge — every query has its own control flow — and serialise; every far query gets a warp)
@@ -195,6 +197,7 @@ static constexpr int kIcpThreads = 512;
 static constexpr int kIcpWarps = kIcpThreads / 32;
 static constexpr int kIcpAcc = 17;  // moments[16] + sum of correspondence distances
 static constexpr int kIcpMaxBlocks = 1024;
+static constexpr int kIcpSmemMaxTargets = 4096;   // 64 KB of target points next to the kernel's other shared memory
 static constexpr int kIcpSplitMin = 6144;   // far queries with more candidate points than this are split by start node (<= 8 entries)
 
 
@@ -300,7 +303,7 @@ __device__ __forceinline__ int icp_gate(const IcpDev& a, int s, int orig, const 
 // CorrespondenceEstimationNormalShooting: one source point per WARP. Among the k nearest, the one with the smallest
 // squared distance to the line through p along the source normal (double); the first minimum in list order wins.
 __device__ __forceinline__ int icp_correspond_shooting(const IcpDev& a, OctStack* st, int s, int orig, const float4 p, bool use_seed,
-                                                       float& d2_out) {
+                                                       float& d2_out, const float4* tg_smem = nullptr) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const bool ok = finite3(p.x, p.y, p.z);
@@ -312,14 +315,15 @@ __device__ __forceinline__ int icp_correspond_shooting(const IcpDev& a, OctStack
     int pj = -1;
     if (lane < k) pj = a.seed[(size_t)s * a.k_search + lane];
     float d = 0.0f;
-    if (pj >= 0) { const float4 t = __ldg(a.tgt_pts + pj); d = dist2(p.x, p.y, p.z, t.x, t.y, t.z); }
+    if (pj >= 0) { const float4 t = tg_smem ? tg_smem[pj] : __ldg(a.tgt_pts + pj); d = dist2(p.x, p.y, p.z, t.x, t.y, t.z); }
     const bool all_valid = __ballot_sync(full, lane >= k || pj >= 0) == full;
     for (int o = 16; o > 0; o >>= 1) d = fmaxf(d, __shfl_xor_sync(full, d, o));
     if (all_valid) bound = d;
   }
   float ld;
   int li;
-  const int cnt = warp_knn(a.grid, st, ok, p.x, p.y, p.z, a.k_search, bound, ld, li);
+  const int cnt = tg_smem ? warp_knn_smem(tg_smem, a.n_tgt, a.grid.n, ok, p.x, p.y, p.z, a.k_search, bound, ld, li)
+                          : warp_knn(a.grid, st, ok, p.x, p.y, p.z, a.k_search, bound, ld, li);
   if (a.seed && lane < a.k_search) a.seed[(size_t)s * a.k_search + lane] = (lane < cnt) ? li : -1;
   int match = -1;
   float d2 = 0.0f;
@@ -329,7 +333,7 @@ __device__ __forceinline__ int icp_correspond_shooting(const IcpDev& a, OctStack
     double dist = DBL_MAX;
     int jdx = 0x7fffffff;
     if (lane < cnt) {
-      const float4 t = __ldg(a.tgt_pts + li);
+      const float4 t = tg_smem ? tg_smem[li] : __ldg(a.tgt_pts + li);
       const float px = t.x - p.x, py = t.y - p.y, pz = t.z - p.z;
       const double V[3] = {px, py, pz};
       const double C0 = N[1] * V[2] - N[2] * V[1], C1 = N[2] * V[0] - N[0] * V[2], C2 = N[0] * V[1] - N[1] * V[0];
@@ -405,7 +409,13 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_kernel(IcpDev a) {
     a.cur_pts[s] = p;
     if (a.cur_nrm) a.cur_nrm[s] = v;
   }
-  far_dir_load(a.grid, sm->dir);
+  float4* tg_smem = nullptr;
+  if (a.tgt_in_smem) {   // small target: resident in shared memory for the whole alignment
+    tg_smem = reinterpret_cast<float4*>(smem_raw + ((sizeof(IcpSmem) + 15) & ~(size_t)15));
+    for (int j = threadIdx.x; j < a.n_tgt; j += kIcpThreads) tg_smem[j] = __ldg(a.tgt_pts + j);
+  } else {
+    far_dir_load(a.grid, sm->dir);
+  }
   FarDir fdir;
   fdir.sdir = sm->dir; fdir.dl = far_dir_level(a.grid);
   // the initialisation above is grid-strided, the iterations use their own ownership maps: one barrier in between
@@ -665,10 +675,10 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_kernel(IcpDev a) {
         const float4 p = a.cur_pts[s];
         const int orig = __float_as_int(p.w);
         float d2 = 0.0f;
-        const int m = icp_correspond_shooting(a, st, s, orig, p, pass > 0, d2);
+        const int m = icp_correspond_shooting(a, st, s, orig, p, pass > 0, d2, tg_smem);
         if (lane == 0) { a.corr_match[orig] = m; a.corr_d2[orig] = d2; }
         if (m >= 0 && lane < kIcpAcc) {
-          const float4 t = __ldg(a.tgt_pts + m);
+          const float4 t = tg_smem ? tg_smem[m] : __ldg(a.tgt_pts + m);
           sm->red[warp][lane] += moment_term(lane, p, t, d2);
         }
         __syncwarp();
@@ -690,7 +700,13 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_kernel(IcpDev a) {
     for (int e = warp; e < kIcpAcc; e += kIcpWarps) {
       const double* base = a.partials + (size_t)(pass & 1) * gridDim.x * kIcpAcc;
       double sum = 0.0;
-      for (int b = lane; b < (int)gridDim.x; b += 32) sum += __ldcg(base + (size_t)b * kIcpAcc + e);
+      for (int b0 = lane; b0 < (int)gridDim.x; b0 += 32 * 8) {   // 8 independent loads in flight, summed in block order
+        double v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const int b = b0 + 32 * k; v[k] = b < (int)gridDim.x ? __ldcg(base + (size_t)b * kIcpAcc + e) : 0.0; }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sum += v[k];
+      }
       sum = warp_sum_d(sum);
       if (lane == 0) sm->totals[e] = sum;
     }
@@ -884,6 +900,63 @@ __global__ void __launch_bounds__(kSaciaThreads) sacia_kernel(SaciaDev a) {
     a.errors[h] = error;
   }
 }
+// Small targets (a segmented cluster after 1 cm sampling: ~1 000 points, 16 KB): the whole target sits in SHARED memory and
+// every transformed source point scans it exhaustively — exact by construction ((d2, index) order), no index, no dependent
+// loads: every thread reads the same target point at the same time (shared-memory broadcast).
+static constexpr int kSaciaSmemMaxTargets = 8192;   // 128 KB of the 227 KB shared memory
+__global__ void __launch_bounds__(kSaciaThreads) sacia_smem_kernel(SaciaDev a, int nt) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* tg = reinterpret_cast<float4*>(smem_raw);
+  __shared__ Mat4 T;
+  const int h = a.h_begin + blockIdx.x;
+  for (int j = threadIdx.x; j < nt; j += kSaciaThreads) tg[j] = __ldg(a.tgt + j);
+  if (threadIdx.x == 0) {
+    double acc[16];
+    for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+    for (int j = 0; j < a.nr_samples; ++j) {
+      const int si = a.samples[(size_t)h * a.nr_samples + j];
+      const int pick = a.picks[(size_t)h * a.nr_samples + j];
+      int ti = a.knn_idx[(size_t)si * a.k_corr + pick];
+      if (ti < 0) ti = a.knn_idx[(size_t)si * a.k_corr];  // fewer than k target features
+      const float4 sp = __ldg(a.src + si), tp = __ldg(a.tgt + ti);
+      const double sv[3] = {sp.x, sp.y, sp.z}, tv[3] = {tp.x, tp.y, tp.z};
+      acc[0] += 1.0;
+      for (int k = 0; k < 3; ++k) { acc[1 + k] += sv[k]; acc[4 + k] += tv[k]; }
+      for (int c = 0; c < 3; ++c)
+        for (int r = 0; r < 3; ++r) acc[7 + c * 3 + r] += tv[r] * sv[c];
+    }
+    Mat4 M;
+    umeyama_from_moments(acc, M);
+    T = M;
+    for (int i = 0; i < 16; ++i) a.transforms[(size_t)h * 16 + i] = M.m[i];
+  }
+  __syncthreads();
+  const Mat4 M = T;
+  float* terms = a.terms + (size_t)blockIdx.x * a.ns;
+  for (int i = threadIdx.x; i < a.ns; i += kSaciaThreads) {
+    const float4 p = __ldg(a.src + i);
+    float x, y, z;
+    xform_point(M, p.x, p.y, p.z, x, y, z);
+    float term = 1.0f;
+    if (finite3(x, y, z)) {
+      float best = FLT_MAX;   // only the DISTANCE of the nearest neighbour enters the score: ties need no index order
+#pragma unroll 4
+      for (int j = 0; j < nt; ++j) {
+        const float4 t = tg[j];
+        const float d2 = dist2(x, y, z, t.x, t.y, t.z);   // a NaN target never compares below
+        best = d2 < best ? d2 : best;
+      }
+      if (best <= a.threshold) term = best / a.threshold;
+    }
+    terms[i] = term;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float error = 0.0f;
+    for (int i = 0; i < a.ns; ++i) error += terms[i];
+    a.errors[h] = error;
+  }
+}
 // first strictly-lower error wins, in hypothesis order
 __global__ void sacia_select_kernel(const float* __restrict__ errors, const float* __restrict__ transforms, int h_begin,
                                     int h_end, ope_reg_result* __restrict__ out) {
@@ -954,7 +1027,8 @@ int fitness_device(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, con
   return OPE_OK;
 }
 
-static int icp_fill(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const ope_icp_params& prm, IcpDev* a) {
+static int icp_fill(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const ope_icp_params& prm, IcpDev* a,
+                    bool allow_smem_target = false) {
   const bool need_src_normals = prm.estimator == OPE_EST_NORMAL_SHOOTING || prm.n_rejectors > 0;
   bool need_tgt_normals = false;
   for (int r = 0; r < prm.n_rejectors; ++r) {
@@ -971,7 +1045,15 @@ static int icp_fill(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, co
     return fail(ctx, OPE_ERR_INVALID, "normal shooting k must be in [1, 32]");
   OPE_TRY(cloud_bbox(ctx, const_cast<ope_cloud*>(tgt)));
   const int kk = prm.estimator == OPE_EST_NORMAL_SHOOTING ? prm.k_search : 1;
-  OPE_TRY(cloud_grid(ctx, tgt, knn_cell_size(tgt, kk), &a->grid));
+  a->n_tgt = (int)tgt->n;
+  const char* force_grid = std::getenv("OPE_ICP_FORCE_GRID");
+  a->tgt_in_smem = (allow_smem_target && prm.estimator == OPE_EST_NORMAL_SHOOTING && tgt->n <= (size_t)kIcpSmemMaxTargets && !force_grid) ? 1 : 0;
+  if (a->tgt_in_smem) {   // no spatial index needed: only the number of finite points (k is clamped to it)
+    std::memset(&a->grid, 0, sizeof(a->grid));
+    a->grid.n = tgt->n_finite;
+  } else {
+    OPE_TRY(cloud_grid(ctx, tgt, knn_cell_size(tgt, kk), &a->grid));
+  }
   a->tgt_pts = tgt->pts; a->tgt_nrm = tgt->normals;
   a->src0_pts = src->pts; a->src0_nrm = src->normals;
   a->n_src = (int)src->n;
@@ -1002,8 +1084,9 @@ int icp_device(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const o
                ope_reg_result* res, ope_correspondence* out_corr_host, ope_cloud** out_aligned) {
   IcpDev a;
   std::memset(&a, 0, sizeof(a));
-  OPE_TRY(icp_fill(ctx, src, tgt, prm, &a));
+  OPE_TRY(icp_fill(ctx, src, tgt, prm, &a, /*allow_smem_target=*/true));
   a.guess = guess;
+  const size_t smem_bytes = ((sizeof(IcpSmem) + 15) & ~(size_t)15) + (a.tgt_in_smem ? tgt->n * sizeof(float4) : 0);
   const size_t n = src->n;
   // the source in Morton order of its own (cached) grid: spatially coherent work order, finite points only
   GridView gsrc;
@@ -1036,10 +1119,10 @@ int icp_device(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const o
   if (rc == OPE_OK && cudaMemsetAsync(bar.p, 0, sizeof(unsigned), ctx->stream) != cudaSuccess) rc = fail(ctx, OPE_ERR_CUDA, "memset failed");
   if (rc == OPE_OK && n > 0 && cudaMemsetAsync(match.p, 0xff, n * sizeof(int), ctx->stream) != cudaSuccess) rc = fail(ctx, OPE_ERR_CUDA, "memset failed");
   if (rc == OPE_OK && n > 0 && cudaMemsetAsync(d2.p, 0, n * sizeof(float), ctx->stream) != cudaSuccess) rc = fail(ctx, OPE_ERR_CUDA, "memset failed");
-  if (rc == OPE_OK) rc = dyn_smem(ctx, (const void*)icp_kernel, sizeof(IcpSmem));
+  if (rc == OPE_OK) rc = dyn_smem(ctx, (const void*)icp_kernel, smem_bytes);
   // cooperative grid: one point per thread (nearest) / per warp (normal shooting), capped by co-residency
   int per_sm = 0;
-  if (rc == OPE_OK && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, icp_kernel, kIcpThreads, sizeof(IcpSmem)) != cudaSuccess)
+  if (rc == OPE_OK && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, icp_kernel, kIcpThreads, smem_bytes) != cudaSuccess)
     rc = fail(ctx, OPE_ERR_CUDA, "occupancy query failed");
   int blocks = 1;
   if (rc == OPE_OK) {
@@ -1075,7 +1158,7 @@ int icp_device(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const o
   if (rc == OPE_OK) {
     void* args[] = {(void*)&a};
     cudaEventRecord(ctx->kev[0][0], ctx->stream);
-    cudaError_t e = cudaLaunchCooperativeKernel((void*)icp_kernel, dim3(blocks), dim3(kIcpThreads), args, sizeof(IcpSmem), ctx->stream);
+    cudaError_t e = cudaLaunchCooperativeKernel((void*)icp_kernel, dim3(blocks), dim3(kIcpThreads), args, smem_bytes, ctx->stream);
     cudaEventRecord(ctx->kev[0][1], ctx->stream);
     ctx->kev_valid[0] = true;
     if (e != cudaSuccess) rc = fail(ctx, OPE_ERR_CUDA, "cooperative launch of icp_kernel failed: %s", cudaGetErrorString(e));
@@ -1205,19 +1288,30 @@ int sacia_device(ope_ctx* ctx, const ope_cloud* src, const float* d_fsrc, const 
   // findSimilarFeatures for every source point at once (K6)
   OPE_TRY(feature_knn_device(ctx, d_ftgt, tgt->n, d_fsrc, ns, 33, K, d_knn.p, d_knn_d2.p));
   SaciaDev a;
-  OPE_TRY(cloud_bbox(ctx, const_cast<ope_cloud*>(tgt)));
-  OPE_TRY(cloud_grid(ctx, tgt, knn_cell_size(tgt, 1), &a.grid));
+  std::memset(&a, 0, sizeof(a));
+  const char* force = std::getenv("OPE_SACIA_PATH");   // "grid" / "smem": force a path (tests); default: by target size
+  const bool use_smem = tgt->n <= (size_t)kSaciaSmemMaxTargets && !(force && std::strcmp(force, "grid") == 0);
+  if (!use_smem) {   // the spatial index is only needed when the target does not fit in shared memory
+    OPE_TRY(cloud_bbox(ctx, const_cast<ope_cloud*>(tgt)));
+    OPE_TRY(cloud_grid(ctx, tgt, knn_cell_size(tgt, 1), &a.grid));
+  }
   a.src = src->pts; a.tgt = tgt->pts; a.ns = (int)ns; a.nr_samples = S; a.k_corr = K;
   a.samples = d_samples.p; a.picks = d_picks.p; a.knn_idx = d_knn.p; a.h_begin = h0;
   a.threshold = (float)prm.max_correspondence_distance;
   a.terms = d_terms.p; a.errors = d_errors.p; a.transforms = d_T.p;
   if (nh > 0) {
     cudaEventRecord(ctx->kev[1][0], ctx->stream);
-    OPE_TRY(dyn_smem(ctx, (const void*)sacia_kernel, sizeof(Nn1Smem<kSaciaThreads>)));
-    sacia_kernel<<<nh, kSaciaThreads, sizeof(Nn1Smem<kSaciaThreads>), ctx->stream>>>(a);
+    if (use_smem) {
+      const size_t bytes = tgt->n * sizeof(float4);
+      OPE_TRY(dyn_smem(ctx, (const void*)sacia_smem_kernel, bytes));
+      sacia_smem_kernel<<<nh, kSaciaThreads, bytes, ctx->stream>>>(a, (int)tgt->n);
+    } else {
+      OPE_TRY(dyn_smem(ctx, (const void*)sacia_kernel, sizeof(Nn1Smem<kSaciaThreads>)));
+      sacia_kernel<<<nh, kSaciaThreads, sizeof(Nn1Smem<kSaciaThreads>), ctx->stream>>>(a);
+    }
     cudaEventRecord(ctx->kev[1][1], ctx->stream);
     ctx->kev_valid[1] = true;
-    OPE_TRY(check_launch(ctx, "sacia_kernel"));
+    OPE_TRY(check_launch(ctx, use_smem ? "sacia_smem_kernel" : "sacia_kernel"));
   }
   sacia_select_kernel<<<1, 32, 0, ctx->stream>>>(d_errors.p, d_T.p, h0, h1, d_res.p);
   OPE_TRY(check_launch(ctx, "sacia_select_kernel"));

@@ -214,9 +214,13 @@ def test_icp_guess_and_aligned_output(ctx, orc, synth, cuda_lib, small_model):
     assert np.array_equal(out, ref)
 
 
-def test_icp_with_normals_d_and_l_configuration(ctx, orc, synth, cuda_lib, model):
+@pytest.mark.parametrize("target_path", ["smem", "grid"])
+def test_icp_with_normals_d_and_l_configuration(ctx, orc, synth, cuda_lib, model, target_path, monkeypatch):
     """The reference's fine stage (D&L/src/poseestimator.cpp:310-341): normal shooting k=20, surface-normal 0.7 +
-    self-occluded 0.6 rejectors, SVD, 100 iterations, eps 1e-8, no distance gating."""
+    self-occluded 0.6 rejectors, SVD, 100 iterations, eps 1e-8, no distance gating — with the small target resident in
+    shared memory (default) and through the spatial index."""
+    if target_path == "grid":
+        monkeypatch.setenv("OPE_ICP_FORCE_GRID", "1")
     T = cuda_lib.T
     cl, _, pose = synth.make_frame(model, 5)
     rng = np.random.default_rng(8)
@@ -249,8 +253,11 @@ def test_icp_no_correspondences(ctx, orc, cuda_lib):
     assert np.array_equal(np.array(list(g.T)), np.array(list(o.T)))
 
 
-def test_sacia_replayed_rng(ctx, orc, synth, cuda_lib, model):
-    """SAC-IA with the same hypothesis sequence replayed: every hypothesis error bit-exact, same winner, same transform."""
+@pytest.mark.parametrize("path", ["smem", "grid"])
+def test_sacia_replayed_rng(ctx, orc, synth, cuda_lib, model, path, monkeypatch):
+    """SAC-IA with the same hypothesis sequence replayed: every hypothesis error bit-exact, same winner, same transform —
+    through both scoring kernels (target resident in shared memory / spatial index)."""
+    monkeypatch.setenv("OPE_SACIA_PATH", path)
     T = cuda_lib.T
     cl, _, pose = synth.make_frame(model, 2)
     sp = model[orc.uniform_sample(model, 0.01)]
