@@ -175,7 +175,8 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()       # a real handle: the legacy default stream (0) would make the ctx create its own
+    torch.cuda.set_stream(stream)      # torch work (L2 flush, events) and the library's kernels share ONE stream
     ctx = cuda_lib.Context(local, stream.cuda_stream)
     model = synth.make_model()
     src, tgt, _ = synth.icp_pair(N_PTS, seed=rank, model=model)

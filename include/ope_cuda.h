@@ -67,6 +67,16 @@ int ope_cloud_invalidate(ope_ctx* ctx, ope_cloud* cloud);
 /* attach normals computed by ope_normals_knn to the cloud (pcl::copyPointCloud(normals, pointnormal), :201) */
 int ope_cloud_set_normals(ope_ctx* ctx, ope_cloud* cloud, const float* normals4);
 
+/* ---- depth image -> cloud (the stage before the path) ------------------------------------------ */
+/* DataGrabber::rgbd2Pcl + depthToMeter (D&L/src/datagrabber.cpp:9-62,121-174): host uint16 depth (rows x cols, row-major) ->
+ * device cloud, compacted in the reference's column-outer / row-inner order, with its row/column swap quirk; Kinect
+ * intrinsics are fx = fy = 525, cx = 319.5, cy = 239.5, scale 1000, z_max 2.0 (:34,146-150). */
+int ope_depth_to_cloud(ope_ctx* ctx, const uint16_t* depth, int rows, int cols, float fx, float fy, float cx, float cy, float scale,
+                       float z_max, ope_cloud** out);
+/* the same for a batch of frames already resident on the device, one launch (layout: see csrc/depth.cu) */
+int ope_depth_to_cloud_batch(ope_ctx* ctx, const uint16_t* d_depth, int frames, int rows, int cols, float fx, float fy, float cx, float cy,
+                             float scale, float z_max, void* d_out, int32_t* d_col_start);
+
 /* ---- spatial search: replaces pcl::search::KdTree / KdTreeFLANN -------------------------- */
 /* nearestKSearch for nq host queries; out_idx/out_d2 are nq*k, padded with -1 / +inf. k <= 32. */
 int ope_knn(ope_ctx* ctx, const ope_cloud* tgt, const void* qry, size_t nq, size_t stride, size_t offset, int k,

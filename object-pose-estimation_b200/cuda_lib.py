@@ -24,7 +24,7 @@ EXPORTS = [
     "ope_ctx_last_kernel_ms", "ope_cloud_invalidate", "ope_ctx_feature_knn_stats",
     "ope_cloud_upload", "ope_cloud_free", "ope_cloud_size", "ope_cloud_has_normals", "ope_cloud_download",
     "ope_cloud_select", "ope_cloud_transform", "ope_cloud_set_normals",
-    "ope_knn", "ope_knn_cloud", "ope_radius_cloud",
+    "ope_knn", "ope_knn_cloud", "ope_radius_cloud", "ope_depth_to_cloud", "ope_depth_to_cloud_batch",
     "ope_uniform_sample", "ope_uniform_sample_cloud", "ope_voxel_grid",
     "ope_normals_knn", "ope_fpfh", "ope_feature_knn",
     "ope_umeyama", "ope_fitness", "ope_correspondences", "ope_icp_align", "ope_sacia_align", "ope_sacia_draw",
@@ -199,6 +199,21 @@ class Context:
                                          None if nr is None else nr.ctypes.data_as(C.c_void_p),
                                          C.c_size_t(0 if nr is None else nr.strides[0]), C.c_size_t(0), C.byref(h)))
         return Cloud(self, h)
+
+    def depth_to_cloud(self, depth, fx=525.0, fy=525.0, cx=319.5, cy=239.5, scale=1000.0, z_max=2.0):
+        """uint16 depth image (rows, cols) on the host -> device cloud (DataGrabber::rgbd2Pcl semantics)"""
+        d = np.ascontiguousarray(depth, np.uint16)
+        h = C.c_void_p()
+        self._chk(lib().ope_depth_to_cloud(self.h, d.ctypes.data_as(C.POINTER(C.c_uint16)), d.shape[0], d.shape[1], C.c_float(fx),
+                                           C.c_float(fy), C.c_float(cx), C.c_float(cy), C.c_float(scale), C.c_float(z_max), C.byref(h)))
+        return Cloud(self, h)
+
+    def depth_to_cloud_batch(self, d_depth_ptr, frames, rows, cols, d_out_ptr, d_col_start_ptr, fx=525.0, fy=525.0, cx=319.5, cy=239.5,
+                             scale=1000.0, z_max=2.0):
+        """device pointers (ints): uint16 depth [frames, rows, cols], float4 out [frames*rows*cols], int32 col_start [frames*cols+1]"""
+        self._chk(lib().ope_depth_to_cloud_batch(self.h, C.c_void_p(d_depth_ptr), frames, rows, cols, C.c_float(fx), C.c_float(fy),
+                                                 C.c_float(cx), C.c_float(cy), C.c_float(scale), C.c_float(z_max), C.c_void_p(d_out_ptr),
+                                                 C.c_void_p(d_col_start_ptr)))
 
     def select(self, cloud, idx):
         idx = np.ascontiguousarray(idx, np.int32)

@@ -782,6 +782,28 @@ int orc_umeyama(const float* src, size_t sstride, const float* tgt, size_t tstri
   return OPE_OK;
 }
 
+// DataGrabber::rgbd2Pcl / depthToMeter (D&L/src/datagrabber.cpp:9-62,121-174), Kinect / Astra branch
+int64_t orc_depth_to_cloud(const uint16_t* depth, int rows, int cols, float fx, float fy, float cx, float cy, float scale, float z_max,
+                           float* out_xyz) {
+  int64_t n = 0;
+  for (int j = 0; j < cols; ++j)
+    for (int i = 0; i < rows; ++i) {
+      const float raw = (float)depth[(size_t)i * cols + j];
+      float X = 0, Y = 0, Z = 0;
+      if (!(raw <= 0.0f)) {
+        Z = raw / scale;
+        X = ((float)i - cx) * Z / fx;  // p_FeatX = row index (sic)
+        Y = ((float)j - cy) * Z / fy;  // p_FeatY = column index (sic)
+      }
+      if (Z == 0 || Z > z_max) continue;
+      out_xyz[3 * n] = Y;      // cloud.x = Y
+      out_xyz[3 * n + 1] = X;  // cloud.y = X
+      out_xyz[3 * n + 2] = Z;
+      ++n;
+    }
+  return n;
+}
+
 int orc_transform(const float* pts, size_t n, size_t stride, const float* normals, const float T[16], float* out_pts,
                   float* out_normals) {
   Mat4 M; std::memcpy(M.m, T, sizeof(M.m));

@@ -62,6 +62,14 @@ int orc_umeyama(const float* src, size_t sstride, const float* tgt, size_t tstri
 int orc_transform(const float* pts, size_t n, size_t stride, const float* normals, const float T[16],
                   float* out_pts /* n*3 */, float* out_normals /* n*4 or NULL */);
 
+/* ---- depth image -> cloud ---- */
+/* DataGrabber::rgbd2Pcl + depthToMeter, D&L/src/datagrabber.cpp:9-62,121-174: columns outer, rows inner; Z = depth / scale;
+ * the reference passes (row, col) as (x, y): y_out = (row - cx) * Z / fx, x_out = (col - cy) * Z / fy (sic); points with
+ * depth == 0, Z == 0 or Z > z_max are dropped; the output is the compacted list in that traversal order.
+ * out_xyz holds rows*cols*3 floats; returns the number of points. */
+int64_t orc_depth_to_cloud(const uint16_t* depth, int rows, int cols, float fx, float fy, float cx, float cy, float scale, float z_max,
+                           float* out_xyz);
+
 /* ---- registration ---- */
 /* Registration::getFitnessScore(max_range), VP/impl/registration_mod.hpp:131-165. */
 int orc_fitness(const float* src, size_t ns, size_t sstride, const float* tgt, size_t nt, size_t tstride,

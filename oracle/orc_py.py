@@ -176,6 +176,15 @@ def umeyama(src, tgt, isrc=None, itgt=None):
     return T.mat4(Tm)
 
 
+def depth_to_cloud(depth, fx=525.0, fy=525.0, cx=319.5, cy=239.5, scale=1000.0, z_max=2.0):
+    d = np.ascontiguousarray(depth, np.uint16)
+    out = np.empty((d.shape[0] * d.shape[1], 3), np.float32)
+    lib().orc_depth_to_cloud.restype = C.c_int64
+    n = lib().orc_depth_to_cloud(d.ctypes.data_as(C.POINTER(C.c_uint16)), d.shape[0], d.shape[1], C.c_float(fx), C.c_float(fy),
+                                 C.c_float(cx), C.c_float(cy), C.c_float(scale), C.c_float(z_max), out.ctypes.data_as(f32p))
+    return out[:n].copy()
+
+
 def transform(pts, M, normals=None):
     p, pp, n, s = _pts(pts)
     out = np.empty((p.shape[0], 3), np.float32)

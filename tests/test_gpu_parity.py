@@ -337,3 +337,45 @@ def test_feature_knn_gemm_path_is_bit_identical_to_the_exact_kernel(ctx, orc, nq
         assert np.array_equal(gi[:200], oi) and np.array_equal(gd[:200], od)
     assert f1 - f0 < nq // 2, "the completeness proof should rarely need the exact kernel"
     assert ctx.last_kernel_ms(2) > 0
+
+
+# ------------------------------------------------------------------------------------ depth image -> cloud (8f-1) ----
+def _depth_mm(cloud):
+    return np.rint(np.nan_to_num(cloud[..., 2], nan=0.0).astype(np.float64) * 1000.0).astype(np.uint16)
+
+
+def test_depth_to_cloud_matches_the_reference_traversal(ctx, orc, synth, small_model):
+    """DataGrabber::rgbd2Pcl on the device: same points, bit for bit, in the reference's column-outer order, including the
+    row/column swap quirk, the Z == 0 / Z > 2 m drop and an image whose size is not a multiple of the 32x32 tile."""
+    _, cloud, _ = synth.make_frame(small_model, 9)
+    d = _depth_mm(cloud)
+    d[10:20, 30:50] = 2500          # beyond the 2 m limit: dropped
+    d[100:130, 600:] = 0            # invalid: dropped
+    for img in (d, d[:471, :613].copy(), np.zeros((480, 640), np.uint16)):
+        ref = orc.depth_to_cloud(img)
+        got = ctx.depth_to_cloud(img)
+        assert len(got) == len(ref)
+        if len(ref):
+            assert np.array_equal(got.download(), ref)
+        got.free()
+
+
+def test_depth_to_cloud_batch_is_the_single_frame_result_per_frame(ctx, orc, synth, small_model):
+    import torch
+    frames = []
+    for f in (3, 4, 5):
+        _, cloud, _ = synth.make_frame(small_model, f)
+        frames.append(_depth_mm(cloud))
+    depth = torch.from_numpy(np.stack(frames).astype(np.int16)).cuda().contiguous()   # raw uint16 bits
+    B, R, Cc = depth.shape
+    out = torch.empty((B * R * Cc, 4), dtype=torch.float32, device="cuda")
+    col = torch.empty(B * Cc + 1, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ctx.depth_to_cloud_batch(depth.data_ptr(), B, R, Cc, out.data_ptr(), col.data_ptr())
+    ctx.synchronize()
+    col = col.cpu().numpy()
+    out = out.cpu().numpy()
+    for f in range(B):
+        ref = orc.depth_to_cloud(frames[f])
+        b, e = col[f * Cc], col[(f + 1) * Cc]
+        assert e - b == len(ref) and np.array_equal(out[b:e, :3], ref)

@@ -31,7 +31,8 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()       # a real handle: the legacy default stream (0) would make the ctx create its own
+    torch.cuda.set_stream(stream)      # torch work (L2 flush, events) and the library's kernels share ONE stream
     ctx = cuda_lib.Context(local, stream.cuda_stream)
     model = synth.make_model()
     distinct = 64
