@@ -117,6 +117,13 @@ int ope_feature_knn(ope_ctx* ctx, const float* ftgt, size_t nt, const float* fqr
 int ope_umeyama(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const int32_t* isrc, const int32_t* itgt,
                 size_t n, float T[16]);
 
+/* TransformationEstimationPointToPlaneLLS (kind = OPE_TE_POINT_TO_PLANE_LLS; the default of IterativeClosestPointWithNormals,
+ * VP/icp_mod.h:352-357) and TransformationEstimationPointToPlane (kind = OPE_TE_POINT_TO_PLANE: Levenberg-Marquardt over the
+ * 6-parameter rigid warp, what BuildModel sets, BM/src/regmeshpcd.cpp:162,193) ::estimateRigidTransformation [UPSTREAM].
+ * tgt must carry normals. lm_info: 3 ints (Eigen LM status, function evaluations, iterations) or NULL. */
+int ope_point_to_plane(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const int32_t* isrc, const int32_t* itgt, size_t n,
+                       int kind, float T[16], int32_t* lm_info);
+
 /* ---- registration --------------------------------------------------------------------------------------------- */
 /* Registration::getFitnessScore(max_range), VP/impl/registration_mod.hpp:131-165. */
 int ope_fitness(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const float T[16], double max_range,

@@ -209,19 +209,54 @@ class TransformationEstimationSVD : public TransformationEstimation<PointSource,
       T = detail::from_c(M);
   }
 };
+// shared front end of TransformationEstimationPointToPlaneLLS / TransformationEstimationPointToPlane
+template <typename PointSource, typename PointTarget, typename Scalar, int Kind>
+class TransformationEstimationPointToPlaneBase : public TransformationEstimation<PointSource, PointTarget, Scalar> {
+ public:
+  typedef Eigen::Matrix4f Matrix4;
+  int opeKind() const override { return Kind; }
+  void estimateRigidTransformation(const PointCloud<PointSource>& src, const PointCloud<PointTarget>& tgt, Matrix4& T) const {
+    T.setIdentity();
+    if (src.points.size() != tgt.points.size()) { detail::pcl_error(name(), "Number or points in source differs than target!"); return; }
+    run(src, tgt, nullptr, nullptr, src.points.size(), T);
+  }
+  void estimateRigidTransformation(const PointCloud<PointSource>& src, const PointCloud<PointTarget>& tgt,
+                                   const Correspondences& corr, Matrix4& T) const {
+    T.setIdentity();
+    std::vector<int32_t> is(corr.size()), it(corr.size());
+    for (size_t i = 0; i < corr.size(); ++i) { is[i] = corr[i].index_query; it[i] = corr[i].index_match; }
+    run(src, tgt, is.data(), it.data(), corr.size(), T);
+  }
+
+ private:
+  // the target point type carries the normals (PointXYZRGBNormal / PointNormal), as PCL requires of these estimators;
+  // detail::upload() takes normal_x.. along when PointT has them
+  static void run(const PointCloud<PointSource>& src, const PointCloud<PointTarget>& tgt, const int32_t* is, const int32_t* it, size_t n,
+                  Matrix4& T) {
+    ope_ctx* ctx = detail::context();
+    detail::DeviceCloud a, b;
+    if (!ctx || n == 0 || !detail::upload(src, a, name()) || !detail::upload(tgt, b, name())) return;
+    float M[16];
+    if (detail::check(ope_point_to_plane(ctx, a.get(), b.get(), is, it, n, Kind, M, nullptr), name())) T = detail::from_c(M);
+  }
+  static const char* name() {
+    return Kind == OPE_TE_POINT_TO_PLANE_LLS ? "pcl::registration::TransformationEstimationPointToPlaneLLS::estimateRigidTransformation"
+                                             : "pcl::registration::TransformationEstimationLM::estimateRigidTransformation";
+  }
+};
+// 6x6 linear least squares, the default of IterativeClosestPointWithNormals (VP/icp_mod.h:352-357)
 template <typename PointSource, typename PointTarget, typename Scalar = float>
-class TransformationEstimationPointToPlaneLLS : public TransformationEstimation<PointSource, PointTarget, Scalar> {
+class TransformationEstimationPointToPlaneLLS
+    : public TransformationEstimationPointToPlaneBase<PointSource, PointTarget, Scalar, OPE_TE_POINT_TO_PLANE_LLS> {
  public:
   typedef std::shared_ptr<TransformationEstimationPointToPlaneLLS<PointSource, PointTarget, Scalar>> Ptr;
-  int opeKind() const override { return OPE_TE_POINT_TO_PLANE_LLS; }
 };
-// Levenberg-Marquardt point-to-plane (BM/src/regmeshpcd.cpp:162,193): not implemented on the device;
-// align() reports it and leaves the transformation at identity rather than silently substituting another estimator.
+// Levenberg-Marquardt over the 6-parameter rigid warp, what BuildModel plugs in (BM/src/regmeshpcd.cpp:162,193)
 template <typename PointSource, typename PointTarget, typename Scalar = float>
-class TransformationEstimationPointToPlane : public TransformationEstimation<PointSource, PointTarget, Scalar> {
+class TransformationEstimationPointToPlane
+    : public TransformationEstimationPointToPlaneBase<PointSource, PointTarget, Scalar, OPE_TE_POINT_TO_PLANE> {
  public:
   typedef std::shared_ptr<TransformationEstimationPointToPlane<PointSource, PointTarget, Scalar>> Ptr;
-  int opeKind() const override { return -1; }
 };
 
 // DefaultConvergenceCriteria::ConvergenceState (VP/default_convergence_criteria_mod.h:73-81)
@@ -434,7 +469,7 @@ class IterativeClosestPoint : public Registration<PointSource, PointTarget, Scal
     }
     const int te = this->transformation_estimation_ ? this->transformation_estimation_->opeKind() : OPE_TE_SVD;
     if (te < 0) {
-      detail::pcl_error(this->reg_name_.c_str(), "TransformationEstimationPointToPlane (Levenberg-Marquardt) is not implemented on the device; use TransformationEstimationSVD");
+      detail::pcl_error(this->reg_name_.c_str(), "this TransformationEstimation is not implemented on the device");
       return;
     }
     prm.transformation = te;

@@ -61,7 +61,9 @@ enum {
 /* transformation estimators */
 enum {
   OPE_TE_SVD = 0,                /* TransformationEstimationSVD (Umeyama), ctor default VP/icp_mod.h:149 */
-  OPE_TE_POINT_TO_PLANE_LLS = 1  /* IterativeClosestPointWithNormals default, VP/icp_mod.h:352-357 */
+  OPE_TE_POINT_TO_PLANE_LLS = 1, /* IterativeClosestPointWithNormals default, VP/icp_mod.h:352-357 */
+  OPE_TE_POINT_TO_PLANE = 2      /* TransformationEstimationPointToPlane (Levenberg-Marquardt on the 6-parameter rigid warp),
+                                    what BuildModel sets: BM/src/regmeshpcd.cpp:162,193 */
 };
 /* which vendored ICP loop */
 enum {

@@ -12,7 +12,7 @@ OPE_ERR_CAPACITY, OPE_ERR_GRID_TOO_LARGE, OPE_ERR_UNSUPPORTED = -5, -6, -7
 CONV_NOT_CONVERGED, CONV_ITERATIONS, CONV_TRANSFORM, CONV_ABS_MSE, CONV_REL_MSE, CONV_NO_CORRESPONDENCES = range(6)
 EST_NEAREST, EST_NORMAL_SHOOTING = 0, 1
 REJ_SURFACE_NORMAL, REJ_SELF_OCCLUDED_NORMAL = 1, 2
-TE_SVD, TE_POINT_TO_PLANE_LLS = 0, 1
+TE_SVD, TE_POINT_TO_PLANE_LLS, TE_POINT_TO_PLANE = 0, 1, 2
 ICP_VARIANT_MOD, ICP_VARIANT_MODCORR = 0, 1
 MAX_REJECTORS = 4
 

@@ -6,9 +6,8 @@
 // output is the COMPACTED list in that traversal order (the organised width/height the reference sets are meaningless).
 //
 // HBM-bound byte shuffle: 2 bytes in per pixel, 16 bytes out per kept pixel. Two passes so that the output order is
-// deterministic without atomics: (1) per-column valid counts, (2) a scan over the columns of every frame, (3) the write pass.
-// A block owns 32 adjacent columns of one frame and walks down the rows 32 at a time: the 32x32 tile of uint16 is loaded
-// row-wise (64-byte coalesced segments), transposed through shared memory, and warp w compacts column w with a ballot.
+// deterministic without atomics: (1) per-column valid counts, (2) a scan over the columns of every frame, (3) the write pass
+// (kernels below).
 // Frames are batched along blockIdx.y so that 1 024 frames (629 MB in, up to 5 GB out) are one launch.
 #include "ope_host.cuh"
 
@@ -30,33 +29,72 @@ __device__ __forceinline__ bool depth_point(const DepthParams& P, int i, int j, 
   return true;
 }
 
-// WRITE = false: col_count[frame * cols + j] = number of kept pixels of column j
-// WRITE = true : col_start (exclusive scan of col_count over the whole batch) gives every column its output offset
-template <bool WRITE>
-__global__ void __launch_bounds__(1024) depth_cloud_kernel(const unsigned short* __restrict__ depth, DepthParams P, int* __restrict__ col_count,
+// Pass 1: col_count[frame * cols + j] = number of kept pixels of column j. No transposition needed: lane = column, warp w
+// walks rows w, w + 32, ... with all its loads independent (up to 16 in flight per thread); the 32 per-warp partial counts of
+// a column are summed through shared memory.
+__global__ void __launch_bounds__(1024) depth_count_kernel(const unsigned short* __restrict__ depth, DepthParams P, int* __restrict__ col_count) {
+  __shared__ int part[32][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int frame = blockIdx.y;
+  const int j = blockIdx.x * 32 + lane;
+  const unsigned short* d = depth + (size_t)frame * P.rows * P.cols;
+  int cnt = 0;
+  if (j < P.cols) {
+    for (int r0 = w; r0 < P.rows; r0 += 32 * 16) {
+      unsigned short v[16];
+#pragma unroll
+      for (int t = 0; t < 16; ++t) { const int i = r0 + 32 * t; v[t] = i < P.rows ? __ldg(d + (size_t)i * P.cols + j) : (unsigned short)0; }
+#pragma unroll
+      for (int t = 0; t < 16; ++t) { float4 pt; cnt += depth_point(P, r0 + 32 * t, j, v[t], pt) ? 1 : 0; }
+    }
+  }
+  part[w][lane] = cnt;
+  __syncthreads();
+  if (w == 0 && j < P.cols) {
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) s += part[k][lane];
+    col_count[(size_t)frame * P.cols + j] = s;
+  }
+}
+
+// Pass 2: col_start (exclusive scan of col_count over the whole batch) gives every column its output offset. A block owns 32
+// adjacent columns of one frame and walks down the rows kChunk at a time: the chunk is loaded row-wise (64-byte segments, 8
+// independent loads per thread), transposed through shared memory, and warp w compacts column w with ballots, writing 32
+// consecutive float4 (512 B) per step.
+static constexpr int kChunk = 256;
+__global__ void __launch_bounds__(1024) depth_write_kernel(const unsigned short* __restrict__ depth, DepthParams P,
                                                            const int* __restrict__ col_start, float4* __restrict__ out) {
-  __shared__ unsigned short tile[32][33];
+  __shared__ unsigned short tile[kChunk][34];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int frame = blockIdx.y;
   const int j0 = blockIdx.x * 32;
   const unsigned short* d = depth + (size_t)frame * P.rows * P.cols;
   const int j = j0 + w;  // this warp's column
   int run = 0;           // kept pixels of column j so far
-  const int base = (WRITE && j < P.cols) ? col_start[(size_t)frame * P.cols + j] : 0;
-  for (int r0 = 0; r0 < P.rows; r0 += 32) {
-    // row-wise load: warp w reads row r0 + w, lanes = 32 adjacent columns
-    const int ri = r0 + w, cj = j0 + lane;
-    tile[w][lane] = (ri < P.rows && cj < P.cols) ? __ldg(d + (size_t)ri * P.cols + cj) : (unsigned short)0;
+  const int base = j < P.cols ? col_start[(size_t)frame * P.cols + j] : 0;
+  for (int r0 = 0; r0 < P.rows; r0 += kChunk) {
+    unsigned short v[kChunk / 32];
+    const int cj = j0 + lane;
+#pragma unroll
+    for (int t = 0; t < kChunk / 32; ++t) {
+      const int ri = r0 + w + 32 * t;
+      v[t] = (ri < P.rows && cj < P.cols) ? __ldg(d + (size_t)ri * P.cols + cj) : (unsigned short)0;
+    }
+#pragma unroll
+    for (int t = 0; t < kChunk / 32; ++t) tile[w + 32 * t][lane] = v[t];
     __syncthreads();
-    const int i = r0 + lane;  // transposed read: lane = row within the chunk, warp = column
-    float4 pt = make_float4(0, 0, 0, 0);
-    const bool keep = (i < P.rows && j < P.cols) && depth_point(P, i, j, tile[lane][w], pt);
-    const unsigned m = __ballot_sync(0xffffffffu, keep);
-    if (WRITE && keep) out[(size_t)base + run + __popc(m & ((1u << lane) - 1u))] = pt;
-    run += __popc(m);
+#pragma unroll
+    for (int t = 0; t < kChunk / 32; ++t) {
+      const int i = r0 + 32 * t + lane;  // transposed read: lane = row within the group, warp = column
+      float4 pt = make_float4(0, 0, 0, 0);
+      const bool keep = (i < P.rows && j < P.cols) && depth_point(P, i, j, tile[32 * t + lane][w], pt);
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (keep) __stcs(out + (size_t)base + run + __popc(m & ((1u << lane) - 1u)), pt);   // streamed: never re-read by this kernel
+      run += __popc(m);
+    }
     __syncthreads();
   }
-  if (!WRITE && lane == 0 && j < P.cols) col_count[(size_t)frame * P.cols + j] = run;
 }
 
 int depth_to_cloud_device(ope_ctx* ctx, const unsigned short* d_depth, int frames, const DepthParams& P, float4* d_out, int* d_col_start,
@@ -64,11 +102,11 @@ int depth_to_cloud_device(ope_ctx* ctx, const unsigned short* d_depth, int frame
   (void)counts_only_then_scan;
   const size_t ncol = (size_t)frames * P.cols;
   dim3 grid(div_up((size_t)P.cols, 32), frames);
-  depth_cloud_kernel<false><<<grid, 1024, 0, ctx->stream>>>(d_depth, P, d_col_start, nullptr, nullptr);
-  OPE_TRY(check_launch(ctx, "depth_cloud_kernel<count>"));
+  depth_count_kernel<<<grid, 1024, 0, ctx->stream>>>(d_depth, P, d_col_start);
+  OPE_TRY(check_launch(ctx, "depth_count_kernel"));
   OPE_TRY(exclusive_scan_i32(ctx, d_col_start, ncol + 1));
-  depth_cloud_kernel<true><<<grid, 1024, 0, ctx->stream>>>(d_depth, P, nullptr, d_col_start, d_out);
-  return check_launch(ctx, "depth_cloud_kernel<write>");
+  depth_write_kernel<<<grid, 1024, 0, ctx->stream>>>(d_depth, P, d_col_start, d_out);
+  return check_launch(ctx, "depth_write_kernel");
 }
 
 }  // namespace ope

@@ -1040,7 +1040,9 @@ static int icp_fill(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, co
   if (need_src_normals && !src->normals) return fail(ctx, OPE_ERR_INVALID, "estimator/rejector needs source normals");
   if (need_tgt_normals && !tgt->normals) return fail(ctx, OPE_ERR_INVALID, "rejector needs target normals");
   if (prm.use_reciprocal) return fail(ctx, OPE_ERR_UNSUPPORTED, "reciprocal correspondences are not implemented");
-  if (prm.transformation != OPE_TE_SVD) return fail(ctx, OPE_ERR_UNSUPPORTED, "only TransformationEstimationSVD is implemented on the device");
+  if (prm.transformation != OPE_TE_SVD && prm.transformation != OPE_TE_POINT_TO_PLANE_LLS && prm.transformation != OPE_TE_POINT_TO_PLANE)
+    return fail(ctx, OPE_ERR_UNSUPPORTED, "unknown transformation estimator %d", prm.transformation);
+  if (prm.transformation != OPE_TE_SVD && !tgt->normals) return fail(ctx, OPE_ERR_INVALID, "point-to-plane estimation needs target normals");
   if (prm.estimator == OPE_EST_NORMAL_SHOOTING && (prm.k_search < 1 || prm.k_search > 32))
     return fail(ctx, OPE_ERR_INVALID, "normal shooting k must be in [1, 32]");
   OPE_TRY(cloud_bbox(ctx, const_cast<ope_cloud*>(tgt)));
@@ -1080,8 +1082,12 @@ static void corr_to_host(const std::vector<int>& match, const std::vector<float>
   if (n) *n = w;
 }
 
+static int icp_stepwise_device(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const ope_icp_params& prm, const Mat4& guess,
+                               ope_reg_result* res, ope_correspondence* out_corr_host, ope_cloud** out_aligned);
+
 int icp_device(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const ope_icp_params& prm, const Mat4& guess,
                ope_reg_result* res, ope_correspondence* out_corr_host, ope_cloud** out_aligned) {
+  if (prm.transformation != OPE_TE_SVD) return icp_stepwise_device(ctx, src, tgt, prm, guess, res, out_corr_host, out_aligned);
   IcpDev a;
   std::memset(&a, 0, sizeof(a));
   OPE_TRY(icp_fill(ctx, src, tgt, prm, &a, /*allow_smem_target=*/true));
@@ -1207,6 +1213,109 @@ int icp_device(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const o
   }
   if (work) ope_cloud_free(ctx, work);
   return rc;
+}
+
+// IterativeClosestPoint::computeTransformation (VP/impl/icp_mod.hpp:118-272) with a point-to-plane transformation estimator
+// (BuildModel's getIcpNormal, BM/src/regmeshpcd.cpp:104-208; IterativeClosestPointWithNormals' default LLS, VP/icp_mod.h:352-357).
+// The estimator is iterative itself (Levenberg-Marquardt: several reductions per ICP iteration, steered by 6x6 algebra on the
+// host), so this loop is sequenced from the host: correspondences + rejectors (one launch), estimation (p2plane.cu), transform
+// in place, DefaultConvergenceCriteria in double on the host. Everything the kernels read stays on the device; per step only
+// the 28 reduced doubles come back.
+static int icp_stepwise_device(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const ope_icp_params& prm, const Mat4& guess,
+                               ope_reg_result* res, ope_correspondence* out_corr_host, ope_cloud** out_aligned) {
+  IcpDev a;
+  std::memset(&a, 0, sizeof(a));
+  OPE_TRY(icp_fill(ctx, src, tgt, prm, &a));
+  const size_t n = src->n;
+  const bool shooting = prm.estimator == OPE_EST_NORMAL_SHOOTING;
+  ope_cloud *work = nullptr, *next = nullptr;   // ping-pong: transform_kernel reads through the read-only path
+  struct Guard { ope_ctx* c; ope_cloud*& w; ~Guard() { if (w) ope_cloud_free(c, w); } } guard{ctx, work}, guard2{ctx, next};
+  OPE_TRY(cloud_alloc(ctx, std::max<size_t>(n, 1), src->normals != nullptr, &work));
+  OPE_TRY(cloud_alloc(ctx, std::max<size_t>(n, 1), src->normals != nullptr, &next));
+  work->n = next->n = n;
+  Mat4 final_t = guess;
+  if (n > 0) OPE_TRY(transform_device(ctx, src, guess, work));   // identity guess: a plain copy
+  Scratch<int> match(ctx), seed(ctx);
+  Scratch<float> d2(ctx);
+  OPE_TRY(match.alloc(n)); OPE_TRY(d2.alloc(n));
+  OPE_TRY(seed.alloc(shooting ? n * (size_t)prm.k_search : n));
+  a.corr_match = match.p; a.corr_d2 = d2.p; a.seed = seed.p;
+  OPE_TRY(dyn_smem(ctx, (const void*)correspond_once_kernel, sizeof(IcpSmem)));
+  const size_t want = shooting ? div_up(n, kIcpWarps) : div_up(n, kIcpThreads);
+  const unsigned blocks = (unsigned)std::max<size_t>(1, std::min<size_t>(want, (size_t)ctx->sm_count * 4));
+  int iterations = 0, state = OPE_CONV_NOT_CONVERGED, similar = 0, n_corr = 0;
+  bool converged = false;
+  double prev_mse = DBL_MAX, cur_mse = DBL_MAX;
+  const double rot_thr = 1.0 - prm.transformation_epsilon, trans_thr = prm.transformation_epsilon;
+  cudaEventRecord(ctx->kev[0][0], ctx->stream);
+  do {
+    a.cur_pts = work->pts; a.cur_nrm = work->normals;
+    if (n > 0) {
+      correspond_once_kernel<<<blocks, kIcpThreads, sizeof(IcpSmem), ctx->stream>>>(a);
+      OPE_TRY(check_launch(ctx, "correspond_once_kernel"));
+    }
+    Mat4 T = mat4_identity();
+    double sum_d2 = 0.0;
+    OPE_TRY(point_to_plane_device(ctx, work->pts, tgt->pts, tgt->normals, nullptr, match.p, d2.p, n, prm.transformation, &T, &n_corr,
+                                  &sum_d2, nullptr));
+    if (n_corr < prm.min_number_correspondences) {   // VP/impl/icp_mod.hpp:232-240
+      state = OPE_CONV_NO_CORRESPONDENCES;
+      converged = false;
+      break;
+    }
+    if (n > 0) OPE_TRY(transform_device(ctx, work, T, next));   // transformCloud(*input_transformed, *input_transformed, transformation_)
+    std::swap(work, next);
+    final_t = mat4_mul(T, final_t);
+    ++iterations;
+    // DefaultConvergenceCriteria::hasConverged (VP/default_convergence_criteria_mod.h:64-282)
+    state = OPE_CONV_NOT_CONVERGED;
+    bool conv = false;
+    auto similar_or_done = [&](int st) {
+      if (similar < prm.max_iterations_similar_transforms) { ++similar; return false; }
+      similar = 0; state = st; return true;
+    };
+    if (iterations >= prm.max_iterations) {
+      if (!prm.failure_after_max_iterations) { state = OPE_CONV_ITERATIONS; conv = true; }
+      else { converged = false; break; }
+    } else {
+      // float trace and float squared norm, widened afterwards: the arithmetic of Matrix4f expressions [UPSTREAM hasConverged]
+      const double cos_angle = 0.5 * (double)(T(0, 0) + T(1, 1) + T(2, 2) - 1);
+      const double tr2 = (double)(T(0, 3) * T(0, 3) + T(1, 3) * T(1, 3) + T(2, 3) * T(2, 3));
+      if (cos_angle >= rot_thr && tr2 <= trans_thr) {
+        conv = similar_or_done(OPE_CONV_TRANSFORM);
+      } else {
+        cur_mse = sum_d2 / (double)n_corr;
+        if (std::fabs(cur_mse - prev_mse) < prm.mse_threshold_absolute) conv = similar_or_done(OPE_CONV_ABS_MSE);
+        else if (std::fabs(cur_mse - prev_mse) / prev_mse < prm.euclidean_fitness_epsilon) conv = similar_or_done(OPE_CONV_REL_MSE);
+        else prev_mse = cur_mse;
+      }
+    }
+    converged = conv;
+    if (prm.force_all_iterations && iterations < prm.max_iterations) converged = false;
+  } while (!converged);
+  cudaEventRecord(ctx->kev[0][1], ctx->stream);
+  ctx->kev_valid[0] = true;
+  std::memcpy(res->T, final_t.m, sizeof(final_t.m));
+  res->converged = converged ? 1 : 0;
+  res->state = state;
+  res->iterations = iterations;
+  res->n_correspondences = n_corr;
+  res->last_mse = cur_mse;
+  res->best_error = 0.0; res->best_iteration = 0; res->reserved = 0;
+  if (out_corr_host && n > 0) {
+    std::vector<int> hm(n);
+    std::vector<float> hd(n);
+    OPE_CUDA_TRY(ctx, cudaMemcpyAsync(hm.data(), match.p, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    OPE_CUDA_TRY(ctx, cudaMemcpyAsync(hd.data(), d2.p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    OPE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    corr_to_host(hm, hd, out_corr_host, nullptr);
+  }
+  if (out_aligned) {
+    if (n > 0) OPE_TRY(transform_device(ctx, src, final_t, work));   // output = *input_ under the final transformation, :269-271
+    *out_aligned = work;
+    work = nullptr;
+  }
+  return OPE_OK;
 }
 
 static inline int libc_random_index(int n) { return (int)(n * (rand() / (RAND_MAX + 1.0))); }
@@ -1397,6 +1506,34 @@ int ope_umeyama(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const 
     OPE_CUDA_TRY(ctx, cudaMemcpyAsync(dt.p, itgt, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   }
   return umeyama_device(ctx, src->pts, tgt->pts, isrc ? ds.p : nullptr, itgt ? dt.p : nullptr, n, T);
+}
+
+int ope_point_to_plane(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const int32_t* isrc, const int32_t* itgt, size_t n,
+                       int kind, float T[16], int32_t* lm_info) {
+  if (!ctx || !src || !tgt || !T) return OPE_ERR_INVALID;
+  if (!tgt->normals) return fail(ctx, OPE_ERR_INVALID, "point-to-plane estimation needs target normals");
+  if ((!isrc && n > src->n) || (!itgt && n > tgt->n)) return fail(ctx, OPE_ERR_INVALID, "n exceeds cloud size");
+  Scratch<int> ds(ctx), dt(ctx);
+  std::vector<int> ident;
+  if (isrc) {
+    for (size_t i = 0; i < n; ++i) if (isrc[i] < 0 || (size_t)isrc[i] >= src->n) return fail(ctx, OPE_ERR_INVALID, "source index out of range");
+    OPE_TRY(ds.alloc(n));
+    OPE_CUDA_TRY(ctx, cudaMemcpyAsync(ds.p, isrc, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (itgt) {
+    for (size_t i = 0; i < n; ++i) if (itgt[i] < 0 || (size_t)itgt[i] >= tgt->n) return fail(ctx, OPE_ERR_INVALID, "target index out of range");
+  } else {
+    ident.resize(n);
+    for (size_t i = 0; i < n; ++i) ident[i] = (int)i;
+    itgt = ident.data();
+  }
+  OPE_TRY(dt.alloc(n));
+  OPE_CUDA_TRY(ctx, cudaMemcpyAsync(dt.p, itgt, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  Mat4 M;
+  int rc = point_to_plane_device(ctx, src->pts, tgt->pts, tgt->normals, isrc ? ds.p : nullptr, dt.p, nullptr, n, kind, &M, nullptr, nullptr, lm_info);
+  cudaStreamSynchronize(ctx->stream);   // the pageable index arrays must outlive their copies
+  if (rc == OPE_OK) std::memcpy(T, M.m, sizeof(M.m));
+  return rc;
 }
 
 int ope_fitness(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const float T[16], double max_range, double* out) {

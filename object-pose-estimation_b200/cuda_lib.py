@@ -27,7 +27,7 @@ EXPORTS = [
     "ope_knn", "ope_knn_cloud", "ope_radius_cloud", "ope_depth_to_cloud", "ope_depth_to_cloud_batch",
     "ope_uniform_sample", "ope_uniform_sample_cloud", "ope_voxel_grid",
     "ope_normals_knn", "ope_fpfh", "ope_feature_knn",
-    "ope_umeyama", "ope_fitness", "ope_correspondences", "ope_icp_align", "ope_sacia_align", "ope_sacia_draw",
+    "ope_umeyama", "ope_point_to_plane", "ope_fitness", "ope_correspondences", "ope_icp_align", "ope_sacia_align", "ope_sacia_draw",
     "ope_pose_tracker_create", "ope_pose_tracker_destroy", "ope_pose_estimate_final", "ope_pose_estimate_final_device",
     "ope_pose_stage_ms", "ope_icp_params_default", "ope_sacia_params_default", "ope_pose_params_default",
 ]
@@ -316,6 +316,18 @@ class Context:
         self._chk(lib().ope_umeyama(self.h, src.h, tgt.h, None if a is None else a.ctypes.data_as(i32p),
                                     None if b is None else b.ctypes.data_as(i32p), C.c_size_t(n), Tm))
         return T.mat4(Tm)
+
+    def point_to_plane(self, src, tgt, isrc=None, itgt=None, n=None, kind=T.TE_POINT_TO_PLANE, want_info=False):
+        """TransformationEstimationPointToPlane (Levenberg-Marquardt) / ...LLS::estimateRigidTransformation; tgt carries normals"""
+        a = None if isrc is None else np.ascontiguousarray(isrc, np.int32)
+        b = None if itgt is None else np.ascontiguousarray(itgt, np.int32)
+        if n is None:
+            n = len(a) if a is not None else (len(b) if b is not None else min(len(src), len(tgt)))
+        Tm = (C.c_float * 16)()
+        info = (C.c_int32 * 3)()
+        self._chk(lib().ope_point_to_plane(self.h, src.h, tgt.h, None if a is None else a.ctypes.data_as(i32p),
+                                           None if b is None else b.ctypes.data_as(i32p), C.c_size_t(n), int(kind), Tm, info))
+        return (T.mat4(Tm), tuple(info)) if want_info else T.mat4(Tm)
 
     def fitness(self, src, tgt, M, max_range=np.finfo(np.float64).max):
         out = C.c_double(0)

@@ -17,6 +17,7 @@
 
 #include "orc_kdtree.h"
 #include "orc_linalg.h"
+#include "orc_lm.h"
 
 using orc::KdTree;
 using orc::Mat4;
@@ -322,6 +323,55 @@ void pointToPlaneLLS(const CloudView& src, const CloudView& tgt, const std::vect
   std::memcpy(T, M.m, sizeof(M.m));
 }
 
+// WarpPointRigid6D::setParam [UPSTREAM registration/warp_point_rigid_6d.h]: x = (tx, ty, tz, qx, qy, qz); qw = sqrt(1 - |q|^2),
+// q normalised, then Eigen's Quaternion::toRotationMatrix; everything in float.
+void warpRigid6D(const float x[6], Mat4& M) {
+  std::memset(M.m, 0, sizeof(M.m));
+  M(0, 3) = x[0]; M(1, 3) = x[1]; M(2, 3) = x[2]; M(3, 3) = 1.0f;
+  float qx = x[3], qy = x[4], qz = x[5];
+  float qw = std::sqrt(1.0f - (((0.0f * 0.0f + qx * qx) + qy * qy) + qz * qz));
+  const float nrm = std::sqrt(((qx * qx + qy * qy) + qz * qz) + qw * qw);
+  qx /= nrm; qy /= nrm; qz /= nrm; qw /= nrm;
+  const float tx = 2.0f * qx, ty = 2.0f * qy, tz = 2.0f * qz;
+  const float twx = tx * qw, twy = ty * qw, twz = tz * qw;
+  const float txx = tx * qx, txy = ty * qx, txz = tz * qx;
+  const float tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+  M(0, 0) = 1.0f - (tyy + tzz); M(0, 1) = txy - twz; M(0, 2) = txz + twy;
+  M(1, 0) = txy + twz; M(1, 1) = 1.0f - (txx + tzz); M(1, 2) = tyz - twx;
+  M(2, 0) = txz - twy; M(2, 1) = tyz + twx; M(2, 2) = 1.0f - (txx + tyy);
+}
+
+// TransformationEstimationPointToPlane [UPSTREAM transformation_estimation_point_to_plane.h + transformation_estimation_lm.hpp],
+// the estimator BuildModel plugs into IterativeClosestPointWithNormals (BM/src/regmeshpcd.cpp:162,193):
+// residual_i = (warp(src_i) - tgt_i) . n_tgt_i, minimised over the 6 warp parameters by Eigen's Levenberg-Marquardt with a
+// forward-difference Jacobian, starting from x = 0. Fewer than 4 pairs: PCL_ERROR and the identity.
+orc::LmRoute g_lm_route = orc::LM_ROUTE_NORMAL_EQ;   // orc_lm_set_route(): the Householder route is a cross-check
+
+void pointToPlaneLM(const CloudView& src, const CloudView& tgt, const std::vector<ope_correspondence>& corr, float T[16],
+                    orc::LmStats* stats = nullptr) {
+  Mat4 I = Mat4::identity();
+  std::memcpy(T, I.m, sizeof(I.m));
+  if (corr.size() < 4) return;
+  auto functor = [&](const float* x, float* fvec) {
+    Mat4 W;
+    warpRigid6D(x, W);
+    for (size_t i = 0; i < corr.size(); ++i) {
+      const float* s = src.p(corr[i].index_query); const float* d = tgt.p(corr[i].index_match); const float* n = tgt.nrm(corr[i].index_match);
+      float w[3];
+      orc::xformPoint(W, s, w);
+      // Vector4f (s - t).dot(n) with w = 0, Eigen's SSE reduction order: (p0 + p2) + (p1 + p3)
+      const float p0 = (w[0] - d[0]) * n[0], p1 = (w[1] - d[1]) * n[1], p2 = (w[2] - d[2]) * n[2], p3 = 0.0f * 0.0f;
+      fvec[i] = (p0 + p2) + (p1 + p3);
+    }
+  };
+  float x[6] = {0, 0, 0, 0, 0, 0};
+  orc::LmStats st = orc::lmMinimize(functor, (int)corr.size(), 6, x, g_lm_route);
+  if (stats) *stats = st;
+  Mat4 W;
+  warpRigid6D(x, W);
+  std::memcpy(T, W.m, sizeof(W.m));
+}
+
 void transformCloud(std::vector<float>& pts, std::vector<float>& normals, bool has_normals, const Mat4& T) {
   size_t n = pts.size() / 3;
   for (size_t i = 0; i < n; ++i) {
@@ -385,6 +435,8 @@ int icpAlign(const CloudView& src, const CloudView& tgt, const KdTree& tgt_tree,
     }
     if (prm.transformation == OPE_TE_POINT_TO_PLANE_LLS) {
       pointToPlaneLLS(cur, tgt, corr, transformation.m);
+    } else if (prm.transformation == OPE_TE_POINT_TO_PLANE) {
+      pointToPlaneLM(cur, tgt, corr, transformation.m);
     } else {
       orc::umeyama(corr.size(), [&](size_t i) { return cur.p(corr[i].index_query); },
                    [&](size_t i) { return tgt.p(corr[i].index_match); }, transformation.m);
@@ -779,6 +831,25 @@ int orc_umeyama(const float* src, size_t sstride, const float* tgt, size_t tstri
   if (!src || !tgt || !T || n == 0) return OPE_ERR_INVALID;
   orc::umeyama(n, [&](size_t i) { return at(src, sstride, is ? is[i] : i); },
                [&](size_t i) { return at(tgt, tstride, it ? it[i] : i); }, T);
+  return OPE_OK;
+}
+
+// 0: normal equations with order-independent double sums (canonical); 1: Householder QR of the full Jacobian (cross-check)
+void orc_lm_set_route(int householder) { g_lm_route = householder ? orc::LM_ROUTE_HOUSEHOLDER : orc::LM_ROUTE_NORMAL_EQ; }
+
+// TransformationEstimationPointToPlane[LLS]::estimateRigidTransformation over explicit index pairs (kind = OPE_TE_*)
+int orc_point_to_plane(const float* src, size_t ns, size_t sstride, const float* tgt, size_t nt, size_t tstride, const float* tgt_normals4,
+                       const int32_t* is, const int32_t* it, size_t n, int kind, float T[16], int32_t* lm_info /* status, nfev, iterations */) {
+  if (!src || !tgt || !tgt_normals4 || !T) return OPE_ERR_INVALID;
+  CloudView s{src, ns, sstride, nullptr}, t{tgt, nt, tstride, tgt_normals4};
+  std::vector<ope_correspondence> corr(n);
+  for (size_t i = 0; i < n; ++i) corr[i] = ope_correspondence{is ? is[i] : (int32_t)i, it ? it[i] : (int32_t)i, 0.0f};
+  if (kind == OPE_TE_POINT_TO_PLANE_LLS) pointToPlaneLLS(s, t, corr, T);
+  else if (kind == OPE_TE_POINT_TO_PLANE) {
+    orc::LmStats st;
+    pointToPlaneLM(s, t, corr, T, &st);
+    if (lm_info) { lm_info[0] = st.status; lm_info[1] = st.nfev; lm_info[2] = st.iterations; }
+  } else return OPE_ERR_UNSUPPORTED;
   return OPE_OK;
 }
 

@@ -62,6 +62,17 @@ int orc_umeyama(const float* src, size_t sstride, const float* tgt, size_t tstri
 int orc_transform(const float* pts, size_t n, size_t stride, const float* normals, const float T[16],
                   float* out_pts /* n*3 */, float* out_normals /* n*4 or NULL */);
 
+/* TransformationEstimationPointToPlaneLLS / TransformationEstimationPointToPlane (Levenberg-Marquardt) [UPSTREAM], the
+ * estimators of IterativeClosestPointWithNormals (VP/icp_mod.h:352-357) and BuildModel (BM/src/regmeshpcd.cpp:162,193).
+ * kind = OPE_TE_POINT_TO_PLANE_LLS | OPE_TE_POINT_TO_PLANE; lm_info (3 ints: status, nfev, iterations) may be NULL. */
+int orc_point_to_plane(const float* src, size_t ns, size_t sstride, const float* tgt, size_t nt, size_t tstride,
+                       const float* tgt_normals4, const int32_t* is, const int32_t* it, size_t n, int kind, float T[16],
+                       int32_t* lm_info);
+
+/* route of the LM linear algebra: 0 = normal equations accumulated in double (canonical), 1 = Householder QR of the full
+ * m x 6 Jacobian as Eigen does (cross-check; oracle/orc_lm.h) */
+void orc_lm_set_route(int householder);
+
 /* ---- depth image -> cloud ---- */
 /* DataGrabber::rgbd2Pcl + depthToMeter, D&L/src/datagrabber.cpp:9-62,121-174: columns outer, rows inner; Z = depth / scale;
  * the reference passes (row, col) as (x, y): y_out = (row - cx) * Z / fx, x_out = (col - cy) * Z / fy (sic); points with

@@ -176,6 +176,27 @@ def umeyama(src, tgt, isrc=None, itgt=None):
     return T.mat4(Tm)
 
 
+def point_to_plane(src, tgt, tgt_normals, isrc=None, itgt=None, kind=None, want_info=False):
+    """TransformationEstimationPointToPlane (kind = T.TE_POINT_TO_PLANE, Levenberg-Marquardt) or ...LLS"""
+    s, sp, ns, ss = _pts(src)
+    t, tp, nt, ts = _pts(tgt)
+    nr = _f32(tgt_normals)
+    assert nr.shape == (t.shape[0], 4)
+    n = min(s.shape[0], t.shape[0]) if isrc is None else len(isrc)
+    a = None if isrc is None else np.ascontiguousarray(isrc, np.int32)
+    b = None if itgt is None else np.ascontiguousarray(itgt, np.int32)
+    Tm = (C.c_float * 16)()
+    info = (C.c_int32 * 3)()
+    _chk(lib().orc_point_to_plane(sp, ns, ss, tp, nt, ts, nr.ctypes.data_as(f32p), None if a is None else a.ctypes.data_as(i32p),
+                                  None if b is None else b.ctypes.data_as(i32p), C.c_size_t(n),
+                                  int(T.TE_POINT_TO_PLANE if kind is None else kind), Tm, info))
+    return (T.mat4(Tm), tuple(info)) if want_info else T.mat4(Tm)
+
+
+def lm_set_route(householder):
+    lib().orc_lm_set_route(int(bool(householder)))
+
+
 def depth_to_cloud(depth, fx=525.0, fy=525.0, cx=319.5, cy=239.5, scale=1000.0, z_max=2.0):
     d = np.ascontiguousarray(depth, np.uint16)
     out = np.empty((d.shape[0] * d.shape[1], 3), np.float32)

@@ -244,7 +244,8 @@ static int run_icp(int argc, char** argv) {
   return 0;
 }
 
-// ---- multi-view chain (BM/src/regmeshpcd.cpp:210-271), SVD estimator (the LM point-to-plane one is SURVEY row f-4) -----
+// ---- multi-view chain (BM/src/regmeshpcd.cpp:210-271): getIcpNormal per pair with the estimator the reference plugs in,
+// TransformationEstimationPointToPlane (Levenberg-Marquardt, :162,193); OPE_CHAIN_TE=svd|lls selects another one -----
 static CloudN::Ptr with_normals(const Cloud::Ptr& c, pcl::search::KdTree<PointT>::Ptr tree) {
   pcl::NormalEstimation<PointT, PointNT> ne;
   ne.setSearchMethod(tree);
@@ -282,8 +283,16 @@ static int run_chain(int argc, char** argv) {
     icp.setEuclideanFitnessEpsilon(1e-8);
     icp.setCorrespondenceEstimation(shoot);
     icp.addCorrespondenceRejector(by_normal);
-    icp.setTransformationEstimation(pcl::registration::TransformationEstimationSVD<PointNT, PointNT>::Ptr(
-        new pcl::registration::TransformationEstimationSVD<PointNT, PointNT>));
+    const char* te = std::getenv("OPE_CHAIN_TE");
+    if (te && std::string(te) == "svd")
+      icp.setTransformationEstimation(pcl::registration::TransformationEstimationSVD<PointNT, PointNT>::Ptr(
+          new pcl::registration::TransformationEstimationSVD<PointNT, PointNT>));
+    else if (te && std::string(te) == "lls")
+      icp.setTransformationEstimation(pcl::registration::TransformationEstimationPointToPlaneLLS<PointNT, PointNT>::Ptr(
+          new pcl::registration::TransformationEstimationPointToPlaneLLS<PointNT, PointNT>));
+    else
+      icp.setTransformationEstimation(pcl::registration::TransformationEstimationPointToPlane<PointNT, PointNT>::Ptr(
+          new pcl::registration::TransformationEstimationPointToPlane<PointNT, PointNT>));
     CloudN moved;
     icp.align(moved);
     const Eigen::Matrix4f T = icp.getFinalTransformation();

@@ -379,3 +379,60 @@ def test_depth_to_cloud_batch_is_the_single_frame_result_per_frame(ctx, orc, syn
         ref = orc.depth_to_cloud(frames[f])
         b, e = col[f * Cc], col[(f + 1) * Cc]
         assert e - b == len(ref) and np.array_equal(out[b:e, :3], ref)
+
+
+# --------------------------------------------------------------- point-to-plane estimators (8a16 / 8f-4) ----
+def _plane_pairs(synth, orc, small_model, seed):
+    rng = np.random.default_rng(seed)
+    tgt = (small_model[rng.permutation(len(small_model))[:6000]] + np.array([0.02, -0.01, 0.9], np.float32)).astype(np.float32)
+    tn = orc.normals_knn(tgt, 12)
+    moved = synth.apply(synth.small_pose(rng, 4, 0.008), tgt) + rng.normal(0, 3e-4, size=tgt.shape)
+    return moved.astype(np.float32), tgt, tn
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_point_to_plane_estimators_match_the_oracle(ctx, orc, synth, cuda_lib, small_model, seed):
+    """TransformationEstimationPointToPlaneLLS and ...PointToPlane (Levenberg-Marquardt on the 6-parameter warp) over explicit
+    pairs: same transform, and for LM the same Eigen status / evaluation count / iteration count as the oracle, which factors the
+    full m x 6 Jacobian by Householder QR while the device works from the fused 6 x 6 normal equations."""
+    T = cuda_lib.T
+    src, tgt, tn = _plane_pairs(synth, orc, small_model, seed)
+    cs, ct = ctx.upload(src), ctx.upload(tgt, tn)
+    rng = np.random.default_rng(seed)
+    cases = [(None, None), (rng.integers(0, len(src), 3000).astype(np.int32),) * 2, (np.arange(3, dtype=np.int32),) * 2]
+    for isrc, itgt in cases:
+        for kind in (T.TE_POINT_TO_PLANE_LLS, T.TE_POINT_TO_PLANE):
+            g, gi = ctx.point_to_plane(cs, ct, isrc, itgt, kind=kind, want_info=True)
+            o, oi = orc.point_to_plane(src, tgt, tn, isrc, itgt, kind=kind, want_info=True)
+            if isrc is not None and len(isrc) == 3:
+                if kind == T.TE_POINT_TO_PLANE:      # fewer than 4 pairs: PCL_ERROR + identity
+                    assert np.array_equal(g, np.eye(4)) and np.array_equal(o, np.eye(4))
+                continue                              # LLS on 3 pairs is singular on both sides; nothing to compare
+            r, t = synth.pose_error(g, o)
+            assert r < ROT_TOL and t < TRANS_TOL, (kind, r, t)
+            if kind == T.TE_POINT_TO_PLANE:
+                assert gi == oi, (gi, oi)
+
+
+def test_icp_with_normals_build_model_configuration(ctx, orc, synth, cuda_lib, small_model):
+    """BuildModel's getIcpNormal (BM/src/regmeshpcd.cpp:104-208): normals k = 12, normal shooting k = 20, surface-normal
+    rejector, TransformationEstimationPointToPlane (LM), eps 1e-8 — on neighbouring turntable views; and the default estimator
+    of IterativeClosestPointWithNormals (LLS) with the same chain."""
+    T = cuda_lib.T
+    views = synth.turntable_views(small_model, n_views=36, first=2)
+    (sp, _), (tp, _) = views
+    sn, tn = orc.normals_knn(sp, 12), orc.normals_knn(tp, 12)
+    for te, iters in ((T.TE_POINT_TO_PLANE, 40), (T.TE_POINT_TO_PLANE_LLS, 40)):
+        kw = dict(max_iterations=iters, transformation_epsilon=1e-8, euclidean_fitness_epsilon=1e-8, estimator=T.EST_NORMAL_SHOOTING,
+                  k_search=20, rejectors=[(T.REJ_SURFACE_NORMAL, 0.7)], with_normals=1, transformation=te)
+        cs, ct = ctx.upload(sp, sn), ctx.upload(tp, tn)
+        g, aligned = ctx.icp(cs, ct, cuda_lib.icp_params(**kw), want_aligned=True)
+        o = orc.icp(sp, tp, orc.icp_params(**kw), src_normals=sn, tgt_normals=tn)
+        _pose_close(synth, T, g.T, o.T)
+        assert g.converged == o.converged and g.state == o.state and g.iterations == o.iterations
+        assert g.n_correspondences == o.n_correspondences
+        assert np.allclose(aligned.download(), synth.apply(T.mat4(g.T), sp), atol=2e-6)
+        # the estimate is a real registration: the relative pose of the two views, to the accuracy a 10 degree step allows
+        truth = views[1][1] @ np.linalg.inv(views[0][1])
+        r, t = synth.pose_error(T.mat4(g.T), truth)
+        assert r < np.deg2rad(3.0) and t < 0.01, (te, r, t)

@@ -244,3 +244,38 @@ def test_pose_estimator_state_machine(orc, synth, model):
     s2 = model[:1000].copy()
     b = pe2.estimate_final(s2, np.zeros((0, 3), np.float32))
     assert b.ran_coarse == 0 and np.array_equal(orc.T.mat4(b.final_pose)[:3, :3].round(5), np.eye(3, dtype=np.float32))
+
+
+def test_point_to_plane_estimators_recover_a_known_transform(orc, synth, small_model):
+    """TransformationEstimationPointToPlane (LM) recovers an exact small motion to float accuracy in a handful of iterations;
+    the LLS estimator (small-angle linearisation, one shot) lands within its linearisation error; fewer than 4 pairs give the
+    identity for LM (transformation_estimation_lm.hpp)."""
+    T = orc.T
+    rng = np.random.default_rng(5)
+    tgt = (small_model[rng.permutation(len(small_model))[:5000]] + np.array([0, 0, 0.9], np.float32)).astype(np.float32)
+    tn = orc.normals_knn(tgt, 12)
+    M = synth.small_pose(rng, 2.0, 0.004)
+    src = synth.apply(np.linalg.inv(M), tgt).astype(np.float32)
+    lm, info = orc.point_to_plane(src, tgt, tn, kind=T.TE_POINT_TO_PLANE, want_info=True)
+    r, t = synth.pose_error(lm, M)
+    assert r < 2e-5 and t < 2e-5, (r, t)
+    assert info[0] in (1, 2, 3) and info[2] <= 8 and info[1] < 80, info     # converged by a tolerance test, quickly
+    lls = orc.point_to_plane(src, tgt, tn, kind=T.TE_POINT_TO_PLANE_LLS)
+    r, t = synth.pose_error(lls, M)
+    assert r < 2e-3 and t < 2e-3, (r, t)
+    few = orc.point_to_plane(src[:3], tgt[:3], tn[:3], kind=T.TE_POINT_TO_PLANE)
+    assert np.array_equal(few, np.eye(4))
+
+
+def test_icp_build_model_configuration_registers_neighbouring_views(orc, synth, small_model):
+    """BM/src/regmeshpcd.cpp:104-208 on two turntable views 10 degrees apart: the LM point-to-plane loop converges to the true
+    relative pose."""
+    T = orc.T
+    views = synth.turntable_views(small_model, n_views=36, first=2)
+    (sp, A), (tp, B) = views
+    sn, tn = orc.normals_knn(sp, 12), orc.normals_knn(tp, 12)
+    kw = dict(max_iterations=40, transformation_epsilon=1e-8, euclidean_fitness_epsilon=1e-8, estimator=T.EST_NORMAL_SHOOTING,
+              k_search=20, rejectors=[(T.REJ_SURFACE_NORMAL, 0.7)], with_normals=1, transformation=T.TE_POINT_TO_PLANE)
+    o = orc.icp(sp, tp, orc.icp_params(**kw), src_normals=sn, tgt_normals=tn)
+    r, t = synth.pose_error(T.mat4(o.T), B @ np.linalg.inv(A))
+    assert r < np.deg2rad(3.0) and t < 0.01, (r, t)
