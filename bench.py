@@ -358,6 +358,22 @@ def pipeline_numbers(ctx, cuda_lib, synth, model, stream, torch, n_gpu_frames=12
     e1.record(stream)
     torch.cuda.synchronize()
     e2e_fps = n_gpu_frames / (e0.elapsed_time(e1) / 1e3)
+    # batched (C5): ope_pose_batch, worker threads with their own streams, the frame-invariant model side cached
+    n_batch, workers = 256, 8
+    batch = {}
+    for host in (False, True):
+        inputs = [(frames if host else targets)[f % n_gpu_frames] for f in range(n_batch)]
+        tb = [tables[f % n_gpu_frames] for f in range(n_batch)]
+        ctx.pose_batch(model, inputs[:32], tables=tb[:32], workers=workers)   # warm the worker contexts
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        res, status = ctx.pose_batch(model, inputs, tables=tb, workers=workers)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        assert (status == 0).all()
+        batch["e2e_frames_per_sec" if host else "frames_per_sec"] = n_batch / (e0.elapsed_time(e1) / 1e3)
+    batch.update({"frames": n_batch, "workers": workers, "api": "ope_pose_batch"})
     # CPU oracle, one core
     t0 = time.perf_counter()
     for f in range(n_cpu_frames):
@@ -368,6 +384,7 @@ def pipeline_numbers(ctx, cuda_lib, synth, model, stream, torch, n_gpu_frames=12
     return {"workload": "C1: estimateFinalPose, 157825-point model vs segmented cluster of a synthetic 640x480 frame, "
                         "UniformSampling 1 cm / 8 mm, FPFH r=0.03, SAC-IA 400x5, ICP-with-normals <=100 it",
             "frames_per_sec": dev_fps, "e2e_frames_per_sec": e2e_fps, "cpu_frames_per_sec": cpu_fps, "cpu_cores": 1,
+            "batched": batch,
             "stage_ms_per_frame": (stage / n_gpu_frames).round(4).tolist(),
             "stage_names": ["downsample", "normals", "fpfh", "sacia", "icp", "fitness", "umeyama+transforms", "total"]}
 

@@ -161,6 +161,18 @@ int ope_pose_estimate_final_device(ope_pose_tracker* t, ope_cloud** source, cons
  * [0] down-sample [1] normals [2] fpfh [3] sac-ia [4] icp [5] fitness [6] dense umeyama + transforms [7] total) */
 int ope_pose_stage_ms(const ope_pose_tracker* t, double out[8]);
 
+/* Batched localisation of independent frames against one model (BASELINE.json configs[4]; SURVEY 8e row 1 + 8f-3): every
+ * frame runs the FIRST-frame path of estimateFinalPose (coarse SAC-IA + fine ICP, a fresh PoseEstimator per frame) with the
+ * full-resolution model as the source. `workers` host threads, each with its own stream and scratch memory, pull frames from a
+ * shared counter so that the small kernels of different frames overlap on the device; the frame-invariant model side (1 cm
+ * sample, normals, FPFH — recomputed per frame by the reference, D&L/src/poseestimator.cpp:34,116) is computed once.
+ * tables: n_frames pre-drawn SAC-IA decision tables, or NULL to draw them here, in frame order, from libc rand() (one
+ * 400 x 5 draw per frame, exactly the stream a serial loop over fresh PoseEstimators would consume).
+ * results: n_frames records; status: n_frames return codes (OPE_OK or the error of that frame) or NULL.
+ * Returns OPE_OK when every frame succeeded, else the first failing frame's code. */
+int ope_pose_batch(ope_ctx* ctx, const ope_pose_params* prm, const float* model_xyz, size_t n_model, const ope_frame_input* frames,
+                   size_t n_frames, const ope_rng_table* tables, int workers, ope_pose_result* results, int32_t* status);
+
 /* defaults of the reference classes (include/ope_types.h) */
 void ope_icp_params_default(ope_icp_params* p);
 void ope_sacia_params_default(ope_sacia_params* p);

@@ -166,6 +166,16 @@ typedef struct ope_pose_result {
   double sacia_best_error;
 } ope_pose_result;
 
+/* One frame of a batch (ope_pose_batch): the segmented scene cluster either as host points (stride/offset in BYTES as in
+ * ope_cloud_upload) or, when points == NULL, as a device-resident cloud that no other call touches during the batch. */
+typedef struct ope_frame_input {
+  const void* points;
+  size_t n;
+  size_t stride;
+  size_t offset;
+  void* cloud;             /* ope_cloud* */
+} ope_frame_input;
+
 #ifdef __cplusplus
 }
 #endif

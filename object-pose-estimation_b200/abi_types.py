@@ -115,6 +115,10 @@ class PoseResult(C.Structure):
     ]
 
 
+class FrameInput(C.Structure):
+    _fields_ = [("points", C.c_void_p), ("n", C.c_size_t), ("stride", C.c_size_t), ("offset", C.c_size_t), ("cloud", C.c_void_p)]
+
+
 def mat4(c_arr):
     """column-major float[16] -> numpy (4,4) row/col indexed like Eigen's M(r,c)."""
     import numpy as np

@@ -333,16 +333,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  static const EncodeTiledFn fn = []() -> EncodeTiledFn {   // initialised once, thread-safe (batch workers call this concurrently)
     void* p = nullptr;
     cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
         qres == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  }
+      return (EncodeTiledFn)p;
+    return nullptr;
+  }();
   return fn;
 }
 // [rows, 128] bf16 row-major operand, box = 64 elements (128 bytes) x box_rows, 128-byte swizzle

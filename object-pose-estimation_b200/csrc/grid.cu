@@ -526,10 +526,18 @@ int ope_ctx_create(int device, void* stream, ope_ctx** out) {
   }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-    uint64_t thr = ~0ull;
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  {
+    cudaMemPoolProps props;
+    std::memset(&props, 0, sizeof(props));
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    uint64_t thr = ~0ull;   // keep everything cached: steady-state calls do not allocate
+    if (cudaMemPoolCreate(&ctx->pool, &props) == cudaSuccess) cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    else { cudaGetLastError(); ctx->pool = nullptr; }
+    cudaMemPool_t dflt;
+    if (!ctx->pool && cudaDeviceGetDefaultMemPool(&dflt, device) == cudaSuccess) cudaMemPoolSetAttribute(dflt, cudaMemPoolAttrReleaseThreshold, &thr);
   }
   ctx->pinned_bytes = 1 << 16;
   if (cudaHostAlloc(&ctx->pinned, ctx->pinned_bytes, cudaHostAllocDefault) != cudaSuccess) {
@@ -567,7 +575,10 @@ void ope_ctx_destroy(ope_ctx* ctx) {
     for (int j = 0; j < 2; ++j) if (ctx->kev[w][j]) cudaEventDestroy(ctx->kev[w][j]);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->stage) cudaFreeHost(ctx->stage);
+  for (ope_ctx* w : ctx->workers) ope_ctx_destroy(w);
+  ctx->workers.clear();
   if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->pool) cudaMemPoolDestroy(ctx->pool);   // allocations still held by live clouds keep their memory until freed
   delete ctx;
 }
 

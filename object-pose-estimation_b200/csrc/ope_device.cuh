@@ -200,64 +200,83 @@ template <> struct t_consts<double> {
   static OPE_HD double dummy_precision() { return 1e-12; }
 };
 
+// One-sided Jacobi rotation of the column pair (ap, aq) of A and the matching columns (vp, vq) of V. Returns whether it rotated.
+// Every index is a compile-time constant after inlining, so A and V live in registers (a dynamically indexed local array
+// would put the whole 3x3 state in local memory and make every access of this serial section an L1 round trip).
+template <typename T>
+OPE_HD bool svd3_rotate(T* ap, T* aq, T* vp, T* vq, T eps2) {
+  const T alpha = ap[0] * ap[0] + ap[1] * ap[1] + ap[2] * ap[2];
+  const T beta = aq[0] * aq[0] + aq[1] * aq[1] + aq[2] * aq[2];
+  const T gamma = ap[0] * aq[0] + ap[1] * aq[1] + ap[2] * aq[2];
+  if (gamma == 0 || gamma * gamma <= eps2 * (alpha * beta)) return false;  // sqrt-free relative test
+  const T zeta = (beta - alpha) / (2 * gamma);
+  const T t = (zeta >= 0 ? (T)1 : (T)-1) / (t_abs(zeta) + t_sqrt<T>(1 + zeta * zeta));
+  const T c = 1 / t_sqrt<T>(1 + t * t);
+  const T s = c * t;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int i = 0; i < 3; ++i) {
+    const T x = ap[i], y = aq[i];
+    ap[i] = c * x - s * y; aq[i] = s * x + c * y;
+    const T vx = vp[i], vy = vq[i];
+    vp[i] = c * vx - s * vy; vq[i] = s * vx + c * vy;
+  }
+  return true;
+}
+// exchange columns i and j (of A, V and the norms) when the later one is strictly larger
+template <typename T>
+OPE_HD void svd3_order(T* ni, T* nj, T* ai, T* aj, T* vi, T* vj) {
+  if (*nj > *ni) {
+    T t = *ni; *ni = *nj; *nj = t;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int k = 0; k < 3; ++k) { t = ai[k]; ai[k] = aj[k]; aj[k] = t; t = vi[k]; vi[k] = vj[k]; vj[k] = t; }
+  }
+}
+
 template <typename T>
 OPE_HD void svd3(const T Ain[9], T U[9], T S[3], T V[9]) {
   T A[9];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
   for (int i = 0; i < 9; ++i) { A[i] = Ain[i]; V[i] = 0; }
   V[0] = V[4] = V[8] = 1;
   const T eps2 = t_consts<T>::jac_eps() * t_consts<T>::jac_eps();
   for (int sweep = 0; sweep < 15; ++sweep) {
-    bool rotated = false;
-    for (int p = 0; p < 2; ++p)
-      for (int q = p + 1; q < 3; ++q) {
-        T* ap = A + 3 * p; T* aq = A + 3 * q;
-        T alpha = ap[0] * ap[0] + ap[1] * ap[1] + ap[2] * ap[2];
-        T beta = aq[0] * aq[0] + aq[1] * aq[1] + aq[2] * aq[2];
-        T gamma = ap[0] * aq[0] + ap[1] * aq[1] + ap[2] * aq[2];
-        if (gamma == 0 || gamma * gamma <= eps2 * (alpha * beta)) continue;  // sqrt-free relative test
-        rotated = true;
-        T zeta = (beta - alpha) / (2 * gamma);
-        T t = (zeta >= 0 ? (T)1 : (T)-1) / (t_abs(zeta) + t_sqrt<T>(1 + zeta * zeta));
-        T c = 1 / t_sqrt<T>(1 + t * t);
-        T s = c * t;
-        for (int i = 0; i < 3; ++i) {
-          T x = ap[i], y = aq[i];
-          ap[i] = c * x - s * y; aq[i] = s * x + c * y;
-          T vx = V[3 * p + i], vy = V[3 * q + i];
-          V[3 * p + i] = c * vx - s * vy; V[3 * q + i] = s * vx + c * vy;
-        }
-      }
+    bool rotated = svd3_rotate<T>(A + 0, A + 3, V + 0, V + 3, eps2);   // (p, q) = (0, 1), (0, 2), (1, 2)
+    rotated = svd3_rotate<T>(A + 0, A + 6, V + 0, V + 6, eps2) || rotated;
+    rotated = svd3_rotate<T>(A + 3, A + 6, V + 3, V + 6, eps2) || rotated;
     if (!rotated) break;
   }
-  T nrm[3];
-  for (int j = 0; j < 3; ++j)
-    nrm[j] = t_sqrt<T>(A[3 * j] * A[3 * j] + A[3 * j + 1] * A[3 * j + 1] + A[3 * j + 2] * A[3 * j + 2]);
-  int ord[3] = {0, 1, 2};
-  for (int i = 0; i < 2; ++i)
-    for (int j = i + 1; j < 3; ++j)
-      if (nrm[ord[j]] > nrm[ord[i]]) { int t = ord[i]; ord[i] = ord[j]; ord[j] = t; }
-  T Vs[9];
-  for (int j = 0; j < 3; ++j) {
-    int o = ord[j];
-    S[j] = nrm[o];
-    for (int i = 0; i < 3; ++i) { Vs[3 * j + i] = V[3 * o + i]; U[3 * j + i] = A[3 * o + i]; }
-  }
-  for (int i = 0; i < 9; ++i) V[i] = Vs[i];
+  // singular values = column norms, sorted descending by the exchanges (0,1), (0,2), (1,2) (strict >: ties keep their order)
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int j = 0; j < 3; ++j) S[j] = t_sqrt<T>(A[3 * j] * A[3 * j] + A[3 * j + 1] * A[3 * j + 1] + A[3 * j + 2] * A[3 * j + 2]);
+  svd3_order<T>(S + 0, S + 1, A + 0, A + 3, V + 0, V + 3);
+  svd3_order<T>(S + 0, S + 2, A + 0, A + 6, V + 0, V + 6);
+  svd3_order<T>(S + 1, S + 2, A + 3, A + 6, V + 3, V + 6);
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int i = 0; i < 9; ++i) U[i] = A[i];
   const T tiny = S[0] * t_consts<T>::tiny_rel();
-  if (S[0] > 0) { for (int i = 0; i < 3; ++i) U[i] /= S[0]; }
+  if (S[0] > 0) { U[0] /= S[0]; U[1] /= S[0]; U[2] /= S[0]; }
   else { U[0] = 1; U[1] = 0; U[2] = 0; }
-  if (S[1] > tiny) { for (int i = 0; i < 3; ++i) U[3 + i] /= S[1]; }
+  if (S[1] > tiny) { U[3] /= S[1]; U[4] /= S[1]; U[5] /= S[1]; }
   else {
     int k = 0;
-    if (t_abs(U[1]) < t_abs(U[k])) k = 1;
-    if (t_abs(U[2]) < t_abs(U[k])) k = 2;
-    T e[3] = {0, 0, 0}; e[k] = 1;
-    T d = U[k];
-    T w[3] = {e[0] - d * U[0], e[1] - d * U[1], e[2] - d * U[2]};
-    T n = t_sqrt<T>(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
-    for (int i = 0; i < 3; ++i) U[3 + i] = w[i] / n;
+    if (t_abs(U[1]) < t_abs(U[k == 0 ? 0 : 1])) k = 1;
+    if (t_abs(U[2]) < t_abs(k == 0 ? U[0] : U[1])) k = 2;
+    const T d = k == 0 ? U[0] : (k == 1 ? U[1] : U[2]);
+    const T w0 = (k == 0 ? (T)1 : (T)0) - d * U[0], w1 = (k == 1 ? (T)1 : (T)0) - d * U[1], w2 = (k == 2 ? (T)1 : (T)0) - d * U[2];
+    const T n = t_sqrt<T>(w0 * w0 + w1 * w1 + w2 * w2);
+    U[3] = w0 / n; U[4] = w1 / n; U[5] = w2 / n;
   }
-  if (S[2] > tiny) { for (int i = 0; i < 3; ++i) U[6 + i] /= S[2]; }
+  if (S[2] > tiny) { U[6] /= S[2]; U[7] /= S[2]; U[8] /= S[2]; }
   else {
     U[6] = U[1] * U[5] - U[2] * U[4];
     U[7] = U[2] * U[3] - U[0] * U[5];

@@ -15,6 +15,8 @@ struct ope_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool owns_stream = false;
+  cudaMemPool_t pool = nullptr;   // this context's own stream-ordered pool: allocations of concurrent contexts (ope_pose_batch
+                                  // workers) never wait on each other's frees
   int sm_count = 148;
   int64_t launches = 0;
   std::string error;
@@ -24,6 +26,8 @@ struct ope_ctx {
   size_t stage_bytes = 0;
   cudaEvent_t kev[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};  // [which][begin/end] around the dominant kernels
   bool kev_valid[3] = {false, false, false};
+  std::vector<ope_ctx*> workers;  // ope_pose_batch: per-thread contexts (own stream, pool, staging), kept warm between calls
+  int icp_max_blocks = 0;      // > 0: cap of the cooperative icp_kernel grid (batch workers share the SMs between frames)
   int64_t feature_knn_gemm_queries = 0;  // queries answered through the tcgen05 distance GEMM ...
   int64_t feature_knn_fallbacks = 0;     // ... of which the exact kernel had to re-answer (candidate set not provably complete)
 };
@@ -90,7 +94,8 @@ template <typename T>
 inline int dalloc(ope_ctx* ctx, T** p, size_t count) {
   *p = nullptr;
   if (count == 0) count = 1;
-  OPE_CUDA_TRY(ctx, cudaMallocAsync((void**)p, count * sizeof(T), ctx->stream));
+  if (ctx->pool) OPE_CUDA_TRY(ctx, cudaMallocFromPoolAsync((void**)p, count * sizeof(T), ctx->pool, ctx->stream));
+  else OPE_CUDA_TRY(ctx, cudaMallocAsync((void**)p, count * sizeof(T), ctx->stream));
   return OPE_OK;
 }
 template <typename T>

@@ -512,4 +512,55 @@ __device__ __forceinline__ int warp_knn_smem(const float4* tg, int nt, int n_fin
   return cnt;
 }
 
+// The same result when a TIGHT bound on the k-th distance is known (the ICP loop: the previous iteration's k neighbours at the
+// query's new position), without the serial insertion chain: pass 1 compacts the few points within the bound into a per-warp
+// shared buffer (ballot + popc, no dependency between steps except the running count), pass 2 ranks them all-against-all
+// (broadcast reads) and scatters the k best into sorted order. (d2, index) pairs are distinct, so the ranks are a permutation
+// and the list equals warp_knn_smem's exactly. buf: kKnnBufCap + 32 float2 entries owned by this warp. Falls back to the
+// insertion scan when the bound admits more than kKnnBufCap points or fewer than k.
+static constexpr int kKnnBufCap = 64;
+__device__ __forceinline__ int warp_knn_smem_bounded(const float4* tg, int nt, int n_finite, bool active, float qx, float qy, float qz,
+                                                     int k, float bound, float2* buf, float& ld, int& li) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  if (k > n_finite) k = n_finite;
+  if (!(active && k > 0)) { ld = FLT_MAX; li = 0x7fffffff; return 0; }
+  if (!(bound < FLT_MAX)) return warp_knn_smem(tg, nt, n_finite, active, qx, qy, qz, k, bound, ld, li);
+  const unsigned lt = (1u << lane) - 1u;
+  int c = 0;
+#pragma unroll 4
+  for (int base = 0; base < nt; base += 32) {
+    const int j = base + lane;
+    float d2 = FLT_MAX;
+    bool cand = false;
+    if (j < nt) {
+      const float4 t = tg[j];
+      d2 = dist2(qx, qy, qz, t.x, t.y, t.z);
+      cand = finite3(t.x, t.y, t.z) && d2 <= bound;
+    }
+    const unsigned m = __ballot_sync(full, cand);
+    if (cand) { const int pos = c + __popc(m & lt); if (pos < kKnnBufCap) buf[pos] = make_float2(d2, __int_as_float(j)); }
+    c += __popc(m);
+  }
+  if (c > kKnnBufCap || c < k) return warp_knn_smem(tg, nt, n_finite, active, qx, qy, qz, k, bound, ld, li);
+  __syncwarp();
+  float2* sorted = buf + kKnnBufCap;
+#pragma unroll
+  for (int h = 0; h < kKnnBufCap / 32; ++h) {
+    const int e = lane + 32 * h;
+    if (e < c) {
+      const float2 mine = buf[e];
+      const int mi = __float_as_int(mine.y);
+      int rank = 0;
+      for (int t = 0; t < c; ++t) { const float2 o = buf[t]; rank += nb_less(o.x, __float_as_int(o.y), mine.x, mi) ? 1 : 0; }
+      if (rank < 32) sorted[rank] = mine;
+    }
+  }
+  __syncwarp();
+  ld = FLT_MAX; li = 0x7fffffff;
+  if (lane < k) { const float2 r = sorted[lane]; ld = r.x; li = __float_as_int(r.y); }
+  __syncwarp();   // the buffer is reused by this warp's next query
+  return k;
+}
+
 }  // namespace ope

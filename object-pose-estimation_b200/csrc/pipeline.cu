@@ -3,7 +3,9 @@
 // Every stage is a call into the kernels of grid.cu / features.cu / registration.cu; only sizes, the 4x4s and the
 // scores cross back to the host between stages.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <thread>
 
 #include "ope_host.cuh"
 
@@ -18,6 +20,12 @@ struct ope_pose_tracker {
   ope_cloud* alignedSource = nullptr;
   ope_cloud* cloudModel = nullptr;
   double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  bool timing = true;              // per-stage CUDA-event laps (each lap synchronises); the batch path turns them off
+  // frame-invariant model side of the coarse stage: the 1 cm sample of the pristine model with its normals,
+  // and its FPFH descriptors. Not owned. Used by the first call of this tracker only (the source IS the model then).
+  const ope_cloud* cache_sp = nullptr;
+  const float* cache_fs = nullptr;
+  size_t cache_model_n = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evt0 = nullptr, evt1 = nullptr;
 };
 
@@ -39,9 +47,10 @@ int clone_cloud(ope_ctx* ctx, const ope_cloud* in, ope_cloud** out) {
 
 struct StageTimer {
   ope_pose_tracker* t;
-  explicit StageTimer(ope_pose_tracker* tr) : t(tr) { cudaEventRecord(t->ev0, t->ctx->stream); }
+  explicit StageTimer(ope_pose_tracker* tr) : t(tr) { if (t->timing) cudaEventRecord(t->ev0, t->ctx->stream); }
   // closes the current interval into slot `s` and starts the next one
   void lap(int s) {
+    if (!t->timing) return;
     cudaEventRecord(t->ev1, t->ctx->stream);
     cudaEventSynchronize(t->ev1);
     float ms = 0;
@@ -139,19 +148,34 @@ int ope_pose_estimate_final_device(ope_pose_tracker* t, ope_cloud** source, cons
   if (nt != 0 && t->fitnessScoreFine > P.coarse_refit_threshold) {
     res->ran_coarse = 1;
     CloudGuard sp(ctx), tp(ctx);
-    OPE_TRY(sub_sample_and_normals(t, tm, p_source, P.coarse_leaf, &sp.c));
-    OPE_TRY(sub_sample_and_normals(t, tm, const_cast<ope_cloud*>(target), P.coarse_leaf, &tp.c));
     DevGuard fs(ctx), ft(ctx);
-    OPE_TRY(fpfh_device(ctx, sp.c, P.fpfh_radius, &fs.p, nullptr));
+    // the model side is frame-invariant: with a cache attached the first call of a tracker reuses the model's
+    // coarse sample, normals and descriptors instead of recomputing them as the reference does every frame (:34,116)
+    const bool cached = t->cache_sp && t->cache_fs && t->firstTimePose == 1 && t->cache_model_n == p_source->n;
+    ope_cloud sp_view;
+    const ope_cloud* spc = nullptr;
+    const float* fsp = nullptr;
+    if (cached) {
+      sp_view = *t->cache_sp;      // shallow view: shared device arrays, private (empty) grid cache
+      sp_view.ctx = ctx; sp_view.grids.clear();
+      spc = &sp_view; fsp = t->cache_fs;
+    } else {
+      OPE_TRY(sub_sample_and_normals(t, tm, p_source, P.coarse_leaf, &sp.c));
+      spc = sp.c;
+    }
+    OPE_TRY(sub_sample_and_normals(t, tm, const_cast<ope_cloud*>(target), P.coarse_leaf, &tp.c));
+    if (!cached) { OPE_TRY(fpfh_device(ctx, sp.c, P.fpfh_radius, &fs.p, nullptr)); fsp = fs.p; }
     OPE_TRY(fpfh_device(ctx, tp.c, P.fpfh_radius, &ft.p, nullptr));
     tm.lap(2);
-    res->n_src_coarse = (int32_t)sp.c->n; res->n_tgt_coarse = (int32_t)tp.c->n;
+    res->n_src_coarse = (int32_t)spc->n; res->n_tgt_coarse = (int32_t)tp.c->n;
     if (t->alignedSource) { ope_cloud_free(ctx, t->alignedSource); t->alignedSource = nullptr; }
     if ((int)tp.c->n < P.min_target_features) {
       OPE_TRY(clone_cloud(ctx, p_source, &t->alignedSource));  // :41
     } else {
       ope_reg_result rr;
-      OPE_TRY(sacia_device(ctx, sp.c, fs.p, tp.c, ft.p, P.sacia, table, nullptr, &rr, nullptr));
+      int src_rc = sacia_device(ctx, spc, fsp, tp.c, ft.p, P.sacia, table, nullptr, &rr, nullptr);
+      if (cached) ope_cloud_invalidate(ctx, &sp_view);   // drop whatever index the view acquired
+      OPE_TRY(src_rc);
       tm.lap(3);
       std::memcpy(coarse.m, rr.T, sizeof(coarse.m));
       res->sacia_best_iteration = rr.best_iteration; res->sacia_best_error = rr.best_error;
@@ -210,6 +234,128 @@ int ope_pose_estimate_final_device(ope_pose_tracker* t, ope_cloud** source, cons
   float ms = 0;
   cudaEventElapsedTime(&ms, t->evt0, t->evt1);
   t->stage_ms[7] = ms;
+  return OPE_OK;
+}
+
+// ---- batched first-frame localisation (C5) ----------------------------------------------------------------------------------
+namespace {
+
+struct BatchShared {
+  const ope_pose_params* prm;
+  const ope_cloud* model;        // full-resolution model (read-only, device)
+  const ope_cloud* sp;           // its coarse sample with normals (read-only)
+  const float* fs;               // FPFH of sp (read-only, device)
+  const ope_frame_input* frames;
+  size_t n_frames;
+  const ope_rng_table* tables;
+  ope_pose_result* results;
+  int32_t* status;
+  std::atomic<size_t> next{0};
+  int device = 0;
+  int icp_blocks = 0;
+};
+
+void batch_worker(BatchShared* S, ope_ctx* ctx, int* first_error, std::string* first_message) {
+  int rc = OPE_OK;
+  cudaSetDevice(S->device);
+  ctx->icp_max_blocks = S->icp_blocks;
+  for (;;) {
+    const size_t f = S->next.fetch_add(1);
+    if (f >= S->n_frames) break;
+    const ope_frame_input& in = S->frames[f];
+    ope_pose_tracker* t = nullptr;
+    rc = ope_pose_tracker_create(ctx, S->prm, &t);
+    ope_cloud* src = nullptr;
+    ope_cloud* tgt_owned = nullptr;
+    const ope_cloud* tgt = nullptr;
+    if (rc == OPE_OK) {
+      t->timing = false;
+      t->cache_sp = S->sp; t->cache_fs = S->fs; t->cache_model_n = S->model->n;
+      rc = clone_cloud(ctx, S->model, &src);
+    }
+    if (rc == OPE_OK) {
+      if (in.points) {
+        if (in.n > 0) rc = ope_cloud_upload(ctx, in.points, in.n, in.stride, in.offset, nullptr, 0, 0, &tgt_owned);
+        tgt = tgt_owned;
+      } else {
+        tgt = (const ope_cloud*)in.cloud;
+      }
+    }
+    if (rc == OPE_OK) rc = ope_pose_estimate_final_device(t, &src, tgt, S->tables ? &S->tables[f] : nullptr, &S->results[f]);
+    if (rc != OPE_OK && *first_error == OPE_OK) { *first_error = rc; *first_message = ctx->error; }
+    if (S->status) S->status[f] = rc;
+    if (src) ope_cloud_free(ctx, src);
+    if (tgt_owned) ope_cloud_free(ctx, tgt_owned);
+    if (t) ope_pose_tracker_destroy(t);
+  }
+  ope_ctx_synchronize(ctx);
+}
+
+}  // namespace
+
+int ope_pose_batch(ope_ctx* ctx, const ope_pose_params* prm, const float* model_xyz, size_t n_model, const ope_frame_input* frames,
+                   size_t n_frames, const ope_rng_table* tables, int workers, ope_pose_result* results, int32_t* status) {
+  if (!ctx || !model_xyz || n_model == 0 || (!frames && n_frames) || !results) return OPE_ERR_INVALID;
+  if (n_frames == 0) return OPE_OK;
+  ope_pose_params P;
+  if (prm) P = *prm; else ope_pose_params_default(&P);
+  workers = std::max(1, std::min<int>(workers > 0 ? workers : 8, (int)std::min<size_t>(n_frames, 64)));
+  // ---- the frame-invariant model side, once ----
+  CloudGuard model(ctx), sp(ctx);
+  DevGuard fs(ctx);
+  OPE_TRY(ope_cloud_upload(ctx, model_xyz, n_model, 12, 0, nullptr, 0, 0, &model.c));
+  {
+    ope_pose_tracker tmp;
+    tmp.ctx = ctx; tmp.prm = P; tmp.timing = false;
+    StageTimer tm(&tmp);
+    OPE_TRY(sub_sample_and_normals(&tmp, tm, model.c, P.coarse_leaf, &sp.c));
+    OPE_TRY(fpfh_device(ctx, sp.c, P.fpfh_radius, &fs.p, nullptr));
+  }
+  // ---- SAC-IA decision tables: replayed, or drawn here in frame order from libc rand() ----
+  std::vector<int32_t> draw_s, draw_p;
+  std::vector<ope_rng_table> drawn;
+  if (!tables) {
+    const int H = P.sacia.max_iterations, S = P.sacia.nr_samples, K = P.sacia.k_correspondences;
+    if (H < 1 || S < 1 || K < 1) return fail(ctx, OPE_ERR_INVALID, "bad SAC-IA parameters");
+    std::vector<float> xyz(3 * std::max<size_t>(sp.c->n, 1));
+    OPE_TRY(ope_cloud_download(ctx, sp.c, xyz.data(), nullptr));
+    draw_s.resize(n_frames * (size_t)H * S); draw_p.resize(n_frames * (size_t)H * S);
+    drawn.resize(n_frames);
+    for (size_t f = 0; f < n_frames; ++f) {
+      float msd = P.sacia.min_sample_distance;   // min_sample_distance_ halves within one align() only
+      int32_t* s = draw_s.data() + f * (size_t)H * S;
+      int32_t* p = draw_p.data() + f * (size_t)H * S;
+      const int rc = ope_sacia_draw(xyz.data(), sp.c->n, 12, H, S, K, &msd, s, p);
+      if (rc != OPE_OK) return fail(ctx, rc, "selectSamples failed");
+      drawn[f] = ope_rng_table{H, S, s, p};
+    }
+    tables = drawn.data();
+  }
+  OPE_TRY(ope_ctx_synchronize(ctx));   // the workers read the model side from their own streams
+  BatchShared S;
+  S.prm = &P; S.model = model.c; S.sp = sp.c; S.fs = fs.p; S.frames = frames; S.n_frames = n_frames; S.tables = tables;
+  S.results = results; S.status = status; S.device = ctx->device;
+  {
+    // the fused ICP loop is a cooperative launch: its blocks must all be co-resident, so concurrent frames only overlap if
+    // each takes a share of the SMs
+    const char* e = std::getenv("OPE_BATCH_ICP_BLOCKS");
+    S.icp_blocks = e ? std::atoi(e) : std::max(8, ctx->sm_count / std::min(workers, 8));
+  }
+  std::vector<int> errs(workers, OPE_OK);
+  std::vector<std::string> msgs(workers);
+  while ((int)ctx->workers.size() < workers) {
+    ope_ctx* w = nullptr;
+    const int rc = ope_ctx_create(ctx->device, nullptr, &w);
+    if (rc != OPE_OK) return fail(ctx, rc, "worker context creation failed");
+    ctx->workers.push_back(w);
+  }
+  std::vector<std::thread> pool;
+  for (int w = 1; w < workers; ++w) pool.emplace_back(batch_worker, &S, ctx->workers[w], &errs[w], &msgs[w]);
+  batch_worker(&S, ctx->workers[0], &errs[0], &msgs[0]);
+  for (auto& th : pool) th.join();
+  cudaSetDevice(ctx->device);
+  for (int w = 0; w < workers; ++w)
+    if (errs[w] != OPE_OK) return fail(ctx, errs[w], "batch worker %d: %s", w, msgs[w].c_str());
   return OPE_OK;
 }
 

@@ -13,6 +13,9 @@
 #include <cmath>
 #include <cstdlib>
 
+#include <map>
+#include <mutex>
+
 #include "ope_host.cuh"
 #include "ope_octet.cuh"
 
@@ -203,6 +206,7 @@ static constexpr int kIcpSplitMin = 6144;   // far queries with more candidate p
 
 struct IcpSmem {
   OctStack wstack[kIcpWarps];   // one traversal stack per warp (far queries / k-NN)
+  float2 knn_buf[kIcpWarps][kKnnBufCap + 32];   // warp_knn_smem_bounded: candidates within the bound + the sorted k best
   LeafList leaves[kIcpWarps];   // collected leaf ranges of the warp's far query
   int dir[kDirEntries];         // upper levels of the target's implicit octree (coop_nn1_far)
   Nn1Smem<kIcpThreads> nn;      // only the one-pass kernel uses the block-local variant
@@ -303,7 +307,7 @@ __device__ __forceinline__ int icp_gate(const IcpDev& a, int s, int orig, const 
 // CorrespondenceEstimationNormalShooting: one source point per WARP. Among the k nearest, the one with the smallest
 // squared distance to the line through p along the source normal (double); the first minimum in list order wins.
 __device__ __forceinline__ int icp_correspond_shooting(const IcpDev& a, OctStack* st, int s, int orig, const float4 p, bool use_seed,
-                                                       float& d2_out, const float4* tg_smem = nullptr) {
+                                                       float& d2_out, const float4* tg_smem = nullptr, float2* knn_buf = nullptr) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const bool ok = finite3(p.x, p.y, p.z);
@@ -322,7 +326,8 @@ __device__ __forceinline__ int icp_correspond_shooting(const IcpDev& a, OctStack
   }
   float ld;
   int li;
-  const int cnt = tg_smem ? warp_knn_smem(tg_smem, a.n_tgt, a.grid.n, ok, p.x, p.y, p.z, a.k_search, bound, ld, li)
+  const int cnt = tg_smem ? (knn_buf ? warp_knn_smem_bounded(tg_smem, a.n_tgt, a.grid.n, ok, p.x, p.y, p.z, a.k_search, bound, knn_buf, ld, li)
+                                     : warp_knn_smem(tg_smem, a.n_tgt, a.grid.n, ok, p.x, p.y, p.z, a.k_search, bound, ld, li))
                           : warp_knn(a.grid, st, ok, p.x, p.y, p.z, a.k_search, bound, ld, li);
   if (a.seed && lane < a.k_search) a.seed[(size_t)s * a.k_search + lane] = (lane < cnt) ? li : -1;
   int match = -1;
@@ -675,7 +680,7 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_kernel(IcpDev a) {
         const float4 p = a.cur_pts[s];
         const int orig = __float_as_int(p.w);
         float d2 = 0.0f;
-        const int m = icp_correspond_shooting(a, st, s, orig, p, pass > 0, d2, tg_smem);
+        const int m = icp_correspond_shooting(a, st, s, orig, p, pass > 0, d2, tg_smem, sm->knn_buf[warp]);
         if (lane == 0) { a.corr_match[orig] = m; a.corr_d2[orig] = d2; }
         if (m >= 0 && lane < kIcpAcc) {
           const float4 t = tg_smem ? tg_smem[m] : __ldg(a.tgt_pts + m);
@@ -976,8 +981,17 @@ __global__ void sacia_select_kernel(const float* __restrict__ errors, const floa
 
 // ================================================================================================ host ==
 // opt a kernel in to `bytes` of dynamic shared memory (B200: up to 227 KB per block)
+// The dynamic shared memory opt-in is a property of the FUNCTION, shared by every stream and host thread of the process
+// (ope_pose_batch runs several contexts concurrently): only ever raise it, under a lock.
 static int dyn_smem(ope_ctx* ctx, const void* fn, size_t bytes) {
-  OPE_CUDA_TRY(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  static std::mutex mu;
+  static std::map<const void*, size_t> granted;
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& have = granted[fn];
+  if (bytes > have) {
+    OPE_CUDA_TRY(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    have = bytes;
+  }
   return OPE_OK;
 }
 
@@ -1133,7 +1147,8 @@ int icp_device(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const o
   int blocks = 1;
   if (rc == OPE_OK) {
     if (per_sm < 1) rc = fail(ctx, OPE_ERR_CUDA, "icp_kernel cannot be resident");
-    const int max_blocks = std::min(per_sm * ctx->sm_count, kIcpMaxBlocks);
+    int max_blocks = std::min(per_sm * ctx->sm_count, kIcpMaxBlocks);
+    if (ctx->icp_max_blocks > 0) max_blocks = std::min(max_blocks, ctx->icp_max_blocks);
     const size_t want = shooting ? (nw + kIcpWarps - 1) / kIcpWarps : (nw + 127) / 128;
     blocks = (int)std::min<size_t>(std::max<size_t>(1, want), (size_t)max_blocks);
   }

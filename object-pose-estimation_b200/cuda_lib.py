@@ -28,7 +28,7 @@ EXPORTS = [
     "ope_uniform_sample", "ope_uniform_sample_cloud", "ope_voxel_grid",
     "ope_normals_knn", "ope_fpfh", "ope_feature_knn",
     "ope_umeyama", "ope_point_to_plane", "ope_fitness", "ope_correspondences", "ope_icp_align", "ope_sacia_align", "ope_sacia_draw",
-    "ope_pose_tracker_create", "ope_pose_tracker_destroy", "ope_pose_estimate_final", "ope_pose_estimate_final_device",
+    "ope_pose_tracker_create", "ope_pose_tracker_destroy", "ope_pose_estimate_final", "ope_pose_estimate_final_device", "ope_pose_batch",
     "ope_pose_stage_ms", "ope_icp_params_default", "ope_sacia_params_default", "ope_pose_params_default",
 ]
 
@@ -305,6 +305,31 @@ class Context:
         self._chk(lib().ope_fpfh(self.h, cloud.h, C.c_float(r), out.ctypes.data_as(f32p),
                                  sp.ctypes.data_as(f32p) if want_spfh else None))
         return (out, sp) if want_spfh else out
+
+    def pose_batch(self, model, frames, prm=None, tables=None, workers=8):
+        """Batched first-frame localisation (C5). frames: list of host arrays (M, >=3) float32 or device Clouds. Returns
+        (list of PoseResult, status array)."""
+        m = np.ascontiguousarray(model[:, :3], np.float32)
+        n = len(frames)
+        arr = (T.FrameInput * max(n, 1))()
+        keep = []
+        for i, f in enumerate(frames):
+            if isinstance(f, Cloud):
+                arr[i] = T.FrameInput(None, 0, 0, 0, f.h)
+            else:
+                a = _f32(f) if len(f) else np.zeros((1, 3), np.float32)
+                keep.append(a)
+                arr[i] = T.FrameInput(a.ctypes.data, len(f), a.strides[0], 0, None)
+        res = (T.PoseResult * max(n, 1))()
+        status = (C.c_int32 * max(n, 1))()
+        tb = None
+        if tables is not None:
+            tb = (T.RngTable * n)(*tables)
+        rc = lib().ope_pose_batch(self.h, None if prm is None else C.byref(prm), m.ctypes.data_as(f32p), C.c_size_t(len(m)), arr,
+                                  C.c_size_t(n), tb, int(workers), res, status)
+        st = np.array(list(status)[:n], np.int32)
+        self._chk(rc)
+        return [res[i] for i in range(n)], st
 
     # ---- registration ----
     def umeyama(self, src, tgt, isrc=None, itgt=None, n=None):

@@ -436,3 +436,41 @@ def test_icp_with_normals_build_model_configuration(ctx, orc, synth, cuda_lib, s
         truth = views[1][1] @ np.linalg.inv(views[0][1])
         r, t = synth.pose_error(T.mat4(g.T), truth)
         assert r < np.deg2rad(3.0) and t < 0.01, (te, r, t)
+
+
+# ------------------------------------------------------------------------------ batched frames (C5, 8e row 1 + 8f-3) ----
+def test_pose_batch_equals_the_serial_first_frame_path(ctx, orc, synth, cuda_lib, model):
+    """ope_pose_batch (worker threads with their own streams, the model side cached, the ICP grid capped so that frames overlap)
+    returns for every frame what a fresh PoseEstimator returns for it on its own — and what the oracle returns."""
+    import ctypes
+    T = cuda_lib.T
+    libc = ctypes.CDLL(None)
+    frames = [synth.make_frame(model, 900 + f)[0] for f in range(6)]
+    frames.append(np.zeros((0, 3), np.float32))          # an empty cluster: no target, identity poses
+    # serial reference on the device: one fresh tracker per frame, SAC-IA drawing from libc rand() in frame order
+    libc.srand(7)
+    serial = []
+    for cl in frames:
+        tr = cuda_lib.PoseTracker(ctx)
+        src = model.copy()
+        serial.append(tr.estimate_final(src, cl))
+        tr.close()
+    libc.srand(7)
+    for workers, clouds in ((3, False), (8, True)):
+        libc.srand(7)
+        inputs = [ctx.upload(f) if (clouds and len(f)) else f for f in frames]
+        got, status = ctx.pose_batch(model, inputs, workers=workers)
+        assert (status == 0).all()
+        for f, (g, s) in enumerate(zip(got, serial)):
+            r, t = synth.pose_error(T.mat4(g.final_pose), T.mat4(s.final_pose))
+            assert r < 1e-6 and t < 1e-6, (workers, f, r, t)
+            assert (g.icp_iterations, g.icp_state, g.icp_converged, g.sacia_best_iteration) == \
+                   (s.icp_iterations, s.icp_state, s.icp_converged, s.sacia_best_iteration)
+            assert g.n_src_coarse == s.n_src_coarse and g.n_tgt_fine == s.n_tgt_fine
+            assert abs(g.fitness - s.fitness) < 1e-9
+    # and against the oracle for the first two frames
+    orc.srand(7)
+    for f in range(2):
+        o = orc.PoseEstimator().estimate_final(model.copy(), frames[f])
+        r, t = synth.pose_error(T.mat4(serial[f].final_pose), np.array(o.final_pose, np.float64).reshape(4, 4).T)
+        assert r < 2e-4 and t < 2e-5, (f, r, t)

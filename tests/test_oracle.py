@@ -279,3 +279,28 @@ def test_icp_build_model_configuration_registers_neighbouring_views(orc, synth, 
     o = orc.icp(sp, tp, orc.icp_params(**kw), src_normals=sn, tgt_normals=tn)
     r, t = synth.pose_error(T.mat4(o.T), B @ np.linalg.inv(A))
     assert r < np.deg2rad(3.0) and t < 0.01, (r, t)
+
+
+def test_lm_normal_equation_route_equals_householder_route(orc, synth, small_model):
+    """The two routes to the pivoted R and Q^T f of the LM Jacobian (oracle/orc_lm.h) — Householder QR of the full m x 6 matrix
+    as Eigen does, and the double-accumulated 6 x 6 normal equations the device uses — drive the solver through the same
+    iterations to the same transform."""
+    T = orc.T
+    views = synth.turntable_views(small_model, n_views=36, first=2)
+    (sp, _), (tp, _) = views
+    tn = orc.normals_knn(tp, 12)
+    rng = np.random.default_rng(3)
+    try:
+        for trial in range(4):
+            idx_s = rng.integers(0, len(sp), 2500).astype(np.int32)
+            d, idx_t = orc.knn(tp, sp[idx_s], 1)[1], orc.knn(tp, sp[idx_s], 1)[0]
+            idx_t = np.asarray(idx_t).reshape(-1).astype(np.int32)
+            out = []
+            for route in (0, 1):
+                orc.lm_set_route(route)
+                out.append(orc.point_to_plane(sp, tp, tn, idx_s, idx_t, kind=T.TE_POINT_TO_PLANE, want_info=True))
+            assert out[0][1] == out[1][1], (out[0][1], out[1][1])
+            r, t = synth.pose_error(out[0][0], out[1][0])
+            assert r < 1e-6 and t < 1e-7, (r, t)
+    finally:
+        orc.lm_set_route(0)
