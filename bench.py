@@ -19,6 +19,8 @@ whole job (N ranks each align their own independent pair: weak scaling, no data-
 --impl reference times the CPU oracle port on all host cores (one independent alignment per core).
 """
 import argparse
+import os
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # ope_pose_batch: one hardware queue per worker stream (before CUDA starts)
 import json
 import os
 import sys

@@ -518,7 +518,7 @@ __device__ __forceinline__ int warp_knn_smem(const float4* tg, int nt, int n_fin
 // (broadcast reads) and scatters the k best into sorted order. (d2, index) pairs are distinct, so the ranks are a permutation
 // and the list equals warp_knn_smem's exactly. buf: kKnnBufCap + 32 float2 entries owned by this warp. Falls back to the
 // insertion scan when the bound admits more than kKnnBufCap points or fewer than k.
-static constexpr int kKnnBufCap = 64;
+static constexpr int kKnnBufCap = 128;
 __device__ __forceinline__ int warp_knn_smem_bounded(const float4* tg, int nt, int n_finite, bool active, float qx, float qy, float qz,
                                                      int k, float bound, float2* buf, float& ld, int& li) {
   const unsigned full = 0xffffffffu;

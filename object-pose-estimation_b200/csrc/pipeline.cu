@@ -259,6 +259,7 @@ void batch_worker(BatchShared* S, ope_ctx* ctx, int* first_error, std::string* f
   int rc = OPE_OK;
   cudaSetDevice(S->device);
   ctx->icp_max_blocks = S->icp_blocks;
+  ctx->icp_prefer_small = true;
   for (;;) {
     const size_t f = S->next.fetch_add(1);
     if (f >= S->n_frames) break;

@@ -803,6 +803,349 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_kernel(IcpDev a) {
   }
 }
 
+// ================================================================ ICP, small clouds: one source point per THREAD ====
+// The DetectAndLocalize fine stage (normal shooting, k = 20) works on ~2 k source points against a ~1.5 k point cluster. The
+// kernel above gives every such query a whole warp and the whole GPU to one alignment; this one keeps the target in shared
+// memory and gives every query ONE thread, so an alignment needs ceil(n / 512) blocks (4 SMs instead of 118) and a batch of
+// independent frames (ope_pose_batch) fills the device with concurrent alignments.
+//   per iteration and thread: bound = largest distance to the previous iteration's k neighbours (tight: they are still the k
+//   nearest for almost every point) -> one pass over the target in shared memory (broadcast reads) collecting the points within
+//   the bound into the thread's column of a shared slab -> all-against-all ranks of those ~k candidates ((d2, index) order, so
+//   the list equals FLANN's) -> point-to-line distances of the k best in double, first minimum in list order -> rejectors ->
+//   double moments, transpose-reduced per warp, summed per block, exchanged through a B-entry table and one grid barrier.
+//   The rare query whose bound admits more than kSlabSlots points, and the first (unseeded) iteration, use the cooperative
+//   warp_knn_smem for that query. Same results as icp_kernel (parity tests run both).
+static constexpr int kSlabSlots = 32;
+static constexpr int kIcpSmallMaxBlocks = 32;
+
+static constexpr int kIcpSmallThreads = 128;   // 4 warps: the per-target scan is a latency chain, so a block gains little from more
+                                               // warps; small blocks let the blocks of SEVERAL alignments share an SM
+template <int THREADS>
+struct IcpSmallSmem {
+  double red[THREADS / 32][kIcpAcc];
+  double totals[kIcpAcc];
+  float2 knn_buf[THREADS / 32][kKnnBufCap + 32];   // warp_knn_smem_bounded scratch for the queries the thread-level scan hands over
+  Mat4 T_inc;
+  int stop;
+};
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 512 / THREADS) icp_small_kernel(IcpDev a) {
+  constexpr int kIcpThreads = THREADS, kIcpWarps = THREADS / 32;   // shadow the wide kernel's constants inside this kernel
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  IcpSmallSmem<THREADS>* sm = reinterpret_cast<IcpSmallSmem<THREADS>*>(smem_raw);
+  float4* tg = reinterpret_cast<float4*>(smem_raw + ((sizeof(IcpSmallSmem<THREADS>) + 15) & ~(size_t)15));
+  const int n_tgt8 = (a.n_tgt + 7) & ~7, n_groups = n_tgt8 >> 3;   // the target in groups of 8 consecutive points, padded with +inf
+  float4* blo = tg + n_tgt8;                                        // bounding box of every group (culling)
+  float4* bhi = blo + n_groups;
+  float2* slab = reinterpret_cast<float2*>(bhi + n_groups);         // [kSlabSlots][kIcpThreads]: column = thread
+  const unsigned full = 0xffffffffu;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int s = blockIdx.x * kIcpThreads + tid;    // this thread's point (sorted position)
+  const bool in_range = s < a.n_work;
+  const bool stale = a.variant == OPE_ICP_VARIANT_MODCORR;
+  const int k = a.k_search < a.grid.n ? a.k_search : a.grid.n;
+  auto col = [&](int slot) -> float2& { return slab[slot * kIcpThreads + tid]; };
+
+  // input_transformed = guess applied to input (VP/impl/icp_mod.hpp:132-139), in sorted order; state lives in registers
+  float4 p = make_float4(0, 0, 0, 0), nv = make_float4(0, 0, 0, 0);
+  int orig = 0;
+  if (in_range) {
+    p = __ldg(a.src_sorted + s);
+    orig = __float_as_int(p.w);
+    if (a.src0_nrm) nv = __ldg(a.src0_nrm + orig);
+    if (!mat4_is_identity(a.guess)) {
+      float x, y, z;
+      xform_point(a.guess, p.x, p.y, p.z, x, y, z);
+      p.x = x; p.y = y; p.z = z;
+      if (a.src0_nrm && finite3(nv.x, nv.y, nv.z)) { xform_normal(a.guess, nv.x, nv.y, nv.z, x, y, z); nv.x = x; nv.y = y; nv.z = z; }
+    }
+  }
+  for (int j = tid; j < n_tgt8; j += kIcpThreads) tg[j] = j < a.n_tgt ? __ldg(a.tgt_pts + j) : make_float4(INFINITY, INFINITY, INFINITY, 0.0f);
+  __syncthreads();
+  // A down-sampled cluster arrives in voxel-key order (x fastest), so eight consecutive points are neighbours: their box is small
+  // and most groups are farther from a query than its bound. Non-finite points never match and stay out of the boxes.
+  for (int g = tid; g < n_groups; g += kIcpThreads) {
+    float4 lo = make_float4(INFINITY, INFINITY, INFINITY, 0.0f), hi = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.0f);
+    for (int u = 0; u < 8; ++u) {
+      const float4 t = tg[8 * g + u];
+      if (!finite3(t.x, t.y, t.z)) continue;
+      lo.x = fminf(lo.x, t.x); lo.y = fminf(lo.y, t.y); lo.z = fminf(lo.z, t.z);
+      hi.x = fmaxf(hi.x, t.x); hi.y = fmaxf(hi.y, t.y); hi.z = fmaxf(hi.z, t.z);
+    }
+    blo[g] = lo; bhi[g] = hi;
+  }
+  __syncthreads();
+  const bool ok = in_range && k > 0 && finite3(p.x, p.y, p.z);
+
+  Mat4 final_t = a.guess;
+  double prev_mse = DBL_MAX, cur_mse = DBL_MAX;
+  int similar = 0, iterations = 0, state = OPE_CONV_NOT_CONVERGED, converged = 0, n_corr = 0;
+  unsigned bar_target = 0;
+  const bool prof = a.phase_cycles != nullptr && blockIdx.x == 0 && tid == 0;
+  long long t_phase[4] = {0, 0, 0, 0};
+
+  // one query through the cooperative scan: the warp serves lane `q`'s point, the sorted result goes to that thread's column
+  auto coop_query = [&](int q, float bound) {
+    const float qx = __shfl_sync(full, p.x, q), qy = __shfl_sync(full, p.y, q), qz = __shfl_sync(full, p.z, q);
+    float ld; int li;
+    const int cnt = warp_knn_smem_bounded(tg, a.n_tgt, a.grid.n, true, qx, qy, qz, a.k_search, bound, sm->knn_buf[warp], ld, li);
+    float2* c = slab + (warp * 32 + q);
+    if (lane < kSlabSlots) c[lane * kIcpThreads] = lane < cnt ? make_float2(ld, __int_as_float(li)) : make_float2(FLT_MAX, __int_as_float(-1));
+    return cnt;
+  };
+
+  for (int pass = 0;; ++pass) {
+    long long t0 = prof ? clock64() : 0;
+    int c = 0;           // entries in this thread's column
+    bool have = false;   // the column already holds this iteration's k nearest
+    bool seeded = pass > 0;
+    if (pass == 0) {
+      // Unseeded start: every eighth thread (a "leader") gets an exact cooperative search; its neighbours in Morton order are
+      // spatially close, and ANY k distinct target points bound a query's k-th distance, so the other seven seed their bound
+      // from the leader's list.
+      const bool leader = (lane & 7) == 0;
+      const unsigned lead = __ballot_sync(full, ok && leader);
+      for (unsigned m = lead; m != 0u; m &= m - 1u) { const int q = __ffs(m) - 1; const int cnt = coop_query(q, FLT_MAX); if (lane == q) { c = cnt; have = true; } }
+      __syncwarp();
+      seeded = !leader && ((lead >> (lane & ~7)) & 1u);
+    }
+    float bound = FLT_MAX;
+    if (ok && !have && seeded) {
+      // the previous iteration's (pass 0: the leader's) k nearest, at this point's position, bound its k-th distance
+      const float2* seed_col = slab + (pass == 0 ? (tid & ~7) : tid);
+      float b = 0.0f;
+      bool all = true;
+#pragma unroll 4
+      for (int j = 0; j < k; ++j) {
+        const int idx = __float_as_int(seed_col[j * kIcpThreads].y);
+        if (idx < 0) { all = false; continue; }
+        const float4 t = tg[idx];
+        b = fmaxf(b, dist2(p.x, p.y, p.z, t.x, t.y, t.z));
+      }
+      if (all) bound = b;
+    }
+    if (pass == 0) __syncwarp();   // the leaders' columns are read above, the others' columns are written below
+    const bool scan = ok && !have && bound < FLT_MAX;
+    if (scan) {
+      // A full column (kSlabSlots entries) keeps the best kSlabSlots seen so far and tightens the bound to its worst entry: rare
+      // (the bound normally admits ~k points), so it is a call, not inline code
+      auto insert_full = [&](float d2, int j) {
+        int worst = 0;
+        float2 wv = col(0);
+        for (int e = 1; e < kSlabSlots; ++e) { const float2 o = col(e); if (nb_less(wv.x, __float_as_int(wv.y), o.x, __float_as_int(o.y))) { wv = o; worst = e; } }
+        if (nb_less(d2, j, wv.x, __float_as_int(wv.y))) {
+          col(worst) = make_float2(d2, __int_as_float(j));
+          float mx = 0.0f;
+          for (int e = 0; e < kSlabSlots; ++e) mx = fmaxf(mx, col(e).x);
+          bound = mx;
+        } else {
+          bound = fminf(bound, wv.x);
+        }
+      };
+      // eight targets per step: the loads (same address in every lane: broadcasts) and the distance arithmetic of a step are
+      // independent of each other and of the slab stores, which only happen for the ~k hits of the whole scan
+      for (int g = 0; g < n_groups; ++g) {
+        const int j0 = 8 * g;
+        {   // squared distance to the group's box, conservatively compared (the float evaluation may round either way)
+          const float4 lo = blo[g], hi = bhi[g];
+          const float ex = fmaxf(fmaxf(lo.x - p.x, p.x - hi.x), 0.0f), ey = fmaxf(fmaxf(lo.y - p.y, p.y - hi.y), 0.0f),
+                      ez = fmaxf(fmaxf(lo.z - p.z, p.z - hi.z), 0.0f);
+          if (!(ex * ex + ey * ey + ez * ez <= bound * 1.0001f + 1e-30f)) continue;
+        }
+        float d2[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const float4 t = tg[j0 + u]; d2[u] = dist2(p.x, p.y, p.z, t.x, t.y, t.z); }
+        unsigned hit = 0u;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) hit |= (d2[u] <= bound ? 1u : 0u) << u;   // non-finite targets give inf / NaN: never a hit
+        if (hit) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {   // predicated stores, no nested branches: the lanes of a warp hit at different u
+            const bool h = (hit >> u) & 1u;
+            const bool room = c < kSlabSlots;
+            if (h & room) col(c) = make_float2(d2[u], __int_as_float(j0 + u));
+            if (h & !room) insert_full(d2[u], j0 + u);
+            c += (h & room) ? 1 : 0;
+          }
+        }
+      }
+    }
+    // whoever could not be served above (no usable seed, or fewer than k points within the bound) gets a cooperative search
+    const bool unserved = ok && !have && (!scan || c < k);
+    const unsigned redo = __ballot_sync(full, unserved);
+    if (a.phase_cycles && blockIdx.x == 0 && lane == 0 && pass > 0) atomicAdd((unsigned long long*)&a.phase_cycles[4], (unsigned long long)__popc(redo));
+    if (a.phase_cycles && blockIdx.x == 0 && ok && pass > 0) atomicAdd((unsigned long long*)&a.phase_cycles[5], (unsigned long long)c);
+    for (unsigned m = redo; m != 0u; m &= m - 1u) {
+      const int q = __ffs(m) - 1;
+      const float bq = __shfl_sync(full, scan ? bound : FLT_MAX, q);
+      const int cnt = coop_query(q, bq);
+      if (lane == q) c = cnt;
+    }
+    __syncwarp();
+    if (prof) { const long long t1 = clock64(); t_phase[0] += t1 - t0; t0 = t1; }
+    // ---- ranks, normal shooting among the k best, compaction of the k best into slots [0, k) ----
+    int match = -1;
+    float d2m = 0.0f;
+    if (ok && c > 0) {
+      const float4 nr = stale ? __ldg(a.src0_nrm + orig) : nv;
+      const double N0 = nr.x, N1 = nr.y, N2 = nr.z;
+      double best = DBL_MAX;
+      int best_idx = -1, first_idx = -1;
+      float best_d2 = 0.0f, first_d2 = 0.0f;
+      // The list order of the reference is ascending (d2, index). Nothing below needs the ranks themselves: the k best are what
+      // remains after dropping the largest entry c - k times (c - k is 0 or 1 for almost every query), the nearest neighbour
+      // is the minimum, and "first minimum in list order" is a tie-break by that same order.
+      while (c > k) {
+        int worst = 0;
+        float2 wv = col(0);
+        for (int e = 1; e < c; ++e) { const float2 o = col(e); if (nb_less(wv.x, __float_as_int(wv.y), o.x, __float_as_int(o.y))) { wv = o; worst = e; } }
+        --c;
+        if (worst != c) col(worst) = col(c);
+      }
+      float best_key = 0.0f;   // d2 of the current winner (its index is best_idx): the list-order key for ties
+#pragma unroll 4
+      for (int e = 0; e < c; ++e) {
+        const float2 mine = col(e);
+        const int mi = __float_as_int(mine.y);
+        if (first_idx < 0 || nb_less(mine.x, mi, first_d2, first_idx)) { first_idx = mi; first_d2 = mine.x; }
+        const float4 t = tg[mi];
+        const float px = t.x - p.x, py = t.y - p.y, pz = t.z - p.z;
+        const double V0 = px, V1 = py, V2 = pz;
+        const double C0 = N1 * V2 - N2 * V1, C1 = N2 * V0 - N0 * V2, C2 = N0 * V1 - N1 * V0;
+        const double dist = C0 * C0 + C1 * C1 + C2 * C2;
+        if (dist < DBL_MAX && (dist < best || (dist == best && nb_less(mine.x, mi, best_key, best_idx)))) {
+          best = dist; best_idx = mi; best_d2 = mine.x; best_key = mine.x;
+        }
+      }
+      // the reference starts from min_index = 0: with no finite candidate it still reports neighbour 0 unless rejected below
+      const int pick_idx = best_idx < 0 ? first_idx : best_idx;
+      const float pick_d2 = best_idx < 0 ? first_d2 : best_d2;
+      const double min_dist = best_idx < 0 ? DBL_MAX : best;
+      if (!(min_dist > a.max_corr_dist)) { match = pick_idx; d2m = pick_d2; }   // sic
+      // rejector chain (VP/impl/icp_mod.hpp:194-208) on register state
+      for (int r = 0; r < a.n_rej && match >= 0; ++r) {
+        const float4 sn = stale ? __ldg(a.src0_nrm + orig) : nv;
+        double score;
+        if (a.rej_kind[r] == OPE_REJ_SURFACE_NORMAL) {
+          const float4 tn = __ldg(a.tgt_nrm + match);
+          score = (double)((sn.x * tn.x) + (sn.y * tn.y) + (sn.z * tn.z));
+        } else {
+          const float4 sp = stale ? __ldg(a.src0_pts + orig) : p;
+          const double sl = (double)sqrtf(sp.x * sp.x + sp.y * sp.y + sp.z * sp.z);
+          score = (double)((sn.x * (-sp.x / sl)) + (sn.y * (-sp.y / sl)) + (sn.z * (-sp.z / sl)));
+        }
+        if (!(score > a.rej_thr[r])) match = -1;
+      }
+    }
+    // slots [c, k) of a short list are invalid for the next bound
+    if (ok) for (int j = (c < k ? c : k); j < k; ++j) col(j) = make_float2(FLT_MAX, __int_as_float(-1));
+    if (in_range) { a.corr_match[orig] = match; a.corr_d2[orig] = d2m; }
+    if (prof) { const long long t1 = clock64(); t_phase[1] += t1 - t0; t0 = t1; }
+    // ---- moments: warp transpose reduction -> block -> table of B partials -> barrier ----
+    {
+      double v[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) v[e] = 0.0;
+      double dsum = 0.0;
+      if (match >= 0) {
+        const float4 t = tg[match];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = moment_term(e, p, t, d2m);
+        dsum = (double)d2m;
+      }
+      int slot;
+      const double wsum = warp_reduce16(v, lane, slot);
+      dsum = warp_sum_d(dsum);
+      if ((lane & 1) == 0) sm->red[warp][slot] = wsum;
+      if (lane == 1) sm->red[warp][16] = dsum;
+    }
+    __syncthreads();
+    double* my_partials = a.partials + ((size_t)(pass & 1) * gridDim.x + blockIdx.x) * kIcpAcc;
+    if (tid < kIcpAcc) {
+      double sum = 0.0;
+#pragma unroll
+      for (int wv = 0; wv < kIcpWarps; ++wv) sum += sm->red[wv][tid];
+      my_partials[tid] = sum;
+    }
+    if (gridDim.x > 1) { bar_target += gridDim.x; grid_barrier(a.barrier, bar_target); } else __syncthreads();
+    if (tid < kIcpAcc) {
+      const double* base = a.partials + (size_t)(pass & 1) * gridDim.x * kIcpAcc;
+      double sum = 0.0;
+      for (int b0 = 0; b0 < (int)gridDim.x; b0 += 8) {   // 8 independent loads in flight, summed in block order
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = b0 + u < (int)gridDim.x ? __ldcg(base + (size_t)(b0 + u) * kIcpAcc + tid) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) sum += v[u];
+      }
+      sm->totals[tid] = sum;
+    }
+    __syncthreads();
+    if (prof) { const long long t1 = clock64(); t_phase[2] += t1 - t0; t0 = t1; }
+    // ---- Umeyama + DefaultConvergenceCriteria, replicated in every block (thread 0) ----
+    if (tid == 0) {
+      int stop = 0;
+      n_corr = (int)sm->totals[0];
+      if (n_corr < a.min_corr) {
+        state = OPE_CONV_NO_CORRESPONDENCES; converged = 0; stop = 2;   // VP/impl/icp_mod.hpp:232-240
+        sm->T_inc = mat4_identity();
+      } else {
+        Mat4 T;
+        umeyama_from_moments(sm->totals, T);
+        sm->T_inc = T;
+        final_t = mat4_mul(T, final_t);
+        ++iterations;
+        state = OPE_CONV_NOT_CONVERGED;
+        int conv = 0;
+        if (iterations >= a.max_iterations) {
+          if (!a.fail_after_max) { state = OPE_CONV_ITERATIONS; conv = 1; }
+          else { conv = 0; stop = 1; }
+        } else {
+          const double cos_angle = 0.5 * (double)(T(0, 0) + T(1, 1) + T(2, 2) - 1);
+          const double translation_sqr = (double)(T(0, 3) * T(0, 3) + T(1, 3) * T(1, 3) + T(2, 3) * T(2, 3));
+          int hit = 0, hit_state = 0;
+          if (cos_angle >= a.rot_thr && translation_sqr <= a.trans_thr) { hit = 1; hit_state = OPE_CONV_TRANSFORM; }
+          else {
+            cur_mse = sm->totals[16] / (double)n_corr;
+            if (fabs(cur_mse - prev_mse) < a.abs_mse_thr) { hit = 1; hit_state = OPE_CONV_ABS_MSE; }
+            else if (fabs(cur_mse - prev_mse) / prev_mse < a.rel_mse_thr) { hit = 1; hit_state = OPE_CONV_REL_MSE; }
+            else prev_mse = cur_mse;
+          }
+          if (hit) {
+            if (similar < a.max_similar) ++similar;
+            else { similar = 0; state = hit_state; conv = 1; }
+          }
+        }
+        converged = conv;
+        if (a.force_all && iterations < a.max_iterations) conv = 0;
+        if (conv) stop = 1;
+      }
+      sm->stop = stop;
+    }
+    __syncthreads();
+    // ---- transformCloud(input_transformed, transformation_) on the registers ----
+    const int stop = sm->stop;
+    if (stop != 2 && in_range && finite3(p.x, p.y, p.z)) {
+      const Mat4 T = sm->T_inc;
+      float x, y, z;
+      xform_point(T, p.x, p.y, p.z, x, y, z);
+      p.x = x; p.y = y; p.z = z;
+      if (a.src0_nrm && finite3(nv.x, nv.y, nv.z)) { xform_normal(T, nv.x, nv.y, nv.z, x, y, z); nv.x = x; nv.y = y; nv.z = z; }
+    }
+    if (prof) { const long long t1 = clock64(); t_phase[3] += t1 - t0; }
+    if (stop) break;
+  }
+  if (prof) for (int i = 0; i < 4; ++i) a.phase_cycles[i] = t_phase[i];
+  if (blockIdx.x == 0 && tid == 0) {
+    ope_reg_result r;
+    for (int i = 0; i < 16; ++i) r.T[i] = final_t.m[i];
+    r.converged = converged; r.state = state; r.iterations = iterations; r.n_correspondences = n_corr;
+    r.last_mse = cur_mse; r.best_error = 0.0; r.best_iteration = 0; r.reserved = 0;
+    *a.result = r;
+  }
+}
+
 // one estimation + rejection pass (no loop) on the clouds as given (cur_* = the caller's clouds, original order)
 __global__ void __launch_bounds__(kIcpThreads, 1) correspond_once_kernel(IcpDev a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1106,7 +1449,7 @@ int icp_device(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const o
   std::memset(&a, 0, sizeof(a));
   OPE_TRY(icp_fill(ctx, src, tgt, prm, &a, /*allow_smem_target=*/true));
   a.guess = guess;
-  const size_t smem_bytes = ((sizeof(IcpSmem) + 15) & ~(size_t)15) + (a.tgt_in_smem ? tgt->n * sizeof(float4) : 0);
+  size_t smem_bytes = ((sizeof(IcpSmem) + 15) & ~(size_t)15) + (a.tgt_in_smem ? tgt->n * sizeof(float4) : 0);
   const size_t n = src->n;
   // the source in Morton order of its own (cached) grid: spatially coherent work order, finite points only
   GridView gsrc;
@@ -1139,13 +1482,30 @@ int icp_device(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const o
   if (rc == OPE_OK && cudaMemsetAsync(bar.p, 0, sizeof(unsigned), ctx->stream) != cudaSuccess) rc = fail(ctx, OPE_ERR_CUDA, "memset failed");
   if (rc == OPE_OK && n > 0 && cudaMemsetAsync(match.p, 0xff, n * sizeof(int), ctx->stream) != cudaSuccess) rc = fail(ctx, OPE_ERR_CUDA, "memset failed");
   if (rc == OPE_OK && n > 0 && cudaMemsetAsync(d2.p, 0, n * sizeof(float), ctx->stream) != cudaSuccess) rc = fail(ctx, OPE_ERR_CUDA, "memset failed");
-  if (rc == OPE_OK) rc = dyn_smem(ctx, (const void*)icp_kernel, smem_bytes);
+  // small clouds against a shared-memory target: one point per thread, ceil(n / 512) blocks (icp_small_kernel)
+  // It trades the latency of one alignment (the wide kernel spreads it over the whole device) for device time per alignment,
+  // so it is what a batch of concurrent alignments wants (ope_pose_batch sets ctx->icp_prefer_small); OPE_ICP_SMALL=1/0 forces.
+  const char* small_env = std::getenv("OPE_ICP_SMALL");
+  const bool want_small = small_env ? std::atoi(small_env) != 0 : ctx->icp_prefer_small;
+  const bool small = want_small && a.tgt_in_smem && shooting && nw > 0 && nw <= (size_t)kIcpSmallMaxBlocks * kIcpSmallThreads &&
+                     prm.k_search <= kSlabSlots;
+  const void* kernel = small ? (const void*)icp_small_kernel<kIcpSmallThreads> : (const void*)icp_kernel;
+  const int threads = small ? kIcpSmallThreads : kIcpThreads;
+  if (small) {
+    const size_t nt8 = (tgt->n + 7) & ~(size_t)7;
+    smem_bytes = ((sizeof(IcpSmallSmem<kIcpSmallThreads>) + 15) & ~(size_t)15) + nt8 * sizeof(float4) + (nt8 / 8) * 2 * sizeof(float4) +
+                 (size_t)kSlabSlots * kIcpSmallThreads * sizeof(float2);
+  }
+  if (rc == OPE_OK) rc = dyn_smem(ctx, kernel, smem_bytes);
   // cooperative grid: one point per thread (nearest) / per warp (normal shooting), capped by co-residency
   int per_sm = 0;
-  if (rc == OPE_OK && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, icp_kernel, kIcpThreads, smem_bytes) != cudaSuccess)
+  if (rc == OPE_OK && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem_bytes) != cudaSuccess)
     rc = fail(ctx, OPE_ERR_CUDA, "occupancy query failed");
   int blocks = 1;
-  if (rc == OPE_OK) {
+  if (rc == OPE_OK && small) {
+    if (per_sm < 1) rc = fail(ctx, OPE_ERR_CUDA, "icp_small_kernel cannot be resident");
+    blocks = (int)((nw + kIcpSmallThreads - 1) / kIcpSmallThreads);
+  } else if (rc == OPE_OK) {
     if (per_sm < 1) rc = fail(ctx, OPE_ERR_CUDA, "icp_kernel cannot be resident");
     int max_blocks = std::min(per_sm * ctx->sm_count, kIcpMaxBlocks);
     if (ctx->icp_max_blocks > 0) max_blocks = std::min(max_blocks, ctx->icp_max_blocks);
@@ -1179,7 +1539,7 @@ int icp_device(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const o
   if (rc == OPE_OK) {
     void* args[] = {(void*)&a};
     cudaEventRecord(ctx->kev[0][0], ctx->stream);
-    cudaError_t e = cudaLaunchCooperativeKernel((void*)icp_kernel, dim3(blocks), dim3(kIcpThreads), args, smem_bytes, ctx->stream);
+    cudaError_t e = cudaLaunchCooperativeKernel(kernel, dim3(blocks), dim3(threads), args, smem_bytes, ctx->stream);
     cudaEventRecord(ctx->kev[0][1], ctx->stream);
     ctx->kev_valid[0] = true;
     if (e != cudaSuccess) rc = fail(ctx, OPE_ERR_CUDA, "cooperative launch of icp_kernel failed: %s", cudaGetErrorString(e));
@@ -1192,7 +1552,15 @@ int icp_device(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const o
   }
   if (rc == OPE_OK && profile) {
     void* h;
-    if (read_back(ctx, phases.p, n_prof * sizeof(long long), &h) == OPE_OK) {
+    if (small) {
+      if (read_back(ctx, phases.p, 6 * sizeof(long long), &h) == OPE_OK) {
+        const long long* c = (const long long*)h;
+        const double it = std::max(res->iterations, 1);
+        fprintf(stderr, "[ope profile] icp_small_kernel blocks=%d, block 0 cycles per iteration: search %.0f | rank+shoot+reject %.0f | moments+barrier %.0f | "
+                "svd+transform %.0f | cooperative re-searches per iteration %.1f | candidates per query %.1f\n", blocks, c[0] / it, c[1] / it,
+                c[2] / it, c[3] / it, c[4] / it, c[5] / it / kIcpSmallThreads);
+      }
+    } else if (read_back(ctx, phases.p, n_prof * sizeof(long long), &h) == OPE_OK) {
       const long long* c = (const long long*)h;
       const double it = std::max(res->iterations, 1);
       if (std::getenv("OPE_PROFILE_ITER")) {

@@ -214,13 +214,16 @@ def test_icp_guess_and_aligned_output(ctx, orc, synth, cuda_lib, small_model):
     assert np.array_equal(out, ref)
 
 
-@pytest.mark.parametrize("target_path", ["smem", "grid"])
+@pytest.mark.parametrize("target_path", ["small", "smem", "grid"])
 def test_icp_with_normals_d_and_l_configuration(ctx, orc, synth, cuda_lib, model, target_path, monkeypatch):
     """The reference's fine stage (D&L/src/poseestimator.cpp:310-341): normal shooting k=20, surface-normal 0.7 +
-    self-occluded 0.6 rejectors, SVD, 100 iterations, eps 1e-8, no distance gating — with the small target resident in
-    shared memory (default) and through the spatial index."""
+    self-occluded 0.6 rejectors, SVD, 100 iterations, eps 1e-8, no distance gating — through all three device paths: the
+    thread-per-query kernel for small clouds (default), the warp-per-query kernel with the target in shared memory, and the
+    warp-per-query kernel over the spatial index."""
     if target_path == "grid":
         monkeypatch.setenv("OPE_ICP_FORCE_GRID", "1")
+    if target_path == "small":
+        monkeypatch.setenv("OPE_ICP_SMALL", "1")
     T = cuda_lib.T
     cl, _, pose = synth.make_frame(model, 5)
     rng = np.random.default_rng(8)

@@ -8,6 +8,8 @@ the per-rank device times are max-reduced and the frame counts summed only to pr
 
 Scenes are generated once (64 distinct frames, cycled) outside the timed region; every frame starts a fresh tracker, so
 SAC-IA runs on every frame (the expensive first-frame path of the reference)."""
+import os
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # ope_pose_batch: one hardware queue per worker stream (before CUDA starts)
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
