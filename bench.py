@@ -361,7 +361,7 @@ def pipeline_numbers(ctx, cuda_lib, synth, model, stream, torch, n_gpu_frames=12
     torch.cuda.synchronize()
     e2e_fps = n_gpu_frames / (e0.elapsed_time(e1) / 1e3)
     # batched (C5): ope_pose_batch, worker threads with their own streams, the frame-invariant model side cached
-    n_batch, workers = 256, 8
+    n_batch, workers = 512, 16
     batch = {}
     for host in (False, True):
         inputs = [(frames if host else targets)[f % n_gpu_frames] for f in range(n_batch)]

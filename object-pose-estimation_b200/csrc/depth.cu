@@ -138,7 +138,7 @@ int ope_depth_to_cloud(ope_ctx* ctx, const uint16_t* depth, int rows, int cols, 
   OPE_TRY(cloud_alloc(ctx, n, false, &c));
   if (n) {
     cudaError_t e = cudaMemcpyAsync(c->pts, tmp.p, n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = ope::stream_sync(ctx);
     if (e != cudaSuccess) { ope_cloud_free(ctx, c); return fail(ctx, OPE_ERR_CUDA, "depth cloud copy failed: %s", cudaGetErrorString(e)); }
   }
   *out = c;

@@ -378,7 +378,7 @@ int ope_normals_knn(ope_ctx* ctx, ope_cloud* cloud, int k, const float viewpoint
   OPE_TRY(normals_device(ctx, cloud, k, viewpoint ? viewpoint : zero));
   if (out4 && cloud->n)
     OPE_CUDA_TRY(ctx, cudaMemcpyAsync(out4, cloud->normals, cloud->n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
-  OPE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  OPE_CUDA_TRY(ctx, ope::stream_sync(ctx));
   return OPE_OK;
 }
 
@@ -392,7 +392,7 @@ int ope_fpfh(ope_ctx* ctx, const ope_cloud* cloud, float radius, float* out, flo
     if (e == cudaSuccess && out_spfh)
       e = cudaMemcpyAsync(out_spfh, s, cloud->n * 33 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
   }
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess) e = ope::stream_sync(ctx);
   dfree(ctx, f); dfree(ctx, s);
   if (e != cudaSuccess) return fail(ctx, OPE_ERR_CUDA, "fpfh download failed: %s", cudaGetErrorString(e));
   return OPE_OK;
@@ -411,7 +411,7 @@ int ope_feature_knn(ope_ctx* ctx, const float* ftgt, size_t nt, const float* fqr
     OPE_CUDA_TRY(ctx, cudaMemcpyAsync(out_idx, di.p, nq * k * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     if (out_d2) OPE_CUDA_TRY(ctx, cudaMemcpyAsync(out_d2, dd.p, nq * k * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   }
-  OPE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  OPE_CUDA_TRY(ctx, ope::stream_sync(ctx));
   return OPE_OK;
 }
 

@@ -573,11 +573,12 @@ int ope_cloud_invalidate(ope_ctx* ctx, ope_cloud* c) {
 void ope_ctx_destroy(ope_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  ope::stream_sync(ctx);
   for (int w = 0; w < 3; ++w)
     for (int j = 0; j < 2; ++j) if (ctx->kev[w][j]) cudaEventDestroy(ctx->kev[w][j]);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->stage) cudaFreeHost(ctx->stage);
+  if (ctx->sync_event) cudaEventDestroy(ctx->sync_event);
   for (ope_ctx* w : ctx->workers) ope_ctx_destroy(w);
   ctx->workers.clear();
   if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
@@ -595,7 +596,7 @@ int ope_ctx_feature_knn_stats(const ope_ctx* ctx, int64_t* gemm_queries, int64_t
 }
 int ope_ctx_synchronize(ope_ctx* ctx) {
   if (!ctx) return OPE_ERR_INVALID;
-  OPE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  OPE_CUDA_TRY(ctx, ope::stream_sync(ctx));
   return OPE_OK;
 }
 
@@ -629,7 +630,7 @@ int ope_cloud_upload(ope_ctx* ctx, const void* pts, size_t n, size_t stride, siz
       }
       e = cudaMemcpyAsync(c->normals, hn, n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream);
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = ope::stream_sync(ctx);
     if (e != cudaSuccess) {
       ope_cloud_free(ctx, c);
       return fail(ctx, OPE_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e));
@@ -660,13 +661,13 @@ int ope_cloud_download(ope_ctx* ctx, const ope_cloud* c, float* xyz, float* norm
   const float4* h = (const float4*)stage;
   if (xyz) {
     OPE_CUDA_TRY(ctx, cudaMemcpyAsync(stage, c->pts, c->n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
-    OPE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    OPE_CUDA_TRY(ctx, ope::stream_sync(ctx));
     for (size_t i = 0; i < c->n; ++i) { xyz[3 * i] = h[i].x; xyz[3 * i + 1] = h[i].y; xyz[3 * i + 2] = h[i].z; }
   }
   if (normals4) {
     if (!c->normals) return fail(ctx, OPE_ERR_INVALID, "cloud has no normals");
     OPE_CUDA_TRY(ctx, cudaMemcpyAsync(stage, c->normals, c->n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
-    OPE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    OPE_CUDA_TRY(ctx, ope::stream_sync(ctx));
     std::memcpy(normals4, stage, c->n * sizeof(float4));
   }
   return OPE_OK;
@@ -680,7 +681,7 @@ int ope_cloud_select(ope_ctx* ctx, const ope_cloud* c, const int32_t* idx, size_
   OPE_TRY(d.alloc(n));
   if (n) OPE_CUDA_TRY(ctx, cudaMemcpyAsync(d.p, idx, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   OPE_TRY(gather_cloud(ctx, c, d.p, n, out));
-  OPE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  OPE_CUDA_TRY(ctx, ope::stream_sync(ctx));
   return OPE_OK;
 }
 
@@ -689,7 +690,7 @@ int ope_cloud_set_normals(ope_ctx* ctx, ope_cloud* c, const float* normals4) {
   if (!c->normals) OPE_TRY(dalloc(ctx, &c->normals, c->n));
   if (c->n) {
     OPE_CUDA_TRY(ctx, cudaMemcpyAsync(c->normals, normals4, c->n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-    OPE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    OPE_CUDA_TRY(ctx, ope::stream_sync(ctx));
   }
   return OPE_OK;
 }
@@ -717,7 +718,7 @@ static int knn_impl(ope_ctx* ctx, const ope_cloud* tgt, const float4* d_qry, siz
   }
   OPE_CUDA_TRY(ctx, cudaMemcpyAsync(out_idx, di.p, nq * k * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   if (out_d2) OPE_CUDA_TRY(ctx, cudaMemcpyAsync(out_d2, dd.p, nq * k * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-  OPE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  OPE_CUDA_TRY(ctx, ope::stream_sync(ctx));
   return OPE_OK;
 }
 
@@ -753,7 +754,7 @@ int ope_radius_cloud(ope_ctx* ctx, const ope_cloud* tgt, const ope_cloud* qry, f
   OPE_TRY(exclusive_scan_i32(ctx, cnt.p, nq + 1));
   std::vector<int> off(nq + 1);
   OPE_CUDA_TRY(ctx, cudaMemcpyAsync(off.data(), cnt.p, (nq + 1) * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  OPE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  OPE_CUDA_TRY(ctx, ope::stream_sync(ctx));
   *total = off[nq];
   if (offsets) for (size_t i = 0; i <= nq; ++i) offsets[i] = off[i];
   if (!out_idx || !out_d2) return OPE_OK;
@@ -767,7 +768,7 @@ int ope_radius_cloud(ope_ctx* ctx, const ope_cloud* tgt, const ope_cloud* qry, f
   OPE_TRY(check_launch(ctx, "radius_fill_kernel"));
   OPE_CUDA_TRY(ctx, cudaMemcpyAsync(out_idx, di.p, (size_t)*total * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   OPE_CUDA_TRY(ctx, cudaMemcpyAsync(out_d2, dd.p, (size_t)*total * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-  OPE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  OPE_CUDA_TRY(ctx, ope::stream_sync(ctx));
   // canonical order of the API: ascending index per query (the device visits cells row by row)
   std::vector<std::pair<int, float>> tmp;
   for (size_t i = 0; i < nq; ++i) {
@@ -786,7 +787,7 @@ int ope_uniform_sample(ope_ctx* ctx, const ope_cloud* cloud, float leaf, int32_t
   OPE_TRY(uniform_sample_device(ctx, const_cast<ope_cloud*>(cloud), leaf, &d, out_n));
   if (*out_n) {
     cudaError_t e = cudaMemcpyAsync(out_idx, d, *out_n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = ope::stream_sync(ctx);
     if (e != cudaSuccess) { dfree(ctx, d); return fail(ctx, OPE_ERR_CUDA, "download failed: %s", cudaGetErrorString(e)); }
   }
   dfree(ctx, d);
@@ -799,7 +800,7 @@ int ope_uniform_sample_cloud(ope_ctx* ctx, const ope_cloud* cloud, float leaf, o
   OPE_TRY(uniform_sample_device(ctx, const_cast<ope_cloud*>(cloud), leaf, &d, &m));
   int rc = gather_cloud(ctx, cloud, d, m, out);
   dfree(ctx, d);
-  if (rc == OPE_OK) OPE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (rc == OPE_OK) OPE_CUDA_TRY(ctx, ope::stream_sync(ctx));
   return rc;
 }
 
@@ -850,7 +851,7 @@ int ope_voxel_grid(ope_ctx* ctx, const ope_cloud* cloud_c, const float* rgb, flo
   cudaError_t e = cudaMemcpyAsync(out_xyz, oxyz.p, (size_t)m * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess && rgb && out_rgb)
     e = cudaMemcpyAsync(out_rgb, orgb.p, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess) e = ope::stream_sync(ctx);
   if (e != cudaSuccess) return done(fail(ctx, OPE_ERR_CUDA, "voxel grid download failed: %s", cudaGetErrorString(e)));
   *out_n = (size_t)m;
   return done(OPE_OK);

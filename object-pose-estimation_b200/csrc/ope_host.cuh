@@ -1,6 +1,7 @@
 // ope_host.cuh — host-side internals of libope_cuda.so: context, device clouds, cached grids, scratch memory.
 #pragma once
 #include <cuda_runtime.h>
+#include <sched.h>
 
 #include <cstdarg>
 #include <cstdio>
@@ -27,6 +28,9 @@ struct ope_ctx {
   cudaEvent_t kev[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};  // [which][begin/end] around the dominant kernels
   bool kev_valid[3] = {false, false, false};
   std::vector<ope_ctx*> workers;  // ope_pose_batch: per-thread contexts (own stream, pool, staging), kept warm between calls
+  cudaEvent_t sync_event = nullptr;  // set: waits sleep on this cudaEventBlockingSync event instead of spinning in cudaStreamSynchronize
+                                     // (ope_pose_batch workers beyond the host's core count)
+  bool sync_yield = false;           // with sync_event: poll it and sched_yield() between polls instead of sleeping
   bool icp_prefer_small = false;  // small clouds: prefer the thread-per-query ICP kernel (least device time per alignment)
   int icp_max_blocks = 0;      // > 0: cap of the cooperative icp_kernel grid (batch workers share the SMs between frames)
   int64_t feature_knn_gemm_queries = 0;  // queries answered through the tcgen05 distance GEMM ...
@@ -115,6 +119,16 @@ struct Scratch {
   Scratch& operator=(const Scratch&) = delete;
 };
 
+// wait for everything queued on the context's stream
+inline cudaError_t stream_sync(ope_ctx* ctx) {
+  if (!ctx->sync_event) return cudaStreamSynchronize(ctx->stream);
+  cudaError_t e = cudaEventRecord(ctx->sync_event, ctx->stream);
+  if (e != cudaSuccess) return e;
+  if (!ctx->sync_yield) return cudaEventSynchronize(ctx->sync_event);
+  while ((e = cudaEventQuery(ctx->sync_event)) == cudaErrorNotReady) sched_yield();   // poll, but hand the core to the other workers
+  return e;
+}
+
 inline int check_launch(ope_ctx* ctx, const char* what) {
   ctx->launches++;
   cudaError_t e = cudaPeekAtLastError();
@@ -129,7 +143,7 @@ inline int check_launch(ope_ctx* ctx, const char* what) {
 inline int read_back(ope_ctx* ctx, const void* dsrc, size_t bytes, void** host) {
   if (bytes > ctx->pinned_bytes) return fail(ctx, OPE_ERR_INVALID, "read_back larger than staging buffer");
   OPE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pinned, dsrc, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  OPE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  OPE_CUDA_TRY(ctx, stream_sync(ctx));
   *host = ctx->pinned;
   return OPE_OK;
 }

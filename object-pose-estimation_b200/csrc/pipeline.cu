@@ -133,7 +133,7 @@ int ope_pose_estimate_final_device(ope_pose_tracker* t, ope_cloud** source, cons
   const ope_pose_params& P = t->prm;
   std::memset(res, 0, sizeof(*res));
   std::memset(t->stage_ms, 0, sizeof(t->stage_ms));
-  cudaEventRecord(t->evt0, ctx->stream);
+  if (t->timing) cudaEventRecord(t->evt0, ctx->stream);
   StageTimer tm(t);
   ope_cloud* p_source = *source;
   const size_t nt = target ? target->n : 0;
@@ -229,11 +229,13 @@ int ope_pose_estimate_final_device(ope_pose_tracker* t, ope_cloud** source, cons
   std::memcpy(res->final_pose, final_pose.m, 64); std::memcpy(res->coarse_pose, coarse.m, 64);
   std::memcpy(res->fine_pose, fine.m, 64); std::memcpy(res->rigid_model_pose, rigid.m, 64);
   res->fitness = t->fitnessScoreFine; res->align_strength = t->alignedStrength;
-  cudaEventRecord(t->evt1, ctx->stream);
-  cudaEventSynchronize(t->evt1);
-  float ms = 0;
-  cudaEventElapsedTime(&ms, t->evt0, t->evt1);
-  t->stage_ms[7] = ms;
+  if (t->timing) {
+    cudaEventRecord(t->evt1, ctx->stream);
+    cudaEventSynchronize(t->evt1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, t->evt0, t->evt1);
+    t->stage_ms[7] = ms;
+  }
   return OPE_OK;
 }
 
@@ -349,6 +351,18 @@ int ope_pose_batch(ope_ctx* ctx, const ope_pose_params* prm, const float* model_
     const int rc = ope_ctx_create(ctx->device, nullptr, &w);
     if (rc != OPE_OK) return fail(ctx, rc, "worker context creation failed");
     ctx->workers.push_back(w);
+  }
+  {
+    // more workers than host cores: their waits must sleep, not spin (OPE_BATCH_BLOCKING_SYNC=0/1 overrides)
+    const char* e = std::getenv("OPE_BATCH_BLOCKING_SYNC");
+    const int mode = e ? std::atoi(e) : (workers > (int)std::thread::hardware_concurrency() ? 2 : 0);   // 0 spin, 1 sleep, 2 poll + yield
+    const bool blocking = mode != 0;
+    for (int w = 0; w < workers; ++w) {
+      ope_ctx* c = ctx->workers[w];
+      c->sync_yield = mode == 2;
+      if (blocking && !c->sync_event) { if (cudaEventCreateWithFlags(&c->sync_event, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess) c->sync_event = nullptr; }
+      if (!blocking && c->sync_event) { cudaEventDestroy(c->sync_event); c->sync_event = nullptr; }
+    }
   }
   std::vector<std::thread> pool;
   for (int w = 1; w < workers; ++w) pool.emplace_back(batch_worker, &S, ctx->workers[w], &errs[w], &msgs[w]);

@@ -1495,6 +1495,12 @@ int icp_device(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const o
     const size_t nt8 = (tgt->n + 7) & ~(size_t)7;
     smem_bytes = ((sizeof(IcpSmallSmem<kIcpSmallThreads>) + 15) & ~(size_t)15) + nt8 * sizeof(float4) + (nt8 / 8) * 2 * sizeof(float4) +
                  (size_t)kSlabSlots * kIcpSmallThreads * sizeof(float2);
+    // Persistent blocks of many concurrent alignments must not fill an SM completely: the short kernels of the other stages
+    // (other frames of a batch) need registers and shared memory next to them. Asking for at least this much shared memory
+    // caps the residency at two blocks per SM.
+    const char* pad = std::getenv("OPE_ICP_SMALL_MIN_SMEM_KB");
+    const size_t min_bytes = (size_t)(pad ? std::atoi(pad) : 0) << 10;   // measured: no gain on B200 with 16-48 concurrent frames; off by default
+    if (smem_bytes < min_bytes) smem_bytes = min_bytes;
   }
   if (rc == OPE_OK) rc = dyn_smem(ctx, kernel, smem_bytes);
   // cooperative grid: one point per thread (nearest) / per warp (normal shooting), capped by co-residency
@@ -1583,7 +1589,7 @@ int icp_device(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const o
     std::vector<float> hd(n);
     cudaError_t e = cudaMemcpyAsync(hm.data(), match.p, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(hd.data(), d2.p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = ope::stream_sync(ctx);
     if (e != cudaSuccess) rc = fail(ctx, OPE_ERR_CUDA, "correspondence download failed: %s", cudaGetErrorString(e));
     else corr_to_host(hm, hd, out_corr_host, nullptr);
   }
@@ -1690,7 +1696,7 @@ static int icp_stepwise_device(ope_ctx* ctx, const ope_cloud* src, const ope_clo
     std::vector<float> hd(n);
     OPE_CUDA_TRY(ctx, cudaMemcpyAsync(hm.data(), match.p, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     OPE_CUDA_TRY(ctx, cudaMemcpyAsync(hd.data(), d2.p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    OPE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    OPE_CUDA_TRY(ctx, ope::stream_sync(ctx));
     corr_to_host(hm, hd, out_corr_host, nullptr);
   }
   if (out_aligned) {
@@ -1813,7 +1819,7 @@ int sacia_device(ope_ctx* ctx, const ope_cloud* src, const float* d_fsrc, const 
   res->iterations = H;
   if (out_errors_host) {
     OPE_CUDA_TRY(ctx, cudaMemcpyAsync(out_errors_host, d_errors.p, (size_t)H * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    OPE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    OPE_CUDA_TRY(ctx, ope::stream_sync(ctx));
   }
   return OPE_OK;
 }
@@ -1868,7 +1874,7 @@ int ope_cloud_transform(ope_ctx* ctx, const ope_cloud* cloud, const float T[16],
   std::memcpy(M.m, T, sizeof(M.m));
   int rc = transform_device(ctx, cloud, M, o);
   if (rc != OPE_OK) { ope_cloud_free(ctx, o); return rc; }
-  OPE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  OPE_CUDA_TRY(ctx, ope::stream_sync(ctx));
   *out = o;
   return OPE_OK;
 }
@@ -1914,7 +1920,7 @@ int ope_point_to_plane(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt,
   OPE_CUDA_TRY(ctx, cudaMemcpyAsync(dt.p, itgt, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   Mat4 M;
   int rc = point_to_plane_device(ctx, src->pts, tgt->pts, tgt->normals, isrc ? ds.p : nullptr, dt.p, nullptr, n, kind, &M, nullptr, nullptr, lm_info);
-  cudaStreamSynchronize(ctx->stream);   // the pageable index arrays must outlive their copies
+  ope::stream_sync(ctx);   // the pageable index arrays must outlive their copies
   if (rc == OPE_OK) std::memcpy(T, M.m, sizeof(M.m));
   return rc;
 }
@@ -1953,7 +1959,7 @@ int ope_correspondences(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt
   std::vector<float> hd(n);
   OPE_CUDA_TRY(ctx, cudaMemcpyAsync(hm.data(), match.p, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   OPE_CUDA_TRY(ctx, cudaMemcpyAsync(hd.data(), d2.p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-  OPE_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  OPE_CUDA_TRY(ctx, ope::stream_sync(ctx));
   corr_to_host(hm, hd, out, out_n);
   return OPE_OK;
 }

@@ -57,14 +57,18 @@ def main():
                 src.free()
             tr.close()
 
-    workers = int(sys.argv[sys.argv.index("--workers") + 1]) if "--workers" in sys.argv else 8
+    workers = int(sys.argv[sys.argv.index("--workers") + 1]) if "--workers" in sys.argv else 16
 
     def run_batch(host):
         # ope_pose_batch: worker threads with their own streams, model side cached; the decision tables are drawn
         # from libc rand() in frame order inside the call
         libc.srand(1)
         inputs = [frames[f % distinct] if host else targets[f % distinct] for f in mine]
-        res, status = ctx.pose_batch(model, inputs, workers=workers)
+        prm = None
+        if os.environ.get("OPE_BENCH_ICP_ITERS"):      # experiment knob: how much of the frame time is the ICP loop
+            prm = cuda_lib.pose_params()
+            prm.icp.max_iterations = int(os.environ["OPE_BENCH_ICP_ITERS"])
+        res, status = ctx.pose_batch(model, inputs, prm=prm, workers=workers)
         assert (status == 0).all()
         return res
 
