@@ -477,3 +477,19 @@ def test_pose_batch_equals_the_serial_first_frame_path(ctx, orc, synth, cuda_lib
         o = orc.PoseEstimator().estimate_final(model.copy(), frames[f])
         r, t = synth.pose_error(T.mat4(serial[f].final_pose), np.array(o.final_pose, np.float64).reshape(4, 4).T)
         assert r < 2e-4 and t < 2e-5, (f, r, t)
+
+
+def test_depth_to_cloud_every_raw_value_and_other_intrinsics(ctx, orc):
+    """The device replaces the three IEEE divisions per pixel by a reciprocal multiply + two exact-residual corrections and the
+    validity tests by an integer interval: every raw value 0..65535, at rows/columns that exercise all signs, with the Kinect
+    intrinsics and with awkward ones (non-representable reciprocals, another scale and range), must still match bit for bit."""
+    raw = np.arange(65536, dtype=np.uint16)
+    img = np.resize(raw, (480, 640)).copy()          # 307 200 pixels: every raw value at least four times, at different (i, j)
+    img[::7, ::5] = raw[(np.arange(img[::7, ::5].size) * 8191) % 65536].reshape(img[::7, ::5].shape)
+    for kw in (dict(), dict(fx=570.3422, fy=571.9631, cx=314.5, cy=235.5, scale=1000.0, z_max=2.0),
+               dict(fx=365.7, fy=366.1, cx=255.2, cy=211.9, scale=5000.0, z_max=4.5), dict(scale=3.0, z_max=1e4)):
+        ref = orc.depth_to_cloud(img, **kw)
+        got = ctx.depth_to_cloud(img, **kw)
+        assert len(got) == len(ref)
+        assert np.array_equal(got.download().view(np.uint32), ref.view(np.uint32))
+        got.free()

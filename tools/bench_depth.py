@@ -39,9 +39,11 @@ t = float(np.median(ms[2:])) * 1e-3
 peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
 npx = Bf * R * Cc
 alg = (2 * npx + 16 * kept) / t / 1e9
-actual = (4 * npx + 16 * kept + 12 * Bf * Cc) / t / 1e9
+two_pass = bool(os.environ.get("OPE_DEPTH_TWO_PASS"))
+actual = ((4 if two_pass else 2) * npx + 16 * kept + (12 if two_pass else 4) * Bf * Cc) / t / 1e9
 print(json.dumps({"workload": "depth->cloud, %d frames of %dx%d (inputs %.0f MB, outputs %.0f MB: far larger than L2)" % (Bf, Cc, R, 2 * npx / 1e6, 16 * kept / 1e6),
                   "frames_per_s": Bf / t, "ms": t * 1e3, "kept_fraction": kept / npx,
                   "roofline": {"bound": "hbm", "achieved": alg, "peak": peak, "unit": "GB/s", "frac": alg / peak,
                                "traffic_model_GBps": actual, "traffic_model_frac": actual / peak,
-                               "note": "algorithmic = 2 B/pixel in + 16 B/kept pixel out; the kernel reads the depth twice (count pass + write pass)"}}))
+                               "kernel": "depth_count_kernel + depth_write_kernel" if two_pass else "depth_fused_kernel",
+                               "note": "algorithmic = 2 B/pixel in + 16 B/kept pixel out; " + ("two passes: the depth is read twice" if two_pass else "single pass with decoupled look-back: traffic = algorithmic + 4 B per column")}}))

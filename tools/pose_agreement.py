@@ -13,7 +13,9 @@ the C ABI, both drawing SAC-IA's decisions from libc rand() seeded like the refe
 
   python tools/pose_agreement.py [--frames 1000]
 """
-import json, os, sys, time
+import os
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+import json, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import numpy as np
@@ -81,7 +83,25 @@ def main():
         ro, to = synth.pose_error(o_fine.reshape(4, 4).T @ o_coarse.reshape(4, 4).T, pose)
         rec_g += rg < np.deg2rad(5) and tg < 0.01
         rec_o += ro < np.deg2rad(5) and to < 0.01
-    print(json.dumps({"frames": n, "agreement": agree / n, "same_icp_state_and_iterations": same_state / n,
+    # the same frames through ope_pose_batch (16 worker streams, model side cached, thread-per-query ICP kernel): every frame
+    # replays the decision table a fresh PoseEstimator draws after srand(1)
+    import orc_py
+    orc_py.srand(1)
+    sp = model[orc_py.uniform_sample(model, 0.01)]
+    table = cuda_lib.rng_table(*orc_py.sacia_draw(sp, 400, 5, 5, 0.01))
+    clusters = [synth.make_frame(model, 1000 + f)[0] for f, *_ in cpu]
+    ctx.pose_batch(model, clusters[:32], tables=[table] * min(32, n), workers=16)   # warm the workers
+    t1 = time.perf_counter()
+    bres, bstatus = ctx.pose_batch(model, clusters, tables=[table] * n, workers=16)
+    batch_s = time.perf_counter() - t1
+    b_agree = b_state = 0
+    for (f, o_pose, o_state, o_conv, o_it, o_fit, o_coarse, o_fine), p in zip(cpu, bres):
+        r, t = synth.pose_error(cuda_lib.T.mat4(p.final_pose), o_pose.reshape(4, 4).T)
+        b_agree += r < 1e-3 and t < 1e-4 and p.icp_state == o_state
+        b_state += (p.icp_state == o_state and p.icp_iterations == o_it)
+    print(json.dumps({"frames": n, "agreement": agree / n, "batch_agreement": b_agree / n,
+                      "batch_same_icp_state_and_iterations": b_state / n, "batch_e2e_s_total": batch_s,
+                      "batch_e2e_frames_per_s": n / batch_s, "batch_failed_frames": int((bstatus != 0).sum()), "same_icp_state_and_iterations": same_state / n,
                       "recovered_vs_truth_gpu": rec_g / n, "recovered_vs_truth_oracle": rec_o / n,
                       "worst_disagreement_rad_m": worst, "cpu_oracle_s_total": cpu_s, "cpu_cores": cores,
                       "cpu_frames_per_s_all_cores": n / cpu_s, "gpu_e2e_s_total": gpu_s, "gpu_e2e_frames_per_s": n / gpu_s}))
