@@ -32,7 +32,10 @@ __device__ __forceinline__ int64_t bin_cell(const Binning& b, float x, float y, 
 }
 
 // per-block min/max/count of finite points -> partials[block][8]
-__global__ void bbox_partial_kernel(const float4* __restrict__ pts, int n, float* __restrict__ partials) {
+// partials[8 * block]; with `ticket` != nullptr the block that finishes last also folds the partials into `out` (one launch
+// instead of two: min / max / count do not depend on the order) and re-arms the ticket for the next call on this context.
+__global__ void bbox_partial_kernel(const float4* __restrict__ pts, int n, float* __restrict__ partials, unsigned* __restrict__ ticket = nullptr,
+                                    float* __restrict__ out = nullptr) {
   float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   int cnt = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -65,6 +68,34 @@ __global__ void bbox_partial_kernel(const float4* __restrict__ pts, int n, float
     float* o = partials + 8 * blockIdx.x;
     for (int d = 0; d < 3; ++d) { o[d] = mn[d]; o[3 + d] = mx[d]; }
     o[6] = __int_as_float(cnt);
+  }
+  if (!ticket) return;
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last || w != 0) return;
+  __threadfence();
+  float fmn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, fmx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  int fc = 0;
+  for (int b = l; b < (int)gridDim.x; b += 32) {
+    const volatile float* p = partials + 8 * b;
+    for (int d = 0; d < 3; ++d) { fmn[d] = fminf(fmn[d], p[d]); fmx[d] = fmaxf(fmx[d], p[3 + d]); }
+    fc += __float_as_int(p[6]);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    for (int d = 0; d < 3; ++d) {
+      fmn[d] = fminf(fmn[d], __shfl_xor_sync(0xffffffffu, fmn[d], o));
+      fmx[d] = fmaxf(fmx[d], __shfl_xor_sync(0xffffffffu, fmx[d], o));
+    }
+    fc += __shfl_xor_sync(0xffffffffu, fc, o);
+  }
+  if (l == 0) {
+    for (int d = 0; d < 3; ++d) { out[d] = fmn[d]; out[3 + d] = fmx[d]; }
+    out[6] = __int_as_float(fc);
+    *ticket = 0u;
   }
 }
 __global__ void bbox_final_kernel(const float* __restrict__ partials, int nblocks, float* __restrict__ out) {
@@ -128,6 +159,41 @@ __global__ void scan_block_kernel(int* __restrict__ data, size_t n, int* __restr
     run += v[j];
   }
 }
+// Exclusive scan of up to a few 10^4 ints by ONE block in one launch (tiles of 4096 with a running carry): the cell tables of the
+// small clouds of the frame path are this size, and a launch costs more than the scan.
+static constexpr int kScan1Threads = 1024;
+__global__ void __launch_bounds__(kScan1Threads) scan_single_kernel(int* __restrict__ data, int n) {
+  __shared__ int warp_sums[kScan1Threads / 32];
+  __shared__ int s_carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int tile = 0; tile < n; tile += kScan1Threads * 4) {
+    const int base = tile + threadIdx.x * 4;
+    int v[4];
+    int sum = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { v[j] = base + j < n ? data[base + j] : 0; sum += v[j]; }
+    int incl = sum;
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    const int carry = s_carry;
+    if (warp == 0) {
+      const int ws = warp_sums[lane];
+      int wi = ws;
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+      warp_sums[lane] = wi - ws;
+      if (lane == 31) s_carry = carry + wi;   // read by everyone only after the next barrier
+    }
+    __syncthreads();
+    int run = carry + warp_sums[warp] + incl - sum;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { if (base + j < n) data[base + j] = run; run += v[j]; }
+    __syncthreads();
+  }
+}
+
 __global__ void scan_add_kernel(int* __restrict__ data, size_t n, const int* __restrict__ block_offsets) {
   const size_t base = ((size_t)blockIdx.x * kThreads + threadIdx.x) * kScanItems;
   const int off = block_offsets[blockIdx.x];
@@ -322,10 +388,15 @@ int cloud_bbox(ope_ctx* ctx, ope_cloud* c) {
   Scratch<float> partials(ctx), fin(ctx);
   OPE_TRY(partials.alloc((size_t)nb * 8));
   OPE_TRY(fin.alloc(8));
-  bbox_partial_kernel<<<nb, kThreads, 0, ctx->stream>>>(c->pts, (int)c->n, partials.p);
-  OPE_TRY(check_launch(ctx, "bbox_partial_kernel"));
-  bbox_final_kernel<<<1, 32, 0, ctx->stream>>>(partials.p, nb, fin.p);
-  OPE_TRY(check_launch(ctx, "bbox_final_kernel"));
+  if (ctx->ticket) {
+    bbox_partial_kernel<<<nb, kThreads, 0, ctx->stream>>>(c->pts, (int)c->n, partials.p, ctx->ticket, fin.p);
+    OPE_TRY(check_launch(ctx, "bbox_partial_kernel"));
+  } else {
+    bbox_partial_kernel<<<nb, kThreads, 0, ctx->stream>>>(c->pts, (int)c->n, partials.p);
+    OPE_TRY(check_launch(ctx, "bbox_partial_kernel"));
+    bbox_final_kernel<<<1, 32, 0, ctx->stream>>>(partials.p, nb, fin.p);
+    OPE_TRY(check_launch(ctx, "bbox_final_kernel"));
+  }
   void* h;
   OPE_TRY(read_back(ctx, fin.p, 8 * sizeof(float), &h));
   const float* f = (const float*)h;
@@ -340,6 +411,10 @@ int exclusive_scan_i32(ope_ctx* ctx, int* data, size_t n) {
   if (n == 0) return OPE_OK;
   const size_t per_block = (size_t)kThreads * kScanItems;
   const size_t nb = (n + per_block - 1) / per_block;
+  if (nb > 1 && n <= 65536) {
+    scan_single_kernel<<<1, kScan1Threads, 0, ctx->stream>>>(data, (int)n);
+    return check_launch(ctx, "scan_single_kernel");
+  }
   if (nb == 1) {
     scan_block_kernel<<<1, kThreads, 0, ctx->stream>>>(data, n, nullptr);
     return check_launch(ctx, "scan_block_kernel");
@@ -550,6 +625,11 @@ int ope_ctx_create(int device, void* stream, ope_ctx** out) {
   }
   for (int w = 0; w < 3; ++w)
     for (int j = 0; j < 2; ++j) cudaEventCreate(&ctx->kev[w][j]);
+  // a zeroed counter for "last block folds the partials" kernels (each such kernel re-arms it before it exits)
+  if (cudaMalloc((void**)&ctx->ticket, sizeof(unsigned)) != cudaSuccess || cudaMemset(ctx->ticket, 0, sizeof(unsigned)) != cudaSuccess) {
+    cudaGetLastError();
+    ctx->ticket = nullptr;
+  }
   *out = ctx;
   return OPE_OK;
 }
@@ -579,6 +659,7 @@ void ope_ctx_destroy(ope_ctx* ctx) {
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->stage) cudaFreeHost(ctx->stage);
   if (ctx->sync_event) cudaEventDestroy(ctx->sync_event);
+  if (ctx->ticket) cudaFree(ctx->ticket);
   for (ope_ctx* w : ctx->workers) ope_ctx_destroy(w);
   ctx->workers.clear();
   if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);

@@ -30,6 +30,7 @@ struct ope_ctx {
   std::vector<ope_ctx*> workers;  // ope_pose_batch: per-thread contexts (own stream, pool, staging), kept warm between calls
   cudaEvent_t sync_event = nullptr;  // set: waits sleep on this cudaEventBlockingSync event instead of spinning in cudaStreamSynchronize
                                      // (ope_pose_batch workers beyond the host's core count)
+  unsigned* ticket = nullptr;        // device counter, zero between kernels (see bbox_partial_kernel)
   bool sync_yield = false;           // with sync_event: poll it and sched_yield() between polls instead of sleeping
   bool icp_prefer_small = false;  // small clouds: prefer the thread-per-query ICP kernel (least device time per alignment)
   int icp_max_blocks = 0;      // > 0: cap of the cooperative icp_kernel grid (batch workers share the SMs between frames)
