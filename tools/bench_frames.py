@@ -57,7 +57,9 @@ def main():
                 src.free()
             tr.close()
 
-    workers = int(sys.argv[sys.argv.index("--workers") + 1]) if "--workers" in sys.argv else 16
+    # one spinning host thread per worker stream: do not oversubscribe the host cores when several ranks share a box
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+    workers = int(sys.argv[sys.argv.index("--workers") + 1]) if "--workers" in sys.argv else max(4, min(16, (os.cpu_count() or 16) // max(local_world, 1)))
 
     def run_batch(host):
         # ope_pose_batch: worker threads with their own streams, model side cached; the decision tables are drawn
@@ -95,7 +97,8 @@ def main():
         print(json.dumps({"metric": "frames_per_sec_fpfh_sacia_icp_640x480", "n_gpus": world, "frames": n, "scaling": "strong",
                           "value": out["frames_per_s"], "e2e": out["e2e_frames_per_s"], "unit": "frames/s",
                           "config": {"workload": "C5: %d independent frames, full first-frame path, frame f -> rank f mod N" % n,
-                                     "mode": "serial trackers" if "--serial" in sys.argv else "ope_pose_batch, %d workers per GPU" % workers}}))
+                                     "mode": "serial trackers" if "--serial" in sys.argv else "ope_pose_batch, %d workers per GPU" % workers,
+                                     "host_cores": os.cpu_count()}}))
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
