@@ -5,6 +5,9 @@
 // 132 FPFH write) plus an m-neighbour gather of 32 B (SPFH pass) / 136 B (FPFH pass) per neighbour from L2.
 #include <algorithm>
 
+#include <cstdlib>
+#include <mutex>
+
 #include "ope_host.cuh"
 #include "ope_octet.cuh"
 
@@ -35,6 +38,52 @@ __global__ void __launch_bounds__(kNormThreads) normals_kernel(GridView g, const
       CovAccum acc;
       acc.reset();
       for (int j = 0; j < cnt; ++j)   // every lane sums the same sequence: uniform, no divergence
+        acc.add(__shfl_sync(0xffffffffu, p.x, j), __shfl_sync(0xffffffffu, p.y, j), __shfl_sync(0xffffffffu, p.z, j));
+      normal_from_accum(acc, cnt, q.x, q.y, q.z, vpx, vpy, vpz, r);
+    }
+    if (lane == 0) out[i] = make_float4(r[0], r[1], r[2], r[3]);
+    __syncwarp();
+  }
+}
+
+// Small clouds (a down-sampled model or cluster: 1-2 k points): no spatial index at all. Every block keeps the whole cloud in
+// shared memory and its warps answer their queries by the exact brute-force warp scan (warp_knn_smem: same (d2, index) list as
+// warp_knn, hence the same normals bit for bit). One launch instead of bounding box + grid build (six launches and a host
+// round trip) + search; what a frame spends on normals falls from ~0.2 ms per cloud to the launch itself.
+static constexpr int kNormSmemMax = 4096;
+__global__ void __launch_bounds__(kNormThreads) normals_smem_kernel(const float4* __restrict__ pts, int n, int k, float vpx, float vpy,
+                                                                    float vpz, float4* __restrict__ out) {
+  extern __shared__ __align__(16) float4 tg_norm[];
+  int fin = 0;
+  for (int j = threadIdx.x; j < n; j += kNormThreads) {
+    const float4 t = __ldg(pts + j);
+    tg_norm[j] = t;
+    fin += finite3(t.x, t.y, t.z) ? 1 : 0;
+  }
+  // number of finite points (nearestKSearch clamps k to it): every thread contributes its count
+  __shared__ int s_fin;
+  if (threadIdx.x == 0) s_fin = 0;
+  __syncthreads();
+  for (int o = 16; o > 0; o >>= 1) fin += __shfl_xor_sync(0xffffffffu, fin, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&s_fin, fin);
+  __syncthreads();
+  const int n_finite = s_fin;
+  const int lane = threadIdx.x & 31;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  const float nan = __int_as_float(0x7fc00000);
+  for (int i = wid; i < n; i += n_warps) {
+    const float4 q = tg_norm[i];
+    const bool ok = finite3(q.x, q.y, q.z);
+    float ld;
+    int li;
+    const int cnt = warp_knn_smem(tg_norm, n, n_finite, ok, q.x, q.y, q.z, k, FLT_MAX, ld, li);
+    float4 p = make_float4(0, 0, 0, 0);
+    if (lane < cnt) p = tg_norm[li];
+    float r[4] = {nan, nan, nan, nan};
+    if (ok && cnt >= 3) {
+      CovAccum acc;
+      acc.reset();
+      for (int j = 0; j < cnt; ++j)
         acc.add(__shfl_sync(0xffffffffu, p.x, j), __shfl_sync(0xffffffffu, p.y, j), __shfl_sync(0xffffffffu, p.z, j));
       normal_from_accum(acc, cnt, q.x, q.y, q.z, vpx, vpy, vpz, r);
     }
@@ -267,6 +316,21 @@ int normals_device(ope_ctx* ctx, ope_cloud* cloud, int k, const float vp[3]) {
   if (k < 1 || k > 32) return fail(ctx, OPE_ERR_INVALID, "normal estimation k must be in [1, 32]");
   if (!cloud->normals) OPE_TRY(dalloc(ctx, &cloud->normals, cloud->n));
   if (cloud->n == 0) return OPE_OK;
+  if (cloud->n <= (size_t)kNormSmemMax && !std::getenv("OPE_NORMALS_FORCE_GRID")) {
+    const size_t bytes = cloud->n * sizeof(float4);
+    static std::mutex mu;
+    static size_t granted = 0;
+    {
+      std::lock_guard<std::mutex> lock(mu);   // the opt-in belongs to the function, shared by all contexts: only ever raise it
+      if (bytes > granted) {
+        OPE_CUDA_TRY(ctx, cudaFuncSetAttribute((const void*)normals_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kNormSmemMax * sizeof(float4))));
+        granted = kNormSmemMax * sizeof(float4);
+      }
+    }
+    const unsigned blocks = (unsigned)std::min<size_t>(div_up(cloud->n * 32, kNormThreads), (size_t)ctx->sm_count * 2);
+    normals_smem_kernel<<<blocks, kNormThreads, bytes, ctx->stream>>>(cloud->pts, (int)cloud->n, k, vp[0], vp[1], vp[2], cloud->normals);
+    return check_launch(ctx, "normals_smem_kernel");
+  }
   OPE_TRY(cloud_bbox(ctx, cloud));
   GridView g;
   OPE_TRY(cloud_grid(ctx, cloud, knn_cell_size(cloud, k), &g));
