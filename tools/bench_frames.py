@@ -59,7 +59,10 @@ def main():
 
     # one spinning host thread per worker stream: do not oversubscribe the host cores when several ranks share a box
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
-    workers = int(sys.argv[sys.argv.index("--workers") + 1]) if "--workers" in sys.argv else max(4, min(16, (os.cpu_count() or 16) // max(local_world, 1)))
+    cores_per_rank = max(1, (os.cpu_count() or 16) // max(local_world, 1))
+    workers = int(sys.argv[sys.argv.index("--workers") + 1]) if "--workers" in sys.argv else 16
+    if workers > cores_per_rank:
+        os.environ.setdefault("OPE_BATCH_BLOCKING_SYNC", "2")   # more worker threads than cores for this rank: poll + yield, do not spin
 
     def run_batch(host):
         # ope_pose_batch: worker threads with their own streams, model side cached; the decision tables are drawn
