@@ -115,3 +115,53 @@ def test_cuda_matches_golden_frame(G, ctx, cuda_lib, synth, orc):
     assert meta == list(G["frame_meta"])
     assert abs(p.fitness - G["frame_fitness"][0]) < FIT_TOL and abs(p.align_strength - G["frame_fitness"][1]) < 1e-3
     tr.close()
+
+
+# ------------------------------------------------------------------ v2: point-to-plane estimators, BuildModel ICP, depth ----
+G2_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "registration_v2.npz")
+BM = dict(max_iterations=40, transformation_epsilon=1e-8, euclidean_fitness_epsilon=1e-8, k_search=20, with_normals=1)
+
+
+@pytest.fixture(scope="module")
+def G2():
+    return dict(np.load(G2_PATH))
+
+
+def _bm_params(mod, te):
+    T = mod.T
+    return mod.icp_params(estimator=T.EST_NORMAL_SHOOTING, rejectors=[(T.REJ_SURFACE_NORMAL, 0.7)], transformation=te, **BM)
+
+
+def test_oracle_reproduces_golden_v2(G2, orc):
+    T = orc.T
+    sp, tp, sn, tn = G2["view0"], G2["view1"], G2["view0_normals"], G2["view1_normals"]
+    assert np.array_equal(orc.normals_knn(sp, 12), sn, equal_nan=True) and np.array_equal(orc.normals_knn(tp, 12), tn, equal_nan=True)
+    lls = orc.point_to_plane(sp, tp, tn, G2["pairs_src"], G2["pairs_tgt"], kind=T.TE_POINT_TO_PLANE_LLS)
+    lm, info = orc.point_to_plane(sp, tp, tn, G2["pairs_src"], G2["pairs_tgt"], kind=T.TE_POINT_TO_PLANE, want_info=True)
+    assert np.array_equal(lls.astype(np.float32), G2["p2p_lls_T"]) and np.array_equal(lm.astype(np.float32), G2["p2p_lm_T"])
+    assert list(info) == list(G2["p2p_lm_info"])
+    for name, te in (("lm", T.TE_POINT_TO_PLANE), ("lls", T.TE_POINT_TO_PLANE_LLS)):
+        r = orc.icp(sp, tp, _bm_params(orc, te), src_normals=sn, tgt_normals=tn)
+        assert np.array_equal(np.array(list(r.T), np.float32), G2["icp_%s_T" % name])
+        assert [r.converged, r.state, r.iterations, r.n_correspondences] == list(G2["icp_%s_meta" % name])
+    assert np.array_equal(orc.depth_to_cloud(G2["depth"]), G2["depth_cloud"])
+
+
+@pytest.mark.gpu
+def test_cuda_matches_golden_v2(G2, ctx, cuda_lib, synth):
+    T = cuda_lib.T
+    sp, tp, sn, tn = G2["view0"], G2["view1"], G2["view0_normals"], G2["view1_normals"]
+    cs, ct = ctx.upload(sp, sn), ctx.upload(tp, tn)
+    for kind, key in ((T.TE_POINT_TO_PLANE_LLS, "p2p_lls_T"), (T.TE_POINT_TO_PLANE, "p2p_lm_T")):
+        g, info = ctx.point_to_plane(cs, ct, G2["pairs_src"], G2["pairs_tgt"], kind=kind, want_info=True)
+        rot, trans = synth.pose_error(g, G2[key].astype(np.float64))
+        assert rot < ROT_TOL and trans < TRANS_TOL, (key, rot, trans)
+        if kind == T.TE_POINT_TO_PLANE:
+            assert list(info) == list(G2["p2p_lm_info"])
+    for name, te in (("lm", T.TE_POINT_TO_PLANE), ("lls", T.TE_POINT_TO_PLANE_LLS)):
+        r = ctx.icp(cs, ct, _bm_params(cuda_lib, te))
+        rot, trans = synth.pose_error(T.mat4(r.T), _m(G2["icp_%s_T" % name]))
+        assert rot < ROT_TOL and trans < TRANS_TOL, (name, rot, trans)
+        assert [r.converged, r.state, r.iterations, r.n_correspondences] == list(G2["icp_%s_meta" % name])
+    got = ctx.depth_to_cloud(G2["depth"])
+    assert np.array_equal(got.download(), G2["depth_cloud"])
