@@ -365,7 +365,12 @@ int ope_pose_batch(ope_ctx* ctx, const ope_pose_params* prm, const float* model_
     }
   }
   std::vector<std::thread> pool;
-  for (int w = 1; w < workers; ++w) pool.emplace_back(batch_worker, &S, ctx->workers[w], &errs[w], &msgs[w]);
+  int started = 1;
+  try {   // nothing may throw across the C ABI: if the host cannot start more threads, the ones that exist do all the work
+    for (int w = 1; w < workers; ++w) { pool.emplace_back(batch_worker, &S, ctx->workers[w], &errs[w], &msgs[w]); ++started; }
+  } catch (...) {
+  }
+  (void)started;
   batch_worker(&S, ctx->workers[0], &errs[0], &msgs[0]);
   for (auto& th : pool) th.join();
   cudaSetDevice(ctx->device);
