@@ -459,6 +459,8 @@ def test_pose_batch_equals_the_serial_first_frame_path(ctx, orc, synth, cuda_lib
     T = cuda_lib.T
     libc = ctypes.CDLL(None)
     frames = [synth.make_frame(model, 900 + f)[0] for f in range(6)]
+    frames.append(frames[0][:60].copy())                 # too few points for the fine stage (< 100) and for SAC-IA's features
+    frames.append(frames[1][::40].copy())                # a sparse cluster
     frames.append(np.zeros((0, 3), np.float32))          # an empty cluster: no target, identity poses
     # serial reference on the device: one fresh tracker per frame, SAC-IA drawing from libc rand() in frame order
     libc.srand(7)
