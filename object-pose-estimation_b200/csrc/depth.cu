@@ -25,17 +25,6 @@ struct DepthParams {
                                // evaluated on the host for all 65 536 raw values with the reference's float arithmetic)
 };
 
-// RN(a / d) for a launch constant d without the general division sequence: q = RN(a * RN(1/d)) is within a few ulp, and each
-// Markstein step q <- RN(q + RN(a - q d) * RN(1/d)) (the residual is exact in an FMA) first makes it faithful, then correctly
-// rounded. Valid away from overflow / underflow, which depth values in metres are. 5 instructions instead of ~15 and no slow path.
-__device__ __forceinline__ float div_by_const(float a, float d, float rd) {
-  float q = a * rd;
-  float e = fmaf(-q, d, a);
-  q = fmaf(e, rd, q);
-  e = fmaf(-q, d, a);
-  return fmaf(e, rd, q);
-}
-
 __device__ __forceinline__ bool depth_keep(const DepthParams& P, unsigned short raw) { return (int)raw >= P.raw_lo && (int)raw <= P.raw_hi; }
 
 __device__ __forceinline__ bool depth_point(const DepthParams& P, int i, int j, unsigned short raw, float4& out) {

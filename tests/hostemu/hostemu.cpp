@@ -143,3 +143,21 @@ void emu_umeyama_moments(const float* s, const float* d, int n, float* T16) {
 }
 
 }  // extern "C"
+
+
+// Exhaustive check of ope::div_by_const against the IEEE division over everything depth -> cloud can feed it: Z = raw / scale for
+// every raw value, then (i - c) * Z / f for every row/column index of a `dim`-pixel axis. Returns the number of mismatches.
+extern "C" long long emu_div_by_const_mismatches(float scale, float f, float c, int dim) {
+  long long bad = 0;
+  const float r_scale = 1.0f / scale, r_f = 1.0f / f;
+  for (int raw = 0; raw <= 65535; ++raw) {
+    const float z_ref = (float)raw / scale;
+    const float z = ope::div_by_const((float)raw, scale, r_scale);
+    if (z != z_ref) { ++bad; continue; }
+    for (int i = 0; i < dim; ++i) {
+      const float num = ((float)i - c) * z;
+      if (ope::div_by_const(num, f, r_f) != num / f) ++bad;
+    }
+  }
+  return bad;
+}

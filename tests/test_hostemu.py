@@ -168,3 +168,12 @@ def test_device_umeyama_variants(emu, orc, synth):
     emu.emu_umeyama_moments(s.ctypes.data_as(f32p), d.ctypes.data_as(f32p), len(s), out)
     r, t = synth.pose_error(orc.T.mat4(out), T)
     assert r < 1e-6 and t < 2e-6
+
+
+@pytest.mark.parametrize("scale,f,c,dim", [(1000.0, 525.0, 319.5, 640), (1000.0, 525.0, 239.5, 480), (5000.0, 365.7, 255.2, 512),
+                                           (1000.0, 570.3422, 314.5, 640), (3.0, 571.9631, 235.5, 480)])
+def test_division_by_launch_constants_is_correctly_rounded(emu, scale, f, c, dim):
+    """depth -> cloud replaces the IEEE divisions by a reciprocal multiply and two exact-residual FMA corrections
+    (ope::div_by_const): for every raw depth value and every pixel index of an axis the result must equal the division's."""
+    emu.emu_div_by_const_mismatches.restype = C.c_longlong
+    assert emu.emu_div_by_const_mismatches(C.c_float(scale), C.c_float(f), C.c_float(c), dim) == 0
