@@ -54,6 +54,7 @@ static constexpr int kNormSmemMax = 4096;
 __global__ void __launch_bounds__(kNormThreads) normals_smem_kernel(const float4* __restrict__ pts, int n, int k, float vpx, float vpy,
                                                                     float vpz, float4* __restrict__ out) {
   extern __shared__ __align__(16) float4 tg_norm[];
+  __shared__ float2 knn_buf[kNormThreads / 32][kKnnBufCap + 32];   // per-warp scratch of the two-pass exact search
   int fin = 0;
   for (int j = threadIdx.x; j < n; j += kNormThreads) {
     const float4 t = __ldg(pts + j);
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(kNormThreads) normals_smem_kernel(const float4
     const bool ok = finite3(q.x, q.y, q.z);
     float ld;
     int li;
-    const int cnt = warp_knn_smem(tg_norm, n, n_finite, ok, q.x, q.y, q.z, k, FLT_MAX, ld, li);
+    const int cnt = warp_knn_smem_bounded(tg_norm, n, n_finite, ok, q.x, q.y, q.z, k, FLT_MAX, knn_buf[threadIdx.x >> 5], ld, li);
     float4 p = make_float4(0, 0, 0, 0);
     if (lane < cnt) p = tg_norm[li];
     float r[4] = {nan, nan, nan, nan};

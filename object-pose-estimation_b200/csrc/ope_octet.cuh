@@ -525,7 +525,31 @@ __device__ __forceinline__ int warp_knn_smem_bounded(const float4* tg, int nt, i
   const int lane = threadIdx.x & 31;
   if (k > n_finite) k = n_finite;
   if (!(active && k > 0)) { ld = FLT_MAX; li = 0x7fffffff; return 0; }
-  if (!(bound < FLT_MAX)) return warp_knn_smem(tg, nt, n_finite, active, qx, qy, qz, k, bound, ld, li);
+  if (!(bound < FLT_MAX)) {
+    // No bound given: make one. Every lane takes the minimum over its own stride of the target; the k lanes with the smallest
+    // minima hold k DISTINCT points, so the k-th smallest of the 32 lane minima bounds the k-th distance (k <= 32). One extra
+    // pass without any list maintenance, instead of ~k ln(n / k) serial insertions.
+    float mn = FLT_MAX;
+#pragma unroll 4
+    for (int base = 0; base < nt; base += 32) {
+      const int j = base + lane;
+      if (j < nt) {
+        const float4 t = tg[j];
+        const float d2 = dist2(qx, qy, qz, t.x, t.y, t.z);
+        if (finite3(t.x, t.y, t.z)) mn = fminf(mn, d2);
+      }
+    }
+    int rank = 0;
+#pragma unroll
+    for (int o = 0; o < 32; ++o) {
+      const float other = __shfl_sync(full, mn, o);
+      rank += (other < mn || (other == mn && o < lane)) ? 1 : 0;
+    }
+    const unsigned holder = __ballot_sync(full, rank == k - 1);   // exactly one lane: the ranks are a permutation
+    const float tau = __shfl_sync(full, mn, __ffs(holder) - 1);
+    if (!(tau < FLT_MAX)) return warp_knn_smem(tg, nt, n_finite, active, qx, qy, qz, k, bound, ld, li);   // fewer than k lanes see a point
+    bound = tau;
+  }
   const unsigned lt = (1u << lane) - 1u;
   int c = 0;
 #pragma unroll 4
