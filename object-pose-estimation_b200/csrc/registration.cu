@@ -125,6 +125,40 @@ __global__ void __launch_bounds__(kNnThreads) fitness_kernel(GridView g, const f
   }
   block_reduce_store<2>(acc, smem, partials + (size_t)blockIdx.x * 2);
 }
+// The same against a small target (a down-sampled cluster) held in shared memory: exact brute force, one query per thread, eight
+// independent distances per step (broadcast loads). No spatial index to build, so the call is two launches instead of eight.
+static constexpr int kFitSmemMax = 4096;
+__global__ void __launch_bounds__(kNnThreads) fitness_smem_kernel(const float4* __restrict__ tgt, int nt, const float4* __restrict__ src, int n,
+                                                                  Mat4 T, float max_range_f, double* __restrict__ partials) {
+  extern __shared__ __align__(16) float4 tg_fit[];
+  __shared__ double smem[(kNnThreads / 32) * 2];
+  const int nt8 = (nt + 7) & ~7;
+  for (int j = threadIdx.x; j < nt8; j += kNnThreads) tg_fit[j] = j < nt ? __ldg(tgt + j) : make_float4(INFINITY, INFINITY, INFINITY, 0.0f);
+  __syncthreads();
+  double acc[2] = {0.0, 0.0};
+  for (int base = blockIdx.x * kNnThreads; base < n; base += gridDim.x * kNnThreads) {
+    const int i = base + (int)threadIdx.x;
+    float x = 0, y = 0, z = 0;
+    bool ok = false;
+    if (i < n) {
+      const float4 p = __ldg(src + i);
+      xform_point(T, p.x, p.y, p.z, x, y, z);
+      ok = finite3(x, y, z);
+    }
+    float best = INFINITY;
+    if (ok) {
+      for (int j0 = 0; j0 < nt8; j0 += 8) {
+        float d2[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const float4 t = tg_fit[j0 + u]; d2[u] = dist2(x, y, z, t.x, t.y, t.z); }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) if (d2[u] < best) best = d2[u];   // NaN (non-finite target point) never wins
+      }
+    }
+    if (ok && best <= max_range_f) { acc[0] += (double)best; acc[1] += 1.0; }   // best = inf: no finite target point
+  }
+  block_reduce_store<2>(acc, smem, partials + (size_t)blockIdx.x * 2);
+}
 __global__ void sum_partials_kernel(const double* __restrict__ partials, int nblocks, int nacc, double* __restrict__ out) {
   // one warp per accumulator, lanes stride over the blocks, fixed shuffle tree
   const int a = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1364,17 +1398,24 @@ int umeyama_device(ope_ctx* ctx, const float4* src, const float4* tgt, const int
 int fitness_device(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const Mat4& T, double max_range, double* out) {
   *out = DBL_MAX;
   if (src->n == 0) return OPE_OK;
-  OPE_TRY(cloud_bbox(ctx, const_cast<ope_cloud*>(tgt)));
-  GridView g;
-  OPE_TRY(cloud_grid(ctx, tgt, knn_cell_size(tgt, 1), &g));
   const int nb = (int)std::min<size_t>(std::max<size_t>(1, (src->n + kNnThreads - 1) / kNnThreads), (size_t)ctx->sm_count * 4);
   Scratch<double> partials(ctx), fin(ctx);
   OPE_TRY(partials.alloc((size_t)nb * 2));
   OPE_TRY(fin.alloc(2));
   const float mr = max_range >= (double)FLT_MAX ? FLT_MAX : (float)max_range;
-  OPE_TRY(dyn_smem(ctx, (const void*)fitness_kernel, sizeof(Nn1Smem<kNnThreads>)));
-  fitness_kernel<<<nb, kNnThreads, sizeof(Nn1Smem<kNnThreads>), ctx->stream>>>(g, src->pts, (int)src->n, T, mr, partials.p);
-  OPE_TRY(check_launch(ctx, "fitness_kernel"));
+  if (tgt->n <= (size_t)kFitSmemMax && !std::getenv("OPE_FITNESS_FORCE_GRID")) {
+    const size_t bytes = ((tgt->n + 7) & ~(size_t)7) * sizeof(float4);
+    OPE_TRY(dyn_smem(ctx, (const void*)fitness_smem_kernel, (size_t)kFitSmemMax * sizeof(float4)));
+    fitness_smem_kernel<<<nb, kNnThreads, bytes, ctx->stream>>>(tgt->pts, (int)tgt->n, src->pts, (int)src->n, T, mr, partials.p);
+    OPE_TRY(check_launch(ctx, "fitness_smem_kernel"));
+  } else {
+    OPE_TRY(cloud_bbox(ctx, const_cast<ope_cloud*>(tgt)));
+    GridView g;
+    OPE_TRY(cloud_grid(ctx, tgt, knn_cell_size(tgt, 1), &g));
+    OPE_TRY(dyn_smem(ctx, (const void*)fitness_kernel, sizeof(Nn1Smem<kNnThreads>)));
+    fitness_kernel<<<nb, kNnThreads, sizeof(Nn1Smem<kNnThreads>), ctx->stream>>>(g, src->pts, (int)src->n, T, mr, partials.p);
+    OPE_TRY(check_launch(ctx, "fitness_kernel"));
+  }
   sum_partials_kernel<<<1, 64, 0, ctx->stream>>>(partials.p, nb, 2, fin.p);
   OPE_TRY(check_launch(ctx, "sum_partials_kernel"));
   void* h;

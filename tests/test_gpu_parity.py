@@ -164,12 +164,23 @@ def test_umeyama_dense(ctx, orc, synth, model):
     assert r < ROT_TOL and t < TRANS_TOL
 
 
-def test_fitness(ctx, orc, synth, small_model):
-    src, tgt, T = synth.icp_pair(5000, seed=9, model=small_model)
+@pytest.mark.parametrize("n,path", [(5000, "grid"), (3000, "smem"), (3000, "grid-forced")])
+def test_fitness(ctx, orc, synth, small_model, n, path, monkeypatch):
+    """getFitnessScore through the spatial index (large targets) and by brute force from shared memory (targets of a few thousand
+    points), with a max_range, NaN points on both sides and a target without any finite point"""
+    if path == "grid-forced":
+        monkeypatch.setenv("OPE_FITNESS_FORCE_GRID", "1")
+    src, tgt, T = synth.icp_pair(n, seed=9, model=small_model)
+    src, tgt = src.copy(), tgt.copy()
+    src[3] = np.nan
+    tgt[11, 2] = np.nan
     a, b = ctx.upload(src), ctx.upload(tgt)
-    g = ctx.fitness(a, b, T)
-    o = orc.fitness(src, tgt, T)
-    assert abs(g - o) < FIT_TOL * max(1.0, abs(o)) and abs(g - o) / o < 1e-6
+    for max_range in (np.finfo(np.float64).max, 1e-5):
+        g = ctx.fitness(a, b, T, max_range)
+        o = orc.fitness(src, tgt, T, max_range)
+        assert abs(g - o) < FIT_TOL * max(1.0, abs(o)) and abs(g - o) / o < 1e-6, (max_range, g, o)
+    none = ctx.upload(np.full((8, 3), np.nan, np.float32))
+    assert ctx.fitness(a, none, T) == orc.fitness(src, np.full((8, 3), np.nan, np.float32), T)
 
 
 def test_correspondences_nearest_and_normal_shooting(ctx, orc, synth, cuda_lib, model):
