@@ -100,11 +100,20 @@ __global__ void __launch_bounds__(kNormThreads) normals_smem_kernel(const float4
 // on the count, so the float bin value is rebuilt exactly by repeated addition afterwards.
 static constexpr int kWarpsPerBlock = 8;
 
+// SMEM = true (clouds of up to kFeatSmemMax points — a down-sampled model or cluster): no spatial index; the block keeps points
+// and normals in shared memory and every warp tests all of them (ascending index, the oracle's order).
+static constexpr int kFeatSmemMax = 2048;
+template <bool SMEM>
 __global__ void spfh_kernel(GridView g, const float4* __restrict__ pts, const float4* __restrict__ nrm, int n, float r2,
                             float* __restrict__ spfh) {
+  extern __shared__ __align__(16) float4 sm_feat[];
   __shared__ int hist[kWarpsPerBlock][33];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int p_idx = blockIdx.x * kWarpsPerBlock + warp;
+  if (SMEM) {
+    for (int j = threadIdx.x; j < n; j += blockDim.x) { sm_feat[j] = __ldg(pts + j); sm_feat[n + j] = __ldg(nrm + j); }
+    __syncthreads();
+  }
   if (p_idx >= n) return;
   hist[warp][lane] = 0;
   if (lane == 0) hist[warp][32] = 0;
@@ -115,17 +124,15 @@ __global__ void spfh_kernel(GridView g, const float4* __restrict__ pts, const fl
     const float4 qn4 = __ldg(nrm + p_idx);
     const float qn[3] = {qn4.x, qn4.y, qn4.z};
     // the traversal is warp-uniform (one query per warp); lanes share each leaf range
-    grid_radius_ranges(
-        g, q.x, q.y, q.z, r2, 64,
-        [&](int b, int e) {
+    auto visit = [&](int b, int e) {
           for (int i = b + lane; i < e; i += 32) {
-            const float4 c = __ldg(g.pts + i);
+            const float4 c = SMEM ? sm_feat[i] : __ldg(g.pts + i);
             const float d2 = dist2(q.x, q.y, q.z, c.x, c.y, c.z);
             if (d2 < r2) {
               ++nb_count;
-              const int j = __float_as_int(c.w);
+              const int j = SMEM ? i : __float_as_int(c.w);
               if (j != p_idx) {
-                const float4 cn4 = __ldg(nrm + j);
+                const float4 cn4 = SMEM ? sm_feat[n + j] : __ldg(nrm + j);
                 const float cn[3] = {cn4.x, cn4.y, cn4.z};
                 int h1, h2, h3;
                 pair_feature_bins(q.x, q.y, q.z, qn, c.x, c.y, c.z, cn, h1, h2, h3);
@@ -135,7 +142,8 @@ __global__ void spfh_kernel(GridView g, const float4* __restrict__ pts, const fl
               }
             }
           }
-        });
+        };
+    if (SMEM) visit(0, n); else grid_radius_ranges(g, q.x, q.y, q.z, r2, 64, visit);
   }
   for (int o = 16; o > 0; o >>= 1) nb_count += __shfl_xor_sync(0xffffffffu, nb_count, o);
   __syncwarp();
@@ -153,10 +161,16 @@ __global__ void spfh_kernel(GridView g, const float4* __restrict__ pts, const fl
 // time (one per lane, coalesced float4 loads); the in-radius ones are then consumed in order, each as one coalesced
 // 132-byte read of its SPFH row, weighted by 1/d2 and accumulated in float like the reference
 // (weightPointSPFHSignature). The three normalisation sums are carried in double.
+template <bool SMEM>
 __global__ void fpfh_kernel(GridView g, const float4* __restrict__ pts, int n, float r2, const float* __restrict__ spfh,
                             float* __restrict__ out) {
+  extern __shared__ __align__(16) float4 sm_feat[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int p_idx = blockIdx.x * kWarpsPerBlock + warp;
+  if (SMEM) {
+    for (int j = threadIdx.x; j < n; j += blockDim.x) sm_feat[j] = __ldg(pts + j);
+    __syncthreads();
+  }
   if (p_idx >= n) return;
   const float4 q = __ldg(pts + p_idx);
   float acc = 0.0f, acc32 = 0.0f;
@@ -164,17 +178,15 @@ __global__ void fpfh_kernel(GridView g, const float4* __restrict__ pts, int n, f
   const bool ok = finite3(q.x, q.y, q.z);
   int found = 0;
   if (ok) {
-    grid_radius_ranges(
-        g, q.x, q.y, q.z, r2, 64,
-        [&](int b, int e) {
+    auto visit = [&](int b, int e) {
           for (int base = b; base < e; base += 32) {
             const int i = base + lane;
             float d2 = FLT_MAX;
             int j = -1;
             if (i < e) {
-              const float4 c = __ldg(g.pts + i);
+              const float4 c = SMEM ? sm_feat[i] : __ldg(g.pts + i);
               d2 = dist2(q.x, q.y, q.z, c.x, c.y, c.z);
-              j = __float_as_int(c.w);
+              j = SMEM ? i : __float_as_int(c.w);
             }
             const bool inr = d2 < r2;
             const unsigned in_mask = __ballot_sync(0xffffffffu, inr);
@@ -197,7 +209,8 @@ __global__ void fpfh_kernel(GridView g, const float4* __restrict__ pts, int n, f
               }
             }
           }
-        });
+        };
+    if (SMEM) visit(0, n); else grid_radius_ranges(g, q.x, q.y, q.z, r2, 64, visit);
   }
   // per-sub-histogram sums: bins 0-10 | 11-21 | 22-32
   const unsigned full = 0xffffffffu;
@@ -349,16 +362,40 @@ int fpfh_device(ope_ctx* ctx, const ope_cloud* cloud, float radius, float** d_fp
   OPE_TRY(dalloc(ctx, &spfh, n * 33));
   int rc = dalloc(ctx, &fpfh, n * 33);
   if (rc != OPE_OK) { dfree(ctx, spfh); return rc; }
-  if (n > 0) {
+  if (n > 0 && n <= (size_t)kFeatSmemMax && !std::getenv("OPE_FPFH_FORCE_GRID")) {
+    // small cloud: both passes from shared memory, no spatial index (two launches instead of eight + a host round trip)
+    const float r2 = radius * radius;
+    const unsigned blocks = div_up(n, kWarpsPerBlock);
+    GridView g;
+    std::memset(&g, 0, sizeof(g));
+    static std::mutex mu;
+    static bool granted = false;
+    {
+      std::lock_guard<std::mutex> lock(mu);
+      if (!granted) {
+        cudaError_t e = cudaFuncSetAttribute((const void*)spfh_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kFeatSmemMax * sizeof(float4)));
+        if (e != cudaSuccess) rc = fail(ctx, OPE_ERR_CUDA, "shared memory opt-in failed: %s", cudaGetErrorString(e));
+        granted = rc == OPE_OK;
+      }
+    }
+    if (rc == OPE_OK) {
+      spfh_kernel<true><<<blocks, kWarpsPerBlock * 32, 2 * n * sizeof(float4), ctx->stream>>>(g, cloud->pts, cloud->normals, (int)n, r2, spfh);
+      rc = check_launch(ctx, "spfh_kernel<smem>");
+    }
+    if (rc == OPE_OK) {
+      fpfh_kernel<true><<<blocks, kWarpsPerBlock * 32, n * sizeof(float4), ctx->stream>>>(g, cloud->pts, (int)n, r2, spfh, fpfh);
+      rc = check_launch(ctx, "fpfh_kernel<smem>");
+    }
+  } else if (n > 0) {
     GridView g;
     rc = cloud_grid(ctx, cloud, radius * 0.5f, &g);
     if (rc == OPE_OK) {
       const float r2 = radius * radius;
       const unsigned blocks = div_up(n, kWarpsPerBlock);
-      spfh_kernel<<<blocks, kWarpsPerBlock * 32, 0, ctx->stream>>>(g, cloud->pts, cloud->normals, (int)n, r2, spfh);
+      spfh_kernel<false><<<blocks, kWarpsPerBlock * 32, 0, ctx->stream>>>(g, cloud->pts, cloud->normals, (int)n, r2, spfh);
       rc = check_launch(ctx, "spfh_kernel");
       if (rc == OPE_OK) {
-        fpfh_kernel<<<blocks, kWarpsPerBlock * 32, 0, ctx->stream>>>(g, cloud->pts, (int)n, r2, spfh, fpfh);
+        fpfh_kernel<false><<<blocks, kWarpsPerBlock * 32, 0, ctx->stream>>>(g, cloud->pts, (int)n, r2, spfh, fpfh);
         rc = check_launch(ctx, "fpfh_kernel");
       }
     }

@@ -125,18 +125,27 @@ def test_normals(ctx, orc, synth, model, k, path, monkeypatch):
         c.free()
 
 
-def test_fpfh_within_tolerance(ctx, orc, synth, model):
+@pytest.mark.parametrize("path", ["smem", "grid"])
+def test_fpfh_within_tolerance(ctx, orc, synth, model, path, monkeypatch):
+    """small clouds are processed from shared memory without a spatial index (neighbours in ascending index order, like the oracle),
+    larger ones (or OPE_FPFH_FORCE_GRID) through the Morton grid"""
+    if path == "grid":
+        monkeypatch.setenv("OPE_FPFH_FORCE_GRID", "1")
     cl, _, _ = synth.make_frame(model, 11)
     pts = cl[orc.uniform_sample(cl, 0.01)]
+    assert len(pts) <= 2048
     nr = orc.normals_knn(pts, 30)
+    pts = pts.copy(); pts[7] = np.nan     # a NaN point: its own histogram is NaN, nobody counts it as a neighbour
     c = ctx.upload(pts, nr)
     g, gs = ctx.fpfh(c, 0.03, want_spfh=True)
     o = orc.fpfh(pts, nr, 0.03)
     os_ = orc.spfh(pts, nr, 0.03)
-    assert np.array_equal(gs, os_), np.abs(gs - os_).max()           # SPFH: integer counts + replayed float adds
-    scale = np.maximum(np.abs(o), 1.0)                                # histograms are percentages (0..100)
-    assert (np.abs(g - o) / scale).max() < FPFH_RTOL
-    sums = g.reshape(len(g), 3, 11).sum(-1)
+    assert np.array_equal(np.isnan(g), np.isnan(o)) and np.array_equal(np.isnan(gs), np.isnan(os_))
+    fin = ~np.isnan(o).any(1)
+    assert np.array_equal(gs[fin], os_[fin]), np.abs(gs[fin] - os_[fin]).max()   # SPFH: integer counts + replayed float adds
+    scale = np.maximum(np.abs(o[fin]), 1.0)                                      # histograms are percentages (0..100)
+    assert (np.abs(g[fin] - o[fin]) / scale).max() < FPFH_RTOL
+    sums = g[fin].reshape(fin.sum(), 3, 11).sum(-1)
     assert np.allclose(sums, 100.0, atol=1e-2)
 
 
