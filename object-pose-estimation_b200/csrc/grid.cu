@@ -164,11 +164,12 @@ __global__ void scan_block_kernel(int* __restrict__ data, size_t n, int* __restr
 static constexpr int kScan1Threads = 1024;
 __global__ void __launch_bounds__(kScan1Threads) scan_single_kernel(int* __restrict__ data, int n) {
   __shared__ int warp_sums[kScan1Threads / 32];
-  __shared__ int s_carry;
+  __shared__ int s_carry[2];   // double-buffered by tile parity: warp 0 writes the next carry while other warps still read this one
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) s_carry = 0;
+  if (threadIdx.x == 0) s_carry[0] = 0;
   __syncthreads();
-  for (int tile = 0; tile < n; tile += kScan1Threads * 4) {
+  int par = 0;
+  for (int tile = 0; tile < n; tile += kScan1Threads * 4, par ^= 1) {
     const int base = tile + threadIdx.x * 4;
     int v[4];
     int sum = 0;
@@ -178,13 +179,13 @@ __global__ void __launch_bounds__(kScan1Threads) scan_single_kernel(int* __restr
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
     if (lane == 31) warp_sums[warp] = incl;
     __syncthreads();
-    const int carry = s_carry;
+    const int carry = s_carry[par];
     if (warp == 0) {
       const int ws = warp_sums[lane];
       int wi = ws;
       for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
       warp_sums[lane] = wi - ws;
-      if (lane == 31) s_carry = carry + wi;   // read by everyone only after the next barrier
+      if (lane == 31) s_carry[par ^ 1] = carry + wi;
     }
     __syncthreads();
     int run = carry + warp_sums[warp] + incl - sum;
@@ -328,6 +329,44 @@ __global__ void uniform_compact_kernel(const unsigned long long* __restrict__ ke
     if (k != ~0ull) out_idx[pos[c]] = (int)(unsigned)(k & 0xffffffffull);
   }
 }
+// Small voxel tables (a down-sampled model or cluster: a few thousand cells): flag, scan and compact in ONE launch by one block
+// (tiles of 4096 cells with a running carry); out_idx receives the selected point indices in ascending voxel-key order, *count
+// their number.
+__global__ void __launch_bounds__(kScan1Threads) uniform_select_single_kernel(const unsigned long long* __restrict__ keys, int ncells,
+                                                                              int* __restrict__ out_idx, int* __restrict__ count) {
+  __shared__ int warp_sums[kScan1Threads / 32];
+  __shared__ int s_carry[2];   // double-buffered by tile parity (see scan_single_kernel)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry[0] = 0;
+  __syncthreads();
+  int par = 0;
+  for (int tile = 0; tile < ncells; tile += kScan1Threads * 4, par ^= 1) {
+    const int base = tile + threadIdx.x * 4;
+    unsigned long long k[4];
+    int sum = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { k[j] = base + j < ncells ? keys[base + j] : ~0ull; sum += k[j] != ~0ull ? 1 : 0; }
+    int incl = sum;
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    const int carry = s_carry[par];
+    if (warp == 0) {
+      const int ws = warp_sums[lane];
+      int wi = ws;
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+      warp_sums[lane] = wi - ws;
+      if (lane == 31) s_carry[par ^ 1] = carry + wi;
+    }
+    __syncthreads();
+    int run = carry + warp_sums[warp] + incl - sum;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (k[j] != ~0ull) out_idx[run++] = (int)(unsigned)(k[j] & 0xffffffffull);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = s_carry[par];
+}
+
 __global__ void occupied_flag_cells_kernel(const int* __restrict__ cell_start, int64_t ncells, int* __restrict__ flags) {
   for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < ncells; c += (int64_t)gridDim.x * blockDim.x)
     flags[c] = cell_start[c + 1] > cell_start[c] ? 1 : 0;
@@ -554,11 +593,24 @@ int uniform_sample_device(ope_ctx* ctx, ope_cloud* cloud, float leaf, int** d_id
   Scratch<unsigned long long> keys(ctx);
   Scratch<int> flags(ctx);
   OPE_TRY(keys.alloc((size_t)ncells));
-  OPE_TRY(flags.alloc((size_t)ncells + 1));
   OPE_CUDA_TRY(ctx, cudaMemsetAsync(keys.p, 0xff, (size_t)ncells * 8, ctx->stream));
-  OPE_CUDA_TRY(ctx, cudaMemsetAsync(flags.p + ncells, 0, sizeof(int), ctx->stream));
   uniform_key_kernel<<<grid_blocks(ctx, cloud->n), kThreads, 0, ctx->stream>>>(cloud->pts, (int)cloud->n, bin, keys.p);
   OPE_TRY(check_launch(ctx, "uniform_key_kernel"));
+  if (ncells <= (1 << 16) && !std::getenv("OPE_UNIFORM_MULTI_PASS")) {
+    // small table: one launch selects; the index buffer is sized for the worst case (every cell / every point occupied)
+    const size_t cap = std::min<size_t>((size_t)ncells, cloud->n);
+    int* idx = nullptr;
+    OPE_TRY(dalloc(ctx, &idx, cap + 1));
+    uniform_select_single_kernel<<<1, kScan1Threads, 0, ctx->stream>>>(keys.p, (int)ncells, idx, idx + cap);
+    int rc = check_launch(ctx, "uniform_select_single_kernel");
+    void* h = nullptr;
+    if (rc == OPE_OK) rc = read_back(ctx, idx + cap, sizeof(int), &h);
+    if (rc != OPE_OK) { dfree(ctx, idx); return rc; }
+    *d_idx = idx; *out_n = (size_t) * (const int*)h;
+    return OPE_OK;
+  }
+  OPE_TRY(flags.alloc((size_t)ncells + 1));
+  OPE_CUDA_TRY(ctx, cudaMemsetAsync(flags.p + ncells, 0, sizeof(int), ctx->stream));
   occupied_flag_u64_kernel<<<grid_blocks(ctx, (size_t)ncells), kThreads, 0, ctx->stream>>>(keys.p, ncells, flags.p);
   OPE_TRY(check_launch(ctx, "occupied_flag_u64_kernel"));
   OPE_TRY(exclusive_scan_i32(ctx, flags.p, (size_t)ncells + 1));
