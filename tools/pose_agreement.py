@@ -40,7 +40,7 @@ def _cpu_frame(f):
     orc.srand(1)
     p = pe.estimate_final(src, cl)
     return (f, np.array(list(p.final_pose), np.float64), p.icp_state, p.icp_converged, p.icp_iterations, p.fitness,
-            np.array(list(p.coarse_pose), np.float64), np.array(list(p.fine_pose), np.float64))
+            np.array(list(p.coarse_pose), np.float64), np.array(list(p.fine_pose), np.float64), p.sacia_best_iteration, p.sacia_best_error)
 
 
 def main():
@@ -62,7 +62,8 @@ def main():
     agree = rec_g = rec_o = same_state = 0
     worst = (0.0, 0.0)
     gpu_s = 0.0
-    for f, o_pose, o_state, o_conv, o_it, o_fit, o_coarse, o_fine in cpu:
+    disagreements = []
+    for f, o_pose, o_state, o_conv, o_it, o_fit, o_coarse, o_fine, o_best, o_err in cpu:
         cl, _, pose = synth.make_frame(model, 1000 + f)
         tr = cuda_lib.PoseTracker(ctx)
         src = model.copy()
@@ -79,6 +80,11 @@ def main():
         same_state += (p.icp_state == o_state and p.icp_iterations == o_it)
         if not ok:
             worst = max(worst, (r, t))
+            rc, tc = synth.pose_error(cuda_lib.T.mat4(p.coarse_pose), o_coarse.reshape(4, 4).T)
+            disagreements.append({"frame": int(f), "final_rot_rad": float(r), "final_trans_m": float(t), "coarse_rot_rad": float(rc),
+                                  "coarse_trans_m": float(tc), "sacia_winner_gpu": int(p.sacia_best_iteration), "sacia_winner_oracle": int(o_best),
+                                  "sacia_error_gpu": float(p.sacia_best_error), "sacia_error_oracle": float(o_err),
+                                  "fitness_gpu": float(p.fitness), "fitness_oracle": float(o_fit)})
         rg, tg = synth.pose_error(cuda_lib.T.mat4(p.fine_pose) @ cuda_lib.T.mat4(p.coarse_pose), pose)
         ro, to = synth.pose_error(o_fine.reshape(4, 4).T @ o_coarse.reshape(4, 4).T, pose)
         rec_g += rg < np.deg2rad(5) and tg < 0.01
@@ -95,13 +101,14 @@ def main():
     bres, bstatus = ctx.pose_batch(model, clusters, tables=[table] * n, workers=16)
     batch_s = time.perf_counter() - t1
     b_agree = b_state = 0
-    for (f, o_pose, o_state, o_conv, o_it, o_fit, o_coarse, o_fine), p in zip(cpu, bres):
+    for (f, o_pose, o_state, o_conv, o_it, o_fit, o_coarse, o_fine, o_best, o_err), p in zip(cpu, bres):
         r, t = synth.pose_error(cuda_lib.T.mat4(p.final_pose), o_pose.reshape(4, 4).T)
         b_agree += r < 1e-3 and t < 1e-4 and p.icp_state == o_state
         b_state += (p.icp_state == o_state and p.icp_iterations == o_it)
     print(json.dumps({"frames": n, "agreement": agree / n, "batch_agreement": b_agree / n,
                       "batch_same_icp_state_and_iterations": b_state / n, "batch_e2e_s_total": batch_s,
-                      "batch_e2e_frames_per_s": n / batch_s, "batch_failed_frames": int((bstatus != 0).sum()), "same_icp_state_and_iterations": same_state / n,
+                      "batch_e2e_frames_per_s": n / batch_s, "batch_failed_frames": int((bstatus != 0).sum()),
+                      "disagreements": disagreements, "same_icp_state_and_iterations": same_state / n,
                       "recovered_vs_truth_gpu": rec_g / n, "recovered_vs_truth_oracle": rec_o / n,
                       "worst_disagreement_rad_m": worst, "cpu_oracle_s_total": cpu_s, "cpu_cores": cores,
                       "cpu_frames_per_s_all_cores": n / cpu_s, "gpu_e2e_s_total": gpu_s, "gpu_e2e_frames_per_s": n / gpu_s}))
