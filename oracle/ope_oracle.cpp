@@ -853,6 +853,54 @@ int orc_point_to_plane(const float* src, size_t ns, size_t sstride, const float*
   return OPE_OK;
 }
 
+// ---- SURVEY 8f-2 groundwork (ORACLE ONLY so far: the product has no segmentation stage yet) -------------------------------
+// pcl::PassThrough::applyFilter for an unorganised cloud, non-negative limits [UPSTREAM filters/impl/passthrough.hpp], as
+// ProcessingPcd::getPassThrough drives it (D&L/src/processingpcd.cpp:8-41): points with a non-finite coordinate are removed, a
+// point is kept iff lo <= field <= hi. field: 0 = x, 1 = y, 2 = z. Writes the kept ORIGINAL indices in ascending order.
+int64_t orc_pass_through(const float* pts, size_t n, size_t stride, int field, float lo, float hi, int32_t* out_idx) {
+  if (!pts || !out_idx || field < 0 || field > 2) return -1;
+  int64_t m = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const float* p = at(pts, stride, i);
+    if (!orc::finite3(p)) continue;
+    const float v = p[field];
+    if (v < lo || v > hi) continue;
+    out_idx[m++] = (int32_t)i;
+  }
+  return m;
+}
+
+// pcl::extractEuclideanClusters [UPSTREAM segmentation/impl/extract_clusters.hpp] as ObjectSegmentationPlane::getClusters sets it
+// up (D&L/src/objectsegmentationplane.cpp:74-90: tolerance 0.05, sizes 300 .. 1e5): region growing over radiusSearch (squared
+// distance < tolerance^2, FLANN semantics), a component is kept iff min_size <= size <= max_size, its indices sorted ascending;
+// clusters ordered by size descending (upstream uses an unstable sort: ties are canonicalised here by the smaller first index).
+// labels[i] = cluster number (0 = largest) or -1; returns the number of clusters.
+int orc_euclidean_clusters(const float* pts, size_t n, size_t stride, float tolerance, int min_size, int max_size, int32_t* labels) {
+  if (!pts || !labels) return -1;
+  for (size_t i = 0; i < n; ++i) labels[i] = -1;
+  KdTree tree; tree.build(pts, n, stride);
+  std::vector<char> processed(n, 0);
+  std::vector<std::vector<int32_t>> clusters;
+  std::vector<Neighbor> nn;
+  const float r2 = tolerance * tolerance;
+  for (size_t i = 0; i < n; ++i) {
+    if (processed[i] || !orc::finite3(at(pts, stride, i))) continue;
+    std::vector<int32_t> q{(int32_t)i};
+    processed[i] = 1;
+    for (size_t h = 0; h < q.size(); ++h) {
+      tree.radius(at(pts, stride, q[h]), r2, nn);
+      for (const auto& v : nn)
+        if (!processed[v.idx]) { processed[v.idx] = 1; q.push_back(v.idx); }
+    }
+    if ((int)q.size() >= min_size && (int)q.size() <= max_size) { std::sort(q.begin(), q.end()); clusters.push_back(std::move(q)); }
+  }
+  std::sort(clusters.begin(), clusters.end(), [](const std::vector<int32_t>& a, const std::vector<int32_t>& b) {
+    return a.size() != b.size() ? a.size() > b.size() : a[0] < b[0];
+  });
+  for (size_t c = 0; c < clusters.size(); ++c) for (int32_t i : clusters[c]) labels[i] = (int32_t)c;
+  return (int)clusters.size();
+}
+
 // DataGrabber::rgbd2Pcl / depthToMeter (D&L/src/datagrabber.cpp:9-62,121-174), Kinect / Astra branch
 int64_t orc_depth_to_cloud(const uint16_t* depth, int rows, int cols, float fx, float fy, float cx, float cy, float scale, float z_max,
                            float* out_xyz) {

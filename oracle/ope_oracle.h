@@ -73,6 +73,14 @@ int orc_point_to_plane(const float* src, size_t ns, size_t sstride, const float*
  * m x 6 Jacobian as Eigen does (cross-check; oracle/orc_lm.h) */
 void orc_lm_set_route(int householder);
 
+/* ---- SURVEY 8f-2 groundwork: oracle only, the product has no segmentation stage yet ---- */
+/* pcl::PassThrough (unorganised, lo <= field <= hi, NaN points removed), D&L/src/processingpcd.cpp:8-41. field 0/1/2 = x/y/z.
+ * out_idx: room for n entries; returns the number kept (ascending original indices) or -1. */
+int64_t orc_pass_through(const float* pts, size_t n, size_t stride, int field, float lo, float hi, int32_t* out_idx);
+/* pcl::EuclideanClusterExtraction (D&L/src/objectsegmentationplane.cpp:74-90): labels[i] = cluster number (0 = largest; ties by
+ * smaller first index) or -1 for points in no kept cluster; returns the number of clusters or -1. */
+int orc_euclidean_clusters(const float* pts, size_t n, size_t stride, float tolerance, int min_size, int max_size, int32_t* labels);
+
 /* ---- depth image -> cloud ---- */
 /* DataGrabber::rgbd2Pcl + depthToMeter, D&L/src/datagrabber.cpp:9-62,121-174: columns outer, rows inner; Z = depth / scale;
  * the reference passes (row, col) as (x, y): y_out = (row - cx) * Z / fx, x_out = (col - cy) * Z / fy (sic); points with

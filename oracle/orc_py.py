@@ -193,6 +193,27 @@ def point_to_plane(src, tgt, tgt_normals, isrc=None, itgt=None, kind=None, want_
     return (T.mat4(Tm), tuple(info)) if want_info else T.mat4(Tm)
 
 
+def pass_through(pts, field, lo, hi):
+    """SURVEY 8f-2 groundwork (oracle only): kept original indices of pcl::PassThrough on field 0/1/2"""
+    p, pp, n, s = _pts(pts)
+    out = np.empty(max(p.shape[0], 1), np.int32)
+    lib().orc_pass_through.restype = C.c_int64
+    m = lib().orc_pass_through(pp, n, s, int(field), C.c_float(lo), C.c_float(hi), out.ctypes.data_as(i32p))
+    if m < 0:
+        raise RuntimeError("orc_pass_through failed")
+    return out[:m].copy()
+
+
+def euclidean_clusters(pts, tolerance=0.05, min_size=300, max_size=100000):
+    """SURVEY 8f-2 groundwork (oracle only): labels per point (0 = largest cluster, -1 = none) and the number of clusters"""
+    p, pp, n, s = _pts(pts)
+    labels = np.empty(max(p.shape[0], 1), np.int32)
+    k = lib().orc_euclidean_clusters(pp, n, s, C.c_float(tolerance), int(min_size), int(max_size), labels.ctypes.data_as(i32p))
+    if k < 0:
+        raise RuntimeError("orc_euclidean_clusters failed")
+    return labels[:p.shape[0]].copy(), k
+
+
 def lm_set_route(householder):
     lib().orc_lm_set_route(int(bool(householder)))
 

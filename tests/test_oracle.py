@@ -304,3 +304,31 @@ def test_lm_normal_equation_route_equals_householder_route(orc, synth, small_mod
             assert r < 1e-6 and t < 1e-7, (r, t)
     finally:
         orc.lm_set_route(0)
+
+
+def test_segmentation_groundwork_pass_through_and_euclidean_clusters(orc, synth, model):
+    """SURVEY 8f-2, oracle only so far: PassThrough against numpy, EuclideanClusterExtraction against the connected components of
+    scipy's radius graph on a synthetic scene (object cluster + table + wall, NaN pixels included)."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    from scipy.spatial import cKDTree
+    _, cloud, _ = synth.make_frame(model, 3)
+    pts = cloud.reshape(-1, 3)[::7].copy()                      # keep the radius graph small
+    fin = np.isfinite(pts).all(1)
+    keep = orc.pass_through(pts, 2, 0.5, 1.2)
+    ref = np.nonzero(fin & (pts[:, 2] >= np.float32(0.5)) & (pts[:, 2] <= np.float32(1.2)))[0]
+    assert np.array_equal(keep, ref)
+    sub = pts[keep][::2]
+    tol = 0.05
+    labels, k = orc.euclidean_clusters(sub, tol, min_size=50, max_size=100000)
+    pairs = cKDTree(sub.astype(np.float64)).query_pairs(tol * (1 - 1e-9), output_type="ndarray")
+    g = coo_matrix((np.ones(len(pairs)), (pairs[:, 0], pairs[:, 1])), shape=(len(sub), len(sub)))
+    ncomp, comp = connected_components(g, directed=False)
+    sizes = np.bincount(comp, minlength=ncomp)
+    kept = [c for c in range(ncomp) if 50 <= sizes[c] <= 100000]
+    assert k == len(kept) and k >= 1
+    # same partition: every kept component maps to exactly one label, largest first
+    order = sorted(kept, key=lambda c: (-sizes[c], np.nonzero(comp == c)[0][0]))
+    for rank, c in enumerate(order):
+        assert (labels[comp == c] == rank).all()
+    assert (labels[~np.isin(comp, kept)] == -1).all()
