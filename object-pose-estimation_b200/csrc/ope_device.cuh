@@ -370,14 +370,25 @@ OPE_HD void umeyama_from_sigma_means(const float sigma[9], const double ms[3], c
     out.m[12 + r] = (float)(mt[r] - rs);
   }
 }
-OPE_HD void umeyama_from_moments(const double* acc, Mat4& out) {
+// acc: raw moments of the pairs RELATIVE TO `origin` (n, sum s', sum t', sum t' s'^T with s' = s - origin, t' = t - origin). The
+// cross-covariance does not depend on the origin, but its float rounding does: sum t s^T / n - mu_t mu_s^T cancels ~3 digits for a
+// 10 cm object at 1 m, which multiplies the 1e-16 summation-order noise of the double sums by 10^3 before the rounding to float;
+// taken about a point of the cloud itself it cancels ~1 digit. The means are shifted back for the translation.
+OPE_HD void umeyama_from_moments(const double* acc, Mat4& out, double ox = 0.0, double oy = 0.0, double oz = 0.0) {
   const double n = acc[0];
   double ms[3], mt[3];
   float sigma[9];
   for (int k = 0; k < 3; ++k) { ms[k] = acc[1 + k] / n; mt[k] = acc[4 + k] / n; }
   for (int c = 0; c < 3; ++c)
     for (int r = 0; r < 3; ++r) sigma[c * 3 + r] = (float)(acc[7 + c * 3 + r] / n - mt[r] * ms[c]);
+  ms[0] += ox; ms[1] += oy; ms[2] += oz;
+  mt[0] += ox; mt[1] += oy; mt[2] += oz;
   umeyama_from_sigma_means(sigma, ms, mt, out);
+}
+// the common origin of a moment accumulation: the first point of the TARGET cloud (0 when it is not finite)
+OPE_HD void moment_origin(float x, float y, float z, double& ox, double& oy, double& oz) {
+  const bool fin = isfinite(x) && isfinite(y) && isfinite(z);
+  ox = fin ? (double)x : 0.0; oy = fin ? (double)y : 0.0; oz = fin ? (double)z : 0.0;
 }
 
 // Eigen::umeyama in float over a handful of pairs, sequential order (SAC-IA: 5 samples). s/d: n*3 arrays.

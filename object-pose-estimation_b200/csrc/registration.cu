@@ -71,20 +71,24 @@ __global__ void moments_kernel(const float4* __restrict__ src, const float4* __r
   __shared__ double smem[(kRedThreads / 32) * kMomentAcc];
   double acc[kMomentAcc];
   for (int a = 0; a < kMomentAcc; ++a) acc[a] = 0.0;
+  double o[3];
+  { const float4 t0 = __ldg(tgt); moment_origin(t0.x, t0.y, t0.z, o[0], o[1], o[2]); }   // relative to the target's first point
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float4 s = __ldg(src + (is ? is[i] : i));
     const float4 t = __ldg(tgt + (it ? it[i] : i));
+    const double sv[3] = {(double)s.x - o[0], (double)s.y - o[1], (double)s.z - o[2]};
+    const double tv[3] = {(double)t.x - o[0], (double)t.y - o[1], (double)t.z - o[2]};
     acc[0] += 1.0;
-    acc[1] += s.x; acc[2] += s.y; acc[3] += s.z;
-    acc[4] += t.x; acc[5] += t.y; acc[6] += t.z;
-    const double sv[3] = {s.x, s.y, s.z}, tv[3] = {t.x, t.y, t.z};
+    acc[1] += sv[0]; acc[2] += sv[1]; acc[3] += sv[2];
+    acc[4] += tv[0]; acc[5] += tv[1]; acc[6] += tv[2];
     for (int c = 0; c < 3; ++c)
       for (int r = 0; r < 3; ++r) acc[7 + c * 3 + r] += tv[r] * sv[c];
   }
   block_reduce_store<kMomentAcc>(acc, smem, partials + (size_t)blockIdx.x * kMomentAcc);
 }
 // one warp per accumulator (lanes stride over the blocks, fixed shuffle tree), then one thread runs the 3x3 Umeyama
-__global__ void umeyama_final_kernel(const double* __restrict__ partials, int nblocks, float* __restrict__ out16) {
+__global__ void umeyama_final_kernel(const double* __restrict__ partials, int nblocks, float* __restrict__ out16,
+                                     const float4* __restrict__ tgt) {
   __shared__ double acc[kMomentAcc];
   const int a = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (a < kMomentAcc) {
@@ -96,7 +100,10 @@ __global__ void umeyama_final_kernel(const double* __restrict__ partials, int nb
   __syncthreads();
   if (threadIdx.x == 0) {
     Mat4 T;
-    umeyama_from_moments(acc, T);
+    double o[3];
+    const float4 t0 = __ldg(tgt);
+    moment_origin(t0.x, t0.y, t0.z, o[0], o[1], o[2]);
+    umeyama_from_moments(acc, T, o[0], o[1], o[2]);
     for (int i = 0; i < 16; ++i) out16[i] = T.m[i];
   }
 }
@@ -297,14 +304,15 @@ __device__ __forceinline__ double warp_reduce16(const double* v, int lane, int& 
 }
 
 // term e (0..16) of the moments of one correspondence (p -> t, squared distance d2)
-__device__ __forceinline__ double moment_term(int e, const float4 p, const float4 t, float d2) {
+// (coordinates relative to the origin o: see ope::umeyama_from_moments)
+__device__ __forceinline__ double moment_term(int e, const float4 p, const float4 t, float d2, const double o[3]) {
   if (e == 0) return 1.0;
-  if (e < 4) return e == 1 ? (double)p.x : (e == 2 ? (double)p.y : (double)p.z);
-  if (e < 7) return e == 4 ? (double)t.x : (e == 5 ? (double)t.y : (double)t.z);
+  if (e < 4) return e == 1 ? (double)p.x - o[0] : (e == 2 ? (double)p.y - o[1] : (double)p.z - o[2]);
+  if (e < 7) return e == 4 ? (double)t.x - o[0] : (e == 5 ? (double)t.y - o[1] : (double)t.z - o[2]);
   if (e < 16) {
     const int c = (e - 7) / 3, r = (e - 7) % 3;
-    const double sv = c == 0 ? p.x : (c == 1 ? p.y : p.z);
-    const double tv = r == 0 ? t.x : (r == 1 ? t.y : t.z);
+    const double sv = c == 0 ? (double)p.x - o[0] : (c == 1 ? (double)p.y - o[1] : (double)p.z - o[2]);
+    const double tv = r == 0 ? (double)t.x - o[0] : (r == 1 ? (double)t.y - o[1] : (double)t.z - o[2]);
     return tv * sv;
   }
   return (double)d2;
@@ -419,6 +427,8 @@ __device__ __forceinline__ void icp_move(const IcpDev& a, const Mat4& T, int s) 
 __global__ void __launch_bounds__(kIcpThreads, 1) icp_kernel(IcpDev a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   IcpSmem* sm = reinterpret_cast<IcpSmem*>(smem_raw);
+  double morg[3];   // origin of the moment accumulation: the target's first point (ope::umeyama_from_moments)
+  { const float4 t0 = a.n_tgt > 0 ? __ldg(a.tgt_pts) : make_float4(0, 0, 0, 0); moment_origin(t0.x, t0.y, t0.z, morg[0], morg[1], morg[2]); }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gwarp = blockIdx.x * kIcpWarps + warp, n_gwarps = gridDim.x * kIcpWarps;
   const bool shooting = a.estimator == OPE_EST_NORMAL_SHOOTING;
@@ -588,7 +598,7 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_kernel(IcpDev a) {
           if (m >= 0) {
             const float4 t = __ldg(a.tgt_pts + m);
 #pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = moment_term(e, p, t, d2);
+            for (int e = 0; e < 16; ++e) v[e] = moment_term(e, p, t, d2, morg);
             dsum = (double)d2;
           }
           int slot;
@@ -697,7 +707,7 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_kernel(IcpDev a) {
             if (m >= 0) {
               const float4 t = __ldg(a.tgt_pts + m);
 #pragma unroll
-              for (int e = 0; e < 16; ++e) v[e] = moment_term(e, p, t, d2);
+              for (int e = 0; e < 16; ++e) v[e] = moment_term(e, p, t, d2, morg);
               dsum = (double)d2;
             }
             int slot;
@@ -718,7 +728,7 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_kernel(IcpDev a) {
         if (lane == 0) { a.corr_match[orig] = m; a.corr_d2[orig] = d2; }
         if (m >= 0 && lane < kIcpAcc) {
           const float4 t = tg_smem ? tg_smem[m] : __ldg(a.tgt_pts + m);
-          sm->red[warp][lane] += moment_term(lane, p, t, d2);
+          sm->red[warp][lane] += moment_term(lane, p, t, d2, morg);
         }
         __syncwarp();
       }
@@ -776,7 +786,9 @@ __global__ void __launch_bounds__(kIcpThreads, 1) icp_kernel(IcpDev a) {
         for (int k = 0; k < 9; ++k) sigma[k] = __shfl_sync(0xffffffffu, sg, k);
         if (lane == 0) {
           Mat4 T;
-          umeyama_from_sigma_means(sigma, ms, mt, T);
+          const double msu[3] = {ms[0] + morg[0], ms[1] + morg[1], ms[2] + morg[2]};   // the moments are relative to morg
+          const double mtu[3] = {mt[0] + morg[0], mt[1] + morg[1], mt[2] + morg[2]};
+          umeyama_from_sigma_means(sigma, msu, mtu, T);
           sm->T_inc = T;
           final_t = mat4_mul(T, final_t);
           ++iterations;
@@ -867,6 +879,8 @@ template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 512 / THREADS) icp_small_kernel(IcpDev a) {
   constexpr int kIcpThreads = THREADS, kIcpWarps = THREADS / 32;   // shadow the wide kernel's constants inside this kernel
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  double morg[3];   // origin of the moment accumulation: the target's first point (ope::umeyama_from_moments)
+  { const float4 t0 = a.n_tgt > 0 ? __ldg(a.tgt_pts) : make_float4(0, 0, 0, 0); moment_origin(t0.x, t0.y, t0.z, morg[0], morg[1], morg[2]); }
   IcpSmallSmem<THREADS>* sm = reinterpret_cast<IcpSmallSmem<THREADS>*>(smem_raw);
   float4* tg = reinterpret_cast<float4*>(smem_raw + ((sizeof(IcpSmallSmem<THREADS>) + 15) & ~(size_t)15));
   const int n_tgt8 = (a.n_tgt + 7) & ~7, n_groups = n_tgt8 >> 3;   // the target in groups of 8 consecutive points, padded with +inf
@@ -1085,7 +1099,7 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) icp_small_kernel(IcpDe
       if (match >= 0) {
         const float4 t = tg[match];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] = moment_term(e, p, t, d2m);
+        for (int e = 0; e < 16; ++e) v[e] = moment_term(e, p, t, d2m, morg);
         dsum = (double)d2m;
       }
       int slot;
@@ -1126,7 +1140,7 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) icp_small_kernel(IcpDe
         sm->T_inc = mat4_identity();
       } else {
         Mat4 T;
-        umeyama_from_moments(sm->totals, T);
+        umeyama_from_moments(sm->totals, T, morg[0], morg[1], morg[2]);
         sm->T_inc = T;
         final_t = mat4_mul(T, final_t);
         ++iterations;
@@ -1387,7 +1401,7 @@ int umeyama_device(ope_ctx* ctx, const float4* src, const float4* tgt, const int
   OPE_TRY(out.alloc(16));
   moments_kernel<<<nb, kRedThreads, 0, ctx->stream>>>(src, tgt, d_isrc, d_itgt, (int)n, partials.p);
   OPE_TRY(check_launch(ctx, "moments_kernel"));
-  umeyama_final_kernel<<<1, 32 * kMomentAcc, 0, ctx->stream>>>(partials.p, nb, out.p);
+  umeyama_final_kernel<<<1, 32 * kMomentAcc, 0, ctx->stream>>>(partials.p, nb, out.p, tgt);
   OPE_TRY(check_launch(ctx, "umeyama_final_kernel"));
   void* h;
   OPE_TRY(read_back(ctx, out.p, 16 * sizeof(float), &h));

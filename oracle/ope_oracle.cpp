@@ -439,7 +439,7 @@ int icpAlign(const CloudView& src, const CloudView& tgt, const KdTree& tgt_tree,
       pointToPlaneLM(cur, tgt, corr, transformation.m);
     } else {
       orc::umeyama(corr.size(), [&](size_t i) { return cur.p(corr[i].index_query); },
-                   [&](size_t i) { return tgt.p(corr[i].index_match); }, transformation.m);
+                   [&](size_t i) { return tgt.p(corr[i].index_match); }, transformation.m, tgt.n > 0 ? tgt.p(0) : nullptr);
     }
     transformCloud(xp, xn, has_normals, transformation);
     final_t = orc::mul(transformation, final_t);
@@ -830,7 +830,7 @@ int orc_umeyama(const float* src, size_t sstride, const float* tgt, size_t tstri
                 size_t n, float T[16]) {
   if (!src || !tgt || !T || n == 0) return OPE_ERR_INVALID;
   orc::umeyama(n, [&](size_t i) { return at(src, sstride, is ? is[i] : i); },
-               [&](size_t i) { return at(tgt, tstride, it ? it[i] : i); }, T);
+               [&](size_t i) { return at(tgt, tstride, it ? it[i] : i); }, T, at(tgt, tstride, 0));
   return OPE_OK;
 }
 
@@ -1130,7 +1130,7 @@ int orc_pose_estimate_final(orc_pose_estimator* pe, float* source, size_t ns, co
     Clock c;
     size_t nm = pe->cloudModel.size() / 3;
     if (nm > 0 && nm <= ns)
-      orc::umeyama(nm, [&](size_t i) { return &pe->cloudModel[3 * i]; }, [&](size_t i) { return &p_source[3 * i]; }, rigid.m);
+      orc::umeyama(nm, [&](size_t i) { return &pe->cloudModel[3 * i]; }, [&](size_t i) { return &p_source[3 * i]; }, rigid.m, &p_source[0]);
     pe->stage[6] += c.lap();
   }
   Mat4 finalPose = orc::mul(rigid, pose);  // :439

@@ -255,16 +255,25 @@ inline void umeyamaFromSigma(const T sigma[9], const T src_mean[3], const T dst_
 // bound of that matrix. From there on it is float like the reference: Jacobi SVD of the float matrix, R = U S V^T in
 // float; the translation mu_dst - R mu_src is closed in double and rounded once. A parallel reduction on the device
 // reproduces this bit for bit (barring ~1e-9-probability double-rounding ties).
+//
+// `origin` (3 floats or null = 0): the moments are accumulated relative to it. The cross-covariance does not depend on the origin,
+// but sum d s^T / n - mu_d mu_s^T cancels ~3 digits for a 10 cm object at 1 m, which multiplies the summation-order noise of the
+// double sums by 10^3 before the rounding to float (observed: one flipped rounding per ~10^5 alignment iterations between two
+// summation orders); about a point of the cloud itself it cancels ~1 digit. Callers pass the first point of the TARGET cloud.
 template <typename SrcAt, typename DstAt>
-inline void umeyama(size_t n, SrcAt srcAt, DstAt dstAt, float Tout[16]) {
+inline void umeyama(size_t n, SrcAt srcAt, DstAt dstAt, float Tout[16], const float* origin = nullptr) {
+  double o[3] = {0.0, 0.0, 0.0};
+  if (origin && finite3(origin)) { o[0] = origin[0]; o[1] = origin[1]; o[2] = origin[2]; }
   double acc[16];
   for (int i = 0; i < 16; ++i) acc[i] = 0.0;
   for (size_t i = 0; i < n; ++i) {
-    const float* s = srcAt(i); const float* d = dstAt(i);
+    const float* sp = srcAt(i); const float* dp = dstAt(i);
+    const double s[3] = {(double)sp[0] - o[0], (double)sp[1] - o[1], (double)sp[2] - o[2]};
+    const double d[3] = {(double)dp[0] - o[0], (double)dp[1] - o[1], (double)dp[2] - o[2]};
     acc[0] += 1.0;
-    for (int k = 0; k < 3; ++k) { acc[1 + k] += (double)s[k]; acc[4 + k] += (double)d[k]; }
+    for (int k = 0; k < 3; ++k) { acc[1 + k] += s[k]; acc[4 + k] += d[k]; }
     for (int c = 0; c < 3; ++c)
-      for (int r = 0; r < 3; ++r) acc[7 + c * 3 + r] += (double)d[r] * (double)s[c];
+      for (int r = 0; r < 3; ++r) acc[7 + c * 3 + r] += d[r] * s[c];
   }
   const double nn = acc[0];
   double ms[3], mt[3];
@@ -272,6 +281,7 @@ inline void umeyama(size_t n, SrcAt srcAt, DstAt dstAt, float Tout[16]) {
   for (int k = 0; k < 3; ++k) { ms[k] = acc[1 + k] / nn; mt[k] = acc[4 + k] / nn; }
   for (int c = 0; c < 3; ++c)
     for (int r = 0; r < 3; ++r) sigma[c * 3 + r] = (float)(acc[7 + c * 3 + r] / nn - mt[r] * ms[c]);
+  for (int k = 0; k < 3; ++k) { ms[k] += o[k]; mt[k] += o[k]; }
   float U[9], S[3], V[9];
   svd3<float>(sigma, U, S, V);
   float Sd[3] = {1, 1, 1};
