@@ -10,6 +10,7 @@
 // All matrices are COLUMN-MAJOR like Eigen: M(r,c) = m[c*rows + r].
 #pragma once
 #include <algorithm>
+#include "orc_kdtree.h"   // orc::finite3
 #include <cfloat>
 #include <cmath>
 #include <cstring>
