@@ -49,7 +49,7 @@ def icp_kwargs():
 # DRAM bytes of ONE launch from ncu --set full captures of these exact workloads (committed under profiles/): what the kernels really
 # moved, to set beside the algorithmic bytes. icp_kernel: the 1.6 MB pair is read once and then lives in L2 (80 MB algorithmic over 50
 # iterations, 5.2 MB from DRAM); depth_fused_kernel: DRAM traffic equals the algorithmic bytes.
-NCU_ICP_DRAM_BYTES = 4797696 + 448768
+NCU_ICP_DRAM_BYTES = 4826624 + 816128
 NCU_DEPTH_DRAM_BYTES = 629331712 + 4976560000
 
 
@@ -259,7 +259,7 @@ def run_ours(args):
     k_ms = float(np.mean(kern_ms))
     achieved = alg_bytes / (k_ms / 1e3) / 1e9
     roofline = {"kernel": "icp_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": NCU_ICP_DRAM_BYTES, "traffic_source": "ncu --set full, profiles/r01_b_icp_full.txt "
+                "frac": achieved / peak, "traffic": NCU_ICP_DRAM_BYTES, "traffic_source": "ncu --set full, profiles/r01_g_icp_full.txt "
                 "(dram__bytes_read.sum + dram__bytes_write.sum of one icp_kernel launch on this workload)",
                 "peak_source": peak_src, "kernel_ms": k_ms,
                 "kernel_share_of_step": k_ms / (total_ms / args.steps),
