@@ -219,15 +219,7 @@ int depth_to_cloud_device(ope_ctx* ctx, const unsigned short* d_depth, int frame
     OPE_TRY(status.alloc((size_t)n_tickets + 1));
     OPE_CUDA_TRY(ctx, cudaMemsetAsync(status.p, 0, ((size_t)n_tickets + 1) * sizeof(unsigned long long), ctx->stream));
     unsigned* ticket = reinterpret_cast<unsigned*>(status.p + n_tickets);
-    static std::mutex mu;
-    static size_t granted = 0;
-    {
-      std::lock_guard<std::mutex> lock(mu);
-      if (tile_bytes > granted) {
-        OPE_CUDA_TRY(ctx, cudaFuncSetAttribute((const void*)depth_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes));
-        granted = tile_bytes;
-      }
-    }
+    OPE_TRY(dyn_smem(ctx, (const void*)depth_fused_kernel, tile_bytes));
     depth_fused_kernel<<<n_tickets, 1024, tile_bytes, ctx->stream>>>(d_depth, P, col_blocks, ticket, status.p, d_col_start, d_out, n_tickets);
     return check_launch(ctx, "depth_fused_kernel");
   }
@@ -247,6 +239,7 @@ extern "C" {
 
 int ope_depth_to_cloud(ope_ctx* ctx, const uint16_t* depth, int rows, int cols, float fx, float fy, float cx, float cy, float scale,
                        float z_max, ope_cloud** out) {
+  OPE_ENTER(ctx);
   if (!ctx || !depth || !out || rows <= 0 || cols <= 0 || !(scale > 0)) return OPE_ERR_INVALID;
   *out = nullptr;
   const size_t npx = (size_t)rows * cols;
@@ -280,6 +273,7 @@ int ope_depth_to_cloud(ope_ctx* ctx, const uint16_t* depth, int rows, int cols, 
  * the last entry is the total number of points; frame f occupies [d_col_start[f*cols], d_col_start[(f+1)*cols])). */
 int ope_depth_to_cloud_batch(ope_ctx* ctx, const uint16_t* d_depth, int frames, int rows, int cols, float fx, float fy, float cx, float cy,
                              float scale, float z_max, void* d_out, int32_t* d_col_start) {
+  OPE_ENTER(ctx);
   if (!ctx || !d_depth || !d_out || !d_col_start || frames <= 0 || rows <= 0 || cols <= 0 || !(scale > 0)) return OPE_ERR_INVALID;
   if ((size_t)frames * rows * cols > 0x7fffffffull) return fail(ctx, OPE_ERR_INVALID, "batch too large for 32-bit point offsets");
   const DepthParams P = depth_params(rows, cols, fx, fy, cx, cy, scale, z_max);

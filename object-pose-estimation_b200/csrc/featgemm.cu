@@ -394,7 +394,7 @@ int feature_knn_gemm_device(ope_ctx* ctx, const float* d_ftgt, size_t nt, const 
   CUtensorMap tmA, tmB;
   OPE_TRY(make_operand_map(ctx, A.p, nq_pad, FG_M, &tmA));
   OPE_TRY(make_operand_map(ctx, B.p, nt_pad, FG_N, &tmB));
-  OPE_CUDA_TRY(ctx, cudaFuncSetAttribute((const void*)featgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FG_SMEM_BYTES));
+  OPE_TRY(dyn_smem(ctx, (const void*)featgemm_kernel, FG_SMEM_BYTES));
   cudaEventRecord(ctx->kev[2][0], ctx->stream);
   featgemm_kernel<<<dim3(m_tiles, splits), FG_THREADS, FG_SMEM_BYTES, ctx->stream>>>(tmA, tmB, (int)nq, total_tiles, tiles_per_split, cidx.p,
                                                                                       cscore.p);

@@ -332,15 +332,7 @@ int normals_device(ope_ctx* ctx, ope_cloud* cloud, int k, const float vp[3]) {
   if (cloud->n == 0) return OPE_OK;
   if (cloud->n <= (size_t)kNormSmemMax && !std::getenv("OPE_NORMALS_FORCE_GRID")) {
     const size_t bytes = cloud->n * sizeof(float4);
-    static std::mutex mu;
-    static size_t granted = 0;
-    {
-      std::lock_guard<std::mutex> lock(mu);   // the opt-in belongs to the function, shared by all contexts: only ever raise it
-      if (bytes > granted) {
-        OPE_CUDA_TRY(ctx, cudaFuncSetAttribute((const void*)normals_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kNormSmemMax * sizeof(float4))));
-        granted = kNormSmemMax * sizeof(float4);
-      }
-    }
+    OPE_TRY(dyn_smem(ctx, (const void*)normals_smem_kernel, kNormSmemMax * sizeof(float4)));
     const unsigned blocks = (unsigned)std::min<size_t>(div_up(cloud->n * 32, kNormThreads), (size_t)ctx->sm_count * 2);
     normals_smem_kernel<<<blocks, kNormThreads, bytes, ctx->stream>>>(cloud->pts, (int)cloud->n, k, vp[0], vp[1], vp[2], cloud->normals);
     return check_launch(ctx, "normals_smem_kernel");
@@ -368,16 +360,7 @@ int fpfh_device(ope_ctx* ctx, const ope_cloud* cloud, float radius, float** d_fp
     const unsigned blocks = div_up(n, kWarpsPerBlock);
     GridView g;
     std::memset(&g, 0, sizeof(g));
-    static std::mutex mu;
-    static bool granted = false;
-    {
-      std::lock_guard<std::mutex> lock(mu);
-      if (!granted) {
-        cudaError_t e = cudaFuncSetAttribute((const void*)spfh_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kFeatSmemMax * sizeof(float4)));
-        if (e != cudaSuccess) rc = fail(ctx, OPE_ERR_CUDA, "shared memory opt-in failed: %s", cudaGetErrorString(e));
-        granted = rc == OPE_OK;
-      }
-    }
+    rc = dyn_smem(ctx, (const void*)spfh_kernel<true>, 2 * kFeatSmemMax * sizeof(float4));
     if (rc == OPE_OK) {
       spfh_kernel<true><<<blocks, kWarpsPerBlock * 32, 2 * n * sizeof(float4), ctx->stream>>>(g, cloud->pts, cloud->normals, (int)n, r2, spfh);
       rc = check_launch(ctx, "spfh_kernel<smem>");
@@ -475,6 +458,7 @@ using namespace ope;
 extern "C" {
 
 int ope_normals_knn(ope_ctx* ctx, ope_cloud* cloud, int k, const float viewpoint[3], float* out4) {
+  OPE_ENTER(ctx);
   if (!ctx || !cloud) return OPE_ERR_INVALID;
   const float zero[3] = {0, 0, 0};
   OPE_TRY(normals_device(ctx, cloud, k, viewpoint ? viewpoint : zero));
@@ -485,6 +469,7 @@ int ope_normals_knn(ope_ctx* ctx, ope_cloud* cloud, int k, const float viewpoint
 }
 
 int ope_fpfh(ope_ctx* ctx, const ope_cloud* cloud, float radius, float* out, float* out_spfh) {
+  OPE_ENTER(ctx);
   if (!ctx || !cloud || !out || !(radius > 0)) return OPE_ERR_INVALID;
   float *f = nullptr, *s = nullptr;
   OPE_TRY(fpfh_device(ctx, cloud, radius, &f, &s));
@@ -502,6 +487,7 @@ int ope_fpfh(ope_ctx* ctx, const ope_cloud* cloud, float radius, float* out, flo
 
 int ope_feature_knn(ope_ctx* ctx, const float* ftgt, size_t nt, const float* fqry, size_t nq, int dim, int k,
                     int32_t* out_idx, float* out_d2) {
+  OPE_ENTER(ctx);
   if (!ctx || !ftgt || !fqry || !out_idx) return OPE_ERR_INVALID;
   Scratch<float> dt(ctx), dq(ctx), dd(ctx);
   Scratch<int> di(ctx);

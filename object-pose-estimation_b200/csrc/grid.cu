@@ -687,6 +687,7 @@ int ope_ctx_create(int device, void* stream, ope_ctx** out) {
 }
 
 double ope_ctx_last_kernel_ms(ope_ctx* ctx, int which) {
+  OPE_ENTER(ctx);
   if (!ctx || which < 0 || which > 2 || !ctx->kev_valid[which]) return -1.0;
   float ms = 0;
   if (cudaEventSynchronize(ctx->kev[which][1]) != cudaSuccess) return -1.0;
@@ -695,6 +696,7 @@ double ope_ctx_last_kernel_ms(ope_ctx* ctx, int which) {
 }
 
 int ope_cloud_invalidate(ope_ctx* ctx, ope_cloud* c) {
+  OPE_ENTER(ctx);
   if (!ctx || !c) return OPE_ERR_INVALID;
   for (auto& g : c->grids) { dfree(ctx, g.cell_start); dfree(ctx, g.sorted); }
   c->grids.clear();
@@ -728,6 +730,7 @@ int ope_ctx_feature_knn_stats(const ope_ctx* ctx, int64_t* gemm_queries, int64_t
   return OPE_OK;
 }
 int ope_ctx_synchronize(ope_ctx* ctx) {
+  OPE_ENTER(ctx);
   if (!ctx) return OPE_ERR_INVALID;
   OPE_CUDA_TRY(ctx, ope::stream_sync(ctx));
   return OPE_OK;
@@ -735,6 +738,7 @@ int ope_ctx_synchronize(ope_ctx* ctx) {
 
 int ope_cloud_upload(ope_ctx* ctx, const void* pts, size_t n, size_t stride, size_t offset, const void* normals,
                      size_t nstride, size_t noffset, ope_cloud** out) {
+  OPE_ENTER(ctx);
   if (!ctx || !out || (n > 0 && (!pts || stride < 12))) return OPE_ERR_INVALID;
   if (n > 0x7fffffffull) return fail(ctx, OPE_ERR_INVALID, "cloud too large");
   ope_cloud* c = nullptr;
@@ -774,6 +778,7 @@ int ope_cloud_upload(ope_ctx* ctx, const void* pts, size_t n, size_t stride, siz
 }
 
 int ope_cloud_free(ope_ctx* ctx, ope_cloud* c) {
+  OPE_ENTER(ctx);
   if (!c) return OPE_OK;
   if (!ctx) ctx = c->ctx;
   for (auto& g : c->grids) { dfree(ctx, g.cell_start); dfree(ctx, g.sorted); }
@@ -787,6 +792,7 @@ size_t ope_cloud_size(const ope_cloud* c) { return c ? c->n : 0; }
 int ope_cloud_has_normals(const ope_cloud* c) { return c && c->normals ? 1 : 0; }
 
 int ope_cloud_download(ope_ctx* ctx, const ope_cloud* c, float* xyz, float* normals4) {
+  OPE_ENTER(ctx);
   if (!ctx || !c) return OPE_ERR_INVALID;
   if (c->n == 0) return OPE_OK;
   void* stage = nullptr;
@@ -807,6 +813,7 @@ int ope_cloud_download(ope_ctx* ctx, const ope_cloud* c, float* xyz, float* norm
 }
 
 int ope_cloud_select(ope_ctx* ctx, const ope_cloud* c, const int32_t* idx, size_t n, ope_cloud** out) {
+  OPE_ENTER(ctx);
   if (!ctx || !c || !out || (n > 0 && !idx)) return OPE_ERR_INVALID;
   for (size_t i = 0; i < n; ++i)
     if (idx[i] < 0 || (size_t)idx[i] >= c->n) return fail(ctx, OPE_ERR_INVALID, "index out of range");
@@ -819,6 +826,7 @@ int ope_cloud_select(ope_ctx* ctx, const ope_cloud* c, const int32_t* idx, size_
 }
 
 int ope_cloud_set_normals(ope_ctx* ctx, ope_cloud* c, const float* normals4) {
+  OPE_ENTER(ctx);
   if (!ctx || !c || !normals4) return OPE_ERR_INVALID;
   if (!c->normals) OPE_TRY(dalloc(ctx, &c->normals, c->n));
   if (c->n) {
@@ -839,8 +847,7 @@ static int knn_impl(ope_ctx* ctx, const ope_cloud* tgt, const float4* d_qry, siz
   OPE_TRY(di.alloc(nq * k));
   OPE_TRY(dd.alloc(nq * k));
   if (k == 1) {
-    OPE_CUDA_TRY(ctx, cudaFuncSetAttribute((const void*)nn1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)sizeof(Nn1Smem<kKnnThreads>)));
+    OPE_TRY(dyn_smem(ctx, (const void*)nn1_kernel, sizeof(Nn1Smem<kKnnThreads>)));
     nn1_kernel<<<(unsigned)std::min<size_t>(div_up(nq, kKnnThreads), (size_t)ctx->sm_count * 4), kKnnThreads,
                  sizeof(Nn1Smem<kKnnThreads>), ctx->stream>>>(g, d_qry, (int)nq, di.p, dd.p);
     OPE_TRY(check_launch(ctx, "nn1_kernel"));
@@ -856,12 +863,14 @@ static int knn_impl(ope_ctx* ctx, const ope_cloud* tgt, const float4* d_qry, siz
 }
 
 int ope_knn_cloud(ope_ctx* ctx, const ope_cloud* tgt, const ope_cloud* qry, int k, int32_t* out_idx, float* out_d2) {
+  OPE_ENTER(ctx);
   if (!ctx || !tgt || !qry || !out_idx) return OPE_ERR_INVALID;
   return knn_impl(ctx, tgt, qry->pts, qry->n, k, out_idx, out_d2);
 }
 
 int ope_knn(ope_ctx* ctx, const ope_cloud* tgt, const void* qry, size_t nq, size_t stride, size_t offset, int k,
             int32_t* out_idx, float* out_d2) {
+  OPE_ENTER(ctx);
   if (!ctx || !tgt || !qry || !out_idx) return OPE_ERR_INVALID;
   ope_cloud* q = nullptr;
   OPE_TRY(ope_cloud_upload(ctx, qry, nq, stride, offset, nullptr, 0, 0, &q));
@@ -872,6 +881,7 @@ int ope_knn(ope_ctx* ctx, const ope_cloud* tgt, const void* qry, size_t nq, size
 
 int ope_radius_cloud(ope_ctx* ctx, const ope_cloud* tgt, const ope_cloud* qry, float radius, int64_t capacity,
                      int64_t* offsets, int32_t* out_idx, float* out_d2, int64_t* total) {
+  OPE_ENTER(ctx);
   if (!ctx || !tgt || !qry || !total || !(radius > 0)) return OPE_ERR_INVALID;
   *total = 0;
   const size_t nq = qry->n;
@@ -915,6 +925,7 @@ int ope_radius_cloud(ope_ctx* ctx, const ope_cloud* tgt, const ope_cloud* qry, f
 }
 
 int ope_uniform_sample(ope_ctx* ctx, const ope_cloud* cloud, float leaf, int32_t* out_idx, size_t* out_n) {
+  OPE_ENTER(ctx);
   if (!ctx || !cloud || !out_idx || !out_n || !(leaf > 0)) return OPE_ERR_INVALID;
   int* d = nullptr;
   OPE_TRY(uniform_sample_device(ctx, const_cast<ope_cloud*>(cloud), leaf, &d, out_n));
@@ -928,6 +939,7 @@ int ope_uniform_sample(ope_ctx* ctx, const ope_cloud* cloud, float leaf, int32_t
 }
 
 int ope_uniform_sample_cloud(ope_ctx* ctx, const ope_cloud* cloud, float leaf, ope_cloud** out) {
+  OPE_ENTER(ctx);
   if (!ctx || !cloud || !out || !(leaf > 0)) return OPE_ERR_INVALID;
   int* d = nullptr; size_t m = 0;
   OPE_TRY(uniform_sample_device(ctx, const_cast<ope_cloud*>(cloud), leaf, &d, &m));
@@ -939,6 +951,7 @@ int ope_uniform_sample_cloud(ope_ctx* ctx, const ope_cloud* cloud, float leaf, o
 
 int ope_voxel_grid(ope_ctx* ctx, const ope_cloud* cloud_c, const float* rgb, float lx, float ly, float lz, float* out_xyz,
                    float* out_rgb, size_t* out_n) {
+  OPE_ENTER(ctx);
   if (!ctx || !cloud_c || !out_xyz || !out_n || !(lx > 0 && ly > 0 && lz > 0)) return OPE_ERR_INVALID;
   ope_cloud* cloud = const_cast<ope_cloud*>(cloud_c);
   *out_n = 0;

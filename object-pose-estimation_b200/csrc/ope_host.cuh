@@ -6,7 +6,10 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/ope_cuda.h"
@@ -146,6 +149,31 @@ inline int read_back(ope_ctx* ctx, const void* dsrc, size_t bytes, void** host) 
   OPE_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pinned, dsrc, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   OPE_CUDA_TRY(ctx, stream_sync(ctx));
   *host = ctx->pinned;
+  return OPE_OK;
+}
+
+// Entry guard of every extern "C" function that takes a context: the calling host thread's current device becomes the
+// context's device (a process may hold contexts on several GPUs; launches and attribute calls go to the CURRENT device).
+inline void enter(const ope_ctx* ctx) {
+  if (!ctx) return;
+  int d = -1;
+  if (cudaGetDevice(&d) != cudaSuccess || d != ctx->device) cudaSetDevice(ctx->device);
+}
+#define OPE_ENTER(ctx) ope::enter(ctx)
+
+// Opt a kernel in to `bytes` of dynamic shared memory (B200: up to 227 KB per block). The opt-in is a property of the
+// (device, function) pair, shared by every stream and host thread of the process (ope_pose_batch runs several contexts
+// concurrently): only ever raise it, under a lock, per device.
+inline int dyn_smem(ope_ctx* ctx, const void* fn, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, size_t> granted;
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& have = granted[std::make_pair(ctx->device, fn)];
+  if (bytes > have) {
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return fail(ctx, OPE_ERR_CUDA, "shared memory opt-in of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    have = bytes;
+  }
   return OPE_OK;
 }
 

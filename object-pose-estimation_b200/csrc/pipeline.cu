@@ -99,6 +99,7 @@ struct DevGuard {
 extern "C" {
 
 int ope_pose_tracker_create(ope_ctx* ctx, const ope_pose_params* prm, ope_pose_tracker** out) {
+  OPE_ENTER(ctx);
   if (!ctx || !out) return OPE_ERR_INVALID;
   ope_pose_tracker* t = new ope_pose_tracker();
   t->ctx = ctx;
@@ -128,6 +129,7 @@ int ope_pose_stage_ms(const ope_pose_tracker* t, double out[8]) {
 
 int ope_pose_estimate_final_device(ope_pose_tracker* t, ope_cloud** source, const ope_cloud* target,
                                    const ope_rng_table* table, ope_pose_result* res) {
+  OPE_ENTER((t ? t->ctx : nullptr));
   if (!t || !source || !*source || !res) return OPE_ERR_INVALID;
   ope_ctx* ctx = t->ctx;
   const ope_pose_params& P = t->prm;
@@ -298,6 +300,7 @@ void batch_worker(BatchShared* S, ope_ctx* ctx, int* first_error, std::string* f
 
 int ope_pose_batch(ope_ctx* ctx, const ope_pose_params* prm, const float* model_xyz, size_t n_model, const ope_frame_input* frames,
                    size_t n_frames, const ope_rng_table* tables, int workers, ope_pose_result* results, int32_t* status) {
+  OPE_ENTER(ctx);
   if (!ctx || !model_xyz || n_model == 0 || (!frames && n_frames) || !results) return OPE_ERR_INVALID;
   if (n_frames == 0) return OPE_OK;
   ope_pose_params P;
@@ -381,6 +384,7 @@ int ope_pose_batch(ope_ctx* ctx, const ope_pose_params* prm, const float* model_
 
 int ope_pose_estimate_final(ope_pose_tracker* t, float* source_xyz, size_t ns, const void* target, size_t nt, size_t tstride,
                             size_t toffset, const ope_rng_table* table, ope_pose_result* res) {
+  OPE_ENTER((t ? t->ctx : nullptr));
   if (!t || !source_xyz || !res) return OPE_ERR_INVALID;
   ope_ctx* ctx = t->ctx;
   ope_cloud* src = nullptr;

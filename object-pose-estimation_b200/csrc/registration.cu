@@ -1371,21 +1371,6 @@ __global__ void sacia_select_kernel(const float* __restrict__ errors, const floa
 }
 
 // ================================================================================================ host ==
-// opt a kernel in to `bytes` of dynamic shared memory (B200: up to 227 KB per block)
-// The dynamic shared memory opt-in is a property of the FUNCTION, shared by every stream and host thread of the process
-// (ope_pose_batch runs several contexts concurrently): only ever raise it, under a lock.
-static int dyn_smem(ope_ctx* ctx, const void* fn, size_t bytes) {
-  static std::mutex mu;
-  static std::map<const void*, size_t> granted;
-  std::lock_guard<std::mutex> lock(mu);
-  size_t& have = granted[fn];
-  if (bytes > have) {
-    OPE_CUDA_TRY(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    have = bytes;
-  }
-  return OPE_OK;
-}
-
 int transform_device(ope_ctx* ctx, const ope_cloud* in, const Mat4& T, ope_cloud* out) {
   if (in->n == 0) return OPE_OK;
   transform_kernel<<<div_up(in->n, 256), 256, 0, ctx->stream>>>(in->pts, in->normals, (int)in->n, T, out->pts, out->normals);
@@ -1922,6 +1907,7 @@ void ope_pose_params_default(ope_pose_params* p) {
 }
 
 int ope_cloud_transform(ope_ctx* ctx, const ope_cloud* cloud, const float T[16], ope_cloud** out) {
+  OPE_ENTER(ctx);
   if (!ctx || !cloud || !T || !out) return OPE_ERR_INVALID;
   ope_cloud* o = nullptr;
   OPE_TRY(cloud_alloc(ctx, cloud->n, cloud->normals != nullptr, &o));
@@ -1936,6 +1922,7 @@ int ope_cloud_transform(ope_ctx* ctx, const ope_cloud* cloud, const float T[16],
 
 int ope_umeyama(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const int32_t* isrc, const int32_t* itgt, size_t n,
                 float T[16]) {
+  OPE_ENTER(ctx);
   if (!ctx || !src || !tgt || !T || n == 0) return OPE_ERR_INVALID;
   if ((!isrc && n > src->n) || (!itgt && n > tgt->n)) return fail(ctx, OPE_ERR_INVALID, "n exceeds cloud size");
   Scratch<int> ds(ctx), dt(ctx);
@@ -1954,6 +1941,7 @@ int ope_umeyama(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const 
 
 int ope_point_to_plane(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const int32_t* isrc, const int32_t* itgt, size_t n,
                        int kind, float T[16], int32_t* lm_info) {
+  OPE_ENTER(ctx);
   if (!ctx || !src || !tgt || !T) return OPE_ERR_INVALID;
   if (!tgt->normals) return fail(ctx, OPE_ERR_INVALID, "point-to-plane estimation needs target normals");
   if ((!isrc && n > src->n) || (!itgt && n > tgt->n)) return fail(ctx, OPE_ERR_INVALID, "n exceeds cloud size");
@@ -1981,6 +1969,7 @@ int ope_point_to_plane(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt,
 }
 
 int ope_fitness(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const float T[16], double max_range, double* out) {
+  OPE_ENTER(ctx);
   if (!ctx || !src || !tgt || !T || !out) return OPE_ERR_INVALID;
   if (tgt->n == 0) return fail(ctx, OPE_ERR_EMPTY, "No input target dataset was given!");
   Mat4 M;
@@ -1990,6 +1979,7 @@ int ope_fitness(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const 
 
 int ope_correspondences(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const ope_icp_params* prm,
                         ope_correspondence* out, size_t* out_n) {
+  OPE_ENTER(ctx);
   if (!ctx || !src || !tgt || !prm || !out || !out_n) return OPE_ERR_INVALID;
   *out_n = 0;
   if (tgt->n == 0) return fail(ctx, OPE_ERR_EMPTY, "No input target dataset was given!");
@@ -2021,6 +2011,7 @@ int ope_correspondences(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt
 
 int ope_icp_align(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const ope_icp_params* prm, const float guess[16],
                   ope_reg_result* res, ope_correspondence* out_corr, ope_cloud** out_aligned) {
+  OPE_ENTER(ctx);
   if (!ctx || !src || !prm || !res) return OPE_ERR_INVALID;
   Mat4 I = mat4_identity();
   std::memset(res, 0, sizeof(*res));
@@ -2046,6 +2037,7 @@ int ope_sacia_draw(const float* src_xyz, size_t ns, size_t stride_bytes, int ite
 
 int ope_sacia_align(ope_ctx* ctx, const ope_cloud* src, const float* fsrc, const ope_cloud* tgt, const float* ftgt,
                     const ope_sacia_params* prm, const ope_rng_table* table, ope_reg_result* res, float* out_errors) {
+  OPE_ENTER(ctx);
   if (!ctx || !src || !fsrc || !tgt || !ftgt || !prm || !res) return OPE_ERR_INVALID;
   Mat4 I = mat4_identity();
   std::memset(res, 0, sizeof(*res));
