@@ -64,6 +64,9 @@ int ope_cloud_transform(ope_ctx* ctx, const ope_cloud* cloud, const float T[16],
 /* drop the cached search grids of a cloud, so the next call rebuilds its index (what setInputTarget's
  * target_cloud_updated_ = true does to the kd-tree, VP/impl/registration_mod.hpp:57-67,80-84) */
 int ope_cloud_invalidate(ope_ctx* ctx, ope_cloud* cloud);
+/* `*dst += *src` (pcl::PointCloud::operator+=, BM/src/regmeshpcd.cpp:254): src's points are appended to dst on the device;
+ * normals are kept only if both clouds carry them; dst's cached search index is dropped. */
+int ope_cloud_append(ope_ctx* ctx, ope_cloud* dst, const ope_cloud* src);
 /* attach normals computed by ope_normals_knn to the cloud (pcl::copyPointCloud(normals, pointnormal), :201) */
 int ope_cloud_set_normals(ope_ctx* ctx, ope_cloud* cloud, const float* normals4);
 
@@ -146,6 +149,16 @@ int ope_sacia_align(ope_ctx* ctx, const ope_cloud* src, const float* fsrc, const
 /* draw the SAC-IA decision table on the host from libc rand() (selectSamples + the pick of findSimilarFeatures) */
 int ope_sacia_draw(const float* src_xyz, size_t ns, size_t stride_bytes, int iterations, int nr_samples,
                    int k_correspondences, float* min_sample_distance, int32_t* samples, int32_t* picks);
+
+/* RegMeshPcd::registerPointClouds (BM/src/regmeshpcd.cpp:210-271) with the merged cloud resident on the device for the whole
+ * chain: for every pair i, source = the merged cloud so far, target = view i+1; getIcpNormal (:62-208): normals k = normal_k (12)
+ * of BOTH clouds recomputed from scratch (the reference recomputes all of them every pair), ICP-with-normals as configured by
+ * `prm` (normal shooting k = 20, surface-normal rejector, TransformationEstimationPointToPlane, eps 1e-8), the source
+ * transformed by the final transformation (:204), then `*aligned += *target` (:254). views: n_views host clouds (points/n/stride/
+ * offset) or device clouds (.cloud); pair_results: n_views-1 records or NULL; *merged: the final cloud (device, caller frees).
+ * The chain does not shard: pair i consumes the output of pair i-1. */
+int ope_register_point_clouds(ope_ctx* ctx, const ope_frame_input* views, size_t n_views, const ope_icp_params* prm, int normal_k,
+                              ope_reg_result* pair_results, ope_cloud** merged);
 
 /* ---- PoseEstimator (D&L/src/poseestimator.cpp:16-448) ---------------------------------------------------------- */
 int ope_pose_tracker_create(ope_ctx* ctx, const ope_pose_params* prm, ope_pose_tracker** out);

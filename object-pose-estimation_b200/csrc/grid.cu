@@ -825,6 +825,28 @@ int ope_cloud_select(ope_ctx* ctx, const ope_cloud* c, const int32_t* idx, size_
   return OPE_OK;
 }
 
+int ope_cloud_append(ope_ctx* ctx, ope_cloud* dst, const ope_cloud* src) {
+  OPE_ENTER(ctx);
+  if (!ctx || !dst || !src) return OPE_ERR_INVALID;
+  if (src->n == 0) return OPE_OK;
+  const size_t n = dst->n + src->n;
+  const bool normals = dst->normals && src->normals;   // the concatenation keeps normals only when both sides carry them
+  float4* pts = nullptr;
+  float4* nrm = nullptr;
+  OPE_TRY(dalloc(ctx, &pts, n));
+  if (normals) { int rc = dalloc(ctx, &nrm, n); if (rc != OPE_OK) { dfree(ctx, pts); return rc; } }
+  cudaError_t e = cudaSuccess;
+  if (dst->n) e = cudaMemcpyAsync(pts, dst->pts, dst->n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(pts + dst->n, src->pts, src->n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream);
+  if (e == cudaSuccess && normals && dst->n) e = cudaMemcpyAsync(nrm, dst->normals, dst->n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream);
+  if (e == cudaSuccess && normals) e = cudaMemcpyAsync(nrm + dst->n, src->normals, src->n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream);
+  if (e != cudaSuccess) { dfree(ctx, pts); dfree(ctx, nrm); return fail(ctx, OPE_ERR_CUDA, "device copy failed: %s", cudaGetErrorString(e)); }
+  ope_cloud_invalidate(ctx, dst);
+  dfree(ctx, dst->pts); dfree(ctx, dst->normals);
+  dst->pts = pts; dst->normals = nrm; dst->n = n;
+  return OPE_OK;
+}
+
 int ope_cloud_set_normals(ope_ctx* ctx, ope_cloud* c, const float* normals4) {
   OPE_ENTER(ctx);
   if (!ctx || !c || !normals4) return OPE_ERR_INVALID;

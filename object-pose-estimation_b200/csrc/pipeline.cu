@@ -382,6 +382,50 @@ int ope_pose_batch(ope_ctx* ctx, const ope_pose_params* prm, const float* model_
   return OPE_OK;
 }
 
+// RegMeshPcd::registerPointClouds, BM/src/regmeshpcd.cpp:210-271 — the whole chain on the device
+int ope_register_point_clouds(ope_ctx* ctx, const ope_frame_input* views, size_t n_views, const ope_icp_params* prm, int normal_k,
+                              ope_reg_result* pair_results, ope_cloud** merged) {
+  OPE_ENTER(ctx);
+  if (!ctx || !views || n_views == 0 || !prm || !merged) return OPE_ERR_INVALID;
+  auto load = [&](const ope_frame_input& v, ope_cloud** out) -> int {
+    if (v.points) return ope_cloud_upload(ctx, v.points, v.n, v.stride, v.offset, nullptr, 0, 0, out);
+    if (!v.cloud) return fail(ctx, OPE_ERR_INVALID, "view without points");
+    ope_cloud view = *(const ope_cloud*)v.cloud;     // private copy without normals: normals are recomputed per pair (:74-90)
+    view.normals = nullptr; view.grids.clear();
+    return clone_cloud(ctx, &view, out);
+  };
+  CloudGuard cur(ctx);
+  OPE_TRY(load(views[0], &cur.c));   // cloudTemp = cloudVector[0], :226
+  const float vp[3] = {0, 0, 0};
+  for (size_t i = 0; i + 1 < n_views; ++i) {
+    CloudGuard tgt(ctx), moved(ctx);
+    OPE_TRY(load(views[i + 1], &tgt.c));
+    ope_reg_result rr;
+    std::memset(&rr, 0, sizeof(rr));
+    for (int j = 0; j < 16; ++j) rr.T[j] = (j % 5 == 0) ? 1.f : 0.f;
+    if (cur.c->n > 0 && tgt.c->n > 0) {
+      ope_cloud_invalidate(ctx, cur.c);
+      OPE_TRY(normals_device(ctx, cur.c, normal_k, vp));   // normEst on the (growing) source and on the view, :82-90
+      OPE_TRY(normals_device(ctx, tgt.c, normal_k, vp));
+      OPE_TRY(icp_device(ctx, cur.c, tgt.c, *prm, mat4_identity(), &rr, nullptr, nullptr));   // :166-199
+    }
+    if (pair_results) pair_results[i] = rr;
+    Mat4 M;
+    std::memcpy(M.m, rr.T, sizeof(M.m));
+    OPE_TRY(cloud_alloc(ctx, cur.c->n, false, &moved.c));
+    ope_cloud view = *cur.c;           // pcl::transformPointCloud(*p_cloudSource, *cloudAligned, T): points only, :204
+    view.normals = nullptr; view.grids.clear();
+    OPE_TRY(transform_device(ctx, &view, M, moved.c));
+    dfree(ctx, tgt.c->normals); tgt.c->normals = nullptr;
+    OPE_TRY(ope_cloud_append(ctx, moved.c, tgt.c));   // *cloudAlignedIcp += *cloudTarget, :254
+    std::swap(cur.c, moved.c);                       // *cloudTemp = *cloudAlignedIcp, :258
+  }
+  OPE_CUDA_TRY(ctx, stream_sync(ctx));
+  *merged = cur.c;
+  cur.c = nullptr;
+  return OPE_OK;
+}
+
 int ope_pose_estimate_final(ope_pose_tracker* t, float* source_xyz, size_t ns, const void* target, size_t nt, size_t tstride,
                             size_t toffset, const ope_rng_table* table, ope_pose_result* res) {
   OPE_ENTER((t ? t->ctx : nullptr));

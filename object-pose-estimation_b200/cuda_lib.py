@@ -23,7 +23,7 @@ EXPORTS = [
     "ope_ctx_create", "ope_ctx_destroy", "ope_last_error", "ope_ctx_synchronize", "ope_ctx_launch_count", "ope_version",
     "ope_ctx_last_kernel_ms", "ope_cloud_invalidate", "ope_ctx_feature_knn_stats",
     "ope_cloud_upload", "ope_cloud_free", "ope_cloud_size", "ope_cloud_has_normals", "ope_cloud_download",
-    "ope_cloud_select", "ope_cloud_transform", "ope_cloud_set_normals",
+    "ope_cloud_select", "ope_cloud_transform", "ope_cloud_set_normals", "ope_cloud_append", "ope_register_point_clouds",
     "ope_knn", "ope_knn_cloud", "ope_radius_cloud", "ope_depth_to_cloud", "ope_depth_to_cloud_batch",
     "ope_uniform_sample", "ope_uniform_sample_cloud", "ope_voxel_grid",
     "ope_normals_knn", "ope_fpfh", "ope_feature_knn",
@@ -226,6 +226,31 @@ class Context:
         self._chk(lib().ope_cloud_transform(self.h, cloud.h, T.mat4_to_c(M), C.byref(h)))
         return Cloud(self, h)
 
+    def append(self, dst, src):
+        """*dst += *src on the device"""
+        self._chk(lib().ope_cloud_append(self.h, dst.h, src.h))
+
+    def _frame_inputs(self, frames):
+        n = len(frames)
+        arr = (T.FrameInput * max(n, 1))()
+        keep = []
+        for i, f in enumerate(frames):
+            if isinstance(f, Cloud):
+                arr[i] = T.FrameInput(None, 0, 0, 0, f.h)
+            else:
+                a = _f32(f) if len(f) else np.zeros((1, 3), np.float32)
+                keep.append(a)
+                arr[i] = T.FrameInput(a.ctypes.data, len(f), a.strides[0], 0, None)
+        return arr, keep
+
+    def register_point_clouds(self, views, prm, normal_k=12):
+        """RegMeshPcd::registerPointClouds on the device: returns (merged Cloud, list of RegResult per pair)"""
+        arr, keep = self._frame_inputs(views)
+        res = (T.RegResult * max(len(views) - 1, 1))()
+        h = C.c_void_p()
+        self._chk(lib().ope_register_point_clouds(self.h, arr, C.c_size_t(len(views)), C.byref(prm), int(normal_k), res, C.byref(h)))
+        return Cloud(self, h), [res[i] for i in range(len(views) - 1)]
+
     def set_normals(self, cloud, normals4):
         nr = _f32(normals4)
         self._chk(lib().ope_cloud_set_normals(self.h, cloud.h, nr.ctypes.data_as(f32p)))
@@ -311,15 +336,7 @@ class Context:
         (list of PoseResult, status array)."""
         m = np.ascontiguousarray(model[:, :3], np.float32)
         n = len(frames)
-        arr = (T.FrameInput * max(n, 1))()
-        keep = []
-        for i, f in enumerate(frames):
-            if isinstance(f, Cloud):
-                arr[i] = T.FrameInput(None, 0, 0, 0, f.h)
-            else:
-                a = _f32(f) if len(f) else np.zeros((1, 3), np.float32)
-                keep.append(a)
-                arr[i] = T.FrameInput(a.ctypes.data, len(f), a.strides[0], 0, None)
+        arr, keep = self._frame_inputs(frames)
         res = (T.PoseResult * max(n, 1))()
         status = (C.c_int32 * max(n, 1))()
         tb = None

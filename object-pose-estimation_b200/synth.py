@@ -78,6 +78,16 @@ def make_model(n_points=157825, seed=0):
     return np.ascontiguousarray(pts, dtype=np.float32)
 
 
+def bundled_model(with_rgb=False):
+    """The model cloud the reference ships (D&L/3DModel/drillNewModelOrigin.pcd, 157 825 points; BASELINE.json configs[0]),
+    from the committed fixture tests/golden/drill_model.npz (made by tests/golden/make_model_fixture.py)."""
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "drill_model.npz")
+    z = np.load(path)
+    xyz = np.ascontiguousarray(z["xyz"], np.float32)
+    return (xyz, z["rgb"]) if with_rgb else xyz
+
+
 # ------------------------------------------------------------------------------------------- poses ----
 def random_rotation(rng):
     q = rng.normal(size=4)

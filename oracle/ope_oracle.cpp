@@ -114,7 +114,7 @@ bool pairFeatures(const float* p1, const float* n1, const float* p2, const float
   float a[3] = {n1[0], n1[1], n1[2]}, b[3] = {n2[0], n2[1], n2[2]};
   float angle1 = (a[0] * dp[0] + a[1] * dp[1] + a[2] * dp[2]) / f4;
   float angle2 = (b[0] * dp[0] + b[1] * dp[1] + b[2] * dp[2]) / f4;
-  if (std::acos(std::fabs(angle1)) > std::acos(std::fabs(angle2))) {
+  if (orc::acos_cr(std::fabs(angle1)) > orc::acos_cr(std::fabs(angle2))) {
     std::swap(a[0], b[0]); std::swap(a[1], b[1]); std::swap(a[2], b[2]);
     dp[0] *= -1; dp[1] *= -1; dp[2] *= -1;
     f3 = -angle2;
@@ -129,7 +129,7 @@ bool pairFeatures(const float* p1, const float* n1, const float* p2, const float
   float w[3];
   orc::cross3(a, v, w);
   f2 = v[0] * b[0] + v[1] * b[1] + v[2] * b[2];
-  f1 = std::atan2(w[0] * b[0] + w[1] * b[1] + w[2] * b[2], a[0] * b[0] + a[1] * b[1] + a[2] * b[2]);
+  f1 = orc::atan2_cr(w[0] * b[0] + w[1] * b[1] + w[2] * b[2], a[0] * b[0] + a[1] * b[1] + a[2] * b[2]);
   return true;
 }
 

@@ -58,6 +58,16 @@ inline void xformNormal(const Mat4& T, const float* n, float* o) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Float transcendentals as CORRECTLY ROUNDED functions: evaluated in double and rounded once. The reference calls
+// libm's float functions (acos/atan2f/cos/sin on float arguments); their last bit depends on the libm build (glibc < 2.41
+// does not promise correct rounding), so the restatement pins them to the ideal value — independent of the host's libm,
+// and what the device computes as well.
+inline float atan2_cr(float y, float x) { return (float)std::atan2((double)y, (double)x); }
+inline float acos_cr(float x) { return (float)std::acos((double)x); }
+inline float cos_cr(float x) { return (float)std::cos((double)x); }
+inline float sin_cr(float x) { return (float)std::sin((double)x); }
+
+// ---------------------------------------------------------------------------------------------
 // pcl::computeRoots2 / computeRoots / eigen33 (smallest eigenvalue + eigenvector), float.
 // m is symmetric 3x3, column-major (indexing symmetric so order is irrelevant).
 inline void computeRoots2(float b, float c, float roots[3]) {
@@ -89,9 +99,9 @@ inline void computeRoots(const float m[9], float roots[3]) {
   float q = half_b * half_b + a_over_3 * a_over_3 * a_over_3;
   if (q > 0.0f) q = 0.0f;
   float rho = std::sqrt(-a_over_3);
-  float theta = std::atan2(std::sqrt(-q), half_b) * s_inv3;
-  float cos_theta = std::cos(theta);
-  float sin_theta = std::sin(theta);
+  float theta = atan2_cr(std::sqrt(-q), half_b) * s_inv3;
+  float cos_theta = cos_cr(theta);
+  float sin_theta = sin_cr(theta);
   roots[0] = c2_over_3 + 2.0f * rho * cos_theta;
   roots[1] = c2_over_3 - rho * (cos_theta + s_sqrt3 * sin_theta);
   roots[2] = c2_over_3 - rho * (cos_theta - s_sqrt3 * sin_theta);
