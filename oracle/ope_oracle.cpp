@@ -204,14 +204,38 @@ struct CloudView {
   const float* nrm(size_t i) const { return normals + 4 * i; }
 };
 
+// `fixed` / `n_fixed`: the reference's own extension (setFixedCorrespondences, VP/icp_mod.h:267-281): pairs the caller pins.
+// determineCorrespondences puts them in FRONT of the estimated ones with distance = squared distance * 1e10 and writes that
+// distance back into the caller's list (VP/impl/correspondence_estimation_mod.hpp:134-161). The reciprocal variant
+// (:216-303) ignores them: a pair (i, j) is kept iff j is i's nearest target point within the distance AND i is j's nearest
+// SOURCE point within the distance (a second tree over the current source, rebuilt whenever the source moved).
 void estimateCorrespondences(const CloudView& src, const CloudView& tgt, const KdTree& tgt_tree,
                              const float* est_src_normals, const ope_icp_params& prm,
-                             std::vector<ope_correspondence>& out) {
+                             std::vector<ope_correspondence>& out, ope_correspondence* fixed = nullptr, size_t n_fixed = 0) {
   out.clear();
-  out.reserve(src.n);
+  out.reserve(src.n + n_fixed);
   if (prm.estimator == OPE_EST_NEAREST) {
     double max_dist_sqr = prm.max_correspondence_distance * prm.max_correspondence_distance;
     Neighbor nn;
+    if (prm.use_reciprocal) {
+      KdTree src_tree; src_tree.build(src.pts, src.n, src.stride);
+      Neighbor back;
+      for (size_t i = 0; i < src.n; ++i) {
+        if (tgt_tree.knn(src.p(i), 1, &nn) == 0) continue;
+        if (nn.d2 > max_dist_sqr) continue;
+        if (src_tree.knn(tgt.p(nn.idx), 1, &back) == 0) continue;
+        if (back.d2 > max_dist_sqr || (int32_t)i != back.idx) continue;
+        out.push_back(ope_correspondence{(int32_t)i, nn.idx, nn.d2});
+      }
+      return;
+    }
+    for (size_t f = 0; f < n_fixed; ++f) {
+      const float* t = tgt.p(fixed[f].index_match);
+      const float* q = src.p(fixed[f].index_query);
+      float px = t[0] - q[0], py = t[1] - q[1], pz = t[2] - q[2];
+      fixed[f].distance = (float)((px * px + py * py + pz * pz) * 1e10);   // float sum, double product, stored as float
+      out.push_back(fixed[f]);
+    }
     for (size_t i = 0; i < src.n; ++i) {
       if (tgt_tree.knn(src.p(i), 1, &nn) == 0) continue;  // (non-finite query in FLANN would assert; skipped)
       if (nn.d2 > max_dist_sqr) continue;
@@ -259,8 +283,8 @@ bool rejectorKeeps(int kind, double thr, const ope_correspondence& c, const floa
 }
 
 void applyRejectors(const ope_icp_params& prm, std::vector<ope_correspondence>& corr, const float* rs_pts,
-                    size_t rs_stride, const float* rs_normals, const CloudView& tgt) {
-  for (int r = 0; r < prm.n_rejectors && r < OPE_MAX_REJECTORS; ++r) {
+                    size_t rs_stride, const float* rs_normals, const CloudView& tgt, int only_first = 0) {
+  for (int r = 0; r < (only_first ? std::min(prm.n_rejectors, 1) : prm.n_rejectors) && r < OPE_MAX_REJECTORS; ++r) {
     size_t w = 0;
     for (size_t i = 0; i < corr.size(); ++i)
       if (rejectorKeeps(prm.rejector_kind[r], prm.rejector_threshold[r], corr[i], rs_pts, rs_stride, rs_normals, tgt))
@@ -404,7 +428,8 @@ double fitnessScore(const float* src, size_t ns, size_t sstride, const KdTree& t
 
 // IterativeClosestPoint::computeTransformation, VP/impl/icp_mod.hpp:118-272 (variant switch: icp_modCorr.hpp).
 int icpAlign(const CloudView& src, const CloudView& tgt, const KdTree& tgt_tree, const ope_icp_params& prm,
-             const Mat4& guess, ope_reg_result* res, std::vector<ope_correspondence>& corr) {
+             const Mat4& guess, ope_reg_result* res, std::vector<ope_correspondence>& corr, ope_correspondence* fixed = nullptr,
+             size_t n_fixed = 0) {
   const bool has_normals = src.normals != nullptr;
   std::vector<float> xp(src.n * 3), xn;
   for (size_t i = 0; i < src.n; ++i) std::memcpy(&xp[3 * i], src.p(i), 12);
@@ -425,9 +450,16 @@ int icpAlign(const CloudView& src, const CloudView& tgt, const KdTree& tgt_tree,
     CloudView cur{xp.data(), src.n, 3, has_normals ? xn.data() : nullptr};
     const bool stale = prm.variant == OPE_ICP_VARIANT_MODCORR;
     const float* est_normals = stale ? src.normals : cur.normals;
-    estimateCorrespondences(cur, tgt, tgt_tree, est_normals, prm, corr);
+    const bool use_fixed = fixed && prm.variant == OPE_ICP_VARIANT_MOD;   // icp_modCorr.h has no setFixedCorrespondences
+    estimateCorrespondences(cur, tgt, tgt_tree, est_normals, prm, corr, use_fixed ? fixed : nullptr, use_fixed ? n_fixed : 0);
     if (stale) applyRejectors(prm, corr, src.pts, src.stride, src.normals, tgt);
     else applyRejectors(prm, corr, cur.pts, 3, cur.normals, tgt);
+    // "Apply the first rejector on the fixed correspondances" and append them (again), VP/impl/icp_mod.hpp:209-225
+    if (use_fixed && prm.n_rejectors > 0) {
+      std::vector<ope_correspondence> again(fixed, fixed + n_fixed);
+      if (!again.empty()) applyRejectors(prm, again, cur.pts, 3, cur.normals, tgt, /*only_first=*/1);
+      corr.insert(corr.end(), again.begin(), again.end());
+    }
     if ((int)corr.size() < prm.min_number_correspondences) {
       state = OPE_CONV_NO_CORRESPONDENCES;
       converged = false;
@@ -959,9 +991,28 @@ int orc_correspondences(const float* src, size_t ns, size_t sstride, const float
   return OPE_OK;
 }
 
+int orc_correspondences_fixed(const float* src, size_t ns, size_t sstride, const float* tgt, size_t nt, size_t tstride,
+                              const ope_icp_params* prm, ope_correspondence* fixed, size_t n_fixed, ope_correspondence* out,
+                              size_t* out_n) {
+  if (!src || !tgt || !prm || !out || !out_n) return OPE_ERR_INVALID;
+  KdTree tree; tree.build(tgt, nt, tstride);
+  CloudView s{src, ns, sstride, nullptr}, t{tgt, nt, tstride, nullptr};
+  std::vector<ope_correspondence> corr;
+  estimateCorrespondences(s, t, tree, nullptr, *prm, corr, fixed, n_fixed);
+  std::copy(corr.begin(), corr.end(), out);
+  *out_n = corr.size();
+  return OPE_OK;
+}
+
 int orc_icp(const float* src, size_t ns, size_t sstride, const float* src_normals, const float* tgt, size_t nt,
             size_t tstride, const float* tgt_normals, const ope_icp_params* prm, const float guess[16], ope_reg_result* res,
             ope_correspondence* out_corr) {
+  return orc_icp_fixed(src, ns, sstride, src_normals, tgt, nt, tstride, tgt_normals, prm, guess, nullptr, 0, res, out_corr);
+}
+
+int orc_icp_fixed(const float* src, size_t ns, size_t sstride, const float* src_normals, const float* tgt, size_t nt,
+                  size_t tstride, const float* tgt_normals, const ope_icp_params* prm, const float guess[16],
+                  ope_correspondence* fixed, size_t n_fixed, ope_reg_result* res, ope_correspondence* out_corr) {
   if (!src || !prm || !res) return OPE_ERR_INVALID;
   Mat4 I = Mat4::identity();
   std::memcpy(res->T, I.m, sizeof(I.m));
@@ -972,7 +1023,7 @@ int orc_icp(const float* src, size_t ns, size_t sstride, const float* src_normal
   Mat4 G = I;
   if (guess) std::memcpy(G.m, guess, sizeof(G.m));
   std::vector<ope_correspondence> corr;
-  int rc = icpAlign(s, t, tree, *prm, G, res, corr);
+  int rc = icpAlign(s, t, tree, *prm, G, res, corr, fixed, n_fixed);
   if (out_corr) std::copy(corr.begin(), corr.end(), out_corr);
   return rc;
 }

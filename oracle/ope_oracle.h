@@ -105,6 +105,20 @@ int orc_icp(const float* src, size_t ns, size_t sstride, const float* src_normal
             const float* tgt, size_t nt, size_t tstride, const float* tgt_normals,
             const ope_icp_params* prm, const float guess[16], ope_reg_result* res,
             ope_correspondence* out_corr);
+/* The same with the reference's own extension, fixed correspondences (IterativeClosestPoint::setFixedCorrespondences,
+ * VP/icp_mod.h:267-281; VP/impl/icp_mod.hpp:150-151,209-225; VP/impl/correspondence_estimation_mod.hpp:134-161): `fixed` is
+ * in/out — every iteration rewrites its distances (squared distance * 1e10). out_corr must hold ns + 2*n_fixed entries.
+ * prm->use_reciprocal selects determineReciprocalCorrespondences (VP/impl/correspondence_estimation_mod.hpp:216-303), which
+ * ignores the fixed list. */
+int orc_icp_fixed(const float* src, size_t ns, size_t sstride, const float* src_normals,
+                  const float* tgt, size_t nt, size_t tstride, const float* tgt_normals,
+                  const ope_icp_params* prm, const float guess[16], ope_correspondence* fixed, size_t n_fixed,
+                  ope_reg_result* res, ope_correspondence* out_corr);
+/* One determineCorrespondences / determineReciprocalCorrespondences pass of the nearest-neighbour estimator with a fixed list
+ * (no rejectors). out holds ns + n_fixed entries. */
+int orc_correspondences_fixed(const float* src, size_t ns, size_t sstride, const float* tgt, size_t nt, size_t tstride,
+                              const ope_icp_params* prm, ope_correspondence* fixed, size_t n_fixed, ope_correspondence* out,
+                              size_t* out_n);
 /* Draw the libc rand() decisions of a SAC-IA run (selectSamples + the pick in findSimilarFeatures)
  * WITHOUT reseeding: consumes the process-wide rand() stream exactly as PCL would. samples/picks hold
  * iterations*nr_samples entries. min_sample_distance is in/out (it is halved after 3*N failed draws). */

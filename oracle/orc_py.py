@@ -267,20 +267,45 @@ def correspondences(src, tgt, prm, src_normals=None, tgt_normals=None):
     return _corr_to_np(buf, m.value)
 
 
-def icp(src, tgt, prm, guess=None, src_normals=None, tgt_normals=None, want_corr=False):
+def fixed_buf(fixed):
+    """(query indices, match indices[, distances]) -> ctypes array of pcl::Correspondence (in/out for the fixed-list calls)"""
+    n = 0 if fixed is None else len(fixed[0])
+    buf = (T.Correspondence * max(n, 1))()
+    for i in range(n):
+        buf[i] = T.Correspondence(int(fixed[0][i]), int(fixed[1][i]), float(fixed[2][i]) if len(fixed) > 2 else 0.0)
+    return buf, n
+
+
+def icp(src, tgt, prm, guess=None, src_normals=None, tgt_normals=None, want_corr=False, fixed=None):
+    """fixed: (query indices, match indices) pinned by the caller (setFixedCorrespondences); with want_corr the rewritten
+    fixed distances are returned as a third element"""
     s, sp, ns, ss = _pts(src)
     t, tp, nt, ts = _pts(tgt)
     sn = None if src_normals is None else _f32(src_normals)
     tn = None if tgt_normals is None else _f32(tgt_normals)
     res = T.RegResult()
-    buf = (T.Correspondence * max(s.shape[0], 1))() if want_corr else None
+    fb, nf = fixed_buf(fixed)
+    buf = (T.Correspondence * max(s.shape[0] + 2 * nf, 1))() if want_corr else None
     g = None if guess is None else T.mat4_to_c(guess)
-    rc = lib().orc_icp(sp, ns, ss, None if sn is None else sn.ctypes.data_as(f32p), tp, nt, ts,
-                       None if tn is None else tn.ctypes.data_as(f32p), C.byref(prm), g, C.byref(res), buf)
+    rc = lib().orc_icp_fixed(sp, ns, ss, None if sn is None else sn.ctypes.data_as(f32p), tp, nt, ts,
+                             None if tn is None else tn.ctypes.data_as(f32p), C.byref(prm), g, fb if nf else None, C.c_size_t(nf),
+                             C.byref(res), buf)
     _chk(rc)
     if want_corr:
-        return res, _corr_to_np(buf, res.n_correspondences)
+        out = (res, _corr_to_np(buf, res.n_correspondences))
+        return out + (_corr_to_np(fb, nf)[2],) if nf else out
     return res
+
+
+def correspondences_fixed(src, tgt, prm, fixed=None):
+    """nearest-neighbour estimator with a fixed list in front / the reciprocal variant (prm.use_reciprocal), no rejectors"""
+    s, sp, ns, ss = _pts(src)
+    t, tp, nt, ts = _pts(tgt)
+    fb, nf = fixed_buf(fixed)
+    buf = (T.Correspondence * max(s.shape[0] + nf, 1))()
+    m = C.c_size_t(0)
+    _chk(lib().orc_correspondences_fixed(sp, ns, ss, tp, nt, ts, C.byref(prm), fb if nf else None, C.c_size_t(nf), buf, C.byref(m)))
+    return _corr_to_np(buf, m.value)
 
 
 def srand(seed):
