@@ -109,11 +109,11 @@ bool pointNormal(const float* pts, size_t stride, const Neighbor* nn, int cnt, c
 bool pairFeatures(const float* p1, const float* n1, const float* p2, const float* n2, float& f1, float& f2,
                   float& f3, float& f4) {
   float dp[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
-  f4 = std::sqrt(dp[0] * dp[0] + dp[1] * dp[1] + dp[2] * dp[2]);
+  f4 = std::sqrt(orc::dot3w0(dp, dp));
   if (f4 == 0.0f) { f1 = f2 = f3 = f4 = 0.0f; return false; }
   float a[3] = {n1[0], n1[1], n1[2]}, b[3] = {n2[0], n2[1], n2[2]};
-  float angle1 = (a[0] * dp[0] + a[1] * dp[1] + a[2] * dp[2]) / f4;
-  float angle2 = (b[0] * dp[0] + b[1] * dp[1] + b[2] * dp[2]) / f4;
+  float angle1 = orc::dot3w0(a, dp) / f4;
+  float angle2 = orc::dot3w0(b, dp) / f4;
   if (orc::acos_cr(std::fabs(angle1)) > orc::acos_cr(std::fabs(angle2))) {
     std::swap(a[0], b[0]); std::swap(a[1], b[1]); std::swap(a[2], b[2]);
     dp[0] *= -1; dp[1] *= -1; dp[2] *= -1;
@@ -123,13 +123,13 @@ bool pairFeatures(const float* p1, const float* n1, const float* p2, const float
   }
   float v[3];
   orc::cross3(dp, a, v);
-  float v_norm = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+  float v_norm = std::sqrt(orc::dot3w0(v, v));
   if (v_norm == 0.0f) { f1 = f2 = f3 = f4 = 0.0f; return false; }
   v[0] /= v_norm; v[1] /= v_norm; v[2] /= v_norm;
   float w[3];
   orc::cross3(a, v, w);
-  f2 = v[0] * b[0] + v[1] * b[1] + v[2] * b[2];
-  f1 = orc::atan2_cr(w[0] * b[0] + w[1] * b[1] + w[2] * b[2], a[0] * b[0] + a[1] * b[1] + a[2] * b[2]);
+  f2 = orc::dot3w0(v, b);
+  f1 = orc::atan2_cr(orc::dot3w0(w, b), orc::dot3w0(a, b));
   return true;
 }
 
@@ -383,9 +383,9 @@ void pointToPlaneLM(const CloudView& src, const CloudView& tgt, const std::vecto
       const float* s = src.p(corr[i].index_query); const float* d = tgt.p(corr[i].index_match); const float* n = tgt.nrm(corr[i].index_match);
       float w[3];
       orc::xformPoint(W, s, w);
-      // Vector4f (s - t).dot(n) with w = 0, Eigen's SSE reduction order: (p0 + p2) + (p1 + p3)
+      // Vector4f (s - t).dot(n) with w = 0: Eigen's packet reduction, order per orc::redux4 (orc_linalg.h)
       const float p0 = (w[0] - d[0]) * n[0], p1 = (w[1] - d[1]) * n[1], p2 = (w[2] - d[2]) * n[2], p3 = 0.0f * 0.0f;
-      fvec[i] = (p0 + p2) + (p1 + p3);
+      fvec[i] = orc::redux4(p0, p1, p2, p3);
     }
   };
   float x[6] = {0, 0, 0, 0, 0, 0};
@@ -634,7 +634,10 @@ void uniformSampleImpl(const float* pts, size_t n, size_t stride, float leaf, st
     if (it == leaves.end()) { leaves.emplace(idx, (int32_t)i); continue; }
     auto diff = [&](const float* q) {
       float a = q[0] - (float)ijk[0], b = q[1] - (float)ijk[1], c = q[2] - (float)ijk[2];
-      float r = a * a; r = r + b * b; r = r + c * c; r = r + 1.0f;  // 4th component: (1 - 0)^2
+      // (pt - ijk.cast<float>()).squaredNorm() over 4 components, the 4th being (1 - 0)^2: left to right unless the cast
+      // vectorises (Eigen >= 3.3), see orc::redux4 / orc::eigen_cast_vectorized (orc_linalg.h)
+      if (orc::eigen_cast_vectorized()) return orc::redux4(a * a, b * b, c * c, 1.0f * 1.0f);
+      float r = a * a; r = r + b * b; r = r + c * c; r = r + 1.0f;
       return r;
     };
     float diff_cur = diff(p), diff_prev = diff(at(pts, stride, it->second));
@@ -1029,6 +1032,11 @@ int orc_icp_fixed(const float* src, size_t ns, size_t sstride, const float* src_
 }
 
 void orc_srand(unsigned seed) { srand(seed); }
+
+void orc_set_eigen_model(int redux_level, int cast_vectorized) {
+  orc::eigen_redux_level() = redux_level;
+  orc::eigen_cast_vectorized() = cast_vectorized != 0;
+}
 
 int orc_sacia_draw(const float* src, size_t ns, size_t sstride, int iterations, int nr_samples, int k_correspondences,
                    float* min_sample_distance, int32_t* samples, int32_t* picks) {

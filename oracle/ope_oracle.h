@@ -131,6 +131,9 @@ int orc_sacia(const float* src, size_t ns, size_t sstride, const float* fsrc,
               const ope_sacia_params* prm, const ope_rng_table* table, ope_reg_result* res,
               float* out_errors /* max_iterations floats or NULL */);
 void orc_srand(unsigned seed);
+/* Which Eigen build the restatement mimics for 4-float packet reductions (oracle/orc_linalg.h: 3 = SSE3+ hadd [default],
+ * 2 = SSE2, 0 = scalar) and whether int->float casts vectorise (Eigen >= 3.3; default 0). Sensitivity tests only. */
+void orc_set_eigen_model(int redux_level, int cast_vectorized);
 
 /* ---- PoseEstimator (D&L/src/poseestimator.cpp:16-448) ---- */
 typedef struct orc_pose_estimator orc_pose_estimator;

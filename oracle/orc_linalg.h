@@ -58,6 +58,30 @@ inline void xformNormal(const Mat4& T, const float* n, float* o) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// The ONE statement of the Eigen build the restatement assumes (two different orders were assumed before).
+// Eigen evaluates a 4-float reduction (Vector4f dot / squaredNorm / norm) as one packet product followed by a horizontal add:
+//   level 3  SSE3 and later, `haddps` twice:          (p0 + p1) + (p2 + p3)      <- ASSUMED (default)
+//   level 2  plain SSE2, movehl + add + shuffle:      (p0 + p2) + (p1 + p3)
+//   level 0  not vectorised (EIGEN_DONT_VECTORIZE):   ((p0 + p1) + p2) + p3
+// Assumed platform: PCL 1.7.1 / 1.7.2 (the only releases the vendored headers compile against) with Eigen 3.2.x,
+// built with PCL's own SSE flags (-msse4.2 -mfpmath=sse), which reach the reference's translation units through
+// PCL_DEFINITIONS (D&L/CMakeLists.txt:60 add_definitions(${PCL_DEFINITIONS})): level 3. For the w = 0 vectors of the pair
+// features and the point-to-plane residual, level 3 equals the plain left-to-right 3-term sum. Expressions Eigen 3.2 cannot
+// vectorise — UniformSampling's `(pt - ijk.cast<float>()).squaredNorm()`: int->float casts have no packet form before
+// Eigen 3.3 — are summed left to right whatever the level (g_cast_vectorized = false); with Eigen >= 3.3 they would follow
+// the level too. orc_set_eigen_model() switches both for the sensitivity test (tests/test_oracle.py); the device implements
+// the default only. This choice is [UPSTREAM]-unpinned: no Eigen exists in this image to check it.
+inline int& eigen_redux_level() { static int level = 3; return level; }
+inline bool& eigen_cast_vectorized() { static bool v = false; return v; }
+inline float redux4(float p0, float p1, float p2, float p3) {
+  const int level = eigen_redux_level();
+  if (level == 3) return (p0 + p1) + (p2 + p3);
+  if (level == 2) return (p0 + p2) + (p1 + p3);
+  return ((p0 + p1) + p2) + p3;
+}
+inline float dot3w0(const float* a, const float* b) { return redux4(a[0] * b[0], a[1] * b[1], a[2] * b[2], 0.0f * 0.0f); }
+
+// ---------------------------------------------------------------------------------------------
 // Float transcendentals as CORRECTLY ROUNDED functions: evaluated in double and rounded once. The reference calls
 // libm's float functions (acos/atan2f/cos/sin on float arguments); their last bit depends on the libm build (glibc < 2.41
 // does not promise correct rounding), so the restatement pins them to the ideal value — independent of the host's libm,

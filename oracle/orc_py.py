@@ -308,6 +308,11 @@ def correspondences_fixed(src, tgt, prm, fixed=None):
     return _corr_to_np(buf, m.value)
 
 
+def set_eigen_model(redux_level=3, cast_vectorized=False):
+    """which Eigen build the oracle mimics for 4-float reductions (default: SSE3+ hadd order, Eigen 3.2 casts)"""
+    lib().orc_set_eigen_model(int(redux_level), int(bool(cast_vectorized)))
+
+
 def srand(seed):
     lib().orc_srand(C.c_uint(seed))
 
