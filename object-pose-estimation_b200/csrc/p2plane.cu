@@ -62,7 +62,7 @@ __device__ __forceinline__ void block_sum_store(double* acc, double* dst) {
 }
 
 // (warp(s) - t) . n as the reference's functor evaluates it: Vector4f with w = 0, Eigen's packet reduction with SSE3+
-// horizontal adds, (p0 + p1) + (p2 + p3) — the one Eigen model of the whole path (oracle/orc_linalg.h)
+// horizontal adds, (p0 + p1) + (p2 + p3) — the one Eigen model of the whole path
 __device__ __forceinline__ float plane_residual(const Mat4& W, const float4 s, const float4 t, const float4 n) {
   float wx, wy, wz;
   xform_point(W, s.x, s.y, s.z, wx, wy, wz);
