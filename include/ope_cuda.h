@@ -140,6 +140,15 @@ int ope_correspondences(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt
  * out_corr (ns entries, last iteration's correspondences_) and out_aligned (device cloud = `output`) may be NULL. */
 int ope_icp_align(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const ope_icp_params* prm,
                   const float guess[16], ope_reg_result* res, ope_correspondence* out_corr, ope_cloud** out_aligned);
+/* The same with the reference's own extension of ICP, fixed correspondences (IterativeClosestPoint::setFixedCorrespondences,
+ * VP/icp_mod.h:267-281; VP/impl/icp_mod.hpp:150-151,209-225; VP/impl/correspondence_estimation_mod.hpp:134-161): pairs the caller
+ * pins enter every iteration's list in front with distance = squared distance * 1e10 and, when rejectors exist, a second time at
+ * the end after rejector 0 alone. `fixed` is in/out (the loop rewrites its distances); out_corr must hold ns + 2 * n_fixed entries.
+ * prm->use_reciprocal (either entry point) selects determineReciprocalCorrespondences (VP/impl/correspondence_estimation_mod.hpp:
+ * 216-303) for the nearest-neighbour estimator. */
+int ope_icp_align_fixed(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const ope_icp_params* prm, const float guess[16],
+                        ope_correspondence* fixed, size_t n_fixed, ope_reg_result* res, ope_correspondence* out_corr,
+                        ope_cloud** out_aligned);
 /* SampleConsensusInitialAlignment::align [UPSTREAM ia_ransac.hpp] (D&L/src/poseestimator.cpp:50-64).
  * fsrc/ftgt: host FPFHSignature33 arrays (ns*33, nt*33). table == NULL: the decisions are drawn from libc rand()
  * exactly as PCL does (the host owns the RNG stream; the device evaluates the whole pool in one launch).

@@ -1225,6 +1225,72 @@ __global__ void __launch_bounds__(kIcpThreads, 1) correspond_once_kernel(IcpDev 
   }
 }
 
+// determineReciprocalCorrespondences, VP/impl/correspondence_estimation_mod.hpp:216-303: a pair (i, m) survives iff i is the
+// nearest SOURCE point of target point m within the distance. gsrc indexes the CURRENT (transformed) source.
+__global__ void __launch_bounds__(kIcpThreads, 1) reciprocal_filter_kernel(GridView gsrc, const float4* __restrict__ tgt_pts, int* match,
+                                                                           int n, float max_d2_f, double max_corr_dist) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  IcpSmem* sm = reinterpret_cast<IcpSmem*>(smem_raw);
+  for (int base = blockIdx.x * kIcpThreads; base < n; base += gridDim.x * kIcpThreads) {
+    const int i = base + (int)threadIdx.x;
+    const int m = i < n ? match[i] : -1;
+    float4 q = make_float4(0, 0, 0, 0);
+    if (m >= 0) q = __ldg(tgt_pts + m);
+    const bool ok = m >= 0 && finite3(q.x, q.y, q.z);
+    float d2 = 0.0f;
+    const int back = block_nn1<kIcpThreads>(gsrc, &sm->nn, ok, q.x, q.y, q.z, max_d2_f, -1, nullptr, d2);
+    if (m >= 0 && !(ok && back == i && !((double)d2 > max_corr_dist * max_corr_dist))) match[i] = -1;
+  }
+}
+
+// The reference's fixed correspondences (VP/impl/correspondence_estimation_mod.hpp:150-165, VP/impl/icp_mod.hpp:209-225): pair j
+// gets distance = squared distance * 1e10 and enters the list twice — in front, through the whole rejector chain (slot j), and
+// at the end, through rejector 0 alone (slot F + j, only when rejectors exist). One small block.
+__global__ void fixed_pairs_kernel(IcpDev a, const int* __restrict__ fq, const int* __restrict__ fm, int n_fixed, int front,
+                                   int* __restrict__ is, int* __restrict__ it, float* __restrict__ d2) {
+  for (int j = threadIdx.x; j < n_fixed; j += blockDim.x) {
+    const int q = fq[j], m = fm[j];
+    const float4 s = a.cur_pts[q], t = __ldg(a.tgt_pts + m);
+    const float px = t.x - s.x, py = t.y - s.y, pz = t.z - s.z;
+    const float dist = front ? (float)((double)(px * px + py * py + pz * pz) * 1e10) : d2[j];   // reciprocal mode: as the caller left it
+    int keep_all = front ? m : -1, keep_first = a.n_rej > 0 ? m : -1;
+    if (front) keep_all = icp_reject(a, q, q, s, m);
+    if (a.n_rej > 0) {
+      IcpDev one = a;
+      one.n_rej = 1;
+      keep_first = icp_reject(one, q, q, s, m);
+    }
+    is[j] = q; it[j] = keep_all; d2[j] = dist;
+    is[n_fixed + j] = q; it[n_fixed + j] = keep_first; d2[n_fixed + j] = dist;
+  }
+}
+
+// raw Umeyama moments (+ pair count and the sum of the correspondence distances) of the pairs (src[is[i]], tgt[it[i]]), it[i] >= 0
+static constexpr int kPairAcc = kMomentAcc + 1;
+__global__ void pairs_moments_kernel(const float4* __restrict__ src, const float4* __restrict__ tgt, const int* __restrict__ is,
+                                     const int* __restrict__ it, const float* __restrict__ d2, int n, double* __restrict__ partials) {
+  __shared__ double smem[(kRedThreads / 32) * kPairAcc];
+  double acc[kPairAcc];
+  for (int a = 0; a < kPairAcc; ++a) acc[a] = 0.0;
+  double o[3];
+  { const float4 t0 = __ldg(tgt); moment_origin(t0.x, t0.y, t0.z, o[0], o[1], o[2]); }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int m = it[i];
+    if (m < 0) continue;
+    const float4 s = __ldg(src + (is ? is[i] : i));
+    const float4 t = __ldg(tgt + m);
+    const double sv[3] = {(double)s.x - o[0], (double)s.y - o[1], (double)s.z - o[2]};
+    const double tv[3] = {(double)t.x - o[0], (double)t.y - o[1], (double)t.z - o[2]};
+    acc[0] += 1.0;
+    acc[1] += sv[0]; acc[2] += sv[1]; acc[3] += sv[2];
+    acc[4] += tv[0]; acc[5] += tv[1]; acc[6] += tv[2];
+    for (int c = 0; c < 3; ++c)
+      for (int r = 0; r < 3; ++r) acc[7 + c * 3 + r] += tv[r] * sv[c];
+    acc[kMomentAcc] += (double)d2[i];
+  }
+  block_reduce_store<kPairAcc>(acc, smem, partials + (size_t)blockIdx.x * kPairAcc);
+}
+
 // ============================================================================================ SAC-IA ====
 struct SaciaDev {
   GridView grid;
@@ -1436,7 +1502,8 @@ static int icp_fill(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, co
   if (prm.n_rejectors < 0 || prm.n_rejectors > OPE_MAX_REJECTORS) return fail(ctx, OPE_ERR_INVALID, "bad rejector count");
   if (need_src_normals && !src->normals) return fail(ctx, OPE_ERR_INVALID, "estimator/rejector needs source normals");
   if (need_tgt_normals && !tgt->normals) return fail(ctx, OPE_ERR_INVALID, "rejector needs target normals");
-  if (prm.use_reciprocal) return fail(ctx, OPE_ERR_UNSUPPORTED, "reciprocal correspondences are not implemented");
+  if (prm.use_reciprocal && prm.estimator != OPE_EST_NEAREST)
+    return fail(ctx, OPE_ERR_UNSUPPORTED, "reciprocal correspondences are implemented for the nearest-neighbour estimator only");
   if (prm.transformation != OPE_TE_SVD && prm.transformation != OPE_TE_POINT_TO_PLANE_LLS && prm.transformation != OPE_TE_POINT_TO_PLANE)
     return fail(ctx, OPE_ERR_UNSUPPORTED, "unknown transformation estimator %d", prm.transformation);
   if (prm.transformation != OPE_TE_SVD && !tgt->normals) return fail(ctx, OPE_ERR_INVALID, "point-to-plane estimation needs target normals");
@@ -1480,11 +1547,13 @@ static void corr_to_host(const std::vector<int>& match, const std::vector<float>
 }
 
 static int icp_stepwise_device(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const ope_icp_params& prm, const Mat4& guess,
-                               ope_reg_result* res, ope_correspondence* out_corr_host, ope_cloud** out_aligned);
+                               ope_reg_result* res, ope_correspondence* out_corr_host, ope_cloud** out_aligned,
+                               ope_correspondence* fixed = nullptr, size_t n_fixed = 0);
 
 int icp_device(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const ope_icp_params& prm, const Mat4& guess,
                ope_reg_result* res, ope_correspondence* out_corr_host, ope_cloud** out_aligned) {
-  if (prm.transformation != OPE_TE_SVD) return icp_stepwise_device(ctx, src, tgt, prm, guess, res, out_corr_host, out_aligned);
+  if (prm.transformation != OPE_TE_SVD || prm.use_reciprocal)
+    return icp_stepwise_device(ctx, src, tgt, prm, guess, res, out_corr_host, out_aligned);
   IcpDev a;
   std::memset(&a, 0, sizeof(a));
   OPE_TRY(icp_fill(ctx, src, tgt, prm, &a, /*allow_smem_target=*/true));
@@ -1650,13 +1719,47 @@ int icp_device(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const o
 // host), so this loop is sequenced from the host: correspondences + rejectors (one launch), estimation (p2plane.cu), transform
 // in place, DefaultConvergenceCriteria in double on the host. Everything the kernels read stays on the device; per step only
 // the 28 reduced doubles come back.
+// Umeyama over explicit pairs for the host-sequenced loop: double moments on the device, the 3x3 SVD on the host (same
+// arithmetic as the fused kernel's lane 0: umeyama_from_moments is host/device code compiled without contraction)
+static int svd_pairs_device(ope_ctx* ctx, const float4* src, const ope_cloud* tgt, const double origin[3], const int* d_is, const int* d_it,
+                            const float* d_d2, size_t n, Mat4* T, int* n_pairs, double* sum_d2) {
+  *T = mat4_identity(); *n_pairs = 0; *sum_d2 = 0.0;
+  if (n == 0) return OPE_OK;
+  const int nb = (int)std::min<size_t>(std::max<size_t>(1, (n + kRedThreads - 1) / kRedThreads), (size_t)ctx->sm_count * 4);
+  Scratch<double> partials(ctx), out(ctx);
+  OPE_TRY(partials.alloc((size_t)nb * kPairAcc));
+  OPE_TRY(out.alloc(kPairAcc));
+  pairs_moments_kernel<<<nb, kRedThreads, 0, ctx->stream>>>(src, tgt->pts, d_is, d_it, d_d2, (int)n, partials.p);
+  OPE_TRY(check_launch(ctx, "pairs_moments_kernel"));
+  sum_partials_kernel<<<1, 32 * kPairAcc, 0, ctx->stream>>>(partials.p, nb, kPairAcc, out.p);
+  OPE_TRY(check_launch(ctx, "sum_partials_kernel"));
+  void* h;
+  OPE_TRY(read_back(ctx, out.p, kPairAcc * sizeof(double), &h));
+  const double* acc = (const double*)h;
+  *n_pairs = (int)acc[0];
+  *sum_d2 = acc[kMomentAcc];
+  if (*n_pairs > 0) umeyama_from_moments(acc, *T, origin[0], origin[1], origin[2]);
+  return OPE_OK;
+}
+
+// The host-sequenced ICP loop: one launch for correspondences + rejectors, optional reciprocal filter and fixed pairs, the
+// transformation estimate (SVD / point-to-plane LLS / LM), the transform, DefaultConvergenceCriteria on the host. Used whenever
+// the fused kernel does not apply: point-to-plane estimators, reciprocal correspondences, fixed correspondences.
 static int icp_stepwise_device(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const ope_icp_params& prm, const Mat4& guess,
-                               ope_reg_result* res, ope_correspondence* out_corr_host, ope_cloud** out_aligned) {
+                               ope_reg_result* res, ope_correspondence* out_corr_host, ope_cloud** out_aligned, ope_correspondence* fixed,
+                               size_t n_fixed) {
   IcpDev a;
   std::memset(&a, 0, sizeof(a));
   OPE_TRY(icp_fill(ctx, src, tgt, prm, &a));
   const size_t n = src->n;
   const bool shooting = prm.estimator == OPE_EST_NORMAL_SHOOTING;
+  // icp_modCorr.h has no setFixedCorrespondences; normal shooting leaves the list out of its result (VP/impl/correspondence_
+  // estimation_normal_shooting_weighted.hpp:81-100)
+  if (prm.variant != OPE_ICP_VARIANT_MOD || shooting) n_fixed = 0;
+  const size_t F = n_fixed;
+  for (size_t j = 0; j < F; ++j)
+    if (fixed[j].index_query < 0 || (size_t)fixed[j].index_query >= n || fixed[j].index_match < 0 || (size_t)fixed[j].index_match >= tgt->n)
+      return fail(ctx, OPE_ERR_INVALID, "fixed correspondence %zu out of range", j);
   ope_cloud *work = nullptr, *next = nullptr;   // ping-pong: transform_kernel reads through the read-only path
   struct Guard { ope_ctx* c; ope_cloud*& w; ~Guard() { if (w) ope_cloud_free(c, w); } } guard{ctx, work}, guard2{ctx, next};
   OPE_TRY(cloud_alloc(ctx, std::max<size_t>(n, 1), src->normals != nullptr, &work));
@@ -1664,14 +1767,36 @@ static int icp_stepwise_device(ope_ctx* ctx, const ope_cloud* src, const ope_clo
   work->n = next->n = n;
   Mat4 final_t = guess;
   if (n > 0) OPE_TRY(transform_device(ctx, src, guess, work));   // identity guess: a plain copy
-  Scratch<int> match(ctx), seed(ctx);
+  // pair arrays: [0, F) fixed pairs through the whole rejector chain, [F, 2F) through rejector 0 alone, [2F, 2F + n) estimated
+  Scratch<int> is(ctx), match(ctx), seed(ctx), fq(ctx), fm(ctx);
   Scratch<float> d2(ctx);
-  OPE_TRY(match.alloc(n)); OPE_TRY(d2.alloc(n));
+  OPE_TRY(match.alloc(n + 2 * F)); OPE_TRY(d2.alloc(n + 2 * F));
   OPE_TRY(seed.alloc(shooting ? n * (size_t)prm.k_search : n));
-  a.corr_match = match.p; a.corr_d2 = d2.p; a.seed = seed.p;
+  std::vector<int> h_is, h_fq(F), h_fm(F);
+  if (F) {
+    OPE_TRY(is.alloc(n + 2 * F)); OPE_TRY(fq.alloc(F)); OPE_TRY(fm.alloc(F));
+    h_is.resize(n + 2 * F);
+    std::vector<float> h_fd(2 * F);
+    for (size_t j = 0; j < F; ++j) { h_fq[j] = fixed[j].index_query; h_fm[j] = fixed[j].index_match; h_fd[j] = h_fd[F + j] = fixed[j].distance; }
+    for (size_t i = 0; i < n; ++i) h_is[2 * F + i] = (int)i;
+    OPE_CUDA_TRY(ctx, cudaMemcpyAsync(is.p, h_is.data(), (n + 2 * F) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    OPE_CUDA_TRY(ctx, cudaMemcpyAsync(fq.p, h_fq.data(), F * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    OPE_CUDA_TRY(ctx, cudaMemcpyAsync(fm.p, h_fm.data(), F * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    OPE_CUDA_TRY(ctx, cudaMemcpyAsync(d2.p, h_fd.data(), 2 * F * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    OPE_CUDA_TRY(ctx, ope::stream_sync(ctx));
+  }
+  a.corr_match = match.p + 2 * F; a.corr_d2 = d2.p + 2 * F; a.seed = seed.p;
   OPE_TRY(dyn_smem(ctx, (const void*)correspond_once_kernel, sizeof(IcpSmem)));
+  if (prm.use_reciprocal) OPE_TRY(dyn_smem(ctx, (const void*)reciprocal_filter_kernel, sizeof(IcpSmem)));
   const size_t want = shooting ? div_up(n, kIcpWarps) : div_up(n, kIcpThreads);
   const unsigned blocks = (unsigned)std::max<size_t>(1, std::min<size_t>(want, (size_t)ctx->sm_count * 4));
+  double origin[3] = {0, 0, 0};
+  if (prm.transformation == OPE_TE_SVD) {   // the moments are taken about the target's first point (see umeyama_from_moments)
+    void* h;
+    OPE_TRY(read_back(ctx, tgt->pts, sizeof(float4), &h));
+    const float4 t0 = *(const float4*)h;
+    moment_origin(t0.x, t0.y, t0.z, origin[0], origin[1], origin[2]);
+  }
   int iterations = 0, state = OPE_CONV_NOT_CONVERGED, similar = 0, n_corr = 0;
   bool converged = false;
   double prev_mse = DBL_MAX, cur_mse = DBL_MAX;
@@ -1683,10 +1808,26 @@ static int icp_stepwise_device(ope_ctx* ctx, const ope_cloud* src, const ope_clo
       correspond_once_kernel<<<blocks, kIcpThreads, sizeof(IcpSmem), ctx->stream>>>(a);
       OPE_TRY(check_launch(ctx, "correspond_once_kernel"));
     }
+    if (prm.use_reciprocal && n > 0) {   // a second index over the source as it stands in this iteration
+      OPE_TRY(ope_cloud_invalidate(ctx, work));
+      OPE_TRY(cloud_bbox(ctx, work));
+      GridView gsrc;
+      OPE_TRY(cloud_grid(ctx, work, knn_cell_size(work, 1), &gsrc));
+      reciprocal_filter_kernel<<<blocks, kIcpThreads, sizeof(IcpSmem), ctx->stream>>>(gsrc, tgt->pts, a.corr_match, (int)n, a.max_d2_f,
+                                                                                      a.max_corr_dist);
+      OPE_TRY(check_launch(ctx, "reciprocal_filter_kernel"));
+    }
+    if (F) {
+      fixed_pairs_kernel<<<1, 128, 0, ctx->stream>>>(a, fq.p, fm.p, (int)F, prm.use_reciprocal ? 0 : 1, is.p, match.p, d2.p);
+      OPE_TRY(check_launch(ctx, "fixed_pairs_kernel"));
+    }
     Mat4 T = mat4_identity();
     double sum_d2 = 0.0;
-    OPE_TRY(point_to_plane_device(ctx, work->pts, tgt->pts, tgt->normals, nullptr, match.p, d2.p, n, prm.transformation, &T, &n_corr,
-                                  &sum_d2, nullptr));
+    if (prm.transformation == OPE_TE_SVD)
+      OPE_TRY(svd_pairs_device(ctx, work->pts, tgt, origin, F ? is.p : nullptr, match.p, d2.p, n + 2 * F, &T, &n_corr, &sum_d2));
+    else
+      OPE_TRY(point_to_plane_device(ctx, work->pts, tgt->pts, tgt->normals, F ? is.p : nullptr, match.p, d2.p, n + 2 * F, prm.transformation,
+                                    &T, &n_corr, &sum_d2, nullptr));
     if (n_corr < prm.min_number_correspondences) {   // VP/impl/icp_mod.hpp:232-240
       state = OPE_CONV_NO_CORRESPONDENCES;
       converged = false;
@@ -1731,13 +1872,19 @@ static int icp_stepwise_device(ope_ctx* ctx, const ope_cloud* src, const ope_clo
   res->n_correspondences = n_corr;
   res->last_mse = cur_mse;
   res->best_error = 0.0; res->best_iteration = 0; res->reserved = 0;
-  if (out_corr_host && n > 0) {
-    std::vector<int> hm(n);
-    std::vector<float> hd(n);
-    OPE_CUDA_TRY(ctx, cudaMemcpyAsync(hm.data(), match.p, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    OPE_CUDA_TRY(ctx, cudaMemcpyAsync(hd.data(), d2.p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  if ((out_corr_host || F) && n + 2 * F > 0) {
+    std::vector<int> hm(n + 2 * F);
+    std::vector<float> hd(n + 2 * F);
+    OPE_CUDA_TRY(ctx, cudaMemcpyAsync(hm.data(), match.p, (n + 2 * F) * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    OPE_CUDA_TRY(ctx, cudaMemcpyAsync(hd.data(), d2.p, (n + 2 * F) * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     OPE_CUDA_TRY(ctx, ope::stream_sync(ctx));
-    corr_to_host(hm, hd, out_corr_host, nullptr);
+    for (size_t j = 0; j < F; ++j) fixed[j].distance = hd[j];   // the loop rewrites the caller's list (it->distance = ...)
+    if (out_corr_host) {   // the reference's order: fixed (whole chain), estimated, fixed again (rejector 0 alone)
+      size_t w = 0;
+      for (size_t j = 0; j < F; ++j) if (hm[j] >= 0) out_corr_host[w++] = ope_correspondence{h_fq[j], hm[j], hd[j]};
+      for (size_t i = 0; i < n; ++i) if (hm[2 * F + i] >= 0) out_corr_host[w++] = ope_correspondence{(int32_t)i, hm[2 * F + i], hd[2 * F + i]};
+      for (size_t j = 0; j < F; ++j) if (hm[F + j] >= 0) out_corr_host[w++] = ope_correspondence{h_fq[j], hm[F + j], hd[F + j]};
+    }
   }
   if (out_aligned) {
     if (n > 0) OPE_TRY(transform_device(ctx, src, final_t, work));   // output = *input_ under the final transformation, :269-271
@@ -2000,6 +2147,15 @@ int ope_correspondences(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt
   const size_t want = shooting ? div_up(n, kIcpWarps) : div_up(n, kIcpThreads);
   correspond_once_kernel<<<(unsigned)std::min<size_t>(want, (size_t)ctx->sm_count * 4), kIcpThreads, sizeof(IcpSmem), ctx->stream>>>(a);
   OPE_TRY(check_launch(ctx, "correspond_once_kernel"));
+  if (prm->use_reciprocal) {   // determineReciprocalCorrespondences: the source's own (cached) index answers the way back
+    OPE_TRY(cloud_bbox(ctx, const_cast<ope_cloud*>(src)));
+    GridView gsrc;
+    OPE_TRY(cloud_grid(ctx, src, knn_cell_size(src, 1), &gsrc));
+    OPE_TRY(dyn_smem(ctx, (const void*)reciprocal_filter_kernel, sizeof(IcpSmem)));
+    reciprocal_filter_kernel<<<(unsigned)std::min<size_t>(div_up(n, kIcpThreads), (size_t)ctx->sm_count * 4), kIcpThreads, sizeof(IcpSmem),
+                               ctx->stream>>>(gsrc, tgt->pts, match.p, (int)n, a.max_d2_f, a.max_corr_dist);
+    OPE_TRY(check_launch(ctx, "reciprocal_filter_kernel"));
+  }
   std::vector<int> hm(n);
   std::vector<float> hd(n);
   OPE_CUDA_TRY(ctx, cudaMemcpyAsync(hm.data(), match.p, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -2022,6 +2178,21 @@ int ope_icp_align(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, cons
   Mat4 G = I;
   if (guess) std::memcpy(G.m, guess, sizeof(G.m));
   return icp_device(ctx, src, tgt, *prm, G, res, out_corr, out_aligned);
+}
+
+int ope_icp_align_fixed(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const ope_icp_params* prm, const float guess[16],
+                        ope_correspondence* fixed, size_t n_fixed, ope_reg_result* res, ope_correspondence* out_corr, ope_cloud** out_aligned) {
+  OPE_ENTER(ctx);
+  if (!ctx || !src || !prm || !res || (n_fixed && !fixed)) return OPE_ERR_INVALID;
+  if (n_fixed == 0) return ope_icp_align(ctx, src, tgt, prm, guess, res, out_corr, out_aligned);
+  Mat4 I = mat4_identity();
+  std::memset(res, 0, sizeof(*res));
+  std::memcpy(res->T, I.m, sizeof(I.m));
+  if (out_aligned) *out_aligned = nullptr;
+  if (!tgt || tgt->n == 0) return fail(ctx, OPE_ERR_EMPTY, "No input target dataset was given!");
+  Mat4 G = I;
+  if (guess) std::memcpy(G.m, guess, sizeof(G.m));
+  return icp_stepwise_device(ctx, src, tgt, *prm, G, res, out_corr, out_aligned, fixed, n_fixed);
 }
 
 int ope_sacia_draw(const float* src_xyz, size_t ns, size_t stride_bytes, int iterations, int nr_samples, int k_correspondences,

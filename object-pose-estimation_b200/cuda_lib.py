@@ -27,7 +27,7 @@ EXPORTS = [
     "ope_knn", "ope_knn_cloud", "ope_radius_cloud", "ope_depth_to_cloud", "ope_depth_to_cloud_batch",
     "ope_uniform_sample", "ope_uniform_sample_cloud", "ope_voxel_grid",
     "ope_normals_knn", "ope_fpfh", "ope_feature_knn",
-    "ope_umeyama", "ope_point_to_plane", "ope_fitness", "ope_correspondences", "ope_icp_align", "ope_sacia_align", "ope_sacia_draw",
+    "ope_umeyama", "ope_point_to_plane", "ope_fitness", "ope_correspondences", "ope_icp_align", "ope_icp_align_fixed", "ope_sacia_align", "ope_sacia_draw",
     "ope_pose_tracker_create", "ope_pose_tracker_destroy", "ope_pose_estimate_final", "ope_pose_estimate_final_device", "ope_pose_batch",
     "ope_pose_stage_ms", "ope_icp_params_default", "ope_sacia_params_default", "ope_pose_params_default",
 ]
@@ -383,18 +383,30 @@ class Context:
         a = np.ctypeslib.as_array(buf)[:m.value]
         return a["index_query"].copy(), a["index_match"].copy(), a["distance"].copy()
 
-    def icp(self, src, tgt, prm, guess=None, want_corr=False, want_aligned=False):
+    def icp(self, src, tgt, prm, guess=None, want_corr=False, want_aligned=False, fixed=None):
+        """fixed: (query indices, match indices) pinned by the caller (setFixedCorrespondences); with want_corr their rewritten
+        distances are appended to the correspondence tuple's container as a further output"""
         res = T.RegResult()
-        buf = (T.Correspondence * max(len(src), 1))() if want_corr else None
+        nf = 0 if fixed is None else len(fixed[0])
+        buf = (T.Correspondence * max(len(src) + 2 * nf, 1))() if want_corr else None
         g = None if guess is None else T.mat4_to_c(guess)
         h = C.c_void_p()
-        rc = lib().ope_icp_align(self.h, src.h, tgt.h if tgt is not None else None, C.byref(prm), g, C.byref(res), buf,
-                                 C.byref(h) if want_aligned else None)
+        if nf:
+            fb = (T.Correspondence * nf)()
+            for i in range(nf):
+                fb[i] = T.Correspondence(int(fixed[0][i]), int(fixed[1][i]), float(fixed[2][i]) if len(fixed) > 2 else 0.0)
+            rc = lib().ope_icp_align_fixed(self.h, src.h, tgt.h if tgt is not None else None, C.byref(prm), g, fb, C.c_size_t(nf),
+                                           C.byref(res), buf, C.byref(h) if want_aligned else None)
+        else:
+            rc = lib().ope_icp_align(self.h, src.h, tgt.h if tgt is not None else None, C.byref(prm), g, C.byref(res), buf,
+                                     C.byref(h) if want_aligned else None)
         self._chk(rc)
         out = [res]
         if want_corr:
             a = np.ctypeslib.as_array(buf)[:res.n_correspondences]
             out.append((a["index_query"].copy(), a["index_match"].copy(), a["distance"].copy()))
+            if nf:
+                out.append(np.ctypeslib.as_array(fb)["distance"].copy())
         if want_aligned:
             out.append(Cloud(self, h))
         return out[0] if len(out) == 1 else tuple(out)

@@ -275,6 +275,68 @@ def test_icp_with_normals_d_and_l_configuration(ctx, orc, synth, cuda_lib, model
         assert abs(gf - of) < FIT_TOL
 
 
+def test_icp_reciprocal_and_fixed_correspondences(ctx, orc, synth, cuda_lib, small_model):
+    """The VP-held extras of a7/a8: determineReciprocalCorrespondences (VP/impl/correspondence_estimation_mod.hpp:216-303) alone
+    and inside the loop, and the reference's fixed correspondences (VP/icp_mod.h:267-281, VP/impl/icp_mod.hpp:209-225) without
+    and with a rejector chain — same list (order included), same rewritten distances, same transform as the oracle, which
+    tests/test_ref.py pins bit-exactly to the reference's own compiled sources."""
+    T = cuda_lib.T
+    src, tgt, _ = synth.icp_pair(4000, seed=6, model=small_model)
+    tgt = tgt[:2500].copy()
+    cs, ct = ctx.upload(src), ctx.upload(tgt)
+    for d in (0.05, 0.003):
+        g = ctx.correspondences(cs, ct, cuda_lib.icp_params(max_correspondence_distance=d, use_reciprocal=1))
+        o = orc.correspondences_fixed(src, tgt, orc.icp_params(max_correspondence_distance=d, use_reciprocal=1))
+        assert len(o[0]) > 100 and all(np.array_equal(a, b) for a, b in zip(g, o))
+    kw = dict(max_iterations=25, max_correspondence_distance=0.05, transformation_epsilon=1e-8, euclidean_fitness_epsilon=1e-8,
+              use_reciprocal=1)
+    g, gc = ctx.icp(cs, ct, cuda_lib.icp_params(**kw), want_corr=True)
+    o, oc = orc.icp(src, tgt, orc.icp_params(**kw), want_corr=True)
+    _pose_close(synth, T, g.T, o.T)
+    assert (g.converged, g.state, g.iterations, g.n_correspondences) == (o.converged, o.state, o.iterations, o.n_correspondences)
+    assert all(np.array_equal(a, b) for a, b in zip(gc, oc))
+    # fixed correspondences: six source points pinned to their third-nearest target point
+    rng = np.random.default_rng(11)
+    fq = rng.choice(len(src), 6, replace=False)
+    fm = orc.knn(tgt, src[fq], 3)[0][:, 2]
+    kw = dict(max_iterations=20, max_correspondence_distance=0.05, transformation_epsilon=1e-10, euclidean_fitness_epsilon=1e-12)
+    g, gc, gd = ctx.icp(cs, ct, cuda_lib.icp_params(**kw), want_corr=True, fixed=(fq, fm))
+    o, oc, od = orc.icp(src, tgt, orc.icp_params(**kw), want_corr=True, fixed=(fq, fm))
+    _pose_close(synth, T, g.T, o.T)
+    assert (g.converged, g.state, g.iterations, g.n_correspondences) == (o.converged, o.state, o.iterations, o.n_correspondences)
+    assert np.array_equal(gc[0], oc[0]) and np.array_equal(gc[1], oc[1]) and np.allclose(gc[2], oc[2], rtol=1e-5, atol=0)
+    assert np.allclose(gd, od, rtol=1e-5, atol=0)
+    sn, tn = orc.normals_knn(src, 12), orc.normals_knn(tgt, 12)
+    cs2, ct2 = ctx.upload(src, sn), ctx.upload(tgt, tn)
+    kw = dict(max_iterations=12, max_correspondence_distance=0.05, transformation_epsilon=1e-10, euclidean_fitness_epsilon=1e-12,
+              rejectors=[(T.REJ_SURFACE_NORMAL, 0.2), (T.REJ_SELF_OCCLUDED_NORMAL, -2.0)])
+    g, gc, gd = ctx.icp(cs2, ct2, cuda_lib.icp_params(**kw), want_corr=True, fixed=(fq, fm))
+    o, oc, od = orc.icp(src, tgt, orc.icp_params(**kw), src_normals=sn, tgt_normals=tn, want_corr=True, fixed=(fq, fm))
+    _pose_close(synth, T, g.T, o.T)
+    assert (g.converged, g.state, g.iterations, g.n_correspondences) == (o.converged, o.state, o.iterations, o.n_correspondences)
+    assert np.array_equal(gc[0], oc[0]) and np.array_equal(gc[1], oc[1])
+
+
+def test_get_icp2_two_stage_point_to_point(ctx, orc, synth, cuda_lib, small_model):
+    """RegMeshPcd::getIcp2 (BM/src/regmeshpcd.cpp:46-59): two plain ICPs in sequence, the second on the first's aligned output
+    with a tighter distance (0.05 / 80 iterations, then 0.005 / 500; transformation epsilon 1e-16, BM/src/regmeshpcd.cpp:16-41,
+    225-226)."""
+    T = cuda_lib.T
+    src, tgt, _ = synth.icp_pair(5000, seed=12, model=small_model)
+    cs, ct = ctx.upload(src), ctx.upload(tgt)
+    o_src, g_src = src, cs
+    for dist, iters in ((0.05, 80), (0.005, 500)):
+        kw = dict(max_iterations=iters, max_correspondence_distance=dist, transformation_epsilon=1e-16)
+        g, aligned = ctx.icp(g_src, ct, cuda_lib.icp_params(**kw), want_aligned=True)
+        o = orc.icp(o_src, tgt, orc.icp_params(**kw))
+        _pose_close(synth, T, g.T, o.T)
+        assert (g.converged, g.state, g.iterations, g.n_correspondences) == (o.converged, o.state, o.iterations, o.n_correspondences)
+        o_src = orc.transform(o_src, T.mat4(o.T))
+        assert np.array_equal(aligned.download(), o_src)
+        g_src = aligned
+        assert abs(ctx.fitness(g_src, ct, np.eye(4)) - orc.fitness(o_src, tgt, np.eye(4))) < FIT_TOL
+
+
 def test_icp_no_correspondences(ctx, orc, cuda_lib):
     rng = np.random.default_rng(0)
     src = rng.random((200, 3)).astype(np.float32)
