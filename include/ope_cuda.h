@@ -44,6 +44,11 @@ double ope_ctx_last_kernel_ms(ope_ctx* ctx, int which);
 /* feature-space k-NN bookkeeping: queries answered through the tcgen05 distance GEMM so far, and how many of them the exact
  * float32 kernel re-answered because the candidate set could not be proven complete */
 int ope_ctx_feature_knn_stats(const ope_ctx* ctx, int64_t* gemm_queries, int64_t* fallbacks);
+/* model-side cache of the pose trackers of this context: the reference recomputes the 1 cm sample, normals and FPFH
+ * of the source cloud every time the coarse stage runs (D&L/src/poseestimator.cpp:34,116); here a source cloud with the same size
+ * and content hash as one seen before (and the same leaf / k / radius) reuses them. Results are bit-identical with and without
+ * the cache (OPE_MODEL_CACHE=0 disables it). hits/misses: coarse stages served from / added to the cache. */
+int ope_ctx_model_cache_stats(const ope_ctx* ctx, int64_t* hits, int64_t* misses);
 /* library / build identification: "ope_cuda <version> sm_100a" */
 const char* ope_version(void);
 

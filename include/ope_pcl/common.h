@@ -241,6 +241,38 @@ inline bool upload(const PointCloud<PointT>& cloud, DeviceCloud& out, const char
   return check(ope_cloud_upload(ctx, base, cloud.points.size(), sizeof(PointT), 0, nbase, sizeof(PointT), noff, out.out()), where);
 }
 
+// PCL keeps the caller's shared_ptr and re-reads *input_ / *target_ on every align(); the shim keeps a device copy instead, so it
+// must notice a cloud that was modified IN PLACE between two calls (the reference does `*p_sourceCloud = *alignedCloud` and
+// re-aligns on the same object): storage address, size and a 64-bit hash of the bytes.
+struct CloudFingerprint {
+  const void* data = nullptr;
+  std::size_t size = 0;
+  std::uint64_t hash = 0;
+  bool operator==(const CloudFingerprint& o) const { return data == o.data && size == o.size && hash == o.hash; }
+  bool operator!=(const CloudFingerprint& o) const { return !(*this == o); }
+};
+template <typename PointT>
+inline CloudFingerprint fingerprint(const PointCloud<PointT>& cloud) {
+  CloudFingerprint f;
+  f.data = cloud.points.empty() ? nullptr : (const void*)cloud.points.data();
+  f.size = cloud.points.size();
+  const std::size_t words = f.size * sizeof(PointT) / 8;
+  const unsigned char* p = (const unsigned char*)f.data;
+  std::uint64_t h0 = 0x9e3779b97f4a7c15ull, h1 = 0xc2b2ae3d27d4eb4full, h2 = 0x165667b19e3779f9ull, h3 = 0x27d4eb2f165667c5ull;
+  std::size_t i = 0;
+  for (; i + 4 <= words; i += 4) {   // four independent multiply-rotate lanes: memory-bound on any host
+    std::uint64_t w[4];
+    std::memcpy(w, p + 8 * i, 32);
+    h0 = (h0 ^ w[0]) * 0x9fb21c651e98df25ull; h0 = (h0 << 29) | (h0 >> 35);
+    h1 = (h1 ^ w[1]) * 0x9fb21c651e98df25ull; h1 = (h1 << 29) | (h1 >> 35);
+    h2 = (h2 ^ w[2]) * 0x9fb21c651e98df25ull; h2 = (h2 << 29) | (h2 >> 35);
+    h3 = (h3 ^ w[3]) * 0x9fb21c651e98df25ull; h3 = (h3 << 29) | (h3 >> 35);
+  }
+  for (; i < words; ++i) { std::uint64_t w; std::memcpy(&w, p + 8 * i, 8); h0 = (h0 ^ w) * 0x9fb21c651e98df25ull; h0 = (h0 << 29) | (h0 >> 35); }
+  f.hash = h0 ^ (h1 * 3) ^ (h2 * 5) ^ (h3 * 7) ^ (std::uint64_t)f.size;
+  return f;
+}
+
 // points from one cloud, normals (normal_x.. + curvature, 16 bytes) from another
 template <typename PointT, typename NormalT>
 inline bool upload_with_normals(const PointCloud<PointT>& cloud, const PointCloud<NormalT>& normals, DeviceCloud& out,

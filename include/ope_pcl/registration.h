@@ -371,11 +371,22 @@ class Registration {
     if (!input_) { detail::pcl_error((reg_name_ + "::compute").c_str(), "No input source dataset was given!"); return false; }
     return detail::context() != nullptr && sync_clouds();
   }
+  // PCL re-reads *input_ / *target_ on every align(): a cloud modified in place since the last upload (the reference does
+  // `*p_sourceCloud = *alignedCloud` and aligns again) is detected by its fingerprint and uploaded again; a changed target also
+  // drops its search index, like target_cloud_updated_ does to the kd-tree (VP/impl/registration_mod.hpp:80-84)
   bool sync_clouds() {
-    if (source_cloud_updated_) { if (!detail::upload(*input_, dsrc_, reg_name_.c_str())) return false; source_cloud_updated_ = false; }
-    if (target_cloud_updated_) { if (!detail::upload(*target_, dtgt_, reg_name_.c_str())) return false; target_cloud_updated_ = false; }
+    const detail::CloudFingerprint fs = detail::fingerprint(*input_), ft = detail::fingerprint(*target_);
+    if (source_cloud_updated_ || fs != src_print_) {
+      if (!detail::upload(*input_, dsrc_, reg_name_.c_str())) return false;
+      source_cloud_updated_ = false; src_print_ = fs;
+    }
+    if (target_cloud_updated_ || ft != tgt_print_) {
+      if (!detail::upload(*target_, dtgt_, reg_name_.c_str())) return false;
+      target_cloud_updated_ = false; tgt_print_ = ft;
+    }
     return true;
   }
+  detail::CloudFingerprint src_print_, tgt_print_;
   // download a device cloud (`output`, same size and order as input_) into the caller's point structs
   void fetch_output(ope_cloud* aligned, PointCloudSource& output) {
     ope_ctx* ctx = detail::context();
@@ -433,6 +444,10 @@ class IterativeClosestPoint : public Registration<PointSource, PointTarget, Scal
   }
   void setUseReciprocalCorrespondences(bool use) { use_reciprocal_correspondence_ = use; }
   bool getUseReciprocalCorrespondences() const { return use_reciprocal_correspondence_; }
+  // the vendored class's fixed correspondences, VP/icp_mod.h:267-281: the caller keeps ownership, align() rewrites the distances
+  void setFixedCorrespondences(Correspondences* correspondences) { corres_fixed_ = correspondences; }
+  Correspondences& getFixedCorrespondences() { return *corres_fixed_; }
+  void clearCorrespondences() { if (corres_fixed_) corres_fixed_->clear(); }
   // additions of the vendored class: VP/icp_mod.h:249-260
   double getAlignStrength() {
     const double total = (double)((this->input_ ? this->input_->points.size() : 0) + (this->target_ ? this->target_->points.size() : 0));
@@ -477,7 +492,11 @@ class IterativeClosestPoint : public Registration<PointSource, PointTarget, Scal
     detail::to_c(guess, G);
     ope_cloud* aligned = nullptr;
     std::memset(&last_, 0, sizeof(last_));
-    const int rc = ope_icp_align(ctx, this->dsrc_.get(), this->dtgt_.get(), &prm, G, &last_, nullptr, &aligned);
+    static_assert(sizeof(Correspondence) == sizeof(ope_correspondence), "pcl::Correspondence layout");
+    const size_t n_fixed = corres_fixed_ ? corres_fixed_->size() : 0;
+    const int rc = ope_icp_align_fixed(ctx, this->dsrc_.get(), this->dtgt_.get(), &prm, G,
+                                       n_fixed ? reinterpret_cast<ope_correspondence*>(corres_fixed_->data()) : nullptr, n_fixed, &last_,
+                                       nullptr, &aligned);
     if (!detail::check(rc, (this->reg_name_ + "::computeTransformation").c_str())) return;
     this->final_transformation_ = detail::from_c(last_.T);
     this->converged_ = last_.converged != 0;
@@ -486,6 +505,7 @@ class IterativeClosestPoint : public Registration<PointSource, PointTarget, Scal
     if (aligned) ope_cloud_free(ctx, aligned);
   }
   bool use_reciprocal_correspondence_ = false;
+  Correspondences* corres_fixed_ = nullptr;
   int variant_ = OPE_ICP_VARIANT_MOD;
   ope_reg_result last_{};
 };
@@ -552,6 +572,7 @@ class SampleConsensusInitialAlignment : public Registration<PointSource, PointTa
     if (!detail::check(rc, where)) return;
     this->final_transformation_ = detail::from_c(last_.T);
     this->converged_ = last_.converged != 0;
+    if (!table_) min_sample_distance_ = (float)last_.last_mse;   // selectSamples halves the MEMBER; it stays halved across align()s
     // transformPointCloud(*input_, output, final_transformation_)
     transformPointCloud(*this->input_, output, this->final_transformation_);
   }

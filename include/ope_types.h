@@ -107,7 +107,8 @@ typedef struct ope_reg_result {
   int32_t state;
   int32_t iterations;
   int32_t n_correspondences;
-  double last_mse;       /* correspondences_cur_mse_ of the last evaluated iteration */
+  double last_mse;       /* ICP: correspondences_cur_mse_ of the last evaluated iteration; SAC-IA: min_sample_distance_ as the
+                            run left it (selectSamples halves the member after 3*N failed draws and it STAYS halved) */
   double best_error;     /* SAC-IA: lowest_error; ICP: unused (0) */
   int32_t best_iteration;/* SAC-IA: index of the winning hypothesis; ICP: unused */
   int32_t reserved;

@@ -416,6 +416,34 @@ int cloud_alloc(ope_ctx* ctx, size_t n, bool with_normals, ope_cloud** out) {
   return OPE_OK;
 }
 
+__global__ void content_hash_kernel(const float4* __restrict__ pts, int n, unsigned long long* __restrict__ out) {
+  unsigned long long acc = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = __ldg(pts + i);
+    unsigned long long a = ((unsigned long long)__float_as_uint(p.x) << 32) | __float_as_uint(p.y);
+    unsigned long long b = ((unsigned long long)__float_as_uint(p.z) << 32) | (unsigned)i;
+    a = (a ^ (b * 0x9fb21c651e98df25ull)) * 0xc2b2ae3d27d4eb4full;
+    a ^= a >> 29;
+    acc += a * 0x165667b19e3779f9ull;     // wrap-around sum: independent of the order the threads arrive in
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
+int cloud_content_hash(ope_ctx* ctx, const ope_cloud* c, unsigned long long* out) {
+  *out = 0;
+  if (c->n == 0) return OPE_OK;
+  Scratch<unsigned long long> d(ctx);
+  OPE_TRY(d.alloc(1));
+  OPE_CUDA_TRY(ctx, cudaMemsetAsync(d.p, 0, sizeof(unsigned long long), ctx->stream));
+  content_hash_kernel<<<std::min(grid_blocks(ctx, c->n), 592), kThreads, 0, ctx->stream>>>(c->pts, (int)c->n, d.p);
+  OPE_TRY(check_launch(ctx, "content_hash_kernel"));
+  void* h;
+  OPE_TRY(read_back(ctx, d.p, sizeof(unsigned long long), &h));
+  *out = *(const unsigned long long*)h ^ (unsigned long long)c->n;
+  return OPE_OK;
+}
+
 int cloud_bbox(ope_ctx* ctx, ope_cloud* c) {
   if (c->bbox_valid) return OPE_OK;
   if (c->n == 0) {
@@ -708,6 +736,8 @@ void ope_ctx_destroy(ope_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   ope::stream_sync(ctx);
+  for (auto& e : ctx->model_cache) { if (e.sp) ope_cloud_free(ctx, e.sp); ope::dfree(ctx, e.fs); }
+  ctx->model_cache.clear();
   for (int w = 0; w < 3; ++w)
     for (int j = 0; j < 2; ++j) if (ctx->kev[w][j]) cudaEventDestroy(ctx->kev[w][j]);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -727,6 +757,12 @@ int ope_ctx_feature_knn_stats(const ope_ctx* ctx, int64_t* gemm_queries, int64_t
   if (!ctx) return OPE_ERR_INVALID;
   if (gemm_queries) *gemm_queries = ctx->feature_knn_gemm_queries;
   if (fallbacks) *fallbacks = ctx->feature_knn_fallbacks;
+  return OPE_OK;
+}
+int ope_ctx_model_cache_stats(const ope_ctx* ctx, int64_t* hits, int64_t* misses) {
+  if (!ctx) return OPE_ERR_INVALID;
+  if (hits) *hits = ctx->model_cache_hits;
+  if (misses) *misses = ctx->model_cache_misses;
   return OPE_OK;
 }
 int ope_ctx_synchronize(ope_ctx* ctx) {

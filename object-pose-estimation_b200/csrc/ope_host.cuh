@@ -15,6 +15,19 @@
 #include "../../include/ope_cuda.h"
 #include "ope_grid.cuh"
 
+struct ope_cloud;
+// the frame-invariant model side of the coarse stage (1 cm sample + normals, FPFH descriptors), keyed by the
+// content of the full-resolution source cloud it was computed from and by the parameters that shape it
+struct ModelCacheEntry {
+  unsigned long long hash = 0;
+  size_t n = 0;
+  float leaf = 0, radius = 0;
+  int k = 0;
+  ope_cloud* sp = nullptr;   // owned
+  float* fs = nullptr;       // owned (device, sp->n * 33)
+  unsigned long long stamp = 0;
+};
+
 struct ope_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -39,6 +52,9 @@ struct ope_ctx {
   int icp_max_blocks = 0;      // > 0: cap of the cooperative icp_kernel grid (batch workers share the SMs between frames)
   int64_t feature_knn_gemm_queries = 0;  // queries answered through the tcgen05 distance GEMM ...
   int64_t feature_knn_fallbacks = 0;     // ... of which the exact kernel had to re-answer (candidate set not provably complete)
+  std::vector<ModelCacheEntry> model_cache;   // at most 4 entries, least recently used replaced (pipeline.cu)
+  unsigned long long model_cache_clock = 0;
+  int64_t model_cache_hits = 0, model_cache_misses = 0;
 };
 
 // How points are binned into cells: c = (int)floorf((p - o) * inv) - min_b, per axis.
@@ -211,6 +227,8 @@ int build_cells(ope_ctx* ctx, const float4* pts, size_t n, const Binning& bin, i
 // device-side versions used by the pipeline
 int uniform_sample_device(ope_ctx* ctx, ope_cloud* cloud, float leaf, int** d_idx, size_t* out_n);
 int gather_cloud(ope_ctx* ctx, const ope_cloud* cloud, const int* d_idx, size_t n, ope_cloud** out);
+// 64-bit content hash of a device cloud's points (order-sensitive), for the model-side cache
+int cloud_content_hash(ope_ctx* ctx, const ope_cloud* cloud, unsigned long long* out);
 
 // ---- features.cu ----
 int normals_device(ope_ctx* ctx, ope_cloud* cloud, int k, const float vp[3]);

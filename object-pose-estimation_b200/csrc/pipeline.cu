@@ -31,6 +31,11 @@ struct ope_pose_tracker {
 
 namespace {
 
+bool model_cache_enabled() {
+  const char* e = std::getenv("OPE_MODEL_CACHE");
+  return !e || std::atoi(e) != 0;
+}
+
 int clone_cloud(ope_ctx* ctx, const ope_cloud* in, ope_cloud** out) {
   ope_cloud* o = nullptr;
   OPE_TRY(cloud_alloc(ctx, in->n, in->normals != nullptr, &o));
@@ -153,20 +158,56 @@ int ope_pose_estimate_final_device(ope_pose_tracker* t, ope_cloud** source, cons
     DevGuard fs(ctx), ft(ctx);
     // the model side is frame-invariant: with a cache attached the first call of a tracker reuses the model's
     // coarse sample, normals and descriptors instead of recomputing them as the reference does every frame (:34,116)
-    const bool cached = t->cache_sp && t->cache_fs && t->firstTimePose == 1 && t->cache_model_n == p_source->n;
+    bool cached = t->cache_sp && t->cache_fs && t->firstTimePose == 1 && t->cache_model_n == p_source->n;
     ope_cloud sp_view;
     const ope_cloud* spc = nullptr;
     const float* fsp = nullptr;
-    if (cached) {
-      sp_view = *t->cache_sp;      // shallow view: shared device arrays, private (empty) grid cache
+    // the context's own cache (every tracker of this context): an unchanged source cloud — same size, same content hash, same
+    // parameters — keeps its coarse sample, normals and descriptors across frames and trackers. OPE_MODEL_CACHE=0 turns it off.
+    ModelCacheEntry* hit = nullptr;
+    unsigned long long src_hash = 0;
+    const bool use_ctx_cache = !cached && model_cache_enabled();
+    if (use_ctx_cache) {
+      OPE_TRY(cloud_content_hash(ctx, p_source, &src_hash));
+      for (auto& e : ctx->model_cache)
+        if (e.hash == src_hash && e.n == p_source->n && e.leaf == P.coarse_leaf && e.k == P.normal_k && e.radius == P.fpfh_radius) hit = &e;
+      if (hit) { hit->stamp = ++ctx->model_cache_clock; ctx->model_cache_hits++; } else ctx->model_cache_misses++;
+      tm.lap(0);
+    }
+    if (cached || hit) {
+      sp_view = cached ? *t->cache_sp : *hit->sp;      // shallow view: shared device arrays, private (empty) grid cache
       sp_view.ctx = ctx; sp_view.grids.clear();
-      spc = &sp_view; fsp = t->cache_fs;
+      spc = &sp_view; fsp = cached ? t->cache_fs : hit->fs;
+      cached = true;
     } else {
       OPE_TRY(sub_sample_and_normals(t, tm, p_source, P.coarse_leaf, &sp.c));
       spc = sp.c;
     }
     OPE_TRY(sub_sample_and_normals(t, tm, const_cast<ope_cloud*>(target), P.coarse_leaf, &tp.c));
-    if (!cached) { OPE_TRY(fpfh_device(ctx, sp.c, P.fpfh_radius, &fs.p, nullptr)); fsp = fs.p; }
+    if (!cached) {
+      OPE_TRY(fpfh_device(ctx, sp.c, P.fpfh_radius, &fs.p, nullptr));
+      fsp = fs.p;
+      if (use_ctx_cache) {   // hand the model side over to the cache (it owns the arrays from here on)
+        ModelCacheEntry e;
+        e.hash = src_hash; e.n = p_source->n; e.leaf = P.coarse_leaf; e.k = P.normal_k; e.radius = P.fpfh_radius;
+        e.sp = sp.c; e.fs = fs.p; e.stamp = ++ctx->model_cache_clock;
+        ope_cloud_invalidate(ctx, e.sp);
+        sp.c = nullptr; fs.p = nullptr;
+        if (ctx->model_cache.size() >= 4) {
+          size_t old = 0;
+          for (size_t i = 1; i < ctx->model_cache.size(); ++i) if (ctx->model_cache[i].stamp < ctx->model_cache[old].stamp) old = i;
+          ope_cloud_free(ctx, ctx->model_cache[old].sp); dfree(ctx, ctx->model_cache[old].fs);
+          ctx->model_cache[old] = e;
+          hit = &ctx->model_cache[old];
+        } else {
+          ctx->model_cache.push_back(e);
+          hit = &ctx->model_cache.back();
+        }
+        sp_view = *hit->sp; sp_view.ctx = ctx; sp_view.grids.clear();
+        spc = &sp_view; fsp = hit->fs;
+        cached = true;     // from here on the arrays are borrowed, exactly like a hit
+      }
+    }
     OPE_TRY(fpfh_device(ctx, tp.c, P.fpfh_radius, &ft.p, nullptr));
     tm.lap(2);
     res->n_src_coarse = (int32_t)spc->n; res->n_tgt_coarse = (int32_t)tp.c->n;

@@ -1931,6 +1931,7 @@ int sacia_device(ope_ctx* ctx, const ope_cloud* src, const float* d_fsrc, const 
   if ((size_t)S > src->n) return fail(ctx, OPE_ERR_INVALID, "The number of samples must not be greater than the number of points");
   int h0 = 0, h1 = H;
   if (prm.hypothesis_end > prm.hypothesis_begin) { h0 = std::max(0, prm.hypothesis_begin); h1 = std::min(H, prm.hypothesis_end); }
+  float final_msd = prm.min_sample_distance;
   // ---- decision table: replayed or drawn from libc rand() ----
   std::vector<int32_t> hs, hp;
   const int32_t *samples = nullptr, *picks = nullptr;
@@ -1946,7 +1947,7 @@ int sacia_device(ope_ctx* ctx, const ope_cloud* src, const float* d_fsrc, const 
       hx = xyz.data();
     }
     hs.resize((size_t)H * S); hp.resize((size_t)H * S);
-    float msd = prm.min_sample_distance;
+    float& msd = final_msd;
     for (int it = 0; it < H; ++it) {
       int rc = draw_samples(hx, src->n, 3, S, msd, hs.data() + (size_t)it * S);
       if (rc != OPE_OK) return fail(ctx, rc, "selectSamples failed");
@@ -2004,6 +2005,7 @@ int sacia_device(ope_ctx* ctx, const ope_cloud* src, const float* d_fsrc, const 
   OPE_TRY(read_back(ctx, d_res.p, sizeof(ope_reg_result), &h));
   std::memcpy(res, h, sizeof(ope_reg_result));
   res->iterations = H;
+  res->last_mse = (double)final_msd;   // min_sample_distance_ as selectSamples left it (it halves the member and keeps it halved)
   if (out_errors_host) {
     OPE_CUDA_TRY(ctx, cudaMemcpyAsync(out_errors_host, d_errors.p, (size_t)H * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     OPE_CUDA_TRY(ctx, ope::stream_sync(ctx));

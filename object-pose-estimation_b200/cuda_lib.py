@@ -21,7 +21,7 @@ i64p = C.POINTER(C.c_int64)
 
 EXPORTS = [
     "ope_ctx_create", "ope_ctx_destroy", "ope_last_error", "ope_ctx_synchronize", "ope_ctx_launch_count", "ope_version",
-    "ope_ctx_last_kernel_ms", "ope_cloud_invalidate", "ope_ctx_feature_knn_stats",
+    "ope_ctx_last_kernel_ms", "ope_cloud_invalidate", "ope_ctx_feature_knn_stats", "ope_ctx_model_cache_stats",
     "ope_cloud_upload", "ope_cloud_free", "ope_cloud_size", "ope_cloud_has_normals", "ope_cloud_download",
     "ope_cloud_select", "ope_cloud_transform", "ope_cloud_set_normals", "ope_cloud_append", "ope_register_point_clouds",
     "ope_knn", "ope_knn_cloud", "ope_radius_cloud", "ope_depth_to_cloud", "ope_depth_to_cloud_batch",
@@ -183,6 +183,12 @@ class Context:
         """(queries answered through the tcgen05 distance GEMM, queries the exact kernel re-answered)"""
         a, b = C.c_int64(0), C.c_int64(0)
         self._chk(lib().ope_ctx_feature_knn_stats(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def model_cache_stats(self):
+        """(coarse stages served from the model-side cache, coarse stages that filled it)"""
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._chk(lib().ope_ctx_model_cache_stats(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
     def invalidate(self, cloud):

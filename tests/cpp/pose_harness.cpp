@@ -25,6 +25,7 @@
 #include <pcl/search/kdtree.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <fstream>
 #include <iostream>
 #include <string>
@@ -235,6 +236,21 @@ static int run_icp(int argc, char** argv) {
   std::printf("\"converged\": %d, \"fitness\": %.17g, \"iterations\": %d, \"state\": %d, \"n_out\": %zu, \"out_sum\": [%.9g, %.9g, %.9g]}\n",
               icp.hasConverged() ? 1 : 0, icp.getFitnessScore(), icp.getNumberOfIterations(), icp.getConvergenceState(), moved.size(), sx,
               sy, sz);
+  // PCL re-reads *input_ on every align(): modify the source cloud IN PLACE (no setInputSource) and align again on the same
+  // object, with a tighter distance — RegMeshPcd::getIcp2's second stage (BM/src/regmeshpcd.cpp:46-59) written the way the
+  // reference's `*p_sourceCloud = *alignedCloud` pattern does it; plus reciprocal correspondences on the second stage
+  if (std::getenv("OPE_ICP_SECOND_STAGE")) {
+    *src = moved;
+    icp.setMaxCorrespondenceDistance(0.005);
+    icp.setMaximumIterations(500);
+    icp.setUseReciprocalCorrespondences(std::atoi(std::getenv("OPE_ICP_SECOND_STAGE")) == 2);
+    Cloud moved2;
+    icp.align(moved2);
+    std::printf("{");
+    print_mat("T", icp.getFinalTransformation());
+    std::printf("\"converged\": %d, \"fitness\": %.17g, \"iterations\": %d, \"state\": %d}\n", icp.hasConverged() ? 1 : 0,
+                icp.getFitnessScore(), icp.getNumberOfIterations(), icp.getConvergenceState());
+  }
   // error behaviour: align() without a target prints an error and leaves the transformation at identity
   pcl::IterativeClosestPoint<PointT, PointT> empty;
   empty.setInputSource(src);

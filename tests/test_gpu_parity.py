@@ -405,6 +405,39 @@ def test_pose_pipeline_matches_oracle(ctx, orc, synth, cuda_lib, model):
         assert np.abs(gsrc - osrc).max() < 1e-4
 
 
+def test_model_side_cache_in_the_tracker_is_invisible(ctx, synth, cuda_lib, model, monkeypatch):
+    """SURVEY 8f-3 inside ope_pose_tracker: fresh trackers handed the same model reuse its 1 cm sample, normals and FPFH (content
+    hash of the source cloud); a changed source (the tracking frame's aligned cloud) misses. Cached and uncached runs must return
+    the same bits."""
+    import ctypes
+    libc = ctypes.CDLL(None)
+    frames = [synth.make_frame(model, 40 + f)[0] for f in range(3)]
+
+    def run():
+        out = []
+        for cl in frames:
+            tr = cuda_lib.PoseTracker(ctx)
+            src = model.copy()
+            libc.srand(3)
+            a = tr.estimate_final(src, cl)
+            libc.srand(3)
+            b = tr.estimate_final(src, cl)           # tracking frame: the source is now the aligned cloud
+            out.append((np.array(list(a.final_pose)), np.array(list(b.final_pose)), a.fitness, b.fitness, a.icp_iterations, src.copy()))
+            tr.close()
+        return out
+
+    monkeypatch.setenv("OPE_MODEL_CACHE", "0")
+    plain = run()
+    monkeypatch.setenv("OPE_MODEL_CACHE", "1")
+    h0, m0 = ctx.model_cache_stats()
+    cached = run()
+    h1, m1 = ctx.model_cache_stats()
+    assert h1 - h0 >= 2 and m1 - m0 >= 1            # frames 2 and 3 hit the entry frame 1 made
+    for p, c in zip(plain, cached):
+        assert np.array_equal(p[0], c[0]) and np.array_equal(p[1], c[1]) and p[2] == c[2] and p[3] == c[3] and p[4] == c[4]
+        assert np.array_equal(p[5], c[5])
+
+
 # ------------------------------------------------------------------------------ tcgen05 feature-distance GEMM ----
 @pytest.mark.parametrize("nq,nt", [(300, 700), (1000, 1500), (2500, 20000)])
 def test_feature_knn_gemm_path_is_bit_identical_to_the_exact_kernel(ctx, orc, nq, nt, monkeypatch):
