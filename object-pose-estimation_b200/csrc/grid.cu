@@ -752,7 +752,12 @@ void ope_ctx_destroy(ope_ctx* ctx) {
 }
 
 const char* ope_last_error(const ope_ctx* ctx) { return ctx ? ctx->error.c_str() : "no context"; }
-int64_t ope_ctx_launch_count(const ope_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int64_t ope_ctx_launch_count(const ope_ctx* ctx) {
+  if (!ctx) return 0;
+  int64_t n = ctx->launches;
+  for (const ope_ctx* w : ctx->workers) n += w->launches;   // ope_pose_batch's worker contexts launch on behalf of this one
+  return n;
+}
 int ope_ctx_feature_knn_stats(const ope_ctx* ctx, int64_t* gemm_queries, int64_t* fallbacks) {
   if (!ctx) return OPE_ERR_INVALID;
   if (gemm_queries) *gemm_queries = ctx->feature_knn_gemm_queries;
