@@ -51,8 +51,8 @@ __global__ void __launch_bounds__(kNormThreads) normals_kernel(GridView g, const
 // warp_knn, hence the same normals bit for bit). One launch instead of bounding box + grid build (six launches and a host
 // round trip) + search; what a frame spends on normals falls from ~0.2 ms per cloud to the launch itself.
 static constexpr int kNormSmemMax = 4096;
-__global__ void __launch_bounds__(kNormThreads) normals_smem_kernel(const float4* __restrict__ pts, int n, int k, float vpx, float vpy,
-                                                                    float vpz, float4* __restrict__ out) {
+__device__ __forceinline__ void normals_smem_body(const float4* __restrict__ pts, int n, int k, float vpx, float vpy, float vpz,
+                                                  float4* __restrict__ out) {
   extern __shared__ __align__(16) float4 tg_norm[];
   __shared__ float2 knn_buf[kNormThreads / 32][kKnnBufCap + 32];   // per-warp scratch of the two-pass exact search
   int fin = 0;
@@ -92,6 +92,19 @@ __global__ void __launch_bounds__(kNormThreads) normals_smem_kernel(const float4
     __syncwarp();
   }
 }
+__global__ void __launch_bounds__(kNormThreads) normals_smem_kernel(const float4* __restrict__ pts, int n, int k, float vpx, float vpy,
+                                                                    float vpz, float4* __restrict__ out) {
+  normals_smem_body(pts, n, k, vpx, vpy, vpz, out);
+}
+// Frame-spanning launch (ope_pose_batch): blockIdx.y = cloud; cloud c has counts[c] points at pts + c * stride. Same body, so the
+// same normals bit for bit as the single-cloud launch.
+__global__ void __launch_bounds__(kNormThreads) normals_smem_batch_kernel(const float4* __restrict__ pts, const int* __restrict__ counts,
+                                                                          int stride, int k, float vpx, float vpy, float vpz,
+                                                                          float4* __restrict__ out) {
+  const int n = counts[blockIdx.y];
+  if (n <= 0 || (int)blockIdx.x * (kNormThreads / 32) >= n) return;   // more blocks than this cloud has points: nothing to do
+  normals_smem_body(pts + (size_t)blockIdx.y * stride, n, k, vpx, vpy, vpz, out + (size_t)blockIdx.y * stride);
+}
 
 // ------------------------------------------------------------------------------------------- SPFH ------
 // warp per point. Lanes stride over the candidate points of each grid row; every in-radius neighbour's three
@@ -104,8 +117,8 @@ static constexpr int kWarpsPerBlock = 8;
 // and normals in shared memory and every warp tests all of them (ascending index, the oracle's order).
 static constexpr int kFeatSmemMax = 2048;
 template <bool SMEM>
-__global__ void spfh_kernel(GridView g, const float4* __restrict__ pts, const float4* __restrict__ nrm, int n, float r2,
-                            float* __restrict__ spfh) {
+__device__ __forceinline__ void spfh_body(const GridView& g, const float4* __restrict__ pts, const float4* __restrict__ nrm, int n, float r2,
+                                          float* __restrict__ spfh) {
   extern __shared__ __align__(16) float4 sm_feat[];
   __shared__ int hist[kWarpsPerBlock][33];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -155,6 +168,21 @@ __global__ void spfh_kernel(GridView g, const float4* __restrict__ pts, const fl
     spfh[(size_t)p_idx * 33 + b] = v;
   }
 }
+template <bool SMEM>
+__global__ void spfh_kernel(GridView g, const float4* __restrict__ pts, const float4* __restrict__ nrm, int n, float r2,
+                            float* __restrict__ spfh) {
+  spfh_body<SMEM>(g, pts, nrm, n, r2, spfh);
+}
+// frame-spanning launch: blockIdx.y = cloud (points / normals at c * stride, histograms at c * stride * 33)
+__global__ void spfh_batch_kernel(const float4* __restrict__ pts, const float4* __restrict__ nrm, const int* __restrict__ counts, int stride,
+                                  float r2, float* __restrict__ spfh) {
+  const int n = counts[blockIdx.y];
+  if (n <= 0 || (int)blockIdx.x * kWarpsPerBlock >= n) return;
+  GridView g;
+  g.n = 0;
+  const size_t o = (size_t)blockIdx.y * stride;
+  spfh_body<true>(g, pts + o, nrm + o, n, r2, spfh + o * 33);
+}
 
 // ------------------------------------------------------------------------------------------- FPFH ------
 // warp per point, lane = histogram bin (lane 0 also carries bin 32). Each leaf range is examined 32 candidates at a
@@ -162,8 +190,8 @@ __global__ void spfh_kernel(GridView g, const float4* __restrict__ pts, const fl
 // 132-byte read of its SPFH row, weighted by 1/d2 and accumulated in float like the reference
 // (weightPointSPFHSignature). The three normalisation sums are carried in double.
 template <bool SMEM>
-__global__ void fpfh_kernel(GridView g, const float4* __restrict__ pts, int n, float r2, const float* __restrict__ spfh,
-                            float* __restrict__ out) {
+__device__ __forceinline__ void fpfh_body(const GridView& g, const float4* __restrict__ pts, int n, float r2, const float* __restrict__ spfh,
+                                          float* __restrict__ out) {
   extern __shared__ __align__(16) float4 sm_feat[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int p_idx = blockIdx.x * kWarpsPerBlock + warp;
@@ -235,6 +263,20 @@ __global__ void fpfh_kernel(GridView g, const float4* __restrict__ pts, int n, f
   o[lane] = acc * (float)sc;
   if (lane == 0) o[32] = acc32 * (float)s3;
 }
+template <bool SMEM>
+__global__ void fpfh_kernel(GridView g, const float4* __restrict__ pts, int n, float r2, const float* __restrict__ spfh,
+                            float* __restrict__ out) {
+  fpfh_body<SMEM>(g, pts, n, r2, spfh, out);
+}
+__global__ void fpfh_batch_kernel(const float4* __restrict__ pts, const int* __restrict__ counts, int stride, float r2,
+                                  const float* __restrict__ spfh, float* __restrict__ out) {
+  const int n = counts[blockIdx.y];
+  if (n <= 0 || (int)blockIdx.x * kWarpsPerBlock >= n) return;
+  GridView g;
+  g.n = 0;
+  const size_t o = (size_t)blockIdx.y * stride;
+  fpfh_body<true>(g, pts + o, n, r2, spfh + o * 33, out + o * 33);
+}
 
 // ------------------------------------------------------------------------------- feature-space k-NN ----
 // Exact float32 ranking: d = sum_c (q_c - t_c)^2 accumulated left to right (FLANN L2_Simple over 33 floats),
@@ -283,6 +325,72 @@ __global__ void feature_knn_kernel(const float* __restrict__ ftgt, int nt, const
     const size_t o = ((size_t)qi * gridDim.y + blockIdx.y) * k;
     for (int j = 0; j < k; ++j) { part_idx[o + j] = j < cnt ? bi[j] : -1; part_d2[o + j] = j < cnt ? bd[j] : INFINITY; }
   }
+}
+// frame-spanning launch: blockIdx.z = frame; targets ftgt + z * stride * dim (nt = counts[z]), the SAME nq queries for every frame
+// (the model's descriptors); partial lists at ((z * nq + qi) * splits + y) * k. t_per_split is fixed for the launch; splits past
+// a frame's end produce empty lists.
+__global__ void feature_knn_batch_kernel(const float* __restrict__ ftgt, const int* __restrict__ counts, int stride,
+                                         const float* __restrict__ fqry, int nq, int dim, int k, int t_per_split, int* __restrict__ part_idx,
+                                         float* __restrict__ part_d2) {
+  extern __shared__ float tile[];  // kFkTile * dim
+  const int frame = blockIdx.z;
+  const int nt = counts[frame];
+  const float* ft = ftgt + (size_t)frame * stride * dim;
+  const int qi = blockIdx.x * kFkQueries + threadIdx.x;
+  const int t_begin = blockIdx.y * t_per_split, t_end = min(nt, t_begin + t_per_split);
+  float q[kFkMaxDim];
+  if (qi < nq)
+    for (int c = 0; c < dim; ++c) q[c] = __ldg(fqry + (size_t)qi * dim + c);
+  float bd[kFkMaxK];
+  int bi[kFkMaxK];
+  int cnt = 0;
+  for (int t0 = t_begin; t0 < t_end; t0 += kFkTile) {
+    const int tn = min(kFkTile, t_end - t0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < tn * dim; e += blockDim.x) tile[e] = __ldg(ft + (size_t)t0 * dim + e);
+    __syncthreads();
+    if (qi < nq) {
+      for (int t = 0; t < tn; ++t) {
+        const float* f = tile + t * dim;
+        float d = 0.0f;
+        for (int c = 0; c < dim; ++c) { float df = q[c] - f[c]; d += df * df; }
+        if (!isfinite(d)) continue;
+        const int idx = t0 + t;
+        if (cnt == k && !nb_less(d, idx, bd[k - 1], bi[k - 1])) continue;
+        int j = cnt < k ? cnt : k - 1;
+        while (j > 0 && nb_less(d, idx, bd[j - 1], bi[j - 1])) { bd[j] = bd[j - 1]; bi[j] = bi[j - 1]; --j; }
+        bd[j] = d; bi[j] = idx;
+        if (cnt < k) ++cnt;
+      }
+    }
+  }
+  if (qi < nq) {
+    const size_t o = (((size_t)frame * nq + qi) * gridDim.y + blockIdx.y) * k;
+    for (int j = 0; j < k; ++j) { part_idx[o + j] = j < cnt ? bi[j] : -1; part_d2[o + j] = j < cnt ? bd[j] : INFINITY; }
+  }
+}
+// merge of the batched partial lists: one thread per (frame, query); out_idx at (frame * nq + qi) * k
+__global__ void feature_knn_batch_merge_kernel(const int* __restrict__ part_idx, const float* __restrict__ part_d2, int nq, int splits, int k,
+                                               int* __restrict__ out_idx) {
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= nq) return;
+  const size_t row = (size_t)blockIdx.y * nq + qi;
+  float bd[kFkMaxK];
+  int bi[kFkMaxK];
+  int cnt = 0;
+  for (int s = 0; s < splits; ++s)
+    for (int e = 0; e < k; ++e) {
+      const size_t o = (row * splits + s) * k + e;
+      const int idx = part_idx[o];
+      if (idx < 0) break;
+      const float d = part_d2[o];
+      if (cnt == k && !nb_less(d, idx, bd[k - 1], bi[k - 1])) continue;
+      int j = cnt < k ? cnt : k - 1;
+      while (j > 0 && nb_less(d, idx, bd[j - 1], bi[j - 1])) { bd[j] = bd[j - 1]; bi[j] = bi[j - 1]; --j; }
+      bd[j] = d; bi[j] = idx;
+      if (cnt < k) ++cnt;
+    }
+  for (int j = 0; j < k; ++j) out_idx[row * k + j] = j < cnt ? bi[j] : -1;
 }
 __global__ void feature_knn_merge_kernel(const int* __restrict__ part_idx, const float* __restrict__ part_d2, int nq,
                                          int splits, int k, const int* __restrict__ qlist, int* __restrict__ out_idx,
@@ -424,6 +532,54 @@ int feature_knn_device(ope_ctx* ctx, const float* d_ftgt, size_t nt, const float
   if (nq == 0) return OPE_OK;
   if (feature_knn_gemm_applicable(nt, nq, dim, k)) return feature_knn_gemm_device(ctx, d_ftgt, nt, d_fqry, nq, dim, k, d_idx, d_d2, nullptr);
   return feature_knn_exact_device(ctx, d_ftgt, nt, d_fqry, nq, dim, k, nullptr, 0, d_idx, d_d2);
+}
+
+// ---- frame-spanning launches for ope_pose_batch: `clouds` clouds of counts[c] <= max_n points at c * stride ----
+int normals_smem_batch(ope_ctx* ctx, const float4* pts, const int* d_counts, int stride, int clouds, int max_n, int k, const float vp[3],
+                       float4* out) {
+  if (k < 1 || k > 32) return fail(ctx, OPE_ERR_INVALID, "normal estimation k must be in [1, 32]");
+  if (max_n > kNormSmemMax) return fail(ctx, OPE_ERR_CAPACITY, "batched normals: cloud larger than the shared-memory path");
+  if (clouds <= 0 || max_n <= 0) return OPE_OK;
+  OPE_TRY(dyn_smem(ctx, (const void*)normals_smem_batch_kernel, kNormSmemMax * sizeof(float4)));
+  // a few blocks per cloud: every block stages the whole cloud in shared memory, so more blocks mean more staging
+  const unsigned bx = (unsigned)std::min<size_t>(div_up((size_t)max_n * 32, kNormThreads), 8);
+  normals_smem_batch_kernel<<<dim3(bx, clouds), kNormThreads, (size_t)max_n * sizeof(float4), ctx->stream>>>(pts, d_counts, stride, k, vp[0],
+                                                                                                           vp[1], vp[2], out);
+  return check_launch(ctx, "normals_smem_batch_kernel");
+}
+int fpfh_smem_batch(ope_ctx* ctx, const float4* pts, const float4* nrm, const int* d_counts, int stride, int clouds, int max_n, float radius,
+                    float* spfh, float* fpfh) {
+  if (max_n > kFeatSmemMax) return fail(ctx, OPE_ERR_CAPACITY, "batched FPFH: cloud larger than the shared-memory path");
+  if (clouds <= 0 || max_n <= 0) return OPE_OK;
+  const float r2 = radius * radius;
+  OPE_TRY(dyn_smem(ctx, (const void*)spfh_batch_kernel, 2 * kFeatSmemMax * sizeof(float4)));
+  OPE_TRY(dyn_smem(ctx, (const void*)fpfh_batch_kernel, kFeatSmemMax * sizeof(float4)));
+  const dim3 grid(div_up((size_t)max_n, kWarpsPerBlock), clouds);
+  spfh_batch_kernel<<<grid, kWarpsPerBlock * 32, 2 * (size_t)max_n * sizeof(float4), ctx->stream>>>(pts, nrm, d_counts, stride, r2, spfh);
+  OPE_TRY(check_launch(ctx, "spfh_batch_kernel"));
+  fpfh_batch_kernel<<<grid, kWarpsPerBlock * 32, (size_t)max_n * sizeof(float4), ctx->stream>>>(pts, d_counts, stride, r2, spfh, fpfh);
+  return check_launch(ctx, "fpfh_batch_kernel");
+}
+// k nearest target descriptors (frame f: ftgt + f * stride * dim, counts[f] rows) of each of the nq shared query descriptors
+int feature_knn_batch(ope_ctx* ctx, const float* ftgt, const int* d_counts, int stride, int frames, int max_nt, const float* fqry, int nq,
+                      int dim, int k, int* out_idx) {
+  if (dim < 1 || dim > kFkMaxDim) return fail(ctx, OPE_ERR_INVALID, "feature dimension must be in [1, %d]", kFkMaxDim);
+  if (k < 1 || k > kFkMaxK) return fail(ctx, OPE_ERR_INVALID, "feature k must be in [1, %d]", kFkMaxK);
+  if (frames <= 0 || nq <= 0) return OPE_OK;
+  const unsigned qblocks = div_up((size_t)nq, kFkQueries);
+  int splits = std::max(1, std::min(4, (max_nt + kFkTile - 1) / kFkTile));
+  int t_per_split = (max_nt + splits - 1) / splits;
+  t_per_split = std::max(kFkTile, (t_per_split + kFkTile - 1) / kFkTile * kFkTile);
+  splits = std::max(1, (max_nt + t_per_split - 1) / t_per_split);
+  Scratch<int> pi(ctx);
+  Scratch<float> pd(ctx);
+  OPE_TRY(pi.alloc((size_t)frames * nq * splits * k));
+  OPE_TRY(pd.alloc((size_t)frames * nq * splits * k));
+  feature_knn_batch_kernel<<<dim3(qblocks, splits, frames), kFkQueries, kFkTile * dim * sizeof(float), ctx->stream>>>(
+      ftgt, d_counts, stride, fqry, nq, dim, k, t_per_split, pi.p, pd.p);
+  OPE_TRY(check_launch(ctx, "feature_knn_batch_kernel"));
+  feature_knn_batch_merge_kernel<<<dim3(div_up((size_t)nq, 128), frames), 128, 0, ctx->stream>>>(pi.p, pd.p, nq, splits, k, out_idx);
+  return check_launch(ctx, "feature_knn_batch_merge_kernel");
 }
 
 int remove_nan_normals_device(ope_ctx* ctx, ope_cloud** cloud) {

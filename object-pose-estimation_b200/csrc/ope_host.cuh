@@ -256,6 +256,35 @@ int sacia_device(ope_ctx* ctx, const ope_cloud* src, const float* d_fsrc, const 
                  float* out_errors_host);
 
 
+// ---- frame-spanning launches (ope_pose_batch, batch.cu): clouds of counts[c] points at c * stride ----
+struct SaciaBatch {
+  const float4* src; int ns;                               // the shared source (the model's coarse sample)
+  const float4* tgt; const int* counts; int stride;        // frame f: tgt + f * stride, counts[f] points
+  int nr_samples, k_corr, H;
+  const int* samples; const int* picks;                    // frame f: + f * H * nr_samples
+  const int* knn_idx;                                      // frame f: + f * ns * k_corr
+  const int* active;                                       // per frame: 0 = skip
+  float threshold;
+  float* errors;                                           // frames * H
+  float* transforms;                                       // frames * H * 16
+};
+struct IcpBatchFrame { const float4* src_pts; const float4* src_nrm; int n_src; const float4* tgt_pts; const float4* tgt_nrm; int n_tgt; };
+int normals_smem_batch(ope_ctx* ctx, const float4* pts, const int* d_counts, int stride, int clouds, int max_n, int k, const float vp[3],
+                       float4* out);
+int fpfh_smem_batch(ope_ctx* ctx, const float4* pts, const float4* nrm, const int* d_counts, int stride, int clouds, int max_n, float radius,
+                    float* spfh, float* fpfh);
+int feature_knn_batch(ope_ctx* ctx, const float* ftgt, const int* d_counts, int stride, int frames, int max_nt, const float* fqry, int nq,
+                      int dim, int k, int* out_idx);
+int sacia_batch_device(ope_ctx* ctx, const SaciaBatch& a, int frames, int max_nt, ope_reg_result* d_results);
+int fitness_batch_device(ope_ctx* ctx, const float4* tgt, const int* tgt_counts, const float4* src, const int* src_counts, int stride, int frames,
+                         int max_nt, const ope_reg_result* d_icp, const int* d_active, double* d_out);
+bool icp_small_batch_applicable(const ope_icp_params& prm, size_t n_src, size_t n_tgt);
+int icp_small_batch_device(ope_ctx* ctx, const ope_icp_params& prm, const IcpBatchFrame* frames, int n_frames, ope_reg_result* d_results);
+
+// ---- batch.cu: one chunk of frames of ope_pose_batch through the frame-spanning launches; done[i] = 1 where frame i was finished ----
+int pose_batch_chunk(ope_ctx* ctx, const ope_pose_params& P, const ope_cloud* d_model, const ope_cloud* sp, const float* d_fs, const Mat4& rigid,
+                     const ope_frame_input* frames, size_t n_frames, const ope_rng_table* tables, ope_pose_result* results, char* done);
+
 // ---- p2plane.cu: TransformationEstimationPointToPlaneLLS / ...PointToPlane (Levenberg-Marquardt) ----
 int point_to_plane_device(ope_ctx* ctx, const float4* src, const float4* tgt, const float4* tgt_n, const int* d_is, const int* d_it,
                           const float* d_d2, size_t n, int kind, Mat4* T, int* n_pairs, double* sum_d2, int32_t* lm_info);

@@ -323,8 +323,13 @@ void batch_worker(BatchShared* S, ope_ctx* ctx, int* first_error, std::string* f
       if (in.points) {
         if (in.n > 0) rc = ope_cloud_upload(ctx, in.points, in.n, in.stride, in.offset, nullptr, 0, 0, &tgt_owned);
         tgt = tgt_owned;
-      } else {
-        tgt = (const ope_cloud*)in.cloud;
+      } else if (in.cloud && ((const ope_cloud*)in.cloud)->n > 0) {
+        // a private copy: the stages cache the bounding box and search grids IN the cloud they work on, and two frames may
+        // name the same caller-owned cloud (or the caller may use it from its own context meanwhile)
+        ope_cloud view = *(const ope_cloud*)in.cloud;
+        view.normals = nullptr; view.grids.clear(); view.bbox_valid = false;
+        rc = clone_cloud(ctx, &view, &tgt_owned);
+        tgt = tgt_owned;
       }
     }
     if (rc == OPE_OK) rc = ope_pose_estimate_final_device(t, &src, tgt, S->tables ? &S->tables[f] : nullptr, &S->results[f]);
@@ -378,10 +383,40 @@ int ope_pose_batch(ope_ctx* ctx, const ope_pose_params* prm, const float* model_
     }
     tables = drawn.data();
   }
+  // ---- frame-spanning launches (batch.cu): one launch per stage for a whole chunk of frames ----
+  std::vector<char> done(n_frames, 0);
+  {
+    const char* mode = std::getenv("OPE_BATCH_MODE");   // "workers": the per-frame path only (one stream per worker thread)
+    if (!(mode && std::strcmp(mode, "workers") == 0)) {
+      Mat4 rigid = mat4_identity();   // the dense Umeyama of the pristine model onto the first frame's source — itself (:425-436)
+      OPE_TRY(umeyama_device(ctx, model.c->pts, model.c->pts, nullptr, nullptr, model.c->n, rigid.m));
+      const char* ce = std::getenv("OPE_BATCH_CHUNK");
+      const size_t chunk = (size_t)std::max(1, ce ? std::atoi(ce) : 296);   // two blocks per SM-sized waves of one-block-per-frame kernels
+      for (size_t f0 = 0; f0 < n_frames; f0 += chunk) {
+        const size_t nf = std::min(chunk, n_frames - f0);
+        OPE_TRY(pose_batch_chunk(ctx, P, model.c, sp.c, fs.p, rigid, frames + f0, nf, tables + f0, results + f0, done.data() + f0));
+      }
+      if (status) for (size_t f = 0; f < n_frames; ++f) if (done[f]) status[f] = OPE_OK;
+    }
+  }
+  // ---- whatever the fast path did not take (tiny / empty / oversized clusters): the per-frame path, worker threads ----
+  std::vector<ope_frame_input> rest_frames;
+  std::vector<ope_rng_table> rest_tables;
+  std::vector<size_t> rest_of;
+  for (size_t f = 0; f < n_frames; ++f)
+    if (!done[f]) { rest_frames.push_back(frames[f]); rest_tables.push_back(tables[f]); rest_of.push_back(f); }
+  if (rest_frames.empty()) return OPE_OK;
+  std::vector<ope_pose_result> rest_results(rest_frames.size());
+  std::vector<int32_t> rest_status(rest_frames.size(), OPE_OK);
+  struct Scatter {   // copies the sub-batch's results back on every exit path
+    std::vector<ope_pose_result>& r; std::vector<int32_t>& st; std::vector<size_t>& of; ope_pose_result* results; int32_t* status;
+    ~Scatter() { for (size_t i = 0; i < of.size(); ++i) { results[of[i]] = r[i]; if (status) status[of[i]] = st[i]; } }
+  } scatter{rest_results, rest_status, rest_of, results, status};
+  workers = std::max(1, std::min<int>(workers, (int)rest_frames.size()));
   OPE_TRY(ope_ctx_synchronize(ctx));   // the workers read the model side from their own streams
   BatchShared S;
-  S.prm = &P; S.model = model.c; S.sp = sp.c; S.fs = fs.p; S.frames = frames; S.n_frames = n_frames; S.tables = tables;
-  S.results = results; S.status = status; S.device = ctx->device;
+  S.prm = &P; S.model = model.c; S.sp = sp.c; S.fs = fs.p; S.frames = rest_frames.data(); S.n_frames = rest_frames.size(); S.tables = rest_tables.data();
+  S.results = rest_results.data(); S.status = rest_status.data(); S.device = ctx->device;
   {
     // the fused ICP loop is a cooperative launch: its blocks must all be co-resident, so concurrent frames only overlap if
     // each takes a share of the SMs

@@ -875,8 +875,10 @@ struct IcpSmallSmem {
   int stop;
 };
 
+// bid / nblk: this block's index among the nblk blocks of ITS alignment (the whole grid for a single alignment, one frame's share
+// of a frame-spanning launch)
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 512 / THREADS) icp_small_kernel(IcpDev a) {
+__device__ __forceinline__ void icp_small_body(const IcpDev& a, const int bid, const int nblk) {
   constexpr int kIcpThreads = THREADS, kIcpWarps = THREADS / 32;   // shadow the wide kernel's constants inside this kernel
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double morg[3];   // origin of the moment accumulation: the target's first point (ope::umeyama_from_moments)
@@ -889,7 +891,7 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) icp_small_kernel(IcpDe
   float2* slab = reinterpret_cast<float2*>(bhi + n_groups);         // [kSlabSlots][kIcpThreads]: column = thread
   const unsigned full = 0xffffffffu;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int s = blockIdx.x * kIcpThreads + tid;    // this thread's point (sorted position)
+  const int s = bid * kIcpThreads + tid;    // this thread's point (sorted position)
   const bool in_range = s < a.n_work;
   const bool stale = a.variant == OPE_ICP_VARIANT_MODCORR;
   const int k = a.k_search < a.grid.n ? a.k_search : a.grid.n;
@@ -930,7 +932,7 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) icp_small_kernel(IcpDe
   double prev_mse = DBL_MAX, cur_mse = DBL_MAX;
   int similar = 0, iterations = 0, state = OPE_CONV_NOT_CONVERGED, converged = 0, n_corr = 0;
   unsigned bar_target = 0;
-  const bool prof = a.phase_cycles != nullptr && blockIdx.x == 0 && tid == 0;
+  const bool prof = a.phase_cycles != nullptr && bid == 0 && tid == 0;
   long long t_phase[4] = {0, 0, 0, 0};
 
   // one query through the cooperative scan: the warp serves lane `q`'s point, the sorted result goes to that thread's column
@@ -1022,8 +1024,8 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) icp_small_kernel(IcpDe
     // whoever could not be served above (no usable seed, or fewer than k points within the bound) gets a cooperative search
     const bool unserved = ok && !have && (!scan || c < k);
     const unsigned redo = __ballot_sync(full, unserved);
-    if (a.phase_cycles && blockIdx.x == 0 && lane == 0 && pass > 0) atomicAdd((unsigned long long*)&a.phase_cycles[4], (unsigned long long)__popc(redo));
-    if (a.phase_cycles && blockIdx.x == 0 && ok && pass > 0) atomicAdd((unsigned long long*)&a.phase_cycles[5], (unsigned long long)c);
+    if (a.phase_cycles && bid == 0 && lane == 0 && pass > 0) atomicAdd((unsigned long long*)&a.phase_cycles[4], (unsigned long long)__popc(redo));
+    if (a.phase_cycles && bid == 0 && ok && pass > 0) atomicAdd((unsigned long long*)&a.phase_cycles[5], (unsigned long long)c);
     for (unsigned m = redo; m != 0u; m &= m - 1u) {
       const int q = __ffs(m) - 1;
       const float bq = __shfl_sync(full, scan ? bound : FLT_MAX, q);
@@ -1109,21 +1111,21 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) icp_small_kernel(IcpDe
       if (lane == 1) sm->red[warp][16] = dsum;
     }
     __syncthreads();
-    double* my_partials = a.partials + ((size_t)(pass & 1) * gridDim.x + blockIdx.x) * kIcpAcc;
+    double* my_partials = a.partials + ((size_t)(pass & 1) * nblk + bid) * kIcpAcc;
     if (tid < kIcpAcc) {
       double sum = 0.0;
 #pragma unroll
       for (int wv = 0; wv < kIcpWarps; ++wv) sum += sm->red[wv][tid];
       my_partials[tid] = sum;
     }
-    if (gridDim.x > 1) { bar_target += gridDim.x; grid_barrier(a.barrier, bar_target); } else __syncthreads();
+    if (nblk > 1) { bar_target += nblk; grid_barrier(a.barrier, bar_target); } else __syncthreads();
     if (tid < kIcpAcc) {
-      const double* base = a.partials + (size_t)(pass & 1) * gridDim.x * kIcpAcc;
+      const double* base = a.partials + (size_t)(pass & 1) * nblk * kIcpAcc;
       double sum = 0.0;
-      for (int b0 = 0; b0 < (int)gridDim.x; b0 += 8) {   // 8 independent loads in flight, summed in block order
+      for (int b0 = 0; b0 < nblk; b0 += 8) {   // 8 independent loads in flight, summed in block order
         double v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = b0 + u < (int)gridDim.x ? __ldcg(base + (size_t)(b0 + u) * kIcpAcc + tid) : 0.0;
+        for (int u = 0; u < 8; ++u) v[u] = b0 + u < nblk ? __ldcg(base + (size_t)(b0 + u) * kIcpAcc + tid) : 0.0;
 #pragma unroll
         for (int u = 0; u < 8; ++u) sum += v[u];
       }
@@ -1185,13 +1187,34 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) icp_small_kernel(IcpDe
     if (stop) break;
   }
   if (prof) for (int i = 0; i < 4; ++i) a.phase_cycles[i] = t_phase[i];
-  if (blockIdx.x == 0 && tid == 0) {
+  if (bid == 0 && tid == 0) {
     ope_reg_result r;
     for (int i = 0; i < 16; ++i) r.T[i] = final_t.m[i];
     r.converged = converged; r.state = state; r.iterations = iterations; r.n_correspondences = n_corr;
     r.last_mse = cur_mse; r.best_error = 0.0; r.best_iteration = 0; r.reserved = 0;
     *a.result = r;
   }
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 512 / THREADS) icp_small_kernel(IcpDev a) {
+  icp_small_body<THREADS>(a, (int)blockIdx.x, (int)gridDim.x);
+}
+// Frame-spanning launch: every block takes a ticket and looks up (alignment, block-in-alignment) in a host-built map that lists
+// the blocks alignment by alignment. Tickets are handed out in the order blocks START, so when a block spins on its alignment's
+// barrier, every block it waits for either runs already or is next in line for the first free slot — which the alignments ahead
+// of it release without waiting for anyone behind them: no deadlock, whatever the dispatch order of the hardware.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 512 / THREADS) icp_small_batch_kernel(const IcpDev* __restrict__ descs, const int2* __restrict__ map,
+                                                                                unsigned* ticket) {
+  __shared__ int s_ticket;
+  __shared__ IcpDev s_desc;
+  if (threadIdx.x == 0) s_ticket = (int)atomicAdd(ticket, 1u);
+  __syncthreads();
+  const int2 fb = map[s_ticket];
+  for (int w = threadIdx.x; w < (int)(sizeof(IcpDev) / 4); w += THREADS) reinterpret_cast<int*>(&s_desc)[w] = reinterpret_cast<const int*>(descs + fb.x)[w];
+  __syncthreads();
+  icp_small_body<THREADS>(s_desc, fb.y, (s_desc.n_work + THREADS - 1) / THREADS);
 }
 
 // one estimation + rejection pass (no loop) on the clouds as given (cur_* = the caller's clouds, original order)
@@ -1418,6 +1441,129 @@ __global__ void __launch_bounds__(kSaciaThreads) sacia_smem_kernel(SaciaDev a, i
     for (int i = 0; i < a.ns; ++i) error += terms[i];
     a.errors[h] = error;
   }
+}
+// Frame-spanning SAC-IA scoring: blockIdx.x = hypothesis, blockIdx.y = frame. Every frame has its own target (tgt + f * stride,
+// counts[f] points, in shared memory), decision table (samples / picks + f * H * S) and feature neighbours (knn_idx + f * ns * k);
+// the source (the model's coarse sample) is shared. Same arithmetic as sacia_smem_kernel: same errors, bit for bit.
+__global__ void __launch_bounds__(kSaciaThreads) sacia_smem_batch_kernel(SaciaBatch a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int f = blockIdx.y, h = blockIdx.x;
+  if (!a.active[f]) return;
+  const int nt = a.counts[f];
+  float4* tg = reinterpret_cast<float4*>(smem_raw);
+  float* terms = reinterpret_cast<float*>(tg + nt);
+  __shared__ Mat4 T;
+  const float4* tgt = a.tgt + (size_t)f * a.stride;
+  for (int j = threadIdx.x; j < nt; j += kSaciaThreads) tg[j] = __ldg(tgt + j);
+  if (threadIdx.x == 0) {
+    double acc[16];
+    for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+    const int* samples = a.samples + ((size_t)f * a.H + h) * a.nr_samples;
+    const int* picks = a.picks + ((size_t)f * a.H + h) * a.nr_samples;
+    const int* knn = a.knn_idx + (size_t)f * a.ns * a.k_corr;
+    for (int j = 0; j < a.nr_samples; ++j) {
+      const int si = samples[j];
+      int ti = knn[(size_t)si * a.k_corr + picks[j]];
+      if (ti < 0) ti = knn[(size_t)si * a.k_corr];  // fewer than k target features
+      const float4 sp = __ldg(a.src + si), tp = __ldg(tgt + ti);
+      const double sv[3] = {sp.x, sp.y, sp.z}, tv[3] = {tp.x, tp.y, tp.z};
+      acc[0] += 1.0;
+      for (int k = 0; k < 3; ++k) { acc[1 + k] += sv[k]; acc[4 + k] += tv[k]; }
+      for (int c = 0; c < 3; ++c)
+        for (int r = 0; r < 3; ++r) acc[7 + c * 3 + r] += tv[r] * sv[c];
+    }
+    Mat4 M;
+    umeyama_from_moments(acc, M);
+    T = M;
+    float* out = a.transforms + ((size_t)f * a.H + h) * 16;
+    for (int i = 0; i < 16; ++i) out[i] = M.m[i];
+  }
+  __syncthreads();
+  const Mat4 M = T;
+  for (int i = threadIdx.x; i < a.ns; i += kSaciaThreads) {
+    const float4 p = __ldg(a.src + i);
+    float x, y, z;
+    xform_point(M, p.x, p.y, p.z, x, y, z);
+    float term = 1.0f;
+    if (finite3(x, y, z)) {
+      float best = FLT_MAX;   // only the DISTANCE of the nearest neighbour enters the score: ties need no index order
+#pragma unroll 4
+      for (int j = 0; j < nt; ++j) {
+        const float4 t = tg[j];
+        const float d2 = dist2(x, y, z, t.x, t.y, t.z);   // a NaN target never compares below
+        best = d2 < best ? d2 : best;
+      }
+      if (best <= a.threshold) term = best / a.threshold;
+    }
+    terms[i] = term;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float error = 0.0f;
+    for (int i = 0; i < a.ns; ++i) error += terms[i];
+    a.errors[(size_t)f * a.H + h] = error;
+  }
+}
+// first strictly-lower error wins, per frame (one thread per frame)
+__global__ void sacia_select_batch_kernel(const float* __restrict__ errors, const float* __restrict__ transforms, const int* __restrict__ active,
+                                          int H, int frames, ope_reg_result* __restrict__ out) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= frames || !active[f]) return;
+  int best = -1;
+  float lowest = 0.0f;
+  for (int h = 0; h < H; ++h) {
+    const float e = errors[(size_t)f * H + h];
+    if (best < 0 || e < lowest) { lowest = e; best = h; }
+  }
+  ope_reg_result r;
+  for (int i = 0; i < 16; ++i) r.T[i] = (best >= 0) ? transforms[((size_t)f * H + best) * 16 + i] : ((i % 5 == 0) ? 1.0f : 0.0f);
+  r.converged = best >= 0; r.state = 0; r.iterations = H; r.n_correspondences = 0; r.last_mse = 0.0;
+  r.best_error = lowest; r.best_iteration = best; r.reserved = 0;
+  out[f] = r;
+}
+// getFitnessScore for every frame of a batch: one block per frame, the frame's target in shared memory, the transform from the
+// frame's ICP result on the device
+__global__ void __launch_bounds__(kNnThreads) fitness_smem_batch_kernel(const float4* __restrict__ tgt, const int* __restrict__ tgt_counts,
+                                                                        const float4* __restrict__ src, const int* __restrict__ src_counts,
+                                                                        int stride, const ope_reg_result* __restrict__ icp,
+                                                                        const int* __restrict__ active, double* __restrict__ out) {
+  extern __shared__ __align__(16) float4 tg_fit[];
+  __shared__ double smem[(kNnThreads / 32) * 2];
+  __shared__ double fin[2];
+  const int f = blockIdx.x;
+  if (!active[f]) return;
+  const int nt = tgt_counts[f], n = src_counts[f];
+  const int nt8 = (nt + 7) & ~7;
+  const float4* tp = tgt + (size_t)f * stride;
+  const float4* sp = src + (size_t)f * stride;
+  for (int j = threadIdx.x; j < nt8; j += kNnThreads) tg_fit[j] = j < nt ? __ldg(tp + j) : make_float4(INFINITY, INFINITY, INFINITY, 0.0f);
+  Mat4 T;
+  for (int i = 0; i < 16; ++i) T.m[i] = icp[f].T[i];
+  __syncthreads();
+  double acc[2] = {0.0, 0.0};
+  for (int base = 0; base < n; base += kNnThreads) {
+    const int i = base + (int)threadIdx.x;
+    float x = 0, y = 0, z = 0;
+    bool ok = false;
+    if (i < n) {
+      const float4 p = __ldg(sp + i);
+      xform_point(T, p.x, p.y, p.z, x, y, z);
+      ok = finite3(x, y, z);
+    }
+    float best = INFINITY;
+    if (ok) {
+      for (int j0 = 0; j0 < nt8; j0 += 8) {
+        float d2[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const float4 t = tg_fit[j0 + u]; d2[u] = dist2(x, y, z, t.x, t.y, t.z); }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) if (d2[u] < best) best = d2[u];
+      }
+    }
+    if (ok && best <= FLT_MAX) { acc[0] += (double)best; acc[1] += 1.0; }
+  }
+  block_reduce_store<2>(acc, smem, fin);
+  if (threadIdx.x == 0) out[f] = fin[1] > 0 ? fin[0] / fin[1] : DBL_MAX;
 }
 // first strictly-lower error wins, in hypothesis order
 __global__ void sacia_select_kernel(const float* __restrict__ errors, const float* __restrict__ transforms, int h_begin,
@@ -2011,6 +2157,112 @@ int sacia_device(ope_ctx* ctx, const ope_cloud* src, const float* d_fsrc, const 
     OPE_CUDA_TRY(ctx, ope::stream_sync(ctx));
   }
   return OPE_OK;
+}
+
+// ---- frame-spanning launches for ope_pose_batch (batch.cu) ----------------------------------------------------------------
+int sacia_batch_device(ope_ctx* ctx, const SaciaBatch& a, int frames, int max_nt, ope_reg_result* d_results) {
+  if (frames <= 0 || a.H <= 0) return OPE_OK;
+  if (a.nr_samples < 1 || a.nr_samples > kSaciaMaxSamples || a.k_corr < 1 || a.k_corr > 16) return fail(ctx, OPE_ERR_INVALID, "bad SAC-IA parameters");
+  if (max_nt > kSaciaSmemMaxTargets) return fail(ctx, OPE_ERR_CAPACITY, "batched SAC-IA: target larger than the shared-memory path");
+  const size_t bytes = (size_t)max_nt * sizeof(float4) + (size_t)a.ns * sizeof(float);
+  OPE_TRY(dyn_smem(ctx, (const void*)sacia_smem_batch_kernel, bytes));
+  cudaEventRecord(ctx->kev[1][0], ctx->stream);
+  sacia_smem_batch_kernel<<<dim3(a.H, frames), kSaciaThreads, bytes, ctx->stream>>>(a);
+  cudaEventRecord(ctx->kev[1][1], ctx->stream);
+  ctx->kev_valid[1] = true;
+  OPE_TRY(check_launch(ctx, "sacia_smem_batch_kernel"));
+  sacia_select_batch_kernel<<<div_up((size_t)frames, 128), 128, 0, ctx->stream>>>(a.errors, a.transforms, a.active, a.H, frames, d_results);
+  return check_launch(ctx, "sacia_select_batch_kernel");
+}
+
+int fitness_batch_device(ope_ctx* ctx, const float4* tgt, const int* tgt_counts, const float4* src, const int* src_counts, int stride, int frames,
+                         int max_nt, const ope_reg_result* d_icp, const int* d_active, double* d_out) {
+  if (frames <= 0) return OPE_OK;
+  if (max_nt > kFitSmemMax) return fail(ctx, OPE_ERR_CAPACITY, "batched fitness: target larger than the shared-memory path");
+  OPE_TRY(dyn_smem(ctx, (const void*)fitness_smem_batch_kernel, (size_t)kFitSmemMax * sizeof(float4)));
+  const size_t bytes = (((size_t)max_nt + 7) & ~(size_t)7) * sizeof(float4);
+  fitness_smem_batch_kernel<<<frames, kNnThreads, bytes, ctx->stream>>>(tgt, tgt_counts, src, src_counts, stride, d_icp, d_active, d_out);
+  return check_launch(ctx, "fitness_smem_batch_kernel");
+}
+
+// ICP-with-normals (normal shooting, small clouds) for many independent alignments in ONE launch. frames[i]: clouds with normals,
+// source points carrying their index in .w; results[i] on the device. Only alignments icp_small_kernel can run (see below).
+bool icp_small_batch_applicable(const ope_icp_params& prm, size_t n_src, size_t n_tgt) {
+  return prm.estimator == OPE_EST_NORMAL_SHOOTING && prm.transformation == OPE_TE_SVD && !prm.use_reciprocal && n_tgt > 0 &&
+         n_tgt <= (size_t)kIcpSmemMaxTargets && n_src > 0 && n_src <= (size_t)kIcpSmallMaxBlocks * kIcpSmallThreads &&
+         prm.k_search >= 1 && prm.k_search <= kSlabSlots;
+}
+int icp_small_batch_device(ope_ctx* ctx, const ope_icp_params& prm, const IcpBatchFrame* frames, int n_frames, ope_reg_result* d_results) {
+  if (n_frames <= 0) return OPE_OK;
+  std::vector<IcpDev> descs((size_t)n_frames);
+  std::vector<int2> map;
+  size_t max_nt = 0, total_src = 0, total_blocks = 0;
+  for (int i = 0; i < n_frames; ++i) {
+    if (!icp_small_batch_applicable(prm, (size_t)frames[i].n_src, (size_t)frames[i].n_tgt)) return fail(ctx, OPE_ERR_UNSUPPORTED, "alignment %d does not fit the small-cloud ICP kernel", i);
+    max_nt = std::max(max_nt, (size_t)frames[i].n_tgt);
+    total_src += (size_t)frames[i].n_src;
+    total_blocks += ((size_t)frames[i].n_src + kIcpSmallThreads - 1) / kIcpSmallThreads;
+  }
+  Scratch<int> match(ctx);
+  Scratch<float> d2(ctx);
+  Scratch<double> partials(ctx);
+  Scratch<unsigned> bars(ctx);
+  Scratch<IcpDev> d_descs(ctx);
+  Scratch<int2> d_map(ctx);
+  OPE_TRY(match.alloc(total_src)); OPE_TRY(d2.alloc(total_src));
+  OPE_TRY(partials.alloc(2 * total_blocks * kIcpAcc));
+  OPE_TRY(bars.alloc((size_t)n_frames + 1));
+  OPE_TRY(d_descs.alloc((size_t)n_frames)); OPE_TRY(d_map.alloc(total_blocks));
+  OPE_CUDA_TRY(ctx, cudaMemsetAsync(bars.p, 0, ((size_t)n_frames + 1) * sizeof(unsigned), ctx->stream));
+  size_t so = 0, bo = 0;
+  map.reserve(total_blocks);
+  for (int i = 0; i < n_frames; ++i) {
+    IcpDev& a = descs[(size_t)i];
+    std::memset(&a, 0, sizeof(a));
+    const IcpBatchFrame& f = frames[i];
+    a.grid.n = f.n_tgt;      // every target point is finite (it survived the sampling and the NaN-normal filter)
+    a.tgt_in_smem = 1; a.n_tgt = f.n_tgt;
+    a.tgt_pts = f.tgt_pts; a.tgt_nrm = f.tgt_nrm;
+    a.src0_pts = f.src_pts; a.src0_nrm = f.src_nrm; a.src_sorted = f.src_pts;
+    a.n_src = f.n_src; a.n_work = f.n_src;
+    a.max_iterations = prm.max_iterations; a.min_corr = prm.min_number_correspondences;
+    a.estimator = prm.estimator; a.k_search = prm.k_search; a.n_rej = prm.n_rejectors;
+    a.transformation = prm.transformation; a.variant = prm.variant; a.force_all = prm.force_all_iterations;
+    for (int r = 0; r < OPE_MAX_REJECTORS; ++r) { a.rej_kind[r] = prm.rejector_kind[r]; a.rej_thr[r] = prm.rejector_threshold[r]; }
+    a.max_corr_dist = prm.max_correspondence_distance;
+    const double m2 = prm.max_correspondence_distance * prm.max_correspondence_distance;
+    a.max_d2_f = (m2 >= (double)FLT_MAX || !(m2 == m2)) ? FLT_MAX : (float)m2;
+    a.rot_thr = 1.0 - prm.transformation_epsilon; a.trans_thr = prm.transformation_epsilon;
+    a.rel_mse_thr = prm.euclidean_fitness_epsilon; a.abs_mse_thr = prm.mse_threshold_absolute;
+    a.max_similar = prm.max_iterations_similar_transforms; a.fail_after_max = prm.failure_after_max_iterations;
+    a.guess = mat4_identity();
+    const int nblk = (f.n_src + kIcpSmallThreads - 1) / kIcpSmallThreads;
+    a.corr_match = match.p + so; a.corr_d2 = d2.p + so;
+    a.partials = partials.p + 2 * bo * kIcpAcc;
+    a.barrier = bars.p + i;
+    a.result = d_results + i;
+    for (int b = 0; b < nblk; ++b) map.push_back(make_int2(i, b));
+    so += (size_t)f.n_src; bo += (size_t)nblk;
+  }
+  for (int r = 0; r < prm.n_rejectors; ++r)
+    if (prm.rejector_kind[r] != OPE_REJ_SURFACE_NORMAL && prm.rejector_kind[r] != OPE_REJ_SELF_OCCLUDED_NORMAL)
+      return fail(ctx, OPE_ERR_UNSUPPORTED, "unknown correspondence rejector kind %d", prm.rejector_kind[r]);
+  OPE_CUDA_TRY(ctx, cudaMemcpyAsync(d_descs.p, descs.data(), descs.size() * sizeof(IcpDev), cudaMemcpyHostToDevice, ctx->stream));
+  OPE_CUDA_TRY(ctx, cudaMemcpyAsync(d_map.p, map.data(), map.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+  OPE_CUDA_TRY(ctx, ope::stream_sync(ctx));   // descs / map live on this stack frame
+  const size_t nt8 = (max_nt + 7) & ~(size_t)7;
+  const size_t smem_bytes = ((sizeof(IcpSmallSmem<kIcpSmallThreads>) + 15) & ~(size_t)15) + nt8 * sizeof(float4) + (nt8 / 8) * 2 * sizeof(float4) +
+                            (size_t)kSlabSlots * kIcpSmallThreads * sizeof(float2);
+  const void* kernel = (const void*)icp_small_batch_kernel<kIcpSmallThreads>;
+  OPE_TRY(dyn_smem(ctx, kernel, smem_bytes));
+  int per_sm = 0;
+  OPE_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kIcpSmallThreads, smem_bytes));
+  if ((size_t)per_sm * ctx->sm_count < (size_t)kIcpSmallMaxBlocks) return fail(ctx, OPE_ERR_CUDA, "icp_small_batch_kernel: one alignment's blocks cannot be co-resident");
+  cudaEventRecord(ctx->kev[0][0], ctx->stream);
+  icp_small_batch_kernel<kIcpSmallThreads><<<(unsigned)total_blocks, kIcpSmallThreads, smem_bytes, ctx->stream>>>(d_descs.p, d_map.p, bars.p + n_frames);
+  cudaEventRecord(ctx->kev[0][1], ctx->stream);
+  ctx->kev_valid[0] = true;
+  return check_launch(ctx, "icp_small_batch_kernel");
 }
 
 }  // namespace ope
