@@ -200,6 +200,13 @@ int ope_pose_stage_ms(const ope_pose_tracker* t, double out[8]);
 int ope_pose_batch(ope_ctx* ctx, const ope_pose_params* prm, const float* model_xyz, size_t n_model, const ope_frame_input* frames,
                    size_t n_frames, const ope_rng_table* tables, int workers, ope_pose_result* results, int32_t* status);
 
+/* Device time per stage of ope_pose_batch's frame-spanning launches (CUDA events on the context's stream), in milliseconds,
+ * accumulated over the calls since the last reset: [0] staging + H2D of the clusters [1] target UniformSampling (1 cm + 8 mm)
+ * [2] target normals [3] SPFH + FPFH [4] feature k-NN [5] SAC-IA pool [6] model under the coarse pose, 8 mm sampling [7] source
+ * normals [8] NaN-normal compaction [9] ICP [10] fitness [11] unused. enable = 1 / 0: switch the laps on / off and reset the
+ * sums; enable < 0: read only. out may be NULL. */
+int ope_pose_batch_stage_ms(ope_ctx* ctx, int enable, double out[12]);
+
 /* defaults of the reference classes (include/ope_types.h) */
 void ope_icp_params_default(ope_icp_params* p);
 void ope_sacia_params_default(ope_sacia_params* p);

@@ -256,6 +256,21 @@ __global__ void __launch_bounds__(kBThreads) compact_normals_batch_kernel(const 
 }
 
 namespace {
+// per-stage device time of the chunk (CUDA events on the context's stream), accumulated into ctx->batch_stage_ms
+struct ChunkTimer {
+  ope_ctx* ctx;
+  cudaEvent_t ev[16];
+  int n = 0;
+  bool on;
+  explicit ChunkTimer(ope_ctx* c) : ctx(c), on(c->batch_timing) { if (on) for (auto& e : ev) cudaEventCreate(&e); mark(); }
+  void mark() { if (on && n < 16) cudaEventRecord(ev[n++], ctx->stream); }
+  ~ChunkTimer() {
+    if (!on) return;
+    cudaEventSynchronize(ev[n - 1]);
+    for (int i = 1; i < n; ++i) { float ms = 0; cudaEventElapsedTime(&ms, ev[i - 1], ev[i]); ctx->batch_stage_ms[i - 1] += ms; }
+    for (auto& e : ev) cudaEventDestroy(e);
+  }
+};
 struct DevGuardF { ope_ctx* ctx; float* p = nullptr; explicit DevGuardF(ope_ctx* c) : ctx(c) {} ~DevGuardF() { dfree(ctx, p); } };
 template <typename T>
 int download(ope_ctx* ctx, const T* d, size_t n, std::vector<T>& h) {
@@ -326,8 +341,10 @@ int pose_batch_chunk(ope_ctx* ctx, const ope_pose_params& P, const ope_cloud* d_
   OPE_CUDA_TRY(ctx, cudaMemsetAsync(d_flags.p, 0, B * sizeof(int), ctx->stream));
   OPE_CUDA_TRY(ctx, cudaMemsetAsync(d_counts.p, 0, 3 * (size_t)B * sizeof(int), ctx->stream));
   OPE_CUDA_TRY(ctx, cudaMemsetAsync(d_ccounts.p, 0, 3 * (size_t)B * sizeof(int), ctx->stream));
+  ChunkTimer tm(ctx);
   OPE_TRY(dyn_smem(ctx, (const void*)bsample_kernel<false>, sizeof(SampleSmem)));
   OPE_TRY(dyn_smem(ctx, (const void*)bsample_kernel<true>, sizeof(SampleSmem)));
+  tm.mark();   // [0] staging + H2D of the clusters
   // ---- target UniformSampling at the coarse and the fine leaf (subSampleAndCalculateNormals, :131-158) ----
   BSampleArgs sa;
   std::memset(&sa, 0, sizeof(sa));
@@ -354,15 +371,19 @@ int pose_batch_chunk(ope_ctx* ctx, const ope_pose_params& P, const ope_cloud* d_
   OPE_CUDA_TRY(ctx, cudaMemcpyAsync(d_active.p, h_active.data(), B * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   for (int i = 0; i < B; ++i) if (!h_active[(size_t)i]) { h_counts[(size_t)i] = 0; h_counts[(size_t)B + i] = 0; }
   OPE_CUDA_TRY(ctx, cudaMemcpyAsync(d_counts.p, h_counts.data(), 2 * (size_t)B * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  tm.mark();   // [1] target sampling
   // ---- normals of tp1 and tp2 in one launch, FPFH of tp1 (estimateCoarsePose, :16-48) ----
   const float vp[3] = {0, 0, 0};
   OPE_TRY(normals_smem_batch(ctx, sampled.p, d_counts.p, kBCap, 2 * B, max_tp, P.normal_k, vp, normals.p));
+  tm.mark();   // [2] target normals
   OPE_TRY(spfh.alloc((size_t)B * kBCap * 33)); OPE_TRY(fpfh.alloc((size_t)B * kBCap * 33));
   OPE_TRY(fpfh_smem_batch(ctx, sampled.p, normals.p, d_counts.p, kBCap, B, max_tp1, P.fpfh_radius, spfh.p, fpfh.p));
+  tm.mark();   // [3] FPFH
   // ---- findSimilarFeatures for every model point at once, SAC-IA pool, first strictly-lower error wins (:50-64) ----
   const int ns = (int)sp->n;
   OPE_TRY(d_knn.alloc((size_t)B * ns * K));
   OPE_TRY(feature_knn_batch(ctx, fpfh.p, d_counts.p, kBCap, B, max_tp1, d_fs, ns, 33, K, d_knn.p));
+  tm.mark();   // [4] feature k-NN
   OPE_TRY(d_samples.alloc((size_t)B * H * S)); OPE_TRY(d_picks.alloc((size_t)B * H * S));
   {
     void* stage = nullptr;
@@ -390,6 +411,7 @@ int pose_batch_chunk(ope_ctx* ctx, const ope_pose_params& P, const ope_cloud* d_
   sb.nr_samples = S; sb.k_corr = K; sb.H = H; sb.samples = d_samples.p; sb.picks = d_picks.p; sb.knn_idx = d_knn.p; sb.active = d_active.p;
   sb.threshold = (float)P.sacia.max_correspondence_distance; sb.errors = errors.p; sb.transforms = transforms.p;
   OPE_TRY(sacia_batch_device(ctx, sb, B, max_tp1, d_coarse.p));
+  tm.mark();   // [5] SAC-IA
   // ---- estimateFinePose (:161-379): the model under the coarse pose sampled at the fine leaf, never materialised ----
   std::memset(&sa, 0, sizeof(sa));
   sa.pts = d_model->pts; sa.n_model = (int)d_model->n; sa.xforms = d_coarse.p; sa.active = d_active.p; sa.flags = d_flags.p;
@@ -406,7 +428,9 @@ int pose_batch_chunk(ope_ctx* ctx, const ope_pose_params& P, const ope_cloud* d_
     max_sp2 = std::max(max_sp2, h_sp2[(size_t)i]);
   }
   OPE_CUDA_TRY(ctx, cudaMemcpyAsync(d_active.p, h_active.data(), B * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  tm.mark();   // [6] model sampling
   OPE_TRY(normals_smem_batch(ctx, sampled.p + 2 * slab, d_counts.p + 2 * (size_t)B, kBCap, B, max_sp2, P.normal_k, vp, normals.p + 2 * slab));
+  tm.mark();   // [7] source normals
   // removeNaNNormalsFromPointCloud on both fine clouds (:215-216): clouds [1] (tp2) and [2] (sp2)
   compact_normals_batch_kernel<<<2 * B, kBThreads, 0, ctx->stream>>>(sampled.p + slab, normals.p + slab, d_counts.p + B, d_active.p, B,
                                                                      compacted.p + slab, cnormals.p + slab, d_ccounts.p + B);
@@ -432,7 +456,9 @@ int pose_batch_chunk(ope_ctx* ctx, const ope_pose_params& P, const ope_cloud* d_
   Scratch<int> d_icp_active(ctx), d_tc(ctx), d_sc(ctx);
   const int NI = (int)icp_frames.size();
   OPE_TRY(d_icp.alloc(NI));
+  tm.mark();   // [8] NaN-normal compaction
   OPE_TRY(icp_small_batch_device(ctx, P.icp, icp_frames.data(), NI, d_icp.p));
+  tm.mark();   // [9] ICP
   // ---- getFitnessScore (:354) of every aligned pair; the ICP results are indexed by their position in icp_frames ----
   OPE_TRY(d_fit.alloc(B));
   {
@@ -446,6 +472,7 @@ int pose_batch_chunk(ope_ctx* ctx, const ope_pose_params& P, const ope_cloud* d_
     OPE_CUDA_TRY(ctx, cudaMemcpyAsync(d_active.p, h_active.data(), B * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     OPE_TRY(fitness_batch_device(ctx, compacted.p + slab, d_ccounts.p + B, compacted.p + 2 * slab, d_ccounts.p + 2 * (size_t)B, kBCap, B, max_tgt,
                                  d_fine.p, d_active.p, d_fit.p));
+    tm.mark();   // [10] fitness
     std::vector<ope_reg_result> h_coarse;
     std::vector<double> h_fit;
     OPE_TRY(download(ctx, d_coarse.p, (size_t)B, h_coarse));

@@ -52,6 +52,8 @@ struct ope_ctx {
   int icp_max_blocks = 0;      // > 0: cap of the cooperative icp_kernel grid (batch workers share the SMs between frames)
   int64_t feature_knn_gemm_queries = 0;  // queries answered through the tcgen05 distance GEMM ...
   int64_t feature_knn_fallbacks = 0;     // ... of which the exact kernel had to re-answer (candidate set not provably complete)
+  bool batch_timing = false;             // ope_pose_batch: per-stage CUDA-event laps of the frame-spanning launches
+  double batch_stage_ms[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   std::vector<ModelCacheEntry> model_cache;   // at most 4 entries, least recently used replaced (pipeline.cu)
   unsigned long long model_cache_clock = 0;
   int64_t model_cache_hits = 0, model_cache_misses = 0;

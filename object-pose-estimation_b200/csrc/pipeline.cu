@@ -502,6 +502,14 @@ int ope_register_point_clouds(ope_ctx* ctx, const ope_frame_input* views, size_t
   return OPE_OK;
 }
 
+// per-stage device time of the frame-spanning launches of ope_pose_batch since the last reset (enable < 0: just read)
+int ope_pose_batch_stage_ms(ope_ctx* ctx, int enable, double out[12]) {
+  if (!ctx) return OPE_ERR_INVALID;
+  if (out) std::memcpy(out, ctx->batch_stage_ms, 12 * sizeof(double));
+  if (enable >= 0) { ctx->batch_timing = enable != 0; std::memset(ctx->batch_stage_ms, 0, sizeof(ctx->batch_stage_ms)); }
+  return OPE_OK;
+}
+
 int ope_pose_estimate_final(ope_pose_tracker* t, float* source_xyz, size_t ns, const void* target, size_t nt, size_t tstride,
                             size_t toffset, const ope_rng_table* table, ope_pose_result* res) {
   OPE_ENTER((t ? t->ctx : nullptr));

@@ -29,7 +29,7 @@ EXPORTS = [
     "ope_normals_knn", "ope_fpfh", "ope_feature_knn",
     "ope_umeyama", "ope_point_to_plane", "ope_fitness", "ope_correspondences", "ope_icp_align", "ope_icp_align_fixed", "ope_sacia_align", "ope_sacia_draw",
     "ope_pose_tracker_create", "ope_pose_tracker_destroy", "ope_pose_estimate_final", "ope_pose_estimate_final_device", "ope_pose_batch",
-    "ope_pose_stage_ms", "ope_icp_params_default", "ope_sacia_params_default", "ope_pose_params_default",
+    "ope_pose_stage_ms", "ope_pose_batch_stage_ms", "ope_icp_params_default", "ope_sacia_params_default", "ope_pose_params_default",
 ]
 
 
@@ -190,6 +190,15 @@ class Context:
         a, b = C.c_int64(0), C.c_int64(0)
         self._chk(lib().ope_ctx_model_cache_stats(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    BATCH_STAGES = ["h2d", "target_sampling", "target_normals", "fpfh", "feature_knn", "sacia", "model_sampling", "source_normals",
+                    "nan_compaction", "icp", "fitness"]
+
+    def batch_stage_ms(self, enable=-1):
+        """per-stage device ms of ope_pose_batch's frame-spanning launches since the last reset; enable=1/0 switches + resets"""
+        out = (C.c_double * 12)()
+        self._chk(lib().ope_pose_batch_stage_ms(self.h, int(enable), out))
+        return dict(zip(self.BATCH_STAGES, list(out)[:11]))
 
     def invalidate(self, cloud):
         self._chk(lib().ope_cloud_invalidate(self.h, cloud.h))

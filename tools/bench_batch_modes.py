@@ -31,6 +31,11 @@ for mode in ("fused", "workers"):
         r, st = ctx.pose_batch(model, clusters, workers=16)
         best = min(best, time.perf_counter() - t0)
     assert (st == 0).all()
+    if mode == "fused":
+        ctx.batch_stage_ms(1)
+        libc.srand(5)
+        ctx.pose_batch(model, clusters, workers=16)
+        out["fused_stage_ms_per_frame"] = {k: round(v / n, 5) for k, v in ctx.batch_stage_ms(0).items()}
     res[mode] = r
     out[mode + "_e2e_frames_per_s"] = n / best
     out[mode + "_launches_per_frame"] = None
