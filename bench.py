@@ -286,6 +286,11 @@ def run_ours(args):
     except Exception as e:
         line["roofline"] = {"error": repr(e)}
 
+    if world > 1:
+        try:
+            line["sharded_sacia"] = sharded_sacia_numbers(ctx, cuda_lib, model, clusters, stream, torch, dist, rank, world)
+        except Exception as e:
+            line["sharded_sacia"] = {"error": repr(e)}
     if rank == 0 and world == 1:
         line["cpu_baseline"] = frames_cpu_baseline(ctx, cuda_lib, synth, model, clusters)
         for key, fn in (("icp", lambda: icp_numbers(ctx, cuda_lib, synth, model, stream, torch, flush, args)),
@@ -302,6 +307,54 @@ def run_ours(args):
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+def sharded_sacia_numbers(ctx, cuda_lib, model, clusters, stream, torch, dist, rank, world, pool=131072):
+    """the path's ONE collective, inside the library: a SAC-IA pool of `pool` hypotheses of one alignment sharded
+    over the ranks — ope_sacia_align_sharded: ncclAllReduce(MIN) of the packed (error, index) key + ncclBroadcast of the 4x4 on the
+    context's stream. Device time (CUDA events, max over ranks) beside one GPU evaluating the whole pool; same winner required."""
+    import ctypes
+    cm, cc = ctx.upload(model), ctx.upload(clusters[0] if rank == 0 else clusters[0])
+    # every rank needs the SAME pair: rank 0's first cluster
+    box = [clusters[0] if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    cc = ctx.upload(box[0])
+    sp_c, tp_c = ctx.uniform_sample_cloud(cm, 0.01), ctx.uniform_sample_cloud(cc, 0.01)
+    ctx.normals_knn(sp_c, 30); ctx.normals_knn(tp_c, 30)
+    sf, tf = ctx.fpfh(sp_c, 0.03), ctx.fpfh(tp_c, 0.03)
+    kw = dict(max_iterations=pool, nr_samples=5, k_correspondences=5, min_sample_distance=0.01, max_correspondence_distance=0.05)
+    ctypes.CDLL(None).srand(1)      # every rank draws the same table from libc rand()
+    table = cuda_lib.rng_table(*cuda_lib.sacia_draw(sp_c.download(), pool, 5, 5, 0.01))
+    uid = [cuda_lib.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    comm = cuda_lib.Comm(ctx, uid[0], world, rank)
+    prm = cuda_lib.sacia_params(**kw)
+
+    def timed(fn):
+        fn()                                        # warm-up (NCCL connects lazily)
+        dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        r = fn()
+        e1.record(stream)
+        e1.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return r, float(t.item())
+
+    one, one_ms = timed(lambda: ctx.sacia(sp_c, sf, tp_c, tf, prm, table))
+    sh, sh_ms = timed(lambda: comm.sacia(sp_c, sf, tp_c, tf, prm, table))
+    same = (sh.best_iteration == one.best_iteration and np.float32(sh.best_error) == np.float32(one.best_error)
+            and np.array_equal(np.array(list(sh.T), np.float32), np.array(list(one.T), np.float32)))
+    ok = torch.tensor([1.0 if same else 0.0], device="cuda")
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    comm.close()
+    if ok.item() != 1.0:
+        raise AssertionError("the sharded pool's winner differs from the single-GPU winner")
+    return {"workload": "one alignment, SAC-IA pool of %d hypotheses x %d source points vs %d target points" % (pool, len(sp_c), len(tp_c)),
+            "api": "ope_sacia_align_sharded (ncclAllReduce MIN of a 64-bit key + ncclBroadcast of 16 floats, in the library)",
+            "one_gpu_ms": one_ms, "sharded_ms": sh_ms, "speedup": one_ms / sh_ms, "ranks": world, "same_winner_on_every_rank": True,
+            "nccl_version": int(cuda_lib.lib().ope_comm_nccl_version())}
 
 
 def frame_roofline(ctx, cuda_lib, synth, model, clusters, stream, torch, n=8):

@@ -28,6 +28,7 @@ extern "C" {
 typedef struct ope_ctx ope_ctx;
 typedef struct ope_cloud ope_cloud;
 typedef struct ope_pose_tracker ope_pose_tracker;
+typedef struct ope_comm ope_comm;
 
 /* ---- context -------------------------------------------------------------------------------------- */
 /* `stream` is a cudaStream_t to run on (e.g. torch.cuda.current_stream().cuda_stream) or NULL to create one. */
@@ -160,6 +161,21 @@ int ope_icp_align_fixed(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt
  * prm->hypothesis_begin/end restrict the evaluated shard (multi-GPU pools); out_errors: max_iterations floats or NULL. */
 int ope_sacia_align(ope_ctx* ctx, const ope_cloud* src, const float* fsrc, const ope_cloud* tgt, const float* ftgt,
                     const ope_sacia_params* prm, const ope_rng_table* table, ope_reg_result* res, float* out_errors);
+/* ---- the SAC-IA hypothesis pool sharded over the GPUs of one box -------------------------------------------
+ * One process per GPU, each with its own ope_ctx. NCCL (libnccl.so.2, bound at run time) carries 8 + 64 bytes per alignment over
+ * NVLink: ncclAllReduce(MIN) of a packed (error bits, hypothesis index) key, then ncclBroadcast of the winner's 4x4, both on the
+ * context's stream. ope_comm_unique_id: rank 0 calls it and hands the bytes (128) to the other ranks by any means (a file,
+ * torch.distributed, MPI); ope_comm_create: every rank, same id, world, own rank (world == 1 needs no id and no NCCL).
+ * ope_sacia_align_sharded: every rank passes the SAME clouds, features and pre-drawn table; rank r evaluates hypotheses
+ * [H r / world, H (r + 1) / world); every rank returns the pool's winner — bit for bit what one GPU returns for the whole pool. */
+int ope_comm_unique_id(void* out, size_t bytes);
+int ope_comm_nccl_version(void);
+int ope_comm_create(ope_ctx* ctx, const void* unique_id, size_t bytes, int world, int rank, ope_comm** out);
+void ope_comm_destroy(ope_comm* comm);
+int ope_comm_rank(const ope_comm* comm);
+int ope_comm_world(const ope_comm* comm);
+int ope_sacia_align_sharded(ope_ctx* ctx, ope_comm* comm, const ope_cloud* src, const float* fsrc, const ope_cloud* tgt, const float* ftgt,
+                            const ope_sacia_params* prm, const ope_rng_table* table, ope_reg_result* res);
 /* draw the SAC-IA decision table on the host from libc rand() (selectSamples + the pick of findSimilarFeatures) */
 int ope_sacia_draw(const float* src_xyz, size_t ns, size_t stride_bytes, int iterations, int nr_samples,
                    int k_correspondences, float* min_sample_distance, int32_t* samples, int32_t* picks);

@@ -27,7 +27,8 @@ EXPORTS = [
     "ope_knn", "ope_knn_cloud", "ope_radius_cloud", "ope_depth_to_cloud", "ope_depth_to_cloud_batch",
     "ope_uniform_sample", "ope_uniform_sample_cloud", "ope_voxel_grid",
     "ope_normals_knn", "ope_fpfh", "ope_feature_knn",
-    "ope_umeyama", "ope_point_to_plane", "ope_fitness", "ope_correspondences", "ope_icp_align", "ope_icp_align_fixed", "ope_sacia_align", "ope_sacia_draw",
+    "ope_umeyama", "ope_point_to_plane", "ope_fitness", "ope_correspondences", "ope_icp_align", "ope_icp_align_fixed", "ope_sacia_align", "ope_sacia_align_sharded",
+    "ope_comm_unique_id", "ope_comm_nccl_version", "ope_comm_create", "ope_comm_destroy", "ope_comm_rank", "ope_comm_world", "ope_sacia_draw",
     "ope_pose_tracker_create", "ope_pose_tracker_destroy", "ope_pose_estimate_final", "ope_pose_estimate_final_device", "ope_pose_batch",
     "ope_pose_stage_ms", "ope_pose_batch_stage_ms", "ope_icp_params_default", "ope_sacia_params_default", "ope_pose_params_default",
 ]
@@ -434,6 +435,38 @@ class Context:
                                         None if table is None else C.byref(table), C.byref(res),
                                         None if errs is None else errs.ctypes.data_as(f32p)))
         return (res, errs) if want_errors else res
+
+
+def comm_unique_id():
+    """rank 0: the 128-byte NCCL unique id to hand to the other ranks"""
+    buf = C.create_string_buffer(128)
+    rc = lib().ope_comm_unique_id(buf, C.c_size_t(128))
+    if rc != 0:
+        raise OpeError(rc, "ope_comm_unique_id (libnccl.so.2 not loadable?)")
+    return buf.raw
+
+
+class Comm:
+    """ope_comm: the library's own NCCL communicator for the sharded SAC-IA pool (one process per GPU)"""
+
+    def __init__(self, ctx, unique_id, world, rank):
+        self.ctx = ctx
+        h = C.c_void_p()
+        uid = None if unique_id is None else C.create_string_buffer(unique_id, 128)
+        ctx._chk(lib().ope_comm_create(ctx.h, uid, C.c_size_t(0 if uid is None else 128), int(world), int(rank), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h and self.ctx.h:
+            lib().ope_comm_destroy(self.h)
+        self.h = None
+
+    def sacia(self, src, fsrc, tgt, ftgt, prm, table):
+        fs, ft = _f32(fsrc), _f32(ftgt)
+        res = T.RegResult()
+        self.ctx._chk(lib().ope_sacia_align_sharded(self.ctx.h, self.h, src.h, fs.ctypes.data_as(f32p), tgt.h, ft.ctypes.data_as(f32p),
+                                                    C.byref(prm), C.byref(table), C.byref(res)))
+        return res
 
 
 def sacia_draw(src_xyz, iterations, nr_samples, k_corr, min_sample_distance):

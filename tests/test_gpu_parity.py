@@ -620,3 +620,35 @@ def test_depth_to_cloud_every_raw_value_and_other_intrinsics(ctx, orc):
         assert len(got) == len(ref)
         assert np.array_equal(got.download().view(np.uint32), ref.view(np.uint32))
         got.free()
+
+
+# ------------------------------------------------------------------------------ the library's own communicator (8e row 2) ----
+def test_sharded_sacia_through_the_library_communicator(ctx, orc, synth, cuda_lib, model):
+    """ope_comm + ope_sacia_align_sharded. With one rank no NCCL is involved and the call must equal ope_sacia_align; with two or
+    more GPUs on the box, two processes (one per GPU, the unique id passed through a file) must both return the single-GPU
+    winner (tools/multigpu_check.py covers torchrun)."""
+    import subprocess, sys, os, json
+    cl, _, _ = synth.make_frame(model, 2)
+    sp = model[orc.uniform_sample(model, 0.01)]
+    tp = cl[orc.uniform_sample(cl, 0.01)]
+    sn, tn = orc.normals_knn(sp, 30), orc.normals_knn(tp, 30)
+    sf, tf = orc.fpfh(sp, sn, 0.03), orc.fpfh(tp, tn, 0.03)
+    kw = dict(max_iterations=400, nr_samples=5, k_correspondences=5, min_sample_distance=0.01, max_correspondence_distance=0.05)
+    orc.srand(1)
+    table = cuda_lib.rng_table(*orc.sacia_draw(sp, 400, 5, 5, 0.01))
+    cs, ct = ctx.upload(sp), ctx.upload(tp)
+    one = ctx.sacia(cs, sf, ct, tf, cuda_lib.sacia_params(**kw), table)
+    comm = cuda_lib.Comm(ctx, None, 1, 0)
+    sh = comm.sacia(cs, sf, ct, tf, cuda_lib.sacia_params(**kw), table)
+    comm.close()
+    assert sh.best_iteration == one.best_iteration and sh.best_error == one.best_error
+    assert np.array_equal(np.array(list(sh.T)), np.array(list(one.T)))
+    import torch
+    if torch.cuda.device_count() < 2:
+        return
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(root, "tools", "multigpu_check.py")], stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "MISMATCH" not in r.stdout, r.stdout[-2000:]

@@ -3,9 +3,11 @@
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/multigpu_check.py
 
-1. SAC-IA hypothesis pool of ONE alignment sharded over the ranks (pre-drawn libc rand() table, ope_sacia_align with
-   hypothesis_begin/end, all_reduce(MIN) of the packed (error, index) key + broadcast of the winner's 4x4): every rank must
-   end with exactly the single-GPU winner.
+1. SAC-IA hypothesis pool of ONE alignment sharded over the ranks, twice: through the LIBRARY's own communicator
+   (ope_comm_create + ope_sacia_align_sharded: ncclAllReduce(MIN) of the packed (error, index) key + ncclBroadcast of the
+   winner's 4x4 on the context's stream, C ABI only; torch.distributed merely ships the 128-byte unique id) with a pool of 400
+   and of 131 072 hypotheses, and through the Python helper (parallel.sharded_sacia). Every rank must end with exactly the
+   single-GPU winner.
 2. A batch of independent frames sharded frame f -> rank f mod N, no data-path collective; the poses are all-gathered only
    to print one line.
 """
@@ -47,7 +49,33 @@ def main():
     err, hyp, T = parallel.sharded_sacia(ctx, cuda_lib, sp_c, sf, tp_c, tf, kw, table)
     ok = (hyp == full.best_iteration and np.float32(err) == np.float32(full.best_error)
           and np.array_equal(T.T.reshape(16), np.array(list(full.T), np.float32)))
-    print("rank %d/%d sharded SAC-IA: winner %d error %.6f %s" % (rank, world, hyp, err, "OK" if ok else "MISMATCH"), flush=True)
+    print("rank %d/%d sharded SAC-IA (torch.distributed helper): winner %d error %.6f %s" % (rank, world, hyp, err, "OK" if ok else "MISMATCH"), flush=True)
+    # the library's own communicator: NCCL inside libope_cuda.so
+    import time
+    uid = [cuda_lib.comm_unique_id() if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(uid, src=0)
+    comm = cuda_lib.Comm(ctx, uid[0], world, rank)
+    for pool in (H, 131072):
+        kw2 = dict(kw, max_iterations=pool)
+        ctypes.CDLL(None).srand(1)
+        s2, p2 = cuda_lib.sacia_draw(sp, pool, 5, 5, 0.01)
+        tb = cuda_lib.rng_table(s2, p2)
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        one = ctx.sacia(sp_c, sf, tp_c, tf, cuda_lib.sacia_params(**kw2), tb)
+        t1 = time.perf_counter()
+        if world > 1:
+            dist.barrier()
+        t2 = time.perf_counter()
+        sh = comm.sacia(sp_c, sf, tp_c, tf, cuda_lib.sacia_params(**kw2), tb)
+        t3 = time.perf_counter()
+        same = (sh.best_iteration == one.best_iteration and np.float32(sh.best_error) == np.float32(one.best_error)
+                and np.array_equal(np.array(list(sh.T), np.float32), np.array(list(one.T), np.float32)))
+        ok = ok and same
+        print("rank %d/%d ope_sacia_align_sharded pool %d: winner %d error %.6f %s | one GPU %.2f ms, sharded %.2f ms"
+              % (rank, world, pool, sh.best_iteration, sh.best_error, "OK" if same else "MISMATCH", (t1 - t0) * 1e3, (t3 - t2) * 1e3), flush=True)
+    comm.close()
     # frame batch
     n_frames = 8
     mine = parallel.shard_units(n_frames, rank, world)
