@@ -86,6 +86,17 @@ int ope_depth_to_cloud(ope_ctx* ctx, const uint16_t* depth, int rows, int cols, 
 int ope_depth_to_cloud_batch(ope_ctx* ctx, const uint16_t* d_depth, int frames, int rows, int cols, float fx, float fy, float cx, float cy,
                              float scale, float z_max, void* d_out, int32_t* d_col_start);
 
+/* ---- scene preparation in front of the path ----------------------------------------------------------------------- */
+/* ProcessingPcd::getPassThrough (D&L/src/processingpcd.cpp:8-41): pcl::PassThrough on z, then y, then x; a point survives iff it
+ * is finite and inside all three closed intervals. limits = x_min, x_max, y_min, y_max, z_min, z_max (the reference's argument
+ * order). *out: the surviving points in input order (device); out_idx (room for ope_cloud_size entries) / out_n may be NULL. */
+int ope_pass_through(ope_ctx* ctx, const ope_cloud* cloud, const float limits[6], ope_cloud** out, int32_t* out_idx, size_t* out_n);
+/* pcl::EuclideanClusterExtraction as ObjectSegmentationPlane::getClusters configures it (D&L/src/objectsegmentationplane.cpp:74-90:
+ * setClusterTolerance(0.05), sizes 300 .. 1e5): connected components of the graph "squared distance < tolerance^2". labels: one
+ * per point — cluster number (0 = largest, as extract() orders them; equal sizes by the smaller first index) or -1. */
+int ope_euclidean_clusters(ope_ctx* ctx, const ope_cloud* cloud, float tolerance, int min_size, int max_size, int32_t* labels,
+                           int* n_clusters);
+
 /* ---- spatial search: replaces pcl::search::KdTree / KdTreeFLANN -------------------------- */
 /* nearestKSearch for nq host queries; out_idx/out_d2 are nq*k, padded with -1 / +inf. k <= 32. */
 int ope_knn(ope_ctx* ctx, const ope_cloud* tgt, const void* qry, size_t nq, size_t stride, size_t offset, int k,

@@ -24,7 +24,7 @@ EXPORTS = [
     "ope_ctx_last_kernel_ms", "ope_cloud_invalidate", "ope_ctx_feature_knn_stats", "ope_ctx_model_cache_stats",
     "ope_cloud_upload", "ope_cloud_free", "ope_cloud_size", "ope_cloud_has_normals", "ope_cloud_download",
     "ope_cloud_select", "ope_cloud_transform", "ope_cloud_set_normals", "ope_cloud_append", "ope_register_point_clouds",
-    "ope_knn", "ope_knn_cloud", "ope_radius_cloud", "ope_depth_to_cloud", "ope_depth_to_cloud_batch",
+    "ope_pass_through", "ope_euclidean_clusters", "ope_knn", "ope_knn_cloud", "ope_radius_cloud", "ope_depth_to_cloud", "ope_depth_to_cloud_batch",
     "ope_uniform_sample", "ope_uniform_sample_cloud", "ope_voxel_grid",
     "ope_normals_knn", "ope_fpfh", "ope_feature_knn",
     "ope_umeyama", "ope_point_to_plane", "ope_fitness", "ope_correspondences", "ope_icp_align", "ope_icp_align_fixed", "ope_sacia_align", "ope_sacia_align_sharded",
@@ -270,6 +270,24 @@ class Context:
     def set_normals(self, cloud, normals4):
         nr = _f32(normals4)
         self._chk(lib().ope_cloud_set_normals(self.h, cloud.h, nr.ctypes.data_as(f32p)))
+
+    # ---- scene preparation (8f-2) ----
+    def pass_through(self, cloud, limits, want_idx=False):
+        """limits = (x_min, x_max, y_min, y_max, z_min, z_max); returns the filtered Cloud (and the kept indices)"""
+        lim = (C.c_float * 6)(*[float(v) for v in limits])
+        h = C.c_void_p()
+        idx = np.empty(max(len(cloud), 1), np.int32) if want_idx else None
+        m = C.c_size_t(0)
+        self._chk(lib().ope_pass_through(self.h, cloud.h, lim, C.byref(h), None if idx is None else idx.ctypes.data_as(i32p), C.byref(m)))
+        out = Cloud(self, h)
+        return (out, idx[:m.value].copy()) if want_idx else out
+
+    def euclidean_clusters(self, cloud, tolerance=0.05, min_size=300, max_size=100000):
+        labels = np.empty(max(len(cloud), 1), np.int32)
+        k = C.c_int(0)
+        self._chk(lib().ope_euclidean_clusters(self.h, cloud.h, C.c_float(tolerance), int(min_size), int(max_size), labels.ctypes.data_as(i32p),
+                                               C.byref(k)))
+        return labels[:len(cloud)].copy(), k.value
 
     # ---- search ----
     def knn(self, tgt, qry, k):

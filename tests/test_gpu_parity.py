@@ -652,3 +652,31 @@ def test_sharded_sacia_through_the_library_communicator(ctx, orc, synth, cuda_li
                         "--master-port", "29533", os.path.join(root, "tools", "multigpu_check.py")], stdout=subprocess.PIPE,
                        stderr=subprocess.STDOUT, text=True, timeout=600, env=env)
     assert r.returncode == 0 and "MISMATCH" not in r.stdout, r.stdout[-2000:]
+
+
+# ------------------------------------------------------------------------------ scene preparation (8f-2) ----
+def test_pass_through_and_euclidean_clusters(ctx, orc, synth, model):
+    """ProcessingPcd::getPassThrough (three closed intervals, NaN removed, order kept) and EuclideanClusterExtraction (tolerance
+    0.05, sizes 300 .. 1e5) on a full 640x480 frame: kept indices and cluster labels bit-exact against the oracle."""
+    _, cloud, _ = synth.make_frame(model, 21)
+    pts = cloud.reshape(-1, 3)
+    c = ctx.upload(pts)
+    limits = (-0.5, 0.5, -0.5, 0.3, 0.5, 1.6)                    # ObjectSegmentationPlane::getFiltered, D&L/src/objectsegmentationplane.cpp:17-18
+    g, gi = ctx.pass_through(c, limits, want_idx=True)
+    keep = np.arange(len(pts), dtype=np.int32)
+    for field, lo, hi in ((2, limits[4], limits[5]), (1, limits[2], limits[3]), (0, limits[0], limits[1])):   # z, y, x
+        keep = keep[orc.pass_through(pts[keep], field, lo, hi)]
+    assert np.array_equal(gi, keep) and np.array_equal(g.download(), pts[keep])
+    # clustering: the object pixels + scattered table / wall points; also NaN points, a tiny component and an empty cloud
+    rng = np.random.default_rng(4)
+    sub = pts[keep][::3].copy()
+    sub[10] = np.nan
+    blob = (rng.normal(0, 0.004, (40, 3)) + np.array([0.3, 0.2, 0.7])).astype(np.float32)    # 40 points: below min_size
+    data = np.concatenate([sub, blob]).astype(np.float32)
+    for tol, mn in ((0.05, 300), (0.012, 50)):
+        gl, gk = ctx.euclidean_clusters(ctx.upload(data), tol, mn, 100000)
+        ol, ok = orc.euclidean_clusters(data, tol, mn, 100000)
+        assert gk == ok and np.array_equal(gl, ol), (tol, gk, ok)
+        assert gk >= 1 and (gl[-40:] == -1).all()
+    gl, gk = ctx.euclidean_clusters(ctx.upload(np.zeros((0, 3), np.float32)))
+    assert gk == 0 and len(gl) == 0
