@@ -97,6 +97,21 @@ int ope_pass_through(ope_ctx* ctx, const ope_cloud* cloud, const float limits[6]
 int ope_euclidean_clusters(ope_ctx* ctx, const ope_cloud* cloud, float tolerance, int min_size, int max_size, int32_t* labels,
                            int* n_clusters);
 
+/* pcl::SACSegmentation as ObjectSegmentationPlane::getPlaneIndicesAndCoeffSAC configures it (D&L/src/objectsegmentationplane.cpp:
+ * 36-55: SACMODEL_PLANE, SAC_RANSAC, threshold 0.01, optimised coefficients; 50 iterations, probability 0.99, the fixed sampling
+ * seed of PCL) on a device cloud without NaN points: refined plane (a, b, c, d), ascending inlier indices (out_idx: room for
+ * ope_cloud_size entries, may be NULL), RANSAC iterations. *found = 0 when no plane exists. prm == NULL: the reference's values. */
+int ope_plane_ransac(ope_ctx* ctx, const ope_cloud* cloud, const ope_segment_params* prm, float coeff[4], int32_t* out_idx, size_t* out_n,
+                     int32_t* iterations, int32_t* found);
+/* ObjectSegmentationPlane::getSegmentedObjectsOnPlane (D&L/src/objectsegmentationplane.cpp:122-282) on a pass-through-filtered
+ * device cloud: table plane, polygonal prism over the padded bounding rectangle of the plane's hull, second plane on the prism's
+ * points, Euclidean clusters of the rest. labels (ope_cloud_size entries): OPE_SEG_OUTSIDE_PRISM / OPE_SEG_PLANE /
+ * OPE_SEG_NO_CLUSTER / cluster number (0 = largest = cloudClusterVector order). plane1 / plane2 / iters may be NULL.
+ * *n_clusters = -1 when a plane fit failed (the reference then hands the whole cloud on, :149-152). */
+int ope_segment_objects_on_plane(ope_ctx* ctx, const ope_cloud* cloud, const ope_segment_params* prm, int32_t* labels, float plane1[4],
+                                 float plane2[4], int32_t iters[2], int32_t* n_clusters);
+void ope_segment_params_default(ope_segment_params* p);
+
 /* ---- spatial search: replaces pcl::search::KdTree / KdTreeFLANN -------------------------- */
 /* nearestKSearch for nq host queries; out_idx/out_d2 are nq*k, padded with -1 / +inf. k <= 32. */
 int ope_knn(ope_ctx* ctx, const ope_cloud* tgt, const void* qry, size_t nq, size_t stride, size_t offset, int k,

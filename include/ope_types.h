@@ -167,6 +167,20 @@ typedef struct ope_pose_result {
   double sacia_best_error;
 } ope_pose_result;
 
+/* ObjectSegmentationPlane::getSegmentedObjectsOnPlane parameter sheet (D&L/src/objectsegmentationplane.cpp:36-90,174-203). */
+typedef struct ope_segment_params {
+  double distance_threshold;     /* 0.01  sacSeg.setDistanceThreshold (:43) */
+  int32_t max_iterations;        /* 50    pcl::SACSegmentation default */
+  int32_t min_cluster_size;      /* 300   (:84) */
+  double probability;            /* 0.99  pcl::SACSegmentation default */
+  double hull_margin;            /* 0.1   padding of the hull's bounding rectangle, a double literal in the reference (:180-183) */
+  float cluster_tolerance;       /* 0.05  (:83) */
+  int32_t max_cluster_size;      /* 1e5   (:85) */
+} ope_segment_params;
+
+/* per-point labels of ope_segment_objects_on_plane */
+enum { OPE_SEG_OUTSIDE_PRISM = -3, OPE_SEG_PLANE = -2, OPE_SEG_NO_CLUSTER = -1 };
+
 /* One frame of a batch (ope_pose_batch): the segmented scene cluster either as host points (stride/offset in BYTES as in
  * ope_cloud_upload) or, when points == NULL, as a device-resident cloud that no other call touches during the batch. */
 typedef struct ope_frame_input {

@@ -115,6 +115,14 @@ class PoseResult(C.Structure):
     ]
 
 
+class SegmentParams(C.Structure):
+    _fields_ = [("distance_threshold", C.c_double), ("max_iterations", C.c_int32), ("min_cluster_size", C.c_int32),
+                ("probability", C.c_double), ("hull_margin", C.c_double), ("cluster_tolerance", C.c_float), ("max_cluster_size", C.c_int32)]
+
+
+SEG_OUTSIDE_PRISM, SEG_PLANE, SEG_NO_CLUSTER = -3, -2, -1
+
+
 class FrameInput(C.Structure):
     _fields_ = [("points", C.c_void_p), ("n", C.c_size_t), ("stride", C.c_size_t), ("offset", C.c_size_t), ("cloud", C.c_void_p)]
 

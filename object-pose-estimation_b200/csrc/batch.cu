@@ -22,6 +22,7 @@
 // computed once per call.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -255,6 +256,83 @@ __global__ void __launch_bounds__(kBThreads) compact_normals_batch_kernel(const 
   if (tid == 0) ocounts[c] = total;
 }
 
+// Work order of the ICP kernel: both fine clouds re-ordered along the Morton curve of their own bounding box, so that the 32 points
+// of a warp and the 8 points of a target group are spatial neighbours (the voxel-key order of the sampling is a z-major raster:
+// thin rows). One block per cloud: bounding box, 30-bit Morton key | position, bitonic sort in shared memory, gather. The clouds
+// stay self-consistent (points and normals move together, .w = new position), so nothing but the order of equal-distance ties
+// and of the double-precision moment sums changes.
+__device__ __forceinline__ unsigned spread10(unsigned v) {
+  v &= 0x3ffu;
+  v = (v | (v << 16)) & 0x030000ffu;
+  v = (v | (v << 8)) & 0x0300f00fu;
+  v = (v | (v << 4)) & 0x030c30c3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+__global__ void __launch_bounds__(kBThreads) morton_sort_batch_kernel(const float4* __restrict__ pts, const float4* __restrict__ nrm,
+                                                                     const int* __restrict__ counts, const int* __restrict__ active, int frames,
+                                                                     float4* __restrict__ opts, float4* __restrict__ onrm) {
+  __shared__ unsigned long long keys[kBCap];
+  __shared__ float red[6][kBThreads / 32];
+  __shared__ float box[6];
+  const int c = blockIdx.x, f = c % frames;
+  if (active && !active[f]) return;
+  const int n = counts[c];
+  if (n <= 0) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t base = (size_t)c * kBCap;
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int i = tid; i < n; i += kBThreads) {
+    const float4 p = __ldg(pts + base + i);
+    lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
+    hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
+  }
+  for (int o = 16; o > 0; o >>= 1)
+    for (int d = 0; d < 3; ++d) { lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o)); hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o)); }
+  if (lane == 0) for (int d = 0; d < 3; ++d) { red[d][warp] = lo[d]; red[3 + d][warp] = hi[d]; }
+  __syncthreads();
+  if (tid < 6) {
+    float v = red[tid][0];
+    for (int w = 1; w < kBThreads / 32; ++w) v = tid < 3 ? fminf(v, red[tid][w]) : fmaxf(v, red[tid][w]);
+    box[tid] = v;
+  }
+  __syncthreads();
+  const float ext = fmaxf(fmaxf(box[3] - box[0], box[4] - box[1]), fmaxf(box[5] - box[2], 1e-9f));
+  const float scale = 1023.0f / ext;
+  int m2 = 1;
+  while (m2 < n) m2 <<= 1;
+  for (int i = tid; i < m2; i += kBThreads) {
+    unsigned long long k = ~0ull;
+    if (i < n) {
+      const float4 p = __ldg(pts + base + i);
+      const unsigned x = (unsigned)fminf(fmaxf((p.x - box[0]) * scale, 0.0f), 1023.0f), y = (unsigned)fminf(fmaxf((p.y - box[1]) * scale, 0.0f), 1023.0f),
+                     z = (unsigned)fminf(fmaxf((p.z - box[2]) * scale, 0.0f), 1023.0f);
+      k = ((unsigned long long)(spread10(x) | (spread10(y) << 1) | (spread10(z) << 2)) << 32) | (unsigned)i;
+    }
+    keys[i] = k;
+  }
+  __syncthreads();
+  for (int k2 = 2; k2 <= m2; k2 <<= 1)
+    for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+      for (int i = tid; i < m2; i += kBThreads) {
+        const int l = i ^ j2;
+        if (l > i) {
+          const bool up = (i & k2) == 0;
+          const unsigned long long ki = keys[i], kl = keys[l];
+          if ((ki > kl) == up) { keys[i] = kl; keys[l] = ki; }
+        }
+      }
+      __syncthreads();
+    }
+  for (int j = tid; j < n; j += kBThreads) {
+    const int src = (int)(unsigned)(keys[j] & 0xffffffffull);
+    float4 p = __ldg(pts + base + src);
+    p.w = __int_as_float(j);
+    opts[base + j] = p;
+    onrm[base + j] = __ldg(nrm + base + src);
+  }
+}
+
 namespace {
 // per-stage device time of the chunk (CUDA events on the context's stream), accumulated into ctx->batch_stage_ms
 struct ChunkTimer {
@@ -437,6 +515,17 @@ int pose_batch_chunk(ope_ctx* ctx, const ope_pose_params& P, const ope_cloud* d_
   OPE_TRY(check_launch(ctx, "compact_normals_batch_kernel"));
   std::vector<int> h_cc;
   OPE_TRY(download(ctx, d_ccounts.p + B, 2 * (size_t)B, h_cc));   // [0..B) tp2, [B..2B) sp2
+  // the ICP's work order: both fine clouds along their Morton curve (the raw samples' arrays are free by now)
+  const char* me = std::getenv("OPE_BATCH_MORTON");
+  const bool morton = !(me && std::atoi(me) == 0);
+  const float4* fine_pts = compacted.p;
+  const float4* fine_nrm = cnormals.p;
+  if (morton) {
+    morton_sort_batch_kernel<<<2 * B, kBThreads, 0, ctx->stream>>>(compacted.p + slab, cnormals.p + slab, d_ccounts.p + B, d_active.p, B,
+                                                                   sampled.p + slab, normals.p + slab);
+    OPE_TRY(check_launch(ctx, "morton_sort_batch_kernel"));
+    fine_pts = sampled.p; fine_nrm = normals.p;
+  }
   std::vector<IcpBatchFrame> icp_frames;
   std::vector<int> icp_of;
   int max_tgt = 0;
@@ -445,8 +534,8 @@ int pose_batch_chunk(ope_ctx* ctx, const ope_pose_params& P, const ope_cloud* d_
     const int nt = h_cc[(size_t)i], nsrc = h_cc[(size_t)B + i];
     if (nt < P.min_target_points || !icp_small_batch_applicable(P.icp, (size_t)nsrc, (size_t)nt)) { h_active[(size_t)i] = 0; continue; }
     IcpBatchFrame fr;
-    fr.tgt_pts = compacted.p + slab + (size_t)i * kBCap; fr.tgt_nrm = cnormals.p + slab + (size_t)i * kBCap; fr.n_tgt = nt;
-    fr.src_pts = compacted.p + 2 * slab + (size_t)i * kBCap; fr.src_nrm = cnormals.p + 2 * slab + (size_t)i * kBCap; fr.n_src = nsrc;
+    fr.tgt_pts = fine_pts + slab + (size_t)i * kBCap; fr.tgt_nrm = fine_nrm + slab + (size_t)i * kBCap; fr.n_tgt = nt;
+    fr.src_pts = fine_pts + 2 * slab + (size_t)i * kBCap; fr.src_nrm = fine_nrm + 2 * slab + (size_t)i * kBCap; fr.n_src = nsrc;
     icp_frames.push_back(fr);
     icp_of.push_back(i);
     max_tgt = std::max(max_tgt, nt);
@@ -470,7 +559,7 @@ int pose_batch_chunk(ope_ctx* ctx, const ope_pose_params& P, const ope_cloud* d_
     for (int j = 0; j < NI; ++j) by_frame[(size_t)icp_of[(size_t)j]] = h_icp[(size_t)j];
     OPE_CUDA_TRY(ctx, cudaMemcpyAsync(d_fine.p, by_frame.data(), (size_t)B * sizeof(ope_reg_result), cudaMemcpyHostToDevice, ctx->stream));
     OPE_CUDA_TRY(ctx, cudaMemcpyAsync(d_active.p, h_active.data(), B * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    OPE_TRY(fitness_batch_device(ctx, compacted.p + slab, d_ccounts.p + B, compacted.p + 2 * slab, d_ccounts.p + 2 * (size_t)B, kBCap, B, max_tgt,
+    OPE_TRY(fitness_batch_device(ctx, fine_pts + slab, d_ccounts.p + B, fine_pts + 2 * slab, d_ccounts.p + 2 * (size_t)B, kBCap, B, max_tgt,
                                  d_fine.p, d_active.p, d_fit.p));
     tm.mark();   // [10] fitness
     std::vector<ope_reg_result> h_coarse;

@@ -1445,16 +1445,60 @@ __global__ void __launch_bounds__(kSaciaThreads) sacia_smem_kernel(SaciaDev a, i
 // Frame-spanning SAC-IA scoring: blockIdx.x = hypothesis, blockIdx.y = frame. Every frame has its own target (tgt + f * stride,
 // counts[f] points, in shared memory), decision table (samples / picks + f * H * S) and feature neighbours (knn_idx + f * ns * k);
 // the source (the model's coarse sample) is shared. Same arithmetic as sacia_smem_kernel: same errors, bit for bit.
+// squared distance from a query to an axis-aligned box (0 inside); an empty box (lo = +inf, hi = -inf) gives +inf
+__device__ __forceinline__ float box_d2(const float4 lo, const float4 hi, float x, float y, float z) {
+  const float ex = fmaxf(fmaxf(lo.x - x, x - hi.x), 0.0f), ey = fmaxf(fmaxf(lo.y - y, y - hi.y), 0.0f), ez = fmaxf(fmaxf(lo.z - z, z - hi.z), 0.0f);
+  return ex * ex + ey * ey + ez * ez;
+}
+// Exact squared distance to the nearest of the nt8 target points in shared memory (padded with +inf to a multiple of 8), pruned by
+// the bounding boxes of groups of 8 consecutive points and of super-groups of 64: a box is skipped only when its distance,
+// compared with slack for the float rounding of the bound, exceeds the best distance found so far — so the result is the same
+// float an exhaustive scan returns. The super-group nearest to the query is scanned first to seed the bound.
+__device__ __forceinline__ float pruned_min_d2(const float4* __restrict__ tg, const float4* __restrict__ glo, const float4* __restrict__ ghi,
+                                               const float4* __restrict__ slo, const float4* __restrict__ shi, int n_super, int n_groups,
+                                               float x, float y, float z) {
+  float best = FLT_MAX;
+  auto scan_super = [&](int sg) {
+    const int g1 = min(n_groups, 8 * sg + 8);
+    for (int g = 8 * sg; g < g1; ++g) {
+      if (!(box_d2(glo[g], ghi[g], x, y, z) <= best * 1.0001f + 1e-30f)) continue;
+      float d2[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { const float4 t = tg[8 * g + u]; d2[u] = dist2(x, y, z, t.x, t.y, t.z); }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) best = d2[u] < best ? d2[u] : best;   // NaN / inf (padding, non-finite targets) never wins
+    }
+  };
+  int first = 0;
+  float first_lb = FLT_MAX;
+  for (int sg = 0; sg < n_super; ++sg) {
+    const float lb = box_d2(slo[sg], shi[sg], x, y, z);
+    if (lb < first_lb) { first_lb = lb; first = sg; }
+  }
+  scan_super(first);
+  for (int sg = 0; sg < n_super; ++sg) {
+    if (sg == first) continue;
+    if (!(box_d2(slo[sg], shi[sg], x, y, z) <= best * 1.0001f + 1e-30f)) continue;
+    scan_super(sg);
+  }
+  return best;
+}
+
 __global__ void __launch_bounds__(kSaciaThreads) sacia_smem_batch_kernel(SaciaBatch a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int f = blockIdx.y, h = blockIdx.x;
   if (!a.active[f]) return;
   const int nt = a.counts[f];
+  const int nt8 = (nt + 7) & ~7, n_groups = nt8 >> 3, n_super = (n_groups + 7) >> 3;
   float4* tg = reinterpret_cast<float4*>(smem_raw);
-  float* terms = reinterpret_cast<float*>(tg + nt);
+  float4* glo = tg + nt8;
+  float4* ghi = glo + n_groups;
+  float4* slo = ghi + n_groups;
+  float4* shi = slo + n_super;
+  float* terms = reinterpret_cast<float*>(shi + n_super);
   __shared__ Mat4 T;
   const float4* tgt = a.tgt + (size_t)f * a.stride;
-  for (int j = threadIdx.x; j < nt; j += kSaciaThreads) tg[j] = __ldg(tgt + j);
+  for (int j = threadIdx.x; j < nt8; j += kSaciaThreads) tg[j] = j < nt ? __ldg(tgt + j) : make_float4(INFINITY, INFINITY, INFINITY, 0.0f);
   if (threadIdx.x == 0) {
     double acc[16];
     for (int i = 0; i < 16; ++i) acc[i] = 0.0;
@@ -1479,6 +1523,28 @@ __global__ void __launch_bounds__(kSaciaThreads) sacia_smem_batch_kernel(SaciaBa
     for (int i = 0; i < 16; ++i) out[i] = M.m[i];
   }
   __syncthreads();
+  // boxes of the groups of 8 consecutive target points (the 1 cm sample arrives in voxel order: neighbours), then of 8 groups
+  for (int g = threadIdx.x; g < n_groups; g += kSaciaThreads) {
+    float4 lo = make_float4(INFINITY, INFINITY, INFINITY, 0.0f), hi = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.0f);
+    for (int u = 0; u < 8; ++u) {
+      const float4 t = tg[8 * g + u];
+      if (!finite3(t.x, t.y, t.z)) continue;
+      lo.x = fminf(lo.x, t.x); lo.y = fminf(lo.y, t.y); lo.z = fminf(lo.z, t.z);
+      hi.x = fmaxf(hi.x, t.x); hi.y = fmaxf(hi.y, t.y); hi.z = fmaxf(hi.z, t.z);
+    }
+    glo[g] = lo; ghi[g] = hi;
+  }
+  __syncthreads();
+  for (int sg = threadIdx.x; sg < n_super; sg += kSaciaThreads) {
+    float4 lo = make_float4(INFINITY, INFINITY, INFINITY, 0.0f), hi = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.0f);
+    for (int g = 8 * sg; g < min(n_groups, 8 * sg + 8); ++g) {
+      const float4 l = glo[g], u = ghi[g];
+      lo.x = fminf(lo.x, l.x); lo.y = fminf(lo.y, l.y); lo.z = fminf(lo.z, l.z);
+      hi.x = fmaxf(hi.x, u.x); hi.y = fmaxf(hi.y, u.y); hi.z = fmaxf(hi.z, u.z);
+    }
+    slo[sg] = lo; shi[sg] = hi;
+  }
+  __syncthreads();
   const Mat4 M = T;
   for (int i = threadIdx.x; i < a.ns; i += kSaciaThreads) {
     const float4 p = __ldg(a.src + i);
@@ -1486,13 +1552,8 @@ __global__ void __launch_bounds__(kSaciaThreads) sacia_smem_batch_kernel(SaciaBa
     xform_point(M, p.x, p.y, p.z, x, y, z);
     float term = 1.0f;
     if (finite3(x, y, z)) {
-      float best = FLT_MAX;   // only the DISTANCE of the nearest neighbour enters the score: ties need no index order
-#pragma unroll 4
-      for (int j = 0; j < nt; ++j) {
-        const float4 t = tg[j];
-        const float d2 = dist2(x, y, z, t.x, t.y, t.z);   // a NaN target never compares below
-        best = d2 < best ? d2 : best;
-      }
+      // only the DISTANCE of the nearest neighbour enters the score: ties need no index order
+      const float best = pruned_min_d2(tg, glo, ghi, slo, shi, n_super, n_groups, x, y, z);
       if (best <= a.threshold) term = best / a.threshold;
     }
     terms[i] = term;
@@ -2164,7 +2225,8 @@ int sacia_batch_device(ope_ctx* ctx, const SaciaBatch& a, int frames, int max_nt
   if (frames <= 0 || a.H <= 0) return OPE_OK;
   if (a.nr_samples < 1 || a.nr_samples > kSaciaMaxSamples || a.k_corr < 1 || a.k_corr > 16) return fail(ctx, OPE_ERR_INVALID, "bad SAC-IA parameters");
   if (max_nt > kSaciaSmemMaxTargets) return fail(ctx, OPE_ERR_CAPACITY, "batched SAC-IA: target larger than the shared-memory path");
-  const size_t bytes = (size_t)max_nt * sizeof(float4) + (size_t)a.ns * sizeof(float);
+  const size_t nt8 = ((size_t)max_nt + 7) & ~(size_t)7, ng = nt8 / 8, nsg = (ng + 7) / 8;
+  const size_t bytes = (nt8 + 2 * ng + 2 * nsg) * sizeof(float4) + (size_t)a.ns * sizeof(float);
   OPE_TRY(dyn_smem(ctx, (const void*)sacia_smem_batch_kernel, bytes));
   cudaEventRecord(ctx->kev[1][0], ctx->stream);
   sacia_smem_batch_kernel<<<dim3(a.H, frames), kSaciaThreads, bytes, ctx->stream>>>(a);

@@ -24,7 +24,7 @@ EXPORTS = [
     "ope_ctx_last_kernel_ms", "ope_cloud_invalidate", "ope_ctx_feature_knn_stats", "ope_ctx_model_cache_stats",
     "ope_cloud_upload", "ope_cloud_free", "ope_cloud_size", "ope_cloud_has_normals", "ope_cloud_download",
     "ope_cloud_select", "ope_cloud_transform", "ope_cloud_set_normals", "ope_cloud_append", "ope_register_point_clouds",
-    "ope_pass_through", "ope_euclidean_clusters", "ope_knn", "ope_knn_cloud", "ope_radius_cloud", "ope_depth_to_cloud", "ope_depth_to_cloud_batch",
+    "ope_pass_through", "ope_euclidean_clusters", "ope_plane_ransac", "ope_segment_objects_on_plane", "ope_segment_params_default", "ope_knn", "ope_knn_cloud", "ope_radius_cloud", "ope_depth_to_cloud", "ope_depth_to_cloud_batch",
     "ope_uniform_sample", "ope_uniform_sample_cloud", "ope_voxel_grid",
     "ope_normals_knn", "ope_fpfh", "ope_feature_knn",
     "ope_umeyama", "ope_point_to_plane", "ope_fitness", "ope_correspondences", "ope_icp_align", "ope_icp_align_fixed", "ope_sacia_align", "ope_sacia_align_sharded",
@@ -288,6 +288,29 @@ class Context:
         self._chk(lib().ope_euclidean_clusters(self.h, cloud.h, C.c_float(tolerance), int(min_size), int(max_size), labels.ctypes.data_as(i32p),
                                                C.byref(k)))
         return labels[:len(cloud)].copy(), k.value
+
+    def plane_ransac(self, cloud, **kw):
+        """pcl::SACSegmentation (plane): (found, coeff[4], inlier indices, iterations)"""
+        prm = T.SegmentParams()
+        lib().ope_segment_params_default(C.byref(prm))
+        _set(prm, kw)
+        coeff = (C.c_float * 4)()
+        idx = np.empty(max(len(cloud), 1), np.int32)
+        m, it, found = C.c_size_t(0), C.c_int32(0), C.c_int32(0)
+        self._chk(lib().ope_plane_ransac(self.h, cloud.h, C.byref(prm), coeff, idx.ctypes.data_as(i32p), C.byref(m), C.byref(it), C.byref(found)))
+        return bool(found.value), np.array(list(coeff), np.float32), idx[:m.value].copy(), it.value
+
+    def segment_objects_on_plane(self, cloud, **kw):
+        """getSegmentedObjectsOnPlane: (labels, n_clusters or -1, plane1, plane2, iterations)"""
+        prm = T.SegmentParams()
+        lib().ope_segment_params_default(C.byref(prm))
+        _set(prm, kw)
+        labels = np.empty(max(len(cloud), 1), np.int32)
+        p1, p2 = (C.c_float * 4)(), (C.c_float * 4)()
+        it = (C.c_int32 * 2)()
+        k = C.c_int32(0)
+        self._chk(lib().ope_segment_objects_on_plane(self.h, cloud.h, C.byref(prm), labels.ctypes.data_as(i32p), p1, p2, it, C.byref(k)))
+        return labels[:len(cloud)].copy(), k.value, np.array(list(p1), np.float32), np.array(list(p2), np.float32), (it[0], it[1])
 
     # ---- search ----
     def knn(self, tgt, qry, k):

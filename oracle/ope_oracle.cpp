@@ -17,6 +17,7 @@
 
 #include "orc_kdtree.h"
 #include "orc_linalg.h"
+#include "orc_segment.h"
 #include "orc_lm.h"
 
 using orc::KdTree;
@@ -934,6 +935,44 @@ int orc_euclidean_clusters(const float* pts, size_t n, size_t stride, float tole
   });
   for (size_t c = 0; c < clusters.size(); ++c) for (int32_t i : clusters[c]) labels[i] = (int32_t)c;
   return (int)clusters.size();
+}
+
+void orc_segment_params_default(ope_segment_params* p) {
+  std::memset(p, 0, sizeof(*p));
+  p->distance_threshold = 0.01; p->max_iterations = 50; p->probability = 0.99; p->hull_margin = 0.1;
+  p->cluster_tolerance = 0.05f; p->min_cluster_size = 300; p->max_cluster_size = 100000;
+}
+
+int orc_segment_objects_on_plane(const float* pts, size_t n, size_t stride, const ope_segment_params* prm, int32_t* labels, float plane1[4],
+                                 float plane2[4], int32_t iters[2]) {
+  if (!pts || !prm || !labels) return -1;
+  for (size_t i = 0; i < n; ++i) labels[i] = OPE_SEG_OUTSIDE_PRISM;
+  std::vector<int32_t> inl, prism;
+  float c1[4], c2[4];
+  int it1 = 0, it2 = 0;
+  if (!orc::planeSegment(pts, n, stride, prm->distance_threshold, prm->max_iterations, prm->probability, c1, inl, &it1)) return -1;
+  float rect[4][3];
+  orc::hullRectangle(pts, stride, inl, c1, prm->hull_margin, rect);
+  orc::prismSelect(pts, n, stride, rect, prism);
+  // cloudObjWithPlane: the prism's points, compacted (:206-213)
+  std::vector<float> sub(prism.size() * 3);
+  for (size_t j = 0; j < prism.size(); ++j) std::memcpy(&sub[3 * j], at(pts, stride, (size_t)prism[j]), 12);
+  std::vector<int32_t> inl2;
+  if (!orc::planeSegment(sub.data(), prism.size(), 3, prm->distance_threshold, prm->max_iterations, prm->probability, c2, inl2, &it2)) return -1;
+  for (int32_t j : prism) labels[j] = OPE_SEG_NO_CLUSTER;
+  std::vector<char> is_plane(prism.size(), 0);
+  for (int32_t j : inl2) { is_plane[(size_t)j] = 1; labels[prism[(size_t)j]] = OPE_SEG_PLANE; }
+  std::vector<float> rest;
+  std::vector<int32_t> rest_of;
+  for (size_t j = 0; j < prism.size(); ++j)
+    if (!is_plane[j]) { rest.insert(rest.end(), &sub[3 * j], &sub[3 * j] + 3); rest_of.push_back(prism[j]); }
+  std::vector<int32_t> cl(std::max<size_t>(rest_of.size(), 1));
+  const int k = orc_euclidean_clusters(rest.data(), rest_of.size(), 3, prm->cluster_tolerance, prm->min_cluster_size, prm->max_cluster_size, cl.data());
+  for (size_t j = 0; j < rest_of.size(); ++j) labels[rest_of[j]] = cl[j] >= 0 ? cl[j] : OPE_SEG_NO_CLUSTER;
+  if (plane1) std::memcpy(plane1, c1, 16);
+  if (plane2) std::memcpy(plane2, c2, 16);
+  if (iters) { iters[0] = it1; iters[1] = it2; }
+  return k < 0 ? 0 : k;
 }
 
 // DataGrabber::rgbd2Pcl / depthToMeter (D&L/src/datagrabber.cpp:9-62,121-174), Kinect / Astra branch

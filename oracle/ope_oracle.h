@@ -81,6 +81,15 @@ int64_t orc_pass_through(const float* pts, size_t n, size_t stride, int field, f
  * smaller first index) or -1 for points in no kept cluster; returns the number of clusters or -1. */
 int orc_euclidean_clusters(const float* pts, size_t n, size_t stride, float tolerance, int min_size, int max_size, int32_t* labels);
 
+/* ObjectSegmentationPlane::getSegmentedObjectsOnPlane (D&L/src/objectsegmentationplane.cpp:122-282) on an already pass-through-
+ * filtered cloud without NaN points: plane RANSAC (+ refit), prism over the padded hull rectangle, second plane, clusters of the
+ * rest. labels[i]: OPE_SEG_OUTSIDE_PRISM / OPE_SEG_PLANE (second plane's inlier) / OPE_SEG_NO_CLUSTER / cluster number (0 = largest).
+ * plane1 / plane2: the two refined plane equations; iters: RANSAC iterations of the two fits. Returns the number of clusters,
+ * -1 when no plane was found (the reference then hands the whole cloud on, :149-152,224-227). */
+int orc_segment_objects_on_plane(const float* pts, size_t n, size_t stride, const ope_segment_params* prm, int32_t* labels, float plane1[4],
+                                 float plane2[4], int32_t iters[2]);
+void orc_segment_params_default(ope_segment_params* p);
+
 /* ---- depth image -> cloud ---- */
 /* DataGrabber::rgbd2Pcl + depthToMeter, D&L/src/datagrabber.cpp:9-62,121-174: columns outer, rows inner; Z = depth / scale;
  * the reference passes (row, col) as (x, y): y_out = (row - cx) * Z / fx, x_out = (col - cy) * Z / fy (sic); points with

@@ -214,6 +214,19 @@ def euclidean_clusters(pts, tolerance=0.05, min_size=300, max_size=100000):
     return labels[:p.shape[0]].copy(), k
 
 
+def segment_objects_on_plane(pts, **kw):
+    """ObjectSegmentationPlane::getSegmentedObjectsOnPlane on a filtered cloud: (labels, n_clusters or -1, plane1, plane2, iterations)"""
+    p, pp, n, s = _pts(pts)
+    prm = T.SegmentParams()
+    lib().orc_segment_params_default(C.byref(prm))
+    _set(prm, kw)
+    labels = np.empty(max(p.shape[0], 1), np.int32)
+    p1, p2 = (C.c_float * 4)(), (C.c_float * 4)()
+    it = (C.c_int32 * 2)()
+    k = lib().orc_segment_objects_on_plane(pp, n, s, C.byref(prm), labels.ctypes.data_as(i32p), p1, p2, it)
+    return labels[:p.shape[0]].copy(), k, np.array(list(p1), np.float32), np.array(list(p2), np.float32), (it[0], it[1])
+
+
 def lm_set_route(householder):
     lib().orc_lm_set_route(int(bool(householder)))
 

@@ -680,3 +680,27 @@ def test_pass_through_and_euclidean_clusters(ctx, orc, synth, model):
         assert gk >= 1 and (gl[-40:] == -1).all()
     gl, gk = ctx.euclidean_clusters(ctx.upload(np.zeros((0, 3), np.float32)))
     assert gk == 0 and len(gl) == 0
+
+
+def test_plane_ransac_prism_and_object_clusters(ctx, orc, synth, model):
+    """The rest of getSegmentedObjectsOnPlane (D&L/src/objectsegmentationplane.cpp:122-282) on full synthetic frames: the table
+    plane by SACSegmentation with PCL's own sampling sequence, the polygonal prism over the padded hull rectangle, the second
+    plane, the clusters — per-point labels, both plane equations and both RANSAC iteration counts equal to the oracle's bit for
+    bit; and the largest non-wall cluster is the object (it contains the analytically known object pixels)."""
+    limits = (-0.5, 0.5, -0.5, 0.3, 0.5, 1.6)
+    for frame in (21, 22, 23):
+        cl, cloud, _ = synth.make_frame(model, frame)
+        c = ctx.upload(cloud.reshape(-1, 3))
+        filt = ctx.pass_through(c, limits)
+        sub = filt.download()
+        found, coeff, inl, it = ctx.plane_ransac(filt)
+        gl, gk, gp1, gp2, git = ctx.segment_objects_on_plane(filt)
+        ol, ok, op1, op2, oit = orc.segment_objects_on_plane(sub)
+        assert found and it == oit[0] and np.array_equal(coeff, op1)
+        assert gk == ok and gk >= 1 and git == oit
+        assert np.array_equal(gp1, op1) and np.array_equal(gp2, op2)
+        assert np.array_equal(gl, ol), (frame, int((gl != ol).sum()))
+        # the object: some cluster holds (nearly) all of the analytically segmented object points that survived the crop
+        keys = set(map(bytes, np.ascontiguousarray(cl)))
+        best = max(sum(bytes(p) in keys for p in np.ascontiguousarray(sub[gl == k])) for k in range(gk))
+        assert best > 0.5 * len(cl)

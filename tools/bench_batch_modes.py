@@ -45,4 +45,9 @@ for a, b in zip(res["fused"], res["workers"]):
              a.icp_state == b.icp_state and a.sacia_best_iteration == b.sacia_best_iteration and a.n_src_fine == b.n_src_fine and
              a.n_tgt_fine == b.n_tgt_fine and abs(a.fitness - b.fitness) < 1e-12 and a.align_strength == b.align_strength)
 out["bit_identical_frames"] = same
+T = cuda_lib.T
+errs = [synth.pose_error(T.mat4(a.final_pose), T.mat4(b.final_pose)) for a, b in zip(res["fused"], res["workers"])]
+out["max_rot_rad"] = max(e[0] for e in errs); out["max_trans_m"] = max(e[1] for e in errs)
+out["same_icp_state_and_iterations"] = sum((a.icp_iterations, a.icp_state, a.icp_converged) == (b.icp_iterations, b.icp_state, b.icp_converged)
+                                           for a, b in zip(res["fused"], res["workers"]))
 print(json.dumps(out))
