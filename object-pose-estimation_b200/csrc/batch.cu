@@ -364,7 +364,8 @@ int download(ope_ctx* ctx, const T* d, size_t n, std::vector<T>& h) {
 // caller runs it through the per-frame path). d_model: the full-resolution model; sp / d_fs: its coarse sample (with normals)
 // and descriptors; rigid: the dense Umeyama of the model onto itself (what every first frame computes, :425-436).
 int pose_batch_chunk(ope_ctx* ctx, const ope_pose_params& P, const ope_cloud* d_model, const ope_cloud* sp, const float* d_fs, const Mat4& rigid,
-                     const ope_frame_input* frames, size_t n_frames, const ope_rng_table* tables, ope_pose_result* results, char* done) {
+                     const ope_frame_input* frames, size_t n_frames, const ope_rng_table* tables, ope_pose_result* results, char* done,
+                     const std::atomic<size_t>* tables_ready, size_t tables_needed) {
   const int B = (int)n_frames;
   const int H = P.sacia.max_iterations, S = P.sacia.nr_samples, K = P.sacia.k_correspondences;
   for (int i = 0; i < B; ++i) done[i] = 0;
@@ -376,7 +377,7 @@ int pose_batch_chunk(ope_ctx* ctx, const ope_pose_params& P, const ope_cloud* d_
   for (int i = 0; i < B; ++i) {
     const ope_frame_input& in = frames[i];
     const size_t n = in.points ? in.n : (in.cloud ? ((const ope_cloud*)in.cloud)->n : 0);
-    if (n == 0 || n > 0x3fffffff || (tables && (tables[i].n_hypotheses != H || tables[i].nr_samples != S))) h_active[(size_t)i] = 0;
+    if (n == 0 || n > 0x3fffffff) h_active[(size_t)i] = 0;
     h_off[(size_t)i] = (int)total; h_cnt[(size_t)i] = h_active[(size_t)i] ? (int)n : 0;
     total += (size_t)h_cnt[(size_t)i];
   }
@@ -470,6 +471,12 @@ int pose_batch_chunk(ope_ctx* ctx, const ope_pose_params& P, const ope_cloud* d_
     OPE_TRY(stage_reserve(ctx, 2 * tb * sizeof(int), &stage));
     int* hs = (int*)stage;
     int* hp = hs + tb;
+    // the tables of this chunk may still be on their way (drawn by a helper thread while the device worked)
+    if (tables_ready) while (tables_ready->load(std::memory_order_acquire) < tables_needed) sched_yield();
+    for (int i = 0; i < B; ++i) {
+      if (h_active[(size_t)i] && (tables[i].n_hypotheses != H || tables[i].nr_samples != S || !tables[i].samples || !tables[i].picks))
+        return fail(ctx, OPE_ERR_INVALID, "decision table of frame %d does not match the SAC-IA parameters", i);
+    }
     for (int i = 0; i < B; ++i) {
       int* s = hs + (size_t)i * H * S;
       int* p = hp + (size_t)i * H * S;
@@ -488,6 +495,23 @@ int pose_batch_chunk(ope_ctx* ctx, const ope_pose_params& P, const ope_cloud* d_
   sb.src = sp->pts; sb.ns = ns; sb.tgt = sampled.p; sb.counts = d_counts.p; sb.stride = kBCap;
   sb.nr_samples = S; sb.k_corr = K; sb.H = H; sb.samples = d_samples.p; sb.picks = d_picks.p; sb.knn_idx = d_knn.p; sb.active = d_active.p;
   sb.threshold = (float)P.sacia.max_correspondence_distance; sb.errors = errors.p; sb.transforms = transforms.p;
+  {
+    const char* me = std::getenv("OPE_BATCH_MORTON");
+    if (!(me && std::atoi(me) == 0)) {   // the distance scan reads a Morton-ordered copy of the target (slot [0] of the compaction arrays is free)
+      morton_sort_batch_kernel<<<B, kBThreads, 0, ctx->stream>>>(sampled.p, normals.p, d_counts.p, d_active.p, B, compacted.p, cnormals.p);
+      OPE_TRY(check_launch(ctx, "morton_sort_batch_kernel"));
+      sb.tgt_scan = compacted.p;
+    }
+  }
+  Scratch<unsigned> d_best(ctx);
+  OPE_TRY(d_best.alloc(B));
+  {
+    std::vector<unsigned> inf((size_t)B, 0x7f800000u);
+    OPE_CUDA_TRY(ctx, cudaMemcpyAsync(d_best.p, inf.data(), (size_t)B * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+    OPE_CUDA_TRY(ctx, stream_sync(ctx));
+  }
+  sb.best_bits = d_best.p;
+  { const char* e = std::getenv("OPE_SACIA_EARLY_EXIT"); sb.early_exit = !(e && std::atoi(e) == 0); }
   OPE_TRY(sacia_batch_device(ctx, sb, B, max_tp1, d_coarse.p));
   tm.mark();   // [5] SAC-IA
   // ---- estimateFinePose (:161-379): the model under the coarse pose sampled at the fine leaf, never materialised ----

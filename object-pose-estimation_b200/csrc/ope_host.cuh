@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <sched.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -262,13 +263,16 @@ int sacia_device(ope_ctx* ctx, const ope_cloud* src, const float* d_fsrc, const 
 struct SaciaBatch {
   const float4* src; int ns;                               // the shared source (the model's coarse sample)
   const float4* tgt; const int* counts; int stride;        // frame f: tgt + f * stride, counts[f] points
+  const float4* tgt_scan;                                  // the same points in any order (null: tgt): what the distance scan reads
   int nr_samples, k_corr, H;
   const int* samples; const int* picks;                    // frame f: + f * H * nr_samples
   const int* knn_idx;                                      // frame f: + f * ns * k_corr
   const int* active;                                       // per frame: 0 = skip
   float threshold;
-  float* errors;                                           // frames * H
+  float* errors;                                           // frames * H (+inf: stopped early, cannot be the winner)
   float* transforms;                                       // frames * H * 16
+  unsigned* best_bits;                                     // per frame: float bits of the lowest complete error so far (init 0x7f800000)
+  int early_exit;                                          // 1: stop a hypothesis whose partial error already exceeds that
 };
 struct IcpBatchFrame { const float4* src_pts; const float4* src_nrm; int n_src; const float4* tgt_pts; const float4* tgt_nrm; int n_tgt; };
 int normals_smem_batch(ope_ctx* ctx, const float4* pts, const int* d_counts, int stride, int clouds, int max_n, int k, const float vp[3],
@@ -285,7 +289,8 @@ int icp_small_batch_device(ope_ctx* ctx, const ope_icp_params& prm, const IcpBat
 
 // ---- batch.cu: one chunk of frames of ope_pose_batch through the frame-spanning launches; done[i] = 1 where frame i was finished ----
 int pose_batch_chunk(ope_ctx* ctx, const ope_pose_params& P, const ope_cloud* d_model, const ope_cloud* sp, const float* d_fs, const Mat4& rigid,
-                     const ope_frame_input* frames, size_t n_frames, const ope_rng_table* tables, ope_pose_result* results, char* done);
+                     const ope_frame_input* frames, size_t n_frames, const ope_rng_table* tables, ope_pose_result* results, char* done,
+                     const std::atomic<size_t>* tables_ready, size_t tables_needed);
 
 // ---- p2plane.cu: TransformationEstimationPointToPlaneLLS / ...PointToPlane (Levenberg-Marquardt) ----
 int point_to_plane_device(ope_ctx* ctx, const float4* src, const float4* tgt, const float4* tgt_n, const int* d_is, const int* d_it,

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <memory>
 #include <thread>
 
 #include "ope_host.cuh"
@@ -364,23 +365,37 @@ int ope_pose_batch(ope_ctx* ctx, const ope_pose_params* prm, const float* model_
     OPE_TRY(fpfh_device(ctx, sp.c, P.fpfh_radius, &fs.p, nullptr));
   }
   // ---- SAC-IA decision tables: replayed, or drawn here in frame order from libc rand() ----
+  // Drawing is inherently serial (one process-wide rand() stream, consumed exactly as a loop over fresh PoseEstimators would) and
+  // costs ~0.1 ms per frame on the host, so a helper thread draws ahead while the device works: `tables_ready` counts the frames
+  // whose table is complete, the chunk loop waits for the ones it needs right before it uploads them.
   std::vector<int32_t> draw_s, draw_p;
   std::vector<ope_rng_table> drawn;
+  std::atomic<size_t> tables_ready{n_frames};
+  std::atomic<int> draw_rc{OPE_OK};
+  std::thread drawer;
+  struct JoinDrawer { std::thread& t; ~JoinDrawer() { if (t.joinable()) t.join(); } } join_drawer{drawer};
   if (!tables) {
     const int H = P.sacia.max_iterations, S = P.sacia.nr_samples, K = P.sacia.k_correspondences;
     if (H < 1 || S < 1 || K < 1) return fail(ctx, OPE_ERR_INVALID, "bad SAC-IA parameters");
-    std::vector<float> xyz(3 * std::max<size_t>(sp.c->n, 1));
-    OPE_TRY(ope_cloud_download(ctx, sp.c, xyz.data(), nullptr));
+    auto xyz = std::make_shared<std::vector<float>>(3 * std::max<size_t>(sp.c->n, 1));
+    OPE_TRY(ope_cloud_download(ctx, sp.c, xyz->data(), nullptr));
     draw_s.resize(n_frames * (size_t)H * S); draw_p.resize(n_frames * (size_t)H * S);
     drawn.resize(n_frames);
-    for (size_t f = 0; f < n_frames; ++f) {
-      float msd = P.sacia.min_sample_distance;   // min_sample_distance_ halves within one align() only
-      int32_t* s = draw_s.data() + f * (size_t)H * S;
-      int32_t* p = draw_p.data() + f * (size_t)H * S;
-      const int rc = ope_sacia_draw(xyz.data(), sp.c->n, 12, H, S, K, &msd, s, p);
-      if (rc != OPE_OK) return fail(ctx, rc, "selectSamples failed");
-      drawn[f] = ope_rng_table{H, S, s, p};
-    }
+    tables_ready.store(0);
+    const size_t n_sp = sp.c->n;
+    const float msd0 = P.sacia.min_sample_distance;
+    auto draw_all = [&, xyz, H, S, K, n_sp, msd0]() {
+      for (size_t f = 0; f < n_frames; ++f) {
+        float msd = msd0;   // min_sample_distance_ halves within one align() only
+        int32_t* s = draw_s.data() + f * (size_t)H * S;
+        int32_t* p = draw_p.data() + f * (size_t)H * S;
+        const int rc = ope_sacia_draw(xyz->data(), n_sp, 12, H, S, K, &msd, s, p);
+        if (rc != OPE_OK) { draw_rc.store(rc); tables_ready.store(n_frames); return; }
+        drawn[f] = ope_rng_table{H, S, s, p};
+        tables_ready.store(f + 1, std::memory_order_release);
+      }
+    };
+    try { drawer = std::thread(draw_all); } catch (...) { draw_all(); }   // no thread available: draw here, as before
     tables = drawn.data();
   }
   // ---- frame-spanning launches (batch.cu): one launch per stage for a whole chunk of frames ----
@@ -394,11 +409,15 @@ int ope_pose_batch(ope_ctx* ctx, const ope_pose_params* prm, const float* model_
       const size_t chunk = (size_t)std::max(1, ce ? std::atoi(ce) : 296);   // two blocks per SM-sized waves of one-block-per-frame kernels
       for (size_t f0 = 0; f0 < n_frames; f0 += chunk) {
         const size_t nf = std::min(chunk, n_frames - f0);
-        OPE_TRY(pose_batch_chunk(ctx, P, model.c, sp.c, fs.p, rigid, frames + f0, nf, tables + f0, results + f0, done.data() + f0));
+        OPE_TRY(pose_batch_chunk(ctx, P, model.c, sp.c, fs.p, rigid, frames + f0, nf, tables + f0, results + f0, done.data() + f0, &tables_ready,
+                                 f0 + nf));
+        if (draw_rc.load() != OPE_OK) return fail(ctx, draw_rc.load(), "selectSamples failed");
       }
       if (status) for (size_t f = 0; f < n_frames; ++f) if (done[f]) status[f] = OPE_OK;
     }
   }
+  if (drawer.joinable()) drawer.join();
+  if (draw_rc.load() != OPE_OK) return fail(ctx, draw_rc.load(), "selectSamples failed");
   // ---- whatever the fast path did not take (tiny / empty / oversized clusters): the per-frame path, worker threads ----
   std::vector<ope_frame_input> rest_frames;
   std::vector<ope_rng_table> rest_tables;

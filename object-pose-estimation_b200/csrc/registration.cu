@@ -1486,7 +1486,8 @@ __device__ __forceinline__ float pruned_min_d2(const float4* __restrict__ tg, co
 
 __global__ void __launch_bounds__(kSaciaThreads) sacia_smem_batch_kernel(SaciaBatch a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int f = blockIdx.y, h = blockIdx.x;
+  // blockIdx.x = frame (fastest): the hypotheses of one frame run one after the other, so the bound below is known early
+  const int f = blockIdx.x, h = blockIdx.y;
   if (!a.active[f]) return;
   const int nt = a.counts[f];
   const int nt8 = (nt + 7) & ~7, n_groups = nt8 >> 3, n_super = (n_groups + 7) >> 3;
@@ -1498,7 +1499,8 @@ __global__ void __launch_bounds__(kSaciaThreads) sacia_smem_batch_kernel(SaciaBa
   float* terms = reinterpret_cast<float*>(shi + n_super);
   __shared__ Mat4 T;
   const float4* tgt = a.tgt + (size_t)f * a.stride;
-  for (int j = threadIdx.x; j < nt8; j += kSaciaThreads) tg[j] = j < nt ? __ldg(tgt + j) : make_float4(INFINITY, INFINITY, INFINITY, 0.0f);
+  const float4* scan = (a.tgt_scan ? a.tgt_scan : a.tgt) + (size_t)f * a.stride;   // a spatially sorted copy makes the boxes tight
+  for (int j = threadIdx.x; j < nt8; j += kSaciaThreads) tg[j] = j < nt ? __ldg(scan + j) : make_float4(INFINITY, INFINITY, INFINITY, 0.0f);
   if (threadIdx.x == 0) {
     double acc[16];
     for (int i = 0; i < 16; ++i) acc[i] = 0.0;
@@ -1546,23 +1548,44 @@ __global__ void __launch_bounds__(kSaciaThreads) sacia_smem_batch_kernel(SaciaBa
   }
   __syncthreads();
   const Mat4 M = T;
-  for (int i = threadIdx.x; i < a.ns; i += kSaciaThreads) {
-    const float4 p = __ldg(a.src + i);
-    float x, y, z;
-    xform_point(M, p.x, p.y, p.z, x, y, z);
-    float term = 1.0f;
-    if (finite3(x, y, z)) {
-      // only the DISTANCE of the nearest neighbour enters the score: ties need no index order
-      const float best = pruned_min_d2(tg, glo, ghi, slo, shi, n_super, n_groups, x, y, z);
-      if (best <= a.threshold) term = best / a.threshold;
+  // The error is the float sum of the terms IN POINT ORDER (bit-exact with the reference's serial `error += ...`); the terms are
+  // >= 0, so every prefix of that sum is a lower bound of the total. After each chunk of kSaciaThreads points thread 0 extends
+  // the prefix and compares it with the lowest COMPLETE error any hypothesis of this frame has published so far: once the prefix
+  // is strictly larger, this hypothesis cannot be the first-lowest one and the block stops (its error is reported as +inf).
+  // Which hypotheses stop early depends on timing; the winner, its error and its transform do not.
+  __shared__ float s_error;
+  __shared__ int s_stop;
+  if (threadIdx.x == 0) { s_error = 0.0f; s_stop = 0; }
+  unsigned* frame_best = a.best_bits + f;
+  for (int base = 0; base < a.ns; base += kSaciaThreads) {
+    const int i = base + (int)threadIdx.x;
+    if (i < a.ns) {
+      const float4 p = __ldg(a.src + i);
+      float x, y, z;
+      xform_point(M, p.x, p.y, p.z, x, y, z);
+      float term = 1.0f;
+      if (finite3(x, y, z)) {
+        // only the DISTANCE of the nearest neighbour enters the score: ties need no index order
+        const float best = pruned_min_d2(tg, glo, ghi, slo, shi, n_super, n_groups, x, y, z);
+        if (best <= a.threshold) term = best / a.threshold;
+      }
+      terms[i] = term;
     }
-    terms[i] = term;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float error = s_error;
+      const int e1 = min(a.ns, base + kSaciaThreads);
+      for (int j = base; j < e1; ++j) error += terms[j];
+      s_error = error;
+      if (a.early_exit && error > __uint_as_float(*(volatile unsigned*)frame_best)) s_stop = 1;
+    }
+    __syncthreads();
+    if (s_stop) break;
   }
-  __syncthreads();
   if (threadIdx.x == 0) {
-    float error = 0.0f;
-    for (int i = 0; i < a.ns; ++i) error += terms[i];
+    const float error = s_stop ? INFINITY : s_error;
     a.errors[(size_t)f * a.H + h] = error;
+    if (!s_stop) atomicMin(frame_best, __float_as_uint(error));   // errors are >= 0: the bit pattern orders like the value
   }
 }
 // first strictly-lower error wins, per frame (one thread per frame)
@@ -2229,7 +2252,7 @@ int sacia_batch_device(ope_ctx* ctx, const SaciaBatch& a, int frames, int max_nt
   const size_t bytes = (nt8 + 2 * ng + 2 * nsg) * sizeof(float4) + (size_t)a.ns * sizeof(float);
   OPE_TRY(dyn_smem(ctx, (const void*)sacia_smem_batch_kernel, bytes));
   cudaEventRecord(ctx->kev[1][0], ctx->stream);
-  sacia_smem_batch_kernel<<<dim3(a.H, frames), kSaciaThreads, bytes, ctx->stream>>>(a);
+  sacia_smem_batch_kernel<<<dim3(frames, a.H), kSaciaThreads, bytes, ctx->stream>>>(a);
   cudaEventRecord(ctx->kev[1][1], ctx->stream);
   ctx->kev_valid[1] = true;
   OPE_TRY(check_launch(ctx, "sacia_smem_batch_kernel"));
@@ -2254,7 +2277,8 @@ bool icp_small_batch_applicable(const ope_icp_params& prm, size_t n_src, size_t 
          n_tgt <= (size_t)kIcpSmemMaxTargets && n_src > 0 && n_src <= (size_t)kIcpSmallMaxBlocks * kIcpSmallThreads &&
          prm.k_search >= 1 && prm.k_search <= kSlabSlots;
 }
-int icp_small_batch_device(ope_ctx* ctx, const ope_icp_params& prm, const IcpBatchFrame* frames, int n_frames, ope_reg_result* d_results) {
+template <int THREADS>
+static int icp_small_batch_launch(ope_ctx* ctx, const ope_icp_params& prm, const IcpBatchFrame* frames, int n_frames, ope_reg_result* d_results) {
   if (n_frames <= 0) return OPE_OK;
   std::vector<IcpDev> descs((size_t)n_frames);
   std::vector<int2> map;
@@ -2263,7 +2287,7 @@ int icp_small_batch_device(ope_ctx* ctx, const ope_icp_params& prm, const IcpBat
     if (!icp_small_batch_applicable(prm, (size_t)frames[i].n_src, (size_t)frames[i].n_tgt)) return fail(ctx, OPE_ERR_UNSUPPORTED, "alignment %d does not fit the small-cloud ICP kernel", i);
     max_nt = std::max(max_nt, (size_t)frames[i].n_tgt);
     total_src += (size_t)frames[i].n_src;
-    total_blocks += ((size_t)frames[i].n_src + kIcpSmallThreads - 1) / kIcpSmallThreads;
+    total_blocks += ((size_t)frames[i].n_src + THREADS - 1) / THREADS;
   }
   Scratch<int> match(ctx);
   Scratch<float> d2(ctx);
@@ -2298,7 +2322,7 @@ int icp_small_batch_device(ope_ctx* ctx, const ope_icp_params& prm, const IcpBat
     a.rel_mse_thr = prm.euclidean_fitness_epsilon; a.abs_mse_thr = prm.mse_threshold_absolute;
     a.max_similar = prm.max_iterations_similar_transforms; a.fail_after_max = prm.failure_after_max_iterations;
     a.guess = mat4_identity();
-    const int nblk = (f.n_src + kIcpSmallThreads - 1) / kIcpSmallThreads;
+    const int nblk = (f.n_src + THREADS - 1) / THREADS;
     a.corr_match = match.p + so; a.corr_d2 = d2.p + so;
     a.partials = partials.p + 2 * bo * kIcpAcc;
     a.barrier = bars.p + i;
@@ -2313,18 +2337,28 @@ int icp_small_batch_device(ope_ctx* ctx, const ope_icp_params& prm, const IcpBat
   OPE_CUDA_TRY(ctx, cudaMemcpyAsync(d_map.p, map.data(), map.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
   OPE_CUDA_TRY(ctx, ope::stream_sync(ctx));   // descs / map live on this stack frame
   const size_t nt8 = (max_nt + 7) & ~(size_t)7;
-  const size_t smem_bytes = ((sizeof(IcpSmallSmem<kIcpSmallThreads>) + 15) & ~(size_t)15) + nt8 * sizeof(float4) + (nt8 / 8) * 2 * sizeof(float4) +
-                            (size_t)kSlabSlots * kIcpSmallThreads * sizeof(float2);
-  const void* kernel = (const void*)icp_small_batch_kernel<kIcpSmallThreads>;
+  const size_t smem_bytes = ((sizeof(IcpSmallSmem<THREADS>) + 15) & ~(size_t)15) + nt8 * sizeof(float4) + (nt8 / 8) * 2 * sizeof(float4) +
+                            (size_t)kSlabSlots * THREADS * sizeof(float2);
+  const void* kernel = (const void*)icp_small_batch_kernel<THREADS>;
   OPE_TRY(dyn_smem(ctx, kernel, smem_bytes));
   int per_sm = 0;
-  OPE_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kIcpSmallThreads, smem_bytes));
+  OPE_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, THREADS, smem_bytes));
   if ((size_t)per_sm * ctx->sm_count < (size_t)kIcpSmallMaxBlocks) return fail(ctx, OPE_ERR_CUDA, "icp_small_batch_kernel: one alignment's blocks cannot be co-resident");
   cudaEventRecord(ctx->kev[0][0], ctx->stream);
-  icp_small_batch_kernel<kIcpSmallThreads><<<(unsigned)total_blocks, kIcpSmallThreads, smem_bytes, ctx->stream>>>(d_descs.p, d_map.p, bars.p + n_frames);
+  icp_small_batch_kernel<THREADS><<<(unsigned)total_blocks, THREADS, smem_bytes, ctx->stream>>>(d_descs.p, d_map.p, bars.p + n_frames);
   cudaEventRecord(ctx->kev[0][1], ctx->stream);
   ctx->kev_valid[0] = true;
   return check_launch(ctx, "icp_small_batch_kernel");
+}
+
+// Threads per block of the frame-spanning ICP launch: a block keeps its alignment's target (points + group boxes) in shared memory
+// next to 256 bytes of candidate slots per thread, so wider blocks share one target copy among more warps: 2 x 256 threads fit an
+// SM where 3 x 128 do (16 resident warps instead of 12 of this latency-bound kernel). OPE_ICP_BATCH_THREADS=128 selects the narrow form.
+int icp_small_batch_device(ope_ctx* ctx, const ope_icp_params& prm, const IcpBatchFrame* frames, int n_frames, ope_reg_result* d_results) {
+  const char* e = std::getenv("OPE_ICP_BATCH_THREADS");
+  const int t = e ? std::atoi(e) : 256;
+  if (t == 128) return icp_small_batch_launch<128>(ctx, prm, frames, n_frames, d_results);
+  return icp_small_batch_launch<256>(ctx, prm, frames, n_frames, d_results);
 }
 
 }  // namespace ope
