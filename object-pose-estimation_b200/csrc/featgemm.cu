@@ -18,7 +18,7 @@
 //   3. featgemm_rerank_kernel recomputes the exact left-to-right float32 distance of every nominated target, ranks by
 //      (distance, index), and PROVES completeness: every target that was not nominated in a candidate list has an approximate
 //      distance >= that list's worst entry, hence an exact distance >= it - eps; if that does not exceed the k-th exact
-//      distance the query is flagged and answered by the exact kernel instead (features.cu). eps bounds the bf16-split
+//      distance the query is flagged and answered by the exact kernel instead (features.cu). eps (derived at its use) bounds the bf16-split
 //      and accumulation error: 1e-4 * ||q|| * max||t|| + 1e-2.
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -122,6 +122,12 @@ __global__ void featgemm_prep_kernel(const float* __restrict__ f, int n, int n_p
     return;
   }
   float s = 0.0f;
+  bool finite_row = true;
+  for (int c = 0; c < dim; ++c) finite_row = finite_row && isfinite(__ldg(f + (size_t)r * dim + c));
+  if (is_target && !finite_row) {   // a non-finite target row has no finite distance to anything: like padding, never nominated
+    o[3 * dim] = __float2bfloat16(-1e30f);
+    return;
+  }
   for (int c = 0; c < dim; ++c) {
     const float x = __ldg(f + (size_t)r * dim + c);
     const __nv_bfloat16 hi = __float2bfloat16(x);
@@ -305,7 +311,14 @@ __global__ void featgemm_rerank_kernel(const float* __restrict__ ftgt, int nt, c
   // completeness proof: in a split that had more real targets than candidate slots, everything that was not nominated has an
   // approximate distance >= the split's worst nominated one
   const float qn2 = qnorm2[qi];
-  const float eps = 1e-4f * sqrtf(qn2) * sqrtf(__uint_as_float(*max_tnorm2_bits)) + 1e-2f;
+  // Error budget of the approximate score s = q.t - |t|^2/2, hence of d = |q|^2 - 2s (Cauchy-Schwarz over the dim products):
+  //   operands: x = hi + lo with |x - hi - lo| <= 2^-17 |x| (two bf16 roundings), and the product q_lo * t_lo is dropped:
+  //             |delta s| <= (2 * 2^-17 + 2^-16) |q||t| = 2^-15 |q||t| = 3.1e-5 |q||t|
+  //   tensor-core accumulation of K = 128 float terms, possibly truncating: <= 128 * 2^-23 * 3 |q||t| = 4.6e-5 |q||t|
+  //   norm columns: 3-way bf16 split of -|t|^2/2, residual 2^-25 relative: negligible
+  // => |delta d| <= 2 * 7.7e-5 |q||t| = 1.5e-4 |q||t|. The proof uses 4e-4 |q| max|t| (2.6x that) plus an absolute 1e-2 for
+  // tiny norms; a query whose margin is thinner falls back to the exact kernel, which costs time, never correctness.
+  const float eps = 4e-4f * sqrtf(qn2) * sqrtf(__uint_as_float(*max_tnorm2_bits)) + 1e-2f;
   bool unsafe = false;
   for (int s = 0; s < n_lists; ++s) {
     // a list whose worst entry is not a real, finite candidate was never full: everything finite in its column group was

@@ -704,3 +704,21 @@ def test_plane_ransac_prism_and_object_clusters(ctx, orc, synth, model):
         keys = set(map(bytes, np.ascontiguousarray(cl)))
         best = max(sum(bytes(p) in keys for p in np.ascontiguousarray(sub[gl == k])) for k in range(gk))
         assert best > 0.5 * len(cl)
+
+
+def test_feature_knn_gemm_near_ties_at_large_norms(ctx, monkeypatch):
+    """the completeness proof of the tcgen05 path must hold where its error budget is tightest — descriptors of large
+    norm (|q||t| ~ 3e4, the FPFH maximum) whose best candidates are separated by less than the tensor-core rounding: the result must
+    still equal the exact kernel's, by proof or by fallback."""
+    rng = np.random.default_rng(9)
+    base = np.zeros((1, 33), np.float32)
+    base[0, [3, 14, 25]] = 100.0                                  # all mass in one bin per sub-histogram: |x| = 173
+    ft = np.repeat(base, 3000, 0) + rng.normal(0, 0.02, (3000, 33)).astype(np.float32)   # 3000 targets within ~0.1 of each other
+    fq = np.repeat(base, 400, 0) + rng.normal(0, 0.02, (400, 33)).astype(np.float32)
+    ft[7] = np.inf                                                # a non-finite target row: never a neighbour
+    monkeypatch.setenv("OPE_FEATURE_KNN", "exact")
+    ei, ed = ctx.feature_knn(ft, fq, 5)
+    monkeypatch.setenv("OPE_FEATURE_KNN", "gemm")
+    gi, gd = ctx.feature_knn(ft, fq, 5)
+    assert np.array_equal(gi, ei) and np.array_equal(gd, ed)
+    assert not (gi == 7).any()
