@@ -212,9 +212,10 @@ int ope_pose_estimate_final_device(ope_pose_tracker* t, ope_cloud** source, cons
     OPE_TRY(fpfh_device(ctx, tp.c, P.fpfh_radius, &ft.p, nullptr));
     tm.lap(2);
     res->n_src_coarse = (int32_t)spc->n; res->n_tgt_coarse = (int32_t)tp.c->n;
-    if (t->alignedSource) { ope_cloud_free(ctx, t->alignedSource); t->alignedSource = nullptr; }
+    // the tracker's state changes only once the stage has succeeded: a failing call leaves alignedSource as it was
+    ope_cloud* fresh = nullptr;
     if ((int)tp.c->n < P.min_target_features) {
-      OPE_TRY(clone_cloud(ctx, p_source, &t->alignedSource));  // :41
+      OPE_TRY(clone_cloud(ctx, p_source, &fresh));  // :41
     } else {
       ope_reg_result rr;
       int src_rc = sacia_device(ctx, spc, fsp, tp.c, ft.p, P.sacia, table, nullptr, &rr, nullptr);
@@ -223,12 +224,15 @@ int ope_pose_estimate_final_device(ope_pose_tracker* t, ope_cloud** source, cons
       tm.lap(3);
       std::memcpy(coarse.m, rr.T, sizeof(coarse.m));
       res->sacia_best_iteration = rr.best_iteration; res->sacia_best_error = rr.best_error;
-      OPE_TRY(cloud_alloc(ctx, p_source->n, false, &t->alignedSource));
+      OPE_TRY(cloud_alloc(ctx, p_source->n, false, &fresh));
       ope_cloud view = *p_source;  // transform points only
       view.normals = nullptr; view.grids.clear();
-      OPE_TRY(transform_device(ctx, &view, coarse, t->alignedSource));  // :67-70
+      const int trc = transform_device(ctx, &view, coarse, fresh);  // :67-70
+      if (trc != OPE_OK) { ope_cloud_free(ctx, fresh); return trc; }
       tm.lap(6);
     }
+    if (t->alignedSource) ope_cloud_free(ctx, t->alignedSource);
+    t->alignedSource = fresh;
   }
   // ---- FINE: estimateFinePose, :161-379 ----
   if (nt != 0 && t->alignedSource) {
@@ -263,9 +267,10 @@ int ope_pose_estimate_final_device(ope_pose_tracker* t, ope_cloud** source, cons
     OPE_TRY(umeyama_device(ctx, t->cloudModel->pts, p_source->pts, nullptr, nullptr, t->cloudModel->n, rigid.m));
   }
   const Mat4 final_pose = mat4_mul(rigid, pose);  // :439
-  if (t->alignedSource) {  // *p_sourceCloud = *alignedSource, :441
+  {  // *p_sourceCloud = *alignedSource, :441 — before any alignment the member is an EMPTY cloud, and so becomes the source
     ope_cloud* copy = nullptr;
-    OPE_TRY(clone_cloud(ctx, t->alignedSource, &copy));
+    if (t->alignedSource) OPE_TRY(clone_cloud(ctx, t->alignedSource, &copy));
+    else OPE_TRY(cloud_alloc(ctx, 0, false, &copy));
     ope_cloud_free(ctx, p_source);
     *source = copy;
   }
