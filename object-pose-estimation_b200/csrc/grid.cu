@@ -737,6 +737,10 @@ void ope_ctx_destroy(ope_ctx* ctx) {
   cudaSetDevice(ctx->device);
   ope::stream_sync(ctx);
   for (auto& e : ctx->model_cache) { if (e.sp) ope_cloud_free(ctx, e.sp); ope::dfree(ctx, e.fs); }
+  if (ctx->batch_model.model) ope_cloud_free(ctx, ctx->batch_model.model);
+  if (ctx->batch_model.sp) ope_cloud_free(ctx, ctx->batch_model.sp);
+  ope::dfree(ctx, ctx->batch_model.fs);
+  ctx->batch_model = BatchModelCache();
   ctx->model_cache.clear();
   for (int w = 0; w < 3; ++w)
     for (int j = 0; j < 2; ++j) if (ctx->kev[w][j]) cudaEventDestroy(ctx->kev[w][j]);

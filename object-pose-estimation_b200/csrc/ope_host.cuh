@@ -29,6 +29,18 @@ struct ModelCacheEntry {
   unsigned long long stamp = 0;
 };
 
+// ope_pose_batch: the device copy of the model it was last called with and everything frame-invariant computed from it
+struct BatchModelCache {
+  unsigned long long hash = 0;   // of the caller's host buffer
+  size_t n = 0;
+  float leaf = 0, radius = 0;
+  int k = 0;
+  ope_cloud* model = nullptr;    // owned: full-resolution model
+  ope_cloud* sp = nullptr;       // owned: its coarse sample with normals
+  float* fs = nullptr;           // owned: FPFH of sp
+  float rigid[16];               // dense Umeyama of the model onto itself
+};
+
 struct ope_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -55,6 +67,7 @@ struct ope_ctx {
   int64_t feature_knn_fallbacks = 0;     // ... of which the exact kernel had to re-answer (candidate set not provably complete)
   bool batch_timing = false;             // ope_pose_batch: per-stage CUDA-event laps of the frame-spanning launches
   double batch_stage_ms[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  BatchModelCache batch_model;
   std::vector<ModelCacheEntry> model_cache;   // at most 4 entries, least recently used replaced (pipeline.cu)
   unsigned long long model_cache_clock = 0;
   int64_t model_cache_hits = 0, model_cache_misses = 0;

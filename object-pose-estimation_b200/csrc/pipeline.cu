@@ -358,16 +358,44 @@ int ope_pose_batch(ope_ctx* ctx, const ope_pose_params* prm, const float* model_
   ope_pose_params P;
   if (prm) P = *prm; else ope_pose_params_default(&P);
   workers = std::max(1, std::min<int>(workers > 0 ? workers : 8, (int)std::min<size_t>(n_frames, 64)));
-  // ---- the frame-invariant model side, once ----
-  CloudGuard model(ctx), sp(ctx);
-  DevGuard fs(ctx);
-  OPE_TRY(ope_cloud_upload(ctx, model_xyz, n_model, 12, 0, nullptr, 0, 0, &model.c));
+  // ---- the frame-invariant model side, once — and kept across calls while the caller's model does not change ----
+  struct Borrowed { ope_cloud* c = nullptr; } model, sp;
+  struct BorrowedF { float* p = nullptr; } fs;
+  Mat4 rigid = mat4_identity();
   {
-    ope_pose_tracker tmp;
-    tmp.ctx = ctx; tmp.prm = P; tmp.timing = false;
-    StageTimer tm(&tmp);
-    OPE_TRY(sub_sample_and_normals(&tmp, tm, model.c, P.coarse_leaf, &sp.c));
-    OPE_TRY(fpfh_device(ctx, sp.c, P.fpfh_radius, &fs.p, nullptr));
+    unsigned long long h = 0x9e3779b97f4a7c15ull;   // content hash of the host buffer (4-byte words)
+    const uint32_t* w = (const uint32_t*)model_xyz;
+    unsigned long long h2 = 0xc2b2ae3d27d4eb4full;
+    const size_t words = n_model * 3;
+    size_t i = 0;
+    for (; i + 2 <= words; i += 2) {
+      h = (h ^ w[i]) * 0x9fb21c651e98df25ull; h = (h << 29) | (h >> 35);
+      h2 = (h2 ^ w[i + 1]) * 0x9fb21c651e98df25ull; h2 = (h2 << 31) | (h2 >> 33);
+    }
+    for (; i < words; ++i) { h = (h ^ w[i]) * 0x9fb21c651e98df25ull; h = (h << 29) | (h >> 35); }
+    h ^= h2 * 3 + n_model;
+    BatchModelCache& C = ctx->batch_model;
+    const bool hit = model_cache_enabled() && C.model && C.hash == h && C.n == n_model && C.leaf == P.coarse_leaf && C.k == P.normal_k &&
+                     C.radius == P.fpfh_radius;
+    if (!hit) {
+      if (C.model) ope_cloud_free(ctx, C.model);
+      if (C.sp) ope_cloud_free(ctx, C.sp);
+      dfree(ctx, C.fs);
+      C = BatchModelCache();
+      OPE_TRY(ope_cloud_upload(ctx, model_xyz, n_model, 12, 0, nullptr, 0, 0, &C.model));
+      ope_pose_tracker tmp;
+      tmp.ctx = ctx; tmp.prm = P; tmp.timing = false;
+      StageTimer tm(&tmp);
+      OPE_TRY(sub_sample_and_normals(&tmp, tm, C.model, P.coarse_leaf, &C.sp));
+      OPE_TRY(fpfh_device(ctx, C.sp, P.fpfh_radius, &C.fs, nullptr));
+      // the dense Umeyama of the pristine model onto the first frame's source — itself (:425-436)
+      Mat4 R = mat4_identity();
+      OPE_TRY(umeyama_device(ctx, C.model->pts, C.model->pts, nullptr, nullptr, C.model->n, R.m));
+      std::memcpy(C.rigid, R.m, sizeof(C.rigid));
+      C.hash = h; C.n = n_model; C.leaf = P.coarse_leaf; C.k = P.normal_k; C.radius = P.fpfh_radius;
+    }
+    model.c = C.model; sp.c = C.sp; fs.p = C.fs;
+    std::memcpy(rigid.m, C.rigid, sizeof(C.rigid));
   }
   // ---- SAC-IA decision tables: replayed, or drawn here in frame order from libc rand() ----
   // Drawing is inherently serial (one process-wide rand() stream, consumed exactly as a loop over fresh PoseEstimators would) and
@@ -408,10 +436,11 @@ int ope_pose_batch(ope_ctx* ctx, const ope_pose_params* prm, const float* model_
   {
     const char* mode = std::getenv("OPE_BATCH_MODE");   // "workers": the per-frame path only (one stream per worker thread)
     if (!(mode && std::strcmp(mode, "workers") == 0)) {
-      Mat4 rigid = mat4_identity();   // the dense Umeyama of the pristine model onto the first frame's source — itself (:425-436)
-      OPE_TRY(umeyama_device(ctx, model.c->pts, model.c->pts, nullptr, nullptr, model.c->n, rigid.m));
+      // frames per chunk: two SM-sized waves of the one-block-per-frame kernels; a small batch is still cut into a few chunks so
+      // that the device can start on the first while the helper thread draws the decision tables of the next
       const char* ce = std::getenv("OPE_BATCH_CHUNK");
-      const size_t chunk = (size_t)std::max(1, ce ? std::atoi(ce) : 296);   // two blocks per SM-sized waves of one-block-per-frame kernels
+      size_t chunk = (size_t)std::max(1, ce ? std::atoi(ce) : 296);
+      if (!ce && n_frames < 3 * chunk) chunk = std::max<size_t>(74, (n_frames + 2) / 3);
       for (size_t f0 = 0; f0 < n_frames; f0 += chunk) {
         const size_t nf = std::min(chunk, n_frames - f0);
         OPE_TRY(pose_batch_chunk(ctx, P, model.c, sp.c, fs.p, rigid, frames + f0, nf, tables + f0, results + f0, done.data() + f0, &tables_ready,

@@ -33,7 +33,7 @@ def sass_lines(so, kernel):
         for line in txt.splitlines():
             m = re.match(r"\s*\.section\s+\.text\.(\S+)", line)
             if m:
-                in_k = kernel in m.group(1)
+                in_k = kernel in m.group(1) and not out   # the first matching function only
                 continue
             if not in_k:
                 continue
@@ -59,11 +59,14 @@ def sass_lines(so, kernel):
 def main():
     rep, so, kernel = sys.argv[1], sys.argv[2], sys.argv[3]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
-                         text=True).stdout
+    # a report may hold several kernels: keep the launches of the one asked for (first of them)
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + re.sub(r"ILi\d+.*", "", kernel), "--launch-count", "1"],
+                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hi = next(i for i, r in enumerate(rows) if "Source" in r and "# Samples" in r)
     hdr = rows[hi]
+    nxt = next((i for i, r in enumerate(rows) if i > hi and "Source" in r and "# Samples" in r), len(rows))
+    rows = rows[:nxt]
     si, ci, ii = hdr.index("Source"), hdr.index("# Samples"), hdr.index("Instructions Executed")
     stall_cols = [(i, c) for i, c in enumerate(hdr) if c.startswith("stall_") and "Not Issued" not in c]
     body = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
