@@ -243,9 +243,10 @@ __global__ void __launch_bounds__(FG_THREADS, 1)
         // Hot path: 31 max operations and one vote per 32 columns. Only when some row of the warp sees a score above its
         // current 16th best does the warp walk the columns; the votes are warp-uniform, so the insertion stays a real,
         // rarely taken branch instead of 256 predicated copies of it.
-        float mx = __uint_as_float(v[0]);
+        float m[8];
 #pragma unroll
-        for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+        for (int j = 0; j < 8; ++j) m[j] = fmaxf(fmaxf(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), fmaxf(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+        const float mx = fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));   // a tree, not a 31-deep chain
         if (__any_sync(0xffffffffu, mx > bs[FG_CAND - 1])) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
