@@ -871,6 +871,7 @@ struct IcpSmallSmem {
   double red[THREADS / 32][kIcpAcc];
   double totals[kIcpAcc];
   float2 knn_buf[THREADS / 32][kKnnBufCap + 32];   // warp_knn_smem_bounded scratch for the queries the thread-level scan hands over
+  float4 wbox[THREADS / 32][2];                    // box around a warp's queries (.w of [0]: the widest bound among them, inflated)
   Mat4 T_inc;
   int stop;
 };
@@ -977,46 +978,78 @@ __device__ __forceinline__ void icp_small_body(const IcpDev& a, const int bid, c
     }
     if (pass == 0) __syncwarp();   // the leaders' columns are read above, the others' columns are written below
     const bool scan = ok && !have && bound < FLT_MAX;
-    if (scan) {
-      // A full column (kSlabSlots entries) keeps the best kSlabSlots seen so far and tightens the bound to its worst entry: rare
-      // (the bound normally admits ~k points), so it is a call, not inline code
-      auto insert_full = [&](float d2, int j) {
-        int worst = 0;
-        float2 wv = col(0);
+    if (__any_sync(full, scan)) {
+      // A full column (kSlabSlots entries) keeps the best kSlabSlots seen so far and tightens the bound to its worst entry, which
+      // is tracked in registers from the first overflow on: one pass over the column per replacement. Rare (the bound normally
+      // admits ~k points), so it is a call, not inline code.
+      int worst = -1;
+      float2 wv = make_float2(0.0f, 0.0f);
+      auto find_worst = [&]() {
+        worst = 0;
+        wv = col(0);
         for (int e = 1; e < kSlabSlots; ++e) { const float2 o = col(e); if (nb_less(wv.x, __float_as_int(wv.y), o.x, __float_as_int(o.y))) { wv = o; worst = e; } }
-        if (nb_less(d2, j, wv.x, __float_as_int(wv.y))) {
-          col(worst) = make_float2(d2, __int_as_float(j));
-          float mx = 0.0f;
-          for (int e = 0; e < kSlabSlots; ++e) mx = fmaxf(mx, col(e).x);
-          bound = mx;
-        } else {
-          bound = fminf(bound, wv.x);
-        }
+        bound = wv.x;   // every entry was admitted under a bound that has only shrunk to the largest entry since
       };
-      // eight targets per step: the loads (same address in every lane: broadcasts) and the distance arithmetic of a step are
-      // independent of each other and of the slab stores, which only happen for the ~k hits of the whole scan
-      for (int g = 0; g < n_groups; ++g) {
-        const int j0 = 8 * g;
-        {   // squared distance to the group's box, conservatively compared (the float evaluation may round either way)
-          const float4 lo = blo[g], hi = bhi[g];
-          const float ex = fmaxf(fmaxf(lo.x - p.x, p.x - hi.x), 0.0f), ey = fmaxf(fmaxf(lo.y - p.y, p.y - hi.y), 0.0f),
-                      ez = fmaxf(fmaxf(lo.z - p.z, p.z - hi.z), 0.0f);
-          if (!(ex * ex + ey * ey + ez * ez <= bound * 1.0001f + 1e-30f)) continue;
+      auto insert_full = [&](float d2, int j) {
+        if (worst < 0) find_worst();
+        if (nb_less(d2, j, wv.x, __float_as_int(wv.y))) { col(worst) = make_float2(d2, __int_as_float(j)); find_worst(); }
+      };
+      // The warp's 32 queries are neighbours on the Morton curve: the box around them, grown by the widest bound among them, is
+      // tested against the group boxes by the warp together (one group per lane, 32 per step); only the groups that pass — a
+      // third of them — reach the per-thread test below. Conservative comparisons throughout: a float box distance can only be
+      // a rounding error above the float distance to a point inside the box.
+      float wlx = scan ? p.x : INFINITY, wly = scan ? p.y : INFINITY, wlz = scan ? p.z : INFINITY;
+      float whx = scan ? p.x : -INFINITY, why = scan ? p.y : -INFINITY, whz = scan ? p.z : -INFINITY;
+      float wb = scan ? bound : 0.0f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        wlx = fminf(wlx, __shfl_xor_sync(full, wlx, o)); wly = fminf(wly, __shfl_xor_sync(full, wly, o)); wlz = fminf(wlz, __shfl_xor_sync(full, wlz, o));
+        whx = fmaxf(whx, __shfl_xor_sync(full, whx, o)); why = fmaxf(why, __shfl_xor_sync(full, why, o)); whz = fmaxf(whz, __shfl_xor_sync(full, whz, o));
+        wb = fmaxf(wb, __shfl_xor_sync(full, wb, o));
+      }
+      if (lane == 0) { sm->wbox[warp][0] = make_float4(wlx, wly, wlz, wb * 1.0002f + 1e-30f); sm->wbox[warp][1] = make_float4(whx, why, whz, 0.0f); }
+      __syncwarp();
+      for (int g0 = 0; g0 < n_groups; g0 += 32) {
+        bool near = false;
+        if (g0 + lane < n_groups) {
+          const float4 lo = blo[g0 + lane], hi = bhi[g0 + lane], wl = sm->wbox[warp][0], wh = sm->wbox[warp][1];
+          const float ex = fmaxf(fmaxf(lo.x - wh.x, wl.x - hi.x), 0.0f), ey = fmaxf(fmaxf(lo.y - wh.y, wl.y - hi.y), 0.0f),
+                      ez = fmaxf(fmaxf(lo.z - wh.z, wl.z - hi.z), 0.0f);
+          near = ex * ex + ey * ey + ez * ez <= wl.w;
         }
-        float d2[8];
+        // eight targets per step: the loads (same address in every lane: broadcasts) and the distance arithmetic of a step are
+        // independent of each other and of the slab stores, which only happen for the ~k hits of the whole scan
+        for (unsigned cand = __ballot_sync(full, near); cand != 0u; cand &= cand - 1u) {
+          const int g = g0 + __ffs(cand) - 1;
+          const int j0 = 8 * g;
+          bool mine = scan;
+          if (mine) {   // squared distance to the group's box, conservatively compared (the float evaluation may round either way)
+            const float4 lo = blo[g], hi = bhi[g];
+            const float ex = fmaxf(fmaxf(lo.x - p.x, p.x - hi.x), 0.0f), ey = fmaxf(fmaxf(lo.y - p.y, p.y - hi.y), 0.0f),
+                        ez = fmaxf(fmaxf(lo.z - p.z, p.z - hi.z), 0.0f);
+            mine = ex * ex + ey * ey + ez * ez <= bound * 1.0001f + 1e-30f;
+          }
+          if (!mine) continue;
+          float d2[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { const float4 t = tg[j0 + u]; d2[u] = dist2(p.x, p.y, p.z, t.x, t.y, t.z); }
-        unsigned hit = 0u;
+          for (int u = 0; u < 8; ++u) { const float4 t = tg[j0 + u]; d2[u] = dist2(p.x, p.y, p.z, t.x, t.y, t.z); }
+          unsigned hit = 0u;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) hit |= (d2[u] <= bound ? 1u : 0u) << u;   // non-finite targets give inf / NaN: never a hit
-        if (hit) {
+          for (int u = 0; u < 8; ++u) hit |= (d2[u] <= bound ? 1u : 0u) << u;   // non-finite targets give inf / NaN: never a hit
+          if (hit == 0u) continue;
+          if (c + __popc(hit) <= kSlabSlots) {
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {   // predicated stores, no nested branches: the lanes of a warp hit at different u
-            const bool h = (hit >> u) & 1u;
-            const bool room = c < kSlabSlots;
-            if (h & room) col(c) = make_float2(d2[u], __int_as_float(j0 + u));
-            if (h & !room) insert_full(d2[u], j0 + u);
-            c += (h & room) ? 1 : 0;
+            for (int u = 0; u < 8; ++u)   // predicated stores, no nested branches: the lanes of a warp hit at different u
+              if ((hit >> u) & 1u) { col(c) = make_float2(d2[u], __int_as_float(j0 + u)); ++c; }
+          } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const bool h = (hit >> u) & 1u;
+              const bool room = c < kSlabSlots;
+              if (h & room) col(c) = make_float2(d2[u], __int_as_float(j0 + u));
+              if (h & !room) insert_full(d2[u], j0 + u);
+              c += (h & room) ? 1 : 0;
+            }
           }
         }
       }
