@@ -436,17 +436,65 @@ int ope_pose_batch(ope_ctx* ctx, const ope_pose_params* prm, const float* model_
   {
     const char* mode = std::getenv("OPE_BATCH_MODE");   // "workers": the per-frame path only (one stream per worker thread)
     if (!(mode && std::strcmp(mode, "workers") == 0)) {
-      // frames per chunk: two SM-sized waves of the one-block-per-frame kernels; a small batch is still cut into a few chunks so
-      // that the device can start on the first while the helper thread draws the decision tables of the next
+      // Chunks of frames run through the frame-spanning launches on a few LANES at once: lane 0 is this thread on this context,
+      // the others are helper threads on worker contexts (own stream, own scratch pool). A lane's host work between its stages
+      // (staging the clusters, copying decision tables, reading counts back) then overlaps the other lanes' kernels instead of
+      // leaving the device idle; chunks are handed out in order, so the helper thread's tables arrive in the order they are needed.
+      // Frames per chunk: at most two SM-sized waves of the one-block-per-frame kernels, and enough chunks for every lane to get
+      // an equal share (a small batch is cut finer, so the device starts while the tables of the later frames are still drawn).
       const char* ce = std::getenv("OPE_BATCH_CHUNK");
+      const char* le = std::getenv("OPE_BATCH_LANES");
+      int lanes = std::max(1, std::min(le ? std::atoi(le) : 2, 8));
+      if (ctx->batch_timing) lanes = 1;   // per-stage device times are only meaningful when the stages do not share the device
       size_t chunk = (size_t)std::max(1, ce ? std::atoi(ce) : 296);
-      if (!ce && n_frames < 3 * chunk) chunk = std::max<size_t>(74, (n_frames + 2) / 3);
-      for (size_t f0 = 0; f0 < n_frames; f0 += chunk) {
-        const size_t nf = std::min(chunk, n_frames - f0);
-        OPE_TRY(pose_batch_chunk(ctx, P, model.c, sp.c, fs.p, rigid, frames + f0, nf, tables + f0, results + f0, done.data() + f0, &tables_ready,
-                                 f0 + nf));
-        if (draw_rc.load() != OPE_OK) return fail(ctx, draw_rc.load(), "selectSamples failed");
+      if (!ce) {
+        const size_t per_round = (size_t)lanes * (lanes > 1 ? 148 : 296);
+        const size_t rounds = std::max<size_t>(lanes > 1 ? 2 : 3, (n_frames + per_round - 1) / per_round);
+        chunk = std::max<size_t>(std::min<size_t>(lanes > 1 ? 32 : 74, n_frames), (n_frames + rounds * lanes - 1) / (rounds * lanes));
       }
+      const size_t n_chunks = (n_frames + chunk - 1) / chunk;
+      lanes = (int)std::min<size_t>((size_t)lanes, n_chunks);
+      while ((int)ctx->workers.size() < lanes - 1) {
+        ope_ctx* w = nullptr;
+        const int rc = ope_ctx_create(ctx->device, nullptr, &w);
+        if (rc != OPE_OK) return fail(ctx, rc, "worker context creation failed");
+        ctx->workers.push_back(w);
+      }
+      if (lanes > 1) OPE_TRY(ope_ctx_synchronize(ctx));   // the other lanes read the model side from their own streams
+      std::atomic<size_t> next_chunk{0};
+      std::atomic<int> lane_rc{OPE_OK};
+      std::mutex lane_mu;
+      std::string lane_msg;
+      auto run_lane = [&](ope_ctx* c) {
+        ope::enter(c);
+        for (;;) {
+          const size_t f0 = next_chunk.fetch_add(1) * chunk;
+          if (f0 >= n_frames || lane_rc.load() != OPE_OK || draw_rc.load() != OPE_OK) break;
+          const size_t nf = std::min(chunk, n_frames - f0);
+          const int rc = pose_batch_chunk(c, P, model.c, sp.c, fs.p, rigid, frames + f0, nf, tables + f0, results + f0, done.data() + f0,
+                                          &tables_ready, f0 + nf);
+          if (rc != OPE_OK) {
+            std::lock_guard<std::mutex> lock(lane_mu);
+            if (lane_rc.load() == OPE_OK) { lane_rc.store(rc); lane_msg = c->error; }
+            break;
+          }
+        }
+        if (c != ctx) stream_sync(c);
+      };
+      {
+        std::vector<std::thread> lane_threads;
+        struct JoinLanes { std::vector<std::thread>& t; ~JoinLanes() { for (auto& th : t) if (th.joinable()) th.join(); } } join_lanes{lane_threads};
+        try {   // nothing may throw across the C ABI: without helper threads this thread takes every chunk
+          for (int l = 1; l < lanes; ++l) lane_threads.emplace_back(run_lane, ctx->workers[(size_t)l - 1]);
+        } catch (...) {
+        }
+        run_lane(ctx);
+      }
+      if (lane_rc.load() != OPE_OK) {
+        if (draw_rc.load() != OPE_OK) tables_ready.store(n_frames);
+        return fail(ctx, lane_rc.load(), "%s", lane_msg.c_str());
+      }
+      if (draw_rc.load() != OPE_OK) return fail(ctx, draw_rc.load(), "selectSamples failed");
       if (status) for (size_t f = 0; f < n_frames; ++f) if (done[f]) status[f] = OPE_OK;
     }
   }

@@ -866,6 +866,26 @@ static constexpr int kIcpSmallMaxBlocks = 32;
 
 static constexpr int kIcpSmallThreads = 128;   // 4 warps: the per-target scan is a latency chain, so a block gains little from more
                                                // warps; small blocks let the blocks of SEVERAL alignments share an SM
+// A thread's column of the candidate slab (entries THREADS apart) as a binary max-heap in (d2, index) order: v sinks from node i
+// of a heap of n entries.
+template <int THREADS>
+__device__ __forceinline__ void heap_sift(float2* column, int i, float2 v, const int n) {
+  for (;;) {
+    const int l = 2 * i + 1;
+    if (l >= n) break;
+    float2 cv = column[l * THREADS];
+    int pick = l;
+    if (l + 1 < n) {
+      const float2 cr = column[(l + 1) * THREADS];
+      if (nb_less(cv.x, __float_as_int(cv.y), cr.x, __float_as_int(cr.y))) { cv = cr; pick = l + 1; }
+    }
+    if (!nb_less(v.x, __float_as_int(v.y), cv.x, __float_as_int(cv.y))) break;
+    column[i * THREADS] = cv;
+    i = pick;
+  }
+  column[i * THREADS] = v;
+}
+
 template <int THREADS>
 struct IcpSmallSmem {
   double red[THREADS / 32][kIcpAcc];
@@ -978,21 +998,27 @@ __device__ __forceinline__ void icp_small_body(const IcpDev& a, const int bid, c
     }
     if (pass == 0) __syncwarp();   // the leaders' columns are read above, the others' columns are written below
     const bool scan = ok && !have && bound < FLT_MAX;
+    int n_ins = 0;   // profile: calls of the overflow path
+    bool heaped = false;                      // the column is full and ordered as a max-heap (see insert_full)
+    float2 root = make_float2(0.0f, 0.0f);    // its root
+    const long long ts0 = a.phase_cycles ? clock64() : 0;
     if (__any_sync(full, scan)) {
-      // A full column (kSlabSlots entries) keeps the best kSlabSlots seen so far and tightens the bound to its worst entry, which
-      // is tracked in registers from the first overflow on: one pass over the column per replacement. Rare (the bound normally
-      // admits ~k points), so it is a call, not inline code.
-      int worst = -1;
-      float2 wv = make_float2(0.0f, 0.0f);
-      auto find_worst = [&]() {
-        worst = 0;
-        wv = col(0);
-        for (int e = 1; e < kSlabSlots; ++e) { const float2 o = col(e); if (nb_less(wv.x, __float_as_int(wv.y), o.x, __float_as_int(o.y))) { wv = o; worst = e; } }
-        bound = wv.x;   // every entry was admitted under a bound that has only shrunk to the largest entry since
-      };
+      // A full column (kSlabSlots entries) keeps the best kSlabSlots seen so far as a max-heap in (d2, index) order — root = slot 0
+      // = the worst entry, cached in registers — and the bound shrinks to the root: log2(kSlabSlots) steps per replacement. Common
+      // only in the first iterations (a seed from a neighbour's list, large increments), where it used to dominate the time.
       auto insert_full = [&](float d2, int j) {
-        if (worst < 0) find_worst();
-        if (nb_less(d2, j, wv.x, __float_as_int(wv.y))) { col(worst) = make_float2(d2, __int_as_float(j)); find_worst(); }
+        ++n_ins;
+        if (!heaped) {
+          for (int i = kSlabSlots / 2 - 1; i >= 0; --i) heap_sift<THREADS>(slab + tid, i, col(i), kSlabSlots);
+          heaped = true;
+          root = col(0);
+          bound = root.x;   // every entry was admitted under a bound that has only shrunk to the largest entry since
+        }
+        if (nb_less(d2, j, root.x, __float_as_int(root.y))) {
+          heap_sift<THREADS>(slab + tid, 0, make_float2(d2, __int_as_float(j)), kSlabSlots);
+          root = col(0);
+          bound = root.x;
+        }
       };
       // The warp's 32 queries are neighbours on the Morton curve: the box around them, grown by the widest bound among them, is
       // tested against the group boxes by the warp together (one group per lane, 32 per step); only the groups that pass — a
@@ -1057,6 +1083,13 @@ __device__ __forceinline__ void icp_small_body(const IcpDev& a, const int bid, c
     // whoever could not be served above (no usable seed, or fewer than k points within the bound) gets a cooperative search
     const bool unserved = ok && !have && (!scan || c < k);
     const unsigned redo = __ballot_sync(full, unserved);
+    if (a.phase_cycles && pass < 64) {
+      unsigned long long* pc = (unsigned long long*)(a.phase_cycles + 16 + pass * 8);
+      const unsigned long long dt = (unsigned long long)(clock64() - ts0);
+      if (lane == 0) { atomicAdd(pc + 0, dt); atomicMax(pc + 1, dt); atomicAdd(pc + 5, 1ull); }
+      if (n_ins > 0) { atomicAdd(pc + 2, (unsigned long long)n_ins); atomicAdd(pc + 3, 1ull); }
+      if (ok) atomicAdd(pc + 4, (unsigned long long)c);
+    }
     if (a.phase_cycles && bid == 0 && lane == 0 && pass > 0) atomicAdd((unsigned long long*)&a.phase_cycles[4], (unsigned long long)__popc(redo));
     if (a.phase_cycles && bid == 0 && ok && pass > 0) atomicAdd((unsigned long long*)&a.phase_cycles[5], (unsigned long long)c);
     for (unsigned m = redo; m != 0u; m &= m - 1u) {
@@ -1079,6 +1112,10 @@ __device__ __forceinline__ void icp_small_body(const IcpDev& a, const int bid, c
       // The list order of the reference is ascending (d2, index). Nothing below needs the ranks themselves: the k best are what
       // remains after dropping the largest entry c - k times (c - k is 0 or 1 for almost every query), the nearest neighbour
       // is the minimum, and "first minimum in list order" is a tie-break by that same order.
+      while (heaped && c > k) {   // pop the root: the last entry sinks from the top
+        --c;
+        if (c > 0) heap_sift<THREADS>(slab + tid, 0, col(c), c);
+      }
       while (c > k) {
         int worst = 0;
         float2 wv = col(0);
@@ -1934,6 +1971,17 @@ int icp_device(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt, const o
       if (read_back(ctx, phases.p, 6 * sizeof(long long), &h) == OPE_OK) {
         const long long* c = (const long long*)h;
         const double it = std::max(res->iterations, 1);
+        if (std::getenv("OPE_PROFILE_ITER")) {
+          std::vector<long long> all(n_prof);
+          if (cudaMemcpy(all.data(), phases.p, n_prof * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            fprintf(stderr, "[ope profile] icp_small per iteration: mean warp scan cycles | slowest warp | overflow calls | threads overflowing | candidates per query\n");
+            for (int p = 0; p < std::min(res->iterations, 64); ++p) {
+              const long long* r = all.data() + 16 + p * 8;
+              fprintf(stderr, "  it %2d: %7.0f %7lld %6lld %5lld %5.1f\n", p, (double)r[0] / (double)std::max<long long>(r[5], 1), r[1], r[2], r[3],
+                      (double)r[4] / (double)std::max<size_t>(nw, 1));
+            }
+          }
+        }
         fprintf(stderr, "[ope profile] icp_small_kernel blocks=%d, block 0 cycles per iteration: search %.0f | rank+shoot+reject %.0f | moments+barrier %.0f | "
                 "svd+transform %.0f | cooperative re-searches per iteration %.1f | candidates per query %.1f\n", blocks, c[0] / it, c[1] / it,
                 c[2] / it, c[3] / it, c[4] / it, c[5] / it / kIcpSmallThreads);
