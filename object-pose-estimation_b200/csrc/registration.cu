@@ -1512,91 +1512,129 @@ __global__ void __launch_bounds__(kSaciaThreads) sacia_smem_kernel(SaciaDev a, i
     a.errors[h] = error;
   }
 }
-// Frame-spanning SAC-IA scoring: blockIdx.x = hypothesis, blockIdx.y = frame. Every frame has its own target (tgt + f * stride,
-// counts[f] points, in shared memory), decision table (samples / picks + f * H * S) and feature neighbours (knn_idx + f * ns * k);
-// the source (the model's coarse sample) is shared. Same arithmetic as sacia_smem_kernel: same errors, bit for bit.
+// Frame-spanning SAC-IA scoring. Every frame has its own target (tgt + f * stride, counts[f] points, in shared memory), decision
+// table (samples / picks + f * H * S) and feature neighbours (knn_idx + f * ns * k); the source (the model's coarse sample) is
+// shared. Same arithmetic as sacia_smem_kernel: same errors, bit for bit.
 // squared distance from a query to an axis-aligned box (0 inside); an empty box (lo = +inf, hi = -inf) gives +inf
 __device__ __forceinline__ float box_d2(const float4 lo, const float4 hi, float x, float y, float z) {
   const float ex = fmaxf(fmaxf(lo.x - x, x - hi.x), 0.0f), ey = fmaxf(fmaxf(lo.y - y, y - hi.y), 0.0f), ez = fmaxf(fmaxf(lo.z - z, z - hi.z), 0.0f);
   return ex * ex + ey * ey + ez * ez;
 }
-// Exact squared distance to the nearest of the nt8 target points in shared memory (padded with +inf to a multiple of 8), pruned by
-// the bounding boxes of groups of 8 consecutive points and of super-groups of 64: a box is skipped only when its distance,
-// compared with slack for the float rounding of the bound, exceeds the best distance found so far — so the result is the same
-// float an exhaustive scan returns. The super-group nearest to the query is scanned first to seed the bound.
-__device__ __forceinline__ float pruned_min_d2(const float4* __restrict__ tg, const float4* __restrict__ glo, const float4* __restrict__ ghi,
-                                               const float4* __restrict__ slo, const float4* __restrict__ shi, int n_super, int n_groups,
-                                               float x, float y, float z) {
-  float best = FLT_MAX;
-  auto scan_super = [&](int sg) {
-    const int g1 = min(n_groups, 8 * sg + 8);
-    for (int g = 8 * sg; g < g1; ++g) {
-      if (!(box_d2(glo[g], ghi[g], x, y, z) <= best * 1.0001f + 1e-30f)) continue;
-      float d2[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) { const float4 t = tg[8 * g + u]; d2[u] = dist2(x, y, z, t.x, t.y, t.z); }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) best = d2[u] < best ? d2[u] : best;   // NaN / inf (padding, non-finite targets) never wins
-    }
-  };
-  int first = 0;
-  float first_lb = FLT_MAX;
-  for (int sg = 0; sg < n_super; ++sg) {
-    const float lb = box_d2(slo[sg], shi[sg], x, y, z);
-    if (lb < first_lb) { first_lb = lb; first = sg; }
+// The batch scores its hypotheses in three launches:
+//   sacia_transform_batch_kernel  one THREAD per (frame, hypothesis): the 5-point Umeyama (double moments, as everywhere)
+//   sacia_seed_batch_kernel       one block per frame: a kSeedG^3 grid around the frame's target; every cell remembers the target
+//                                 point nearest to its centre. A query looks up its (clamped) cell and starts its search from that
+//                                 point's distance: a bound within a cell size of the answer, so the box tests prune from the start
+//   sacia_score_batch_kernel      blockIdx.x = frame, blockIdx.y = kSaciaHypPerBlock consecutive hypotheses: the target, its group
+//                                 boxes and the seed grid are staged once per block
+static constexpr int kSeedG = 12;
+static constexpr int kSeedCells = kSeedG * kSeedG * kSeedG;
+static constexpr int kSaciaHypPerBlock = 8;
+
+__global__ void __launch_bounds__(128) sacia_transform_batch_kernel(SaciaBatch a, int frames) {
+  const int idx = blockIdx.x * 128 + threadIdx.x;
+  if (idx >= frames * a.H) return;
+  const int f = idx / a.H, h = idx - f * a.H;
+  if (!a.active[f]) return;
+  const float4* tgt = a.tgt + (size_t)f * a.stride;
+  double acc[16];
+  for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+  const int* samples = a.samples + ((size_t)f * a.H + h) * a.nr_samples;
+  const int* picks = a.picks + ((size_t)f * a.H + h) * a.nr_samples;
+  const int* knn = a.knn_idx + (size_t)f * a.ns * a.k_corr;
+  for (int j = 0; j < a.nr_samples; ++j) {
+    const int si = samples[j];
+    int ti = knn[(size_t)si * a.k_corr + picks[j]];
+    if (ti < 0) ti = knn[(size_t)si * a.k_corr];  // fewer than k target features
+    const float4 sp = __ldg(a.src + si), tp = __ldg(tgt + ti);
+    const double sv[3] = {sp.x, sp.y, sp.z}, tv[3] = {tp.x, tp.y, tp.z};
+    acc[0] += 1.0;
+    for (int k = 0; k < 3; ++k) { acc[1 + k] += sv[k]; acc[4 + k] += tv[k]; }
+    for (int c = 0; c < 3; ++c)
+      for (int r = 0; r < 3; ++r) acc[7 + c * 3 + r] += tv[r] * sv[c];
   }
-  scan_super(first);
-  for (int sg = 0; sg < n_super; ++sg) {
-    if (sg == first) continue;
-    if (!(box_d2(slo[sg], shi[sg], x, y, z) <= best * 1.0001f + 1e-30f)) continue;
-    scan_super(sg);
-  }
-  return best;
+  Mat4 M;
+  umeyama_from_moments(acc, M);
+  float* out = a.transforms + ((size_t)f * a.H + h) * 16;
+  for (int i = 0; i < 16; ++i) out[i] = M.m[i];
 }
 
-__global__ void __launch_bounds__(kSaciaThreads) sacia_smem_batch_kernel(SaciaBatch a) {
+__global__ void __launch_bounds__(kSaciaThreads) sacia_seed_batch_kernel(SaciaBatch a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // blockIdx.x = frame (fastest): the hypotheses of one frame run one after the other, so the bound below is known early
-  const int f = blockIdx.x, h = blockIdx.y;
+  float4* tg = reinterpret_cast<float4*>(smem_raw);
+  __shared__ float red[6][kSaciaThreads / 32];
+  __shared__ float box[6];
+  const int f = blockIdx.x;
   if (!a.active[f]) return;
   const int nt = a.counts[f];
-  const int nt8 = (nt + 7) & ~7, n_groups = nt8 >> 3, n_super = (n_groups + 7) >> 3;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float4* scan = (a.tgt_scan ? a.tgt_scan : a.tgt) + (size_t)f * a.stride;
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int j = tid; j < nt; j += kSaciaThreads) {
+    const float4 t = __ldg(scan + j);
+    tg[j] = t;
+    if (finite3(t.x, t.y, t.z)) {
+      lo[0] = fminf(lo[0], t.x); lo[1] = fminf(lo[1], t.y); lo[2] = fminf(lo[2], t.z);
+      hi[0] = fmaxf(hi[0], t.x); hi[1] = fmaxf(hi[1], t.y); hi[2] = fmaxf(hi[2], t.z);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1)
+    for (int d = 0; d < 3; ++d) { lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o)); hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o)); }
+  if (lane == 0) for (int d = 0; d < 3; ++d) { red[d][warp] = lo[d]; red[3 + d][warp] = hi[d]; }
+  __syncthreads();
+  if (tid < 6) {
+    float v = red[tid][0];
+    for (int w = 1; w < kSaciaThreads / 32; ++w) v = tid < 3 ? fminf(v, red[tid][w]) : fmaxf(v, red[tid][w]);
+    box[tid] = v;
+  }
+  __syncthreads();
+  // a cubic grid over the bounding box grown by a quarter of its largest extent on every side (queries near the target, but
+  // outside its box, still get a cell of their own; farther ones use the nearest border cell)
+  float ext = fmaxf(fmaxf(box[3] - box[0], box[4] - box[1]), box[5] - box[2]);
+  if (!(ext > 1e-6f) || !(ext < FLT_MAX)) ext = 1e-6f;
+  const float cell = 1.5f * ext / (float)kSeedG;
+  float org[3];
+  for (int d = 0; d < 3; ++d) { org[d] = 0.5f * (box[d] + box[3 + d]) - 0.5f * cell * (float)kSeedG; if (!(fabsf(org[d]) < FLT_MAX)) org[d] = 0.0f; }
+  if (tid == 0) a.seed_geo[f] = make_float4(org[0], org[1], org[2], 1.0f / cell);
+  for (int c = tid; c < kSeedCells; c += kSaciaThreads) {
+    const int cx = c % kSeedG, cy = (c / kSeedG) % kSeedG, cz = c / (kSeedG * kSeedG);
+    const float x = org[0] + ((float)cx + 0.5f) * cell, y = org[1] + ((float)cy + 0.5f) * cell, z = org[2] + ((float)cz + 0.5f) * cell;
+    float best = FLT_MAX;
+    int arg = 0;
+#pragma unroll 4
+    for (int j = 0; j < nt; ++j) {
+      const float4 t = tg[j];
+      const float d2 = dist2(x, y, z, t.x, t.y, t.z);
+      if (d2 < best) { best = d2; arg = j; }   // NaN / inf (non-finite targets) never wins
+    }
+    a.seed_tab[(size_t)f * kSeedCells + c] = (unsigned short)arg;
+  }
+}
+
+__global__ void __launch_bounds__(kSaciaThreads) sacia_score_batch_kernel(SaciaBatch a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // blockIdx.x = frame (fastest): the hypothesis groups of one frame run one after the other, so the bound below is known early
+  const int f = blockIdx.x;
+  if (!a.active[f]) return;
+  const int nt = a.counts[f];
+  const int nt8 = (nt + 7) & ~7, n_groups = nt8 >> 3;
   float4* tg = reinterpret_cast<float4*>(smem_raw);
   float4* glo = tg + nt8;
   float4* ghi = glo + n_groups;
-  float4* slo = ghi + n_groups;
-  float4* shi = slo + n_super;
-  float* terms = reinterpret_cast<float*>(shi + n_super);
+  float* terms = reinterpret_cast<float*>(ghi + n_groups);
+  unsigned short* seed = reinterpret_cast<unsigned short*>(terms + a.ns);
   __shared__ Mat4 T;
-  const float4* tgt = a.tgt + (size_t)f * a.stride;
+  __shared__ float wpart[2][kSaciaThreads / 32];
+  __shared__ float s_best[2];
+  const unsigned full = 0xffffffffu;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float4* scan = (a.tgt_scan ? a.tgt_scan : a.tgt) + (size_t)f * a.stride;   // a spatially sorted copy makes the boxes tight
-  for (int j = threadIdx.x; j < nt8; j += kSaciaThreads) tg[j] = j < nt ? __ldg(scan + j) : make_float4(INFINITY, INFINITY, INFINITY, 0.0f);
-  if (threadIdx.x == 0) {
-    double acc[16];
-    for (int i = 0; i < 16; ++i) acc[i] = 0.0;
-    const int* samples = a.samples + ((size_t)f * a.H + h) * a.nr_samples;
-    const int* picks = a.picks + ((size_t)f * a.H + h) * a.nr_samples;
-    const int* knn = a.knn_idx + (size_t)f * a.ns * a.k_corr;
-    for (int j = 0; j < a.nr_samples; ++j) {
-      const int si = samples[j];
-      int ti = knn[(size_t)si * a.k_corr + picks[j]];
-      if (ti < 0) ti = knn[(size_t)si * a.k_corr];  // fewer than k target features
-      const float4 sp = __ldg(a.src + si), tp = __ldg(tgt + ti);
-      const double sv[3] = {sp.x, sp.y, sp.z}, tv[3] = {tp.x, tp.y, tp.z};
-      acc[0] += 1.0;
-      for (int k = 0; k < 3; ++k) { acc[1 + k] += sv[k]; acc[4 + k] += tv[k]; }
-      for (int c = 0; c < 3; ++c)
-        for (int r = 0; r < 3; ++r) acc[7 + c * 3 + r] += tv[r] * sv[c];
-    }
-    Mat4 M;
-    umeyama_from_moments(acc, M);
-    T = M;
-    float* out = a.transforms + ((size_t)f * a.H + h) * 16;
-    for (int i = 0; i < 16; ++i) out[i] = M.m[i];
-  }
+  for (int j = tid; j < nt8; j += kSaciaThreads) tg[j] = j < nt ? __ldg(scan + j) : make_float4(INFINITY, INFINITY, INFINITY, 0.0f);
+  for (int c = tid; c < kSeedCells; c += kSaciaThreads) seed[c] = a.seed_tab[(size_t)f * kSeedCells + c];
+  const float4 geo = a.seed_geo[f];
   __syncthreads();
-  // boxes of the groups of 8 consecutive target points (the 1 cm sample arrives in voxel order: neighbours), then of 8 groups
-  for (int g = threadIdx.x; g < n_groups; g += kSaciaThreads) {
+  // boxes of the groups of 8 consecutive target points
+  for (int g = tid; g < n_groups; g += kSaciaThreads) {
     float4 lo = make_float4(INFINITY, INFINITY, INFINITY, 0.0f), hi = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.0f);
     for (int u = 0; u < 8; ++u) {
       const float4 t = tg[8 * g + u];
@@ -1606,56 +1644,97 @@ __global__ void __launch_bounds__(kSaciaThreads) sacia_smem_batch_kernel(SaciaBa
     }
     glo[g] = lo; ghi[g] = hi;
   }
-  __syncthreads();
-  for (int sg = threadIdx.x; sg < n_super; sg += kSaciaThreads) {
-    float4 lo = make_float4(INFINITY, INFINITY, INFINITY, 0.0f), hi = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.0f);
-    for (int g = 8 * sg; g < min(n_groups, 8 * sg + 8); ++g) {
-      const float4 l = glo[g], u = ghi[g];
-      lo.x = fminf(lo.x, l.x); lo.y = fminf(lo.y, l.y); lo.z = fminf(lo.z, l.z);
-      hi.x = fmaxf(hi.x, u.x); hi.y = fmaxf(hi.y, u.y); hi.z = fmaxf(hi.z, u.z);
-    }
-    slo[sg] = lo; shi[sg] = hi;
-  }
-  __syncthreads();
-  const Mat4 M = T;
-  // The error is the float sum of the terms IN POINT ORDER (bit-exact with the reference's serial `error += ...`); the terms are
-  // >= 0, so every prefix of that sum is a lower bound of the total. After each chunk of kSaciaThreads points thread 0 extends
-  // the prefix and compares it with the lowest COMPLETE error any hypothesis of this frame has published so far: once the prefix
-  // is strictly larger, this hypothesis cannot be the first-lowest one and the block stops (its error is reported as +inf).
-  // Which hypotheses stop early depends on timing; the winner, its error and its transform do not.
-  __shared__ float s_error;
-  __shared__ int s_stop;
-  if (threadIdx.x == 0) { s_error = 0.0f; s_stop = 0; }
   unsigned* frame_best = a.best_bits + f;
-  for (int base = 0; base < a.ns; base += kSaciaThreads) {
-    const int i = base + (int)threadIdx.x;
-    if (i < a.ns) {
-      const float4 p = __ldg(a.src + i);
-      float x, y, z;
-      xform_point(M, p.x, p.y, p.z, x, y, z);
-      float term = 1.0f;
-      if (finite3(x, y, z)) {
-        // only the DISTANCE of the nearest neighbour enters the score: ties need no index order
-        const float best = pruned_min_d2(tg, glo, ghi, slo, shi, n_super, n_groups, x, y, z);
-        if (best <= a.threshold) term = best / a.threshold;
+  const int h_end = min(a.H, ((int)blockIdx.y + 1) * kSaciaHypPerBlock);
+  for (int h = (int)blockIdx.y * kSaciaHypPerBlock; h < h_end; ++h) {
+    // (this barrier also closes the previous hypothesis: thread 0's final sum has read the terms)
+    if (tid < 16) T.m[tid] = __ldg(a.transforms + ((size_t)f * a.H + h) * 16 + tid);
+    __syncthreads();
+    const Mat4 M = T;
+    // The error is the float sum of the terms IN POINT ORDER (bit-exact with the reference's serial `error += ...`), formed by one
+    // thread — but only for a hypothesis that gets that far. The terms are >= 0, so every prefix of that sum is a lower bound of
+    // the total, and ANY summation order of a prefix is within n * 2^-24 (relative) of the serial one: after every chunk of
+    // kSaciaThreads points the block adds the chunk up in parallel and compares that sum, shrunk by twice that bound, with the lowest
+    // COMPLETE error any hypothesis of this frame has published so far. Once it is larger, the serial total would be larger too:
+    // this hypothesis cannot be the first-lowest one and stops (its error is reported as +inf). Which hypotheses stop early
+    // depends on timing; the winner, its error and its transform do not.
+    float run = 0.0f;
+    bool stop = false;
+    int chunk = 0;
+    const float shrink = 1.0f - 4.0f * (float)(a.ns + 32) * 5.97e-8f;   // twice the bound 2 n 2^-24 on the gap between two summation orders
+    for (int base = 0; base < a.ns; base += kSaciaThreads, ++chunk) {
+      const int i = base + tid;
+      float term = 0.0f;
+      float x = 0.0f, y = 0.0f, z = 0.0f;
+      bool search = false;
+      if (i < a.ns) {
+        const float4 p = __ldg(a.src + i);
+        xform_point(M, p.x, p.y, p.z, x, y, z);
+        term = 1.0f;
+        search = finite3(x, y, z);
       }
-      terms[i] = term;
+      // only the DISTANCE of the nearest neighbour enters the score: ties need no index order
+      float best = FLT_MAX;
+      if (search) {
+        const float fx = fminf(fmaxf((x - geo.x) * geo.w, 0.0f), (float)(kSeedG - 1)), fy = fminf(fmaxf((y - geo.y) * geo.w, 0.0f), (float)(kSeedG - 1)),
+                    fz = fminf(fmaxf((z - geo.z) * geo.w, 0.0f), (float)(kSeedG - 1));
+        const float4 t = tg[seed[((int)fz * kSeedG + (int)fy) * kSeedG + (int)fx]];
+        const float d2 = dist2(x, y, z, t.x, t.y, t.z);
+        if (d2 < best) best = d2;
+      }
+      // the box around the warp's 32 queries (consecutive model points: neighbours), grown by the widest bound among them, against
+      // the group boxes, one group per lane; the groups that pass go through the per-thread test. Conservative comparisons: a
+      // float box distance can only be a rounding error above the float distance to a point inside the box.
+      float wlx = search ? x : INFINITY, wly = search ? y : INFINITY, wlz = search ? z : INFINITY;
+      float whx = search ? x : -INFINITY, why = search ? y : -INFINITY, whz = search ? z : -INFINITY;
+      float wb = search ? best : 0.0f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        wlx = fminf(wlx, __shfl_xor_sync(full, wlx, o)); wly = fminf(wly, __shfl_xor_sync(full, wly, o)); wlz = fminf(wlz, __shfl_xor_sync(full, wlz, o));
+        whx = fmaxf(whx, __shfl_xor_sync(full, whx, o)); why = fmaxf(why, __shfl_xor_sync(full, why, o)); whz = fmaxf(whz, __shfl_xor_sync(full, whz, o));
+        wb = fmaxf(wb, __shfl_xor_sync(full, wb, o));
+      }
+      const float wlim = wb * 1.0002f + 1e-30f;
+      for (int g0 = 0; g0 < n_groups; g0 += 32) {
+        bool near = false;
+        if (g0 + lane < n_groups) {
+          const float4 lo = glo[g0 + lane], hi = ghi[g0 + lane];
+          const float ex = fmaxf(fmaxf(lo.x - whx, wlx - hi.x), 0.0f), ey = fmaxf(fmaxf(lo.y - why, wly - hi.y), 0.0f),
+                      ez = fmaxf(fmaxf(lo.z - whz, wlz - hi.z), 0.0f);
+          near = ex * ex + ey * ey + ez * ez <= wlim;
+        }
+        for (unsigned cand = __ballot_sync(full, near); cand != 0u; cand &= cand - 1u) {
+          const int g = g0 + __ffs(cand) - 1;
+          if (!search || !(box_d2(glo[g], ghi[g], x, y, z) <= best * 1.0001f + 1e-30f)) continue;
+          float d2[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { const float4 t = tg[8 * g + u]; d2[u] = dist2(x, y, z, t.x, t.y, t.z); }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) best = d2[u] < best ? d2[u] : best;   // NaN / inf (padding, non-finite targets) never wins
+        }
+      }
+      if (search && best <= a.threshold) term = best / a.threshold;
+      if (i < a.ns) terms[i] = term;
+      float part = term;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(full, part, o);
+      const int par = chunk & 1;
+      if (lane == 0) wpart[par][warp] = part;
+      if (tid == 0) s_best[par] = __uint_as_float(*(volatile unsigned*)frame_best);
+      __syncthreads();
+#pragma unroll
+      for (int w = 0; w < kSaciaThreads / 32; ++w) run += wpart[par][w];
+      if (a.early_exit && run * shrink > s_best[par]) { stop = true; break; }   // the same values in every thread
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float error = s_error;
-      const int e1 = min(a.ns, base + kSaciaThreads);
-      for (int j = base; j < e1; ++j) error += terms[j];
-      s_error = error;
-      if (a.early_exit && error > __uint_as_float(*(volatile unsigned*)frame_best)) s_stop = 1;
+    if (tid == 0) {
+      float error = INFINITY;
+      if (!stop) {
+        error = 0.0f;
+        for (int j = 0; j < a.ns; ++j) error += terms[j];
+        atomicMin(frame_best, __float_as_uint(error));   // errors are >= 0: the bit pattern orders like the value
+      }
+      a.errors[(size_t)f * a.H + h] = error;
     }
-    __syncthreads();
-    if (s_stop) break;
-  }
-  if (threadIdx.x == 0) {
-    const float error = s_stop ? INFINITY : s_error;
-    a.errors[(size_t)f * a.H + h] = error;
-    if (!s_stop) atomicMin(frame_best, __float_as_uint(error));   // errors are >= 0: the bit pattern orders like the value
   }
 }
 // first strictly-lower error wins, per frame (one thread per frame)
@@ -2325,18 +2404,29 @@ int sacia_device(ope_ctx* ctx, const ope_cloud* src, const float* d_fsrc, const 
 }
 
 // ---- frame-spanning launches for ope_pose_batch (batch.cu) ----------------------------------------------------------------
-int sacia_batch_device(ope_ctx* ctx, const SaciaBatch& a, int frames, int max_nt, ope_reg_result* d_results) {
+int sacia_batch_device(ope_ctx* ctx, const SaciaBatch& a_in, int frames, int max_nt, ope_reg_result* d_results) {
+  SaciaBatch a = a_in;
   if (frames <= 0 || a.H <= 0) return OPE_OK;
   if (a.nr_samples < 1 || a.nr_samples > kSaciaMaxSamples || a.k_corr < 1 || a.k_corr > 16) return fail(ctx, OPE_ERR_INVALID, "bad SAC-IA parameters");
   if (max_nt > kSaciaSmemMaxTargets) return fail(ctx, OPE_ERR_CAPACITY, "batched SAC-IA: target larger than the shared-memory path");
-  const size_t nt8 = ((size_t)max_nt + 7) & ~(size_t)7, ng = nt8 / 8, nsg = (ng + 7) / 8;
-  const size_t bytes = (nt8 + 2 * ng + 2 * nsg) * sizeof(float4) + (size_t)a.ns * sizeof(float);
-  OPE_TRY(dyn_smem(ctx, (const void*)sacia_smem_batch_kernel, bytes));
+  if (max_nt > 65535) return fail(ctx, OPE_ERR_CAPACITY, "batched SAC-IA: target larger than the seed grid's index type");
+  Scratch<unsigned short> seed_tab(ctx);
+  Scratch<float4> seed_geo(ctx);
+  OPE_TRY(seed_tab.alloc((size_t)frames * kSeedCells)); OPE_TRY(seed_geo.alloc((size_t)frames));
+  a.seed_tab = seed_tab.p; a.seed_geo = seed_geo.p;
+  const size_t nt8 = ((size_t)max_nt + 7) & ~(size_t)7, ng = nt8 / 8;
+  const size_t bytes = (nt8 + 2 * ng) * sizeof(float4) + (size_t)a.ns * sizeof(float) + (size_t)kSeedCells * sizeof(unsigned short);
+  sacia_transform_batch_kernel<<<div_up((size_t)frames * a.H, 128), 128, 0, ctx->stream>>>(a, frames);
+  OPE_TRY(check_launch(ctx, "sacia_transform_batch_kernel"));
+  OPE_TRY(dyn_smem(ctx, (const void*)sacia_seed_batch_kernel, nt8 * sizeof(float4)));
+  sacia_seed_batch_kernel<<<frames, kSaciaThreads, nt8 * sizeof(float4), ctx->stream>>>(a);
+  OPE_TRY(check_launch(ctx, "sacia_seed_batch_kernel"));
+  OPE_TRY(dyn_smem(ctx, (const void*)sacia_score_batch_kernel, bytes));
   cudaEventRecord(ctx->kev[1][0], ctx->stream);
-  sacia_smem_batch_kernel<<<dim3(frames, a.H), kSaciaThreads, bytes, ctx->stream>>>(a);
+  sacia_score_batch_kernel<<<dim3(frames, (a.H + kSaciaHypPerBlock - 1) / kSaciaHypPerBlock), kSaciaThreads, bytes, ctx->stream>>>(a);
   cudaEventRecord(ctx->kev[1][1], ctx->stream);
   ctx->kev_valid[1] = true;
-  OPE_TRY(check_launch(ctx, "sacia_smem_batch_kernel"));
+  OPE_TRY(check_launch(ctx, "sacia_score_batch_kernel"));
   sacia_select_batch_kernel<<<div_up((size_t)frames, 128), 128, 0, ctx->stream>>>(a.errors, a.transforms, a.active, a.H, frames, d_results);
   return check_launch(ctx, "sacia_select_batch_kernel");
 }
