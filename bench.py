@@ -215,6 +215,10 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    # concurrent chunk lanes of ope_pose_batch: the library's own default (one per host core this rank can count on, 2..8), pinned
+    # here so that the line can say what ran
+    cores = max(1, len(os.sched_getaffinity(0)) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
+    lanes = int(os.environ.setdefault("OPE_BATCH_LANES", str(min(8, max(2, cores - 1)))))
     stream = torch.cuda.Stream()       # a real handle: the legacy default stream (0) would make the ctx create its own
     torch.cuda.set_stream(stream)      # torch work (L2 flush, events) and the library's calls share ONE stream
     ctx = cuda_lib.Context(local, stream.cuda_stream)
@@ -278,7 +282,8 @@ def run_ours(args):
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_step": N_FRAMES, "l2": "flushed between steps (256 MiB write)",
-                       "sharding": "frame f -> rank f mod N, no collective", "api": "ope_pose_batch", "workers_per_rank": WORKERS,
+                       "sharding": "frame f -> rank f mod N, no collective", "api": "ope_pose_batch", "workers_per_rank": WORKERS, "chunk_lanes_per_rank": lanes,
+                       "host_cores_per_rank": cores,
                        "sacia_tables": "drawn from libc rand() inside the timed region (ope_sacia_draw)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clocks}
@@ -372,7 +377,7 @@ def frame_roofline(ctx, cuda_lib, synth, model, clusters, stream, torch, n=8):
     bytes_ = sum(r.icp_iterations * (32.0 * r.n_src_fine + 32.0 * r.n_tgt_fine + 64.0) for r in res)
     k_ms = st["icp"]
     a = bytes_ / (k_ms * 1e-3) / 1e9
-    return {"kernel": "icp_small_batch_kernel (one launch per chunk of 296 frames)", "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s",
+    return {"kernel": "icp_small_batch_kernel (timed on one lane: one launch per chunk of <= 296 frames, nothing else on the device)", "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s",
             "frac": a / peak, "traffic": NCU_ICP_BATCH_DRAM_BYTES, "traffic_source": "ncu --set full of one launch over 296 frames "
             "(profiles/r02_b_batch_kernels_full.txt): dram__bytes_read.sum + dram__bytes_write.sum", "peak_source": peak_src,
             "kernel_ms_per_frame": k_ms / len(clusters), "kernel_share_of_step": k_ms / total,

@@ -26,6 +26,8 @@
 #include <cstring>
 #include <vector>
 
+#include <chrono>
+#include <cstdio>
 #include "ope_host.cuh"
 #include "ope_device.cuh"
 
@@ -338,14 +340,25 @@ namespace {
 struct ChunkTimer {
   ope_ctx* ctx;
   cudaEvent_t ev[16];
+  std::chrono::steady_clock::time_point host[16];
   int n = 0;
-  bool on;
-  explicit ChunkTimer(ope_ctx* c) : ctx(c), on(c->batch_timing) { if (on) for (auto& e : ev) cudaEventCreate(&e); mark(); }
-  void mark() { if (on && n < 16) cudaEventRecord(ev[n++], ctx->stream); }
+  bool on, trace;
+  explicit ChunkTimer(ope_ctx* c) : ctx(c), on(c->batch_timing), trace(c->batch_timing && std::getenv("OPE_BATCH_TRACE") != nullptr) {
+    if (on) for (auto& e : ev) cudaEventCreate(&e);
+    mark();
+  }
+  void mark() { if (on && n < 16) { host[n] = std::chrono::steady_clock::now(); cudaEventRecord(ev[n++], ctx->stream); } }
   ~ChunkTimer() {
     if (!on) return;
     cudaEventSynchronize(ev[n - 1]);
-    for (int i = 1; i < n; ++i) { float ms = 0; cudaEventElapsedTime(&ms, ev[i - 1], ev[i]); ctx->batch_stage_ms[i - 1] += ms; }
+    for (int i = 1; i < n; ++i) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+      ctx->batch_stage_ms[i - 1] += ms;
+      // OPE_BATCH_TRACE: the host's wall clock between the same marks (the device time includes what the device waited for the host)
+      if (trace) fprintf(stderr, "[ope batch] stage %2d: device %8.3f ms, host %8.3f ms\n", i - 1, ms,
+                         std::chrono::duration<double, std::milli>(host[i] - host[i - 1]).count());
+    }
     for (auto& e : ev) cudaEventDestroy(e);
   }
 };

@@ -287,6 +287,7 @@ struct SaciaBatch {
   unsigned* best_bits;                                     // per frame: float bits of the lowest complete error so far (init 0x7f800000)
   int early_exit;                                          // 1: stop a hypothesis whose partial error already exceeds that
   unsigned short* seed_tab; float4* seed_geo;              // set by sacia_batch_device: per frame, the seed grid of the distance search
+  const float4* src_scan;                                  // set by sacia_batch_device: the source in scoring order, .w = original index
 };
 struct IcpBatchFrame { const float4* src_pts; const float4* src_nrm; int n_src; const float4* tgt_pts; const float4* tgt_nrm; int n_tgt; };
 int normals_smem_batch(ope_ctx* ctx, const float4* pts, const int* d_counts, int stride, int clouds, int max_n, int k, const float vp[3],

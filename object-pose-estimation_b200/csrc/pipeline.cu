@@ -7,6 +7,7 @@
 #include <cmath>
 #include <memory>
 #include <thread>
+#include <sched.h>
 
 #include "ope_host.cuh"
 
@@ -444,13 +445,30 @@ int ope_pose_batch(ope_ctx* ctx, const ope_pose_params* prm, const float* model_
       // an equal share (a small batch is cut finer, so the device starts while the tables of the later frames are still drawn).
       const char* ce = std::getenv("OPE_BATCH_CHUNK");
       const char* le = std::getenv("OPE_BATCH_LANES");
-      int lanes = std::max(1, std::min(le ? std::atoi(le) : 2, 8));
+      // lanes: one host thread each, plus the thread that draws the tables — as many as this process has cores for (its affinity
+      // mask, shared with the other ranks of a torchrun-style launch on the same node), at most 8
+      int cores = (int)std::thread::hardware_concurrency();
+      {
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) cores = CPU_COUNT(&set);
+        const char* lw = std::getenv("LOCAL_WORLD_SIZE");
+        if (lw && std::atoi(lw) > 1) cores = std::max(1, cores / std::atoi(lw));
+      }
+      int lanes = std::max(1, std::min(le ? std::atoi(le) : std::max(2, cores - 1), 8));
       if (ctx->batch_timing) lanes = 1;   // per-stage device times are only meaningful when the stages do not share the device
       size_t chunk = (size_t)std::max(1, ce ? std::atoi(ce) : 296);
       if (!ce) {
-        const size_t per_round = (size_t)lanes * (lanes > 1 ? 148 : 296);
-        const size_t rounds = std::max<size_t>(lanes > 1 ? 2 : 3, (n_frames + per_round - 1) / per_round);
-        chunk = std::max<size_t>(std::min<size_t>(lanes > 1 ? 32 : 74, n_frames), (n_frames + rounds * lanes - 1) / (rounds * lanes));
+        if (lanes > 1) {
+          // measured (tools/bench_batch_lanes.py): many small chunks in flight beat few large ones — ~32 frames per chunk, every
+          // lane the same number of chunks
+          const size_t per_round = (size_t)lanes * 32;
+          const size_t rounds = std::max<size_t>(1, (n_frames + per_round / 2) / per_round);
+          chunk = std::max<size_t>(std::min<size_t>(8, n_frames), (n_frames + rounds * lanes - 1) / (rounds * lanes));
+        } else {
+          const size_t rounds = std::max<size_t>(3, (n_frames + 295) / 296);
+          chunk = std::max<size_t>(std::min<size_t>(74, n_frames), (n_frames + rounds - 1) / rounds);
+        }
       }
       const size_t n_chunks = (n_frames + chunk - 1) / chunk;
       lanes = (int)std::min<size_t>((size_t)lanes, n_chunks);
@@ -461,6 +479,13 @@ int ope_pose_batch(ope_ctx* ctx, const ope_pose_params* prm, const float* model_
         ctx->workers.push_back(w);
       }
       if (lanes > 1) OPE_TRY(ope_ctx_synchronize(ctx));   // the other lanes read the model side from their own streams
+      for (int l = 1; l < lanes; ++l) {   // more threads than cores: the helper lanes' waits poll and yield instead of spinning
+        ope_ctx* c = ctx->workers[(size_t)l - 1];
+        const bool crowded = lanes + 1 > cores;
+        if (crowded && !c->sync_event && cudaEventCreateWithFlags(&c->sync_event, cudaEventDisableTiming) != cudaSuccess) c->sync_event = nullptr;
+        c->sync_yield = crowded && c->sync_event;
+        if (!crowded && c->sync_event) { cudaEventDestroy(c->sync_event); c->sync_event = nullptr; }
+      }
       std::atomic<size_t> next_chunk{0};
       std::atomic<int> lane_rc{OPE_OK};
       std::mutex lane_mu;

@@ -16,6 +16,7 @@
 #include <map>
 #include <mutex>
 
+#include <chrono>
 #include "ope_host.cuh"
 #include "ope_octet.cuh"
 
@@ -1531,6 +1532,73 @@ static constexpr int kSeedG = 12;
 static constexpr int kSeedCells = kSeedG * kSeedG * kSeedG;
 static constexpr int kSaciaHypPerBlock = 8;
 
+// The scoring kernel's work order of the source: along the Morton curve of its bounding box, so that the 32 points of a warp are
+// neighbours (the coarse sample arrives in voxel-key order: rows across the whole model). .w carries the original index: the terms
+// are stored — and finally summed — in the original order. One block; more than kSaciaOrderMax points keep their order.
+static constexpr int kSaciaOrderMax = 4096;
+__global__ void __launch_bounds__(kSaciaThreads) sacia_source_order_kernel(const float4* __restrict__ src, int n, float4* __restrict__ out) {
+  __shared__ unsigned long long keys[kSaciaOrderMax];
+  __shared__ float red[6][kSaciaThreads / 32];
+  __shared__ float box[6];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (n > kSaciaOrderMax) {
+    for (int i = tid; i < n; i += kSaciaThreads) { float4 p = __ldg(src + i); p.w = __int_as_float(i); out[i] = p; }
+    return;
+  }
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int i = tid; i < n; i += kSaciaThreads) {
+    const float4 p = __ldg(src + i);
+    if (!finite3(p.x, p.y, p.z)) continue;
+    lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
+    hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
+  }
+  for (int o = 16; o > 0; o >>= 1)
+    for (int d = 0; d < 3; ++d) { lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o)); hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o)); }
+  if (lane == 0) for (int d = 0; d < 3; ++d) { red[d][warp] = lo[d]; red[3 + d][warp] = hi[d]; }
+  __syncthreads();
+  if (tid < 6) {
+    float v = red[tid][0];
+    for (int w = 1; w < kSaciaThreads / 32; ++w) v = tid < 3 ? fminf(v, red[tid][w]) : fmaxf(v, red[tid][w]);
+    box[tid] = v;
+  }
+  __syncthreads();
+  const float ext = fmaxf(fmaxf(box[3] - box[0], box[4] - box[1]), fmaxf(box[5] - box[2], 1e-9f));
+  const float scale = 1023.0f / ext;
+  int m2 = 1;
+  while (m2 < n) m2 <<= 1;
+  for (int i = tid; i < m2; i += kSaciaThreads) {
+    unsigned long long k = ~0ull;
+    if (i < n) {
+      const float4 p = __ldg(src + i);
+      unsigned code = 0x3fffffffu;   // non-finite points last
+      if (finite3(p.x, p.y, p.z))
+        code = morton3((unsigned)fminf(fmaxf((p.x - box[0]) * scale, 0.0f), 1023.0f), (unsigned)fminf(fmaxf((p.y - box[1]) * scale, 0.0f), 1023.0f),
+                       (unsigned)fminf(fmaxf((p.z - box[2]) * scale, 0.0f), 1023.0f));
+      k = ((unsigned long long)code << 32) | (unsigned)i;
+    }
+    keys[i] = k;
+  }
+  __syncthreads();
+  for (int k2 = 2; k2 <= m2; k2 <<= 1)
+    for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+      for (int i = tid; i < m2; i += kSaciaThreads) {
+        const int l = i ^ j2;
+        if (l > i) {
+          const bool up = (i & k2) == 0;
+          const unsigned long long ki = keys[i], kl = keys[l];
+          if ((ki > kl) == up) { keys[i] = kl; keys[l] = ki; }
+        }
+      }
+      __syncthreads();
+    }
+  for (int j = tid; j < n; j += kSaciaThreads) {
+    const int from = (int)(unsigned)(keys[j] & 0xffffffffull);
+    float4 p = __ldg(src + from);
+    p.w = __int_as_float(from);
+    out[j] = p;
+  }
+}
+
 __global__ void __launch_bounds__(128) sacia_transform_batch_kernel(SaciaBatch a, int frames) {
   const int idx = blockIdx.x * 128 + threadIdx.x;
   if (idx >= frames * a.H) return;
@@ -1652,8 +1720,8 @@ __global__ void __launch_bounds__(kSaciaThreads) sacia_score_batch_kernel(SaciaB
     __syncthreads();
     const Mat4 M = T;
     // The error is the float sum of the terms IN POINT ORDER (bit-exact with the reference's serial `error += ...`), formed by one
-    // thread — but only for a hypothesis that gets that far. The terms are >= 0, so every prefix of that sum is a lower bound of
-    // the total, and ANY summation order of a prefix is within n * 2^-24 (relative) of the serial one: after every chunk of
+    // thread — but only for a hypothesis that gets that far. The terms are >= 0, so the sum of any subset of them is a lower bound
+    // of the total, and ANY summation order is within n * 2^-24 (relative) of the serial one: after every chunk of
     // kSaciaThreads points the block adds the chunk up in parallel and compares that sum, shrunk by twice that bound, with the lowest
     // COMPLETE error any hypothesis of this frame has published so far. Once it is larger, the serial total would be larger too:
     // this hypothesis cannot be the first-lowest one and stops (its error is reported as +inf). Which hypotheses stop early
@@ -1667,8 +1735,10 @@ __global__ void __launch_bounds__(kSaciaThreads) sacia_score_batch_kernel(SaciaB
       float term = 0.0f;
       float x = 0.0f, y = 0.0f, z = 0.0f;
       bool search = false;
+      int orig = 0;
       if (i < a.ns) {
-        const float4 p = __ldg(a.src + i);
+        const float4 p = __ldg(a.src_scan + i);
+        orig = __float_as_int(p.w);
         xform_point(M, p.x, p.y, p.z, x, y, z);
         term = 1.0f;
         search = finite3(x, y, z);
@@ -1714,7 +1784,7 @@ __global__ void __launch_bounds__(kSaciaThreads) sacia_score_batch_kernel(SaciaB
         }
       }
       if (search && best <= a.threshold) term = best / a.threshold;
-      if (i < a.ns) terms[i] = term;
+      if (i < a.ns) terms[orig] = term;
       float part = term;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(full, part, o);
@@ -2414,6 +2484,11 @@ int sacia_batch_device(ope_ctx* ctx, const SaciaBatch& a_in, int frames, int max
   Scratch<float4> seed_geo(ctx);
   OPE_TRY(seed_tab.alloc((size_t)frames * kSeedCells)); OPE_TRY(seed_geo.alloc((size_t)frames));
   a.seed_tab = seed_tab.p; a.seed_geo = seed_geo.p;
+  Scratch<float4> src_scan(ctx);
+  OPE_TRY(src_scan.alloc((size_t)a.ns));
+  sacia_source_order_kernel<<<1, kSaciaThreads, 0, ctx->stream>>>(a.src, a.ns, src_scan.p);
+  OPE_TRY(check_launch(ctx, "sacia_source_order_kernel"));
+  a.src_scan = src_scan.p;
   const size_t nt8 = ((size_t)max_nt + 7) & ~(size_t)7, ng = nt8 / 8;
   const size_t bytes = (nt8 + 2 * ng) * sizeof(float4) + (size_t)a.ns * sizeof(float) + (size_t)kSeedCells * sizeof(unsigned short);
   sacia_transform_batch_kernel<<<div_up((size_t)frames * a.H, 128), 128, 0, ctx->stream>>>(a, frames);
@@ -2451,6 +2526,10 @@ bool icp_small_batch_applicable(const ope_icp_params& prm, size_t n_src, size_t 
 template <int THREADS>
 static int icp_small_batch_launch(ope_ctx* ctx, const ope_icp_params& prm, const IcpBatchFrame* frames, int n_frames, ope_reg_result* d_results) {
   if (n_frames <= 0) return OPE_OK;
+  const bool trace = std::getenv("OPE_BATCH_TRACE") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
+  const auto t_enter = now();
   std::vector<IcpDev> descs((size_t)n_frames);
   std::vector<int2> map;
   size_t max_nt = 0, total_src = 0, total_blocks = 0;
@@ -2506,7 +2585,9 @@ static int icp_small_batch_launch(ope_ctx* ctx, const ope_icp_params& prm, const
       return fail(ctx, OPE_ERR_UNSUPPORTED, "unknown correspondence rejector kind %d", prm.rejector_kind[r]);
   OPE_CUDA_TRY(ctx, cudaMemcpyAsync(d_descs.p, descs.data(), descs.size() * sizeof(IcpDev), cudaMemcpyHostToDevice, ctx->stream));
   OPE_CUDA_TRY(ctx, cudaMemcpyAsync(d_map.p, map.data(), map.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+  const double t_prep = ms_since(t_enter);
   OPE_CUDA_TRY(ctx, ope::stream_sync(ctx));   // descs / map live on this stack frame
+  if (trace) fprintf(stderr, "[ope batch] icp launch: host preparation %.3f ms, then %.3f ms until the stream had drained\n", t_prep, ms_since(t_enter) - t_prep);
   const size_t nt8 = (max_nt + 7) & ~(size_t)7;
   const size_t smem_bytes = ((sizeof(IcpSmallSmem<THREADS>) + 15) & ~(size_t)15) + nt8 * sizeof(float4) + (nt8 / 8) * 2 * sizeof(float4) +
                             (size_t)kSlabSlots * THREADS * sizeof(float2);
