@@ -210,8 +210,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"     # the version banner goes to stdout; this run prints exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / logs: stdout carries exactly one JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -240,8 +239,8 @@ def run_ours(args):
         return res
 
     libc.srand(1)
-    for _ in range(max(args.warmup, 3)):
-        step(targets[:max(64, len(targets) // 8)])
+    for _ in range(max(args.warmup, 3)):   # full steps: the chunking (and with it the memory pool's shape) depends on the batch size
+        step(targets)
 
     def timed(inputs):
         sampler = ClockSampler(local)
@@ -269,6 +268,7 @@ def run_ours(args):
     total_ms, launches, clocks, _ = timed(targets)
     value = N_FRAMES * args.steps / (total_ms / 1e3)
     # ---- e2e: host buffers in (H2D of every cluster), results out (D2H of every ope_pose_result) ----
+    step(clusters)   # untimed: the pinned staging buffers of the host path grow to this batch
     e2e_ms, _, _, last = timed(clusters)
     e2e_value = N_FRAMES * args.steps / (e2e_ms / 1e3)
     h2d = int(sum(len(c) for c in clusters)) * 16 + len(model) * 12

@@ -2354,30 +2354,148 @@ static int icp_stepwise_device(ope_ctx* ctx, const ope_cloud* src, const ope_clo
   return OPE_OK;
 }
 
-static inline int libc_random_index(int n) { return (int)(n * (rand() / (RAND_MAX + 1.0))); }
+// ---- the process-wide libc rand() stream, consumed in bulk ----------------------------------------------------------------
+// SAC-IA draws ~4 000 numbers per alignment from rand(), and they must be THE numbers a loop over fresh PoseEstimators would get
+// from the process's stream. glibc's rand() takes a lock per call (~25 ns); its generator itself (random_r.c: an additive
+// feedback generator over 7 / 15 / 31 / 63 words, or an LCG for the 8-byte state) is three instructions. A session borrows the
+// stream through the public API — initstate() hands back the live state array with the rear pointer's position encoded in front
+// of it — advances it in place, and gives it back with setstate(), which resumes from exactly where the session stopped. A
+// one-time self-test replays a few numbers against rand() itself (and rewinds); on any mismatch, or on another libc, every draw
+// goes through rand().
+class LibcRandSession {
+ public:
+  LibcRandSession() {
+#if defined(__GLIBC__)
+    if (!usable()) return;
+    begin();
+#endif
+  }
+  ~LibcRandSession() {
+#if defined(__GLIBC__)
+    if (state_) end();
+#endif
+  }
+  LibcRandSession(const LibcRandSession&) = delete;
+  LibcRandSession& operator=(const LibcRandSession&) = delete;
+  inline int next() {
+#if defined(__GLIBC__)
+    if (state_) return step();
+#endif
+    return rand();
+  }
+  // [UPSTREAM ia_ransac.hpp getRandomIndex]: n * (rand() / (RAND_MAX + 1.0)), truncated
+  inline int index(int n) { return (int)(n * (next() / (RAND_MAX + 1.0))); }
+
+ private:
+#if defined(__GLIBC__)
+  int32_t* word_ = nullptr;    // what initstate() returned: the word in front of the state array
+  int32_t* state_ = nullptr;   // null: not borrowed, next() calls rand()
+  int32_t *fptr_ = nullptr, *rptr_ = nullptr, *end_ = nullptr;
+  int type_ = 0;
+  alignas(8) char parked_[128];   // the state libc uses while its own is borrowed (nobody draws from it)
+
+  bool begin() {
+    static const int kDeg[5] = {0, 7, 15, 31, 63}, kSep[5] = {0, 3, 1, 3, 1};
+    borrow_mutex().lock();   // one borrower at a time (concurrent drawers would interleave their numbers anyway)
+    char* prev = initstate(1u, parked_, sizeof(parked_));
+    if (!prev) { borrow_mutex().unlock(); return false; }
+    word_ = reinterpret_cast<int32_t*>(prev);
+    type_ = word_[0] % 5;
+    const int rear = word_[0] / 5;
+    if (type_ < 0 || type_ > 4 || (type_ > 0 && (rear < 0 || rear >= kDeg[type_]))) {
+      setstate(prev);
+      word_ = nullptr;
+      borrow_mutex().unlock();
+      return false;
+    }
+    state_ = word_ + 1;
+    if (type_ > 0) { rptr_ = state_ + rear; fptr_ = state_ + (rear + kSep[type_]) % kDeg[type_]; end_ = state_ + kDeg[type_]; }
+    return true;
+  }
+  void end() {
+    word_[0] = type_ == 0 ? 0 : (int32_t)(5 * (rptr_ - state_) + type_);
+    setstate(reinterpret_cast<char*>(word_));
+    state_ = nullptr;
+    borrow_mutex().unlock();
+  }
+  static std::mutex& borrow_mutex() { static std::mutex m; return m; }
+  inline int step() {
+    if (type_ == 0) {
+      const int32_t v = (int32_t)(((uint32_t)state_[0] * 1103515245u + 12345u) & 0x7fffffffu);
+      state_[0] = v;
+      return v;
+    }
+    const uint32_t v = (uint32_t)*fptr_ + (uint32_t)*rptr_;
+    *fptr_ = (int32_t)v;
+    ++fptr_;
+    if (fptr_ >= end_) { fptr_ = state_; ++rptr_; }
+    else { ++rptr_; if (rptr_ >= end_) rptr_ = state_; }
+    return (int)(v >> 1);
+  }
+  // once per process: eight numbers from a borrowed copy against eight from rand(), then the stream is put back where it was
+  static bool usable() {
+    static std::once_flag once;
+    static bool ok = false;
+    std::call_once(once, [] {
+      if (const char* e = std::getenv("OPE_LIBC_RAND_FAST")) { if (std::atoi(e) == 0) return; }
+      static int32_t rewind[65];   // the stream's state before the test; libc runs on this copy afterwards
+      int fast[8], slow[8];
+      {
+        LibcRandSession probe(0);
+        if (!probe.begin()) return;
+        const int words = probe.type_ == 0 ? 2 : (int)(probe.end_ - probe.state_) + 1;
+        probe.end();                                   // encodes the rear pointer into word_[0]; libc is back on its own state
+        std::memcpy(rewind, probe.word_, (size_t)words * sizeof(int32_t));
+        if (!probe.begin()) return;
+        for (int i = 0; i < 8; ++i) fast[i] = probe.step();
+        std::memcpy(probe.word_, rewind, (size_t)words * sizeof(int32_t));   // undo
+        probe.state_ = nullptr;
+        setstate(reinterpret_cast<char*>(probe.word_));
+        borrow_mutex().unlock();
+      }
+      for (int i = 0; i < 8; ++i) slow[i] = rand();
+      setstate(reinterpret_cast<char*>(rewind));       // rewind: libc continues on the saved copy, eight numbers earlier
+      ok = std::memcmp(fast, slow, sizeof(fast)) == 0;
+    });
+    return ok;
+  }
+  explicit LibcRandSession(int) {}   // the self-test's probe: no borrowing in the constructor
+#endif
+};
+
+// the smallest float s with sqrtf(s) >= m: `sqrtf(s) < m` (sqrtf is correctly rounded and monotone) is exactly `s < that`
+static float sqrt_threshold(float m) {
+  if (!(m > 0.0f)) return 0.0f;                      // nothing is closer than a non-positive (or NaN) distance
+  float c = m * m;
+  if (!(c < INFINITY)) return INFINITY;              // (a distance limit beyond sqrt(FLT_MAX): every finite distance is closer)
+  while (c > 0.0f && std::sqrt(c) >= m) c = std::nextafter(c, 0.0f);
+  while (std::sqrt(c) < m) c = std::nextafter(c, INFINITY);
+  return c;
+}
 
 // selectSamples [UPSTREAM ia_ransac.hpp] on the host: it consumes libc rand() serially (SURVEY hard part 3)
-static int draw_samples(const float* src, size_t ns, size_t stride_f, int nr_samples, float& min_sample_distance, int32_t* out) {
+static int draw_samples(LibcRandSession& rng, const float* src, size_t ns, size_t stride_f, int nr_samples, float& min_sample_distance,
+                        int32_t* out) {
   if (nr_samples > (int)ns) return OPE_ERR_INVALID;
   int without = 0;
   const int max_without = (int)(3 * ns);
   int cnt = 0;
+  float too_close = sqrt_threshold(min_sample_distance);   // squared-distance form of `distance < min_sample_distance`
   while (cnt < nr_samples) {
-    const int si = libc_random_index((int)ns);
+    const int si = rng.index((int)ns);
     bool valid = true;
+    const float* a = src + (size_t)si * stride_f;
     for (int i = 0; i < cnt; ++i) {
-      const float* a = src + (size_t)si * stride_f;
       const float* b = src + (size_t)out[i] * stride_f;
       const float dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
-      volatile float s = dx * dx;
+      float s = dx * dx;     // (this file is compiled without contraction: three roundings, like the reference's float code)
       s = s + dy * dy;
       s = s + dz * dz;
-      const float dist = std::sqrt((float)s);
-      if (si == out[i] || dist < min_sample_distance) { valid = false; break; }
+      if (si == out[i] || s < too_close) { valid = false; break; }
     }
     if (valid) { out[cnt++] = si; without = 0; }
     else ++without;
-    if (without >= max_without) { min_sample_distance *= 0.5f; without = 0; }
+    if (without >= max_without) { min_sample_distance *= 0.5f; too_close = sqrt_threshold(min_sample_distance); without = 0; }
   }
   return OPE_OK;
 }
@@ -2408,10 +2526,11 @@ int sacia_device(ope_ctx* ctx, const ope_cloud* src, const float* d_fsrc, const 
     }
     hs.resize((size_t)H * S); hp.resize((size_t)H * S);
     float& msd = final_msd;
+    LibcRandSession rng;
     for (int it = 0; it < H; ++it) {
-      int rc = draw_samples(hx, src->n, 3, S, msd, hs.data() + (size_t)it * S);
+      int rc = draw_samples(rng, hx, src->n, 3, S, msd, hs.data() + (size_t)it * S);
       if (rc != OPE_OK) return fail(ctx, rc, "selectSamples failed");
-      for (int s = 0; s < S; ++s) hp[(size_t)it * S + s] = libc_random_index(K);
+      for (int s = 0; s < S; ++s) hp[(size_t)it * S + s] = rng.index(K);
     }
     samples = hs.data(); picks = hp.data();
   }
@@ -2800,10 +2919,11 @@ int ope_icp_align_fixed(ope_ctx* ctx, const ope_cloud* src, const ope_cloud* tgt
 int ope_sacia_draw(const float* src_xyz, size_t ns, size_t stride_bytes, int iterations, int nr_samples, int k_correspondences,
                    float* min_sample_distance, int32_t* samples, int32_t* picks) {
   if (!src_xyz || !samples || !picks || !min_sample_distance || stride_bytes % 4 != 0 || stride_bytes < 12) return OPE_ERR_INVALID;
+  LibcRandSession rng;
   for (int it = 0; it < iterations; ++it) {
-    int rc = draw_samples(src_xyz, ns, stride_bytes / 4, nr_samples, *min_sample_distance, samples + (size_t)it * nr_samples);
+    int rc = draw_samples(rng, src_xyz, ns, stride_bytes / 4, nr_samples, *min_sample_distance, samples + (size_t)it * nr_samples);
     if (rc != OPE_OK) return rc;
-    for (int s = 0; s < nr_samples; ++s) picks[(size_t)it * nr_samples + s] = libc_random_index(k_correspondences);
+    for (int s = 0; s < nr_samples; ++s) picks[(size_t)it * nr_samples + s] = rng.index(k_correspondences);
   }
   return OPE_OK;
 }
