@@ -479,12 +479,25 @@ int ope_pose_batch(ope_ctx* ctx, const ope_pose_params* prm, const float* model_
         ctx->workers.push_back(w);
       }
       if (lanes > 1) OPE_TRY(ope_ctx_synchronize(ctx));   // the other lanes read the model side from their own streams
-      for (int l = 1; l < lanes; ++l) {   // more threads than cores: the helper lanes' waits poll and yield instead of spinning
-        ope_ctx* c = ctx->workers[(size_t)l - 1];
-        const bool crowded = lanes + 1 > cores;
-        if (crowded && !c->sync_event && cudaEventCreateWithFlags(&c->sync_event, cudaEventDisableTiming) != cudaSuccess) c->sync_event = nullptr;
-        c->sync_yield = crowded && c->sync_event;
-        if (!crowded && c->sync_event) { cudaEventDestroy(c->sync_event); c->sync_event = nullptr; }
+      // How a lane waits for its stream: spinning is quickest but keeps a core; with fewer cores than lanes + table thread + one
+      // for everybody else, the waits sleep on a blocking event instead (OPE_BATCH_LANE_SYNC = spin | yield | block overrides)
+      int wait_mode = lanes + 2 > cores ? 2 : 0;   // 0 spin, 1 poll + yield, 2 block
+      if (const char* e = std::getenv("OPE_BATCH_LANE_SYNC")) wait_mode = std::strcmp(e, "block") == 0 ? 2 : std::strcmp(e, "yield") == 0 ? 1 : 0;
+      struct WaitMode {   // applied to every lane's context for this call, the caller's own context gets its setting back
+        ope_ctx* main; cudaEvent_t saved_event; bool saved_yield; cudaEvent_t mine = nullptr;
+        explicit WaitMode(ope_ctx* c) : main(c), saved_event(c->sync_event), saved_yield(c->sync_yield) {}
+        ~WaitMode() { main->sync_event = saved_event; main->sync_yield = saved_yield; if (mine) cudaEventDestroy(mine); }
+      } wait_guard(ctx);
+      if (lanes > 1) {
+        for (int l = 0; l < lanes; ++l) {
+          ope_ctx* c = l == 0 ? ctx : ctx->workers[(size_t)l - 1];
+          if (l > 0 && c->sync_event) { cudaEventDestroy(c->sync_event); c->sync_event = nullptr; }
+          cudaEvent_t ev = nullptr;
+          if (wait_mode != 0 && cudaEventCreateWithFlags(&ev, (wait_mode == 2 ? cudaEventBlockingSync : 0) | cudaEventDisableTiming) != cudaSuccess) ev = nullptr;
+          if (l == 0) wait_guard.mine = ev;
+          c->sync_event = ev;
+          c->sync_yield = wait_mode == 1 && ev;
+        }
       }
       std::atomic<size_t> next_chunk{0};
       std::atomic<int> lane_rc{OPE_OK};
