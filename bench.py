@@ -210,7 +210,11 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / logs: stdout carries exactly one JSON line
+        # NCCL's version banner and logs go to stderr — stdout carries exactly one JSON line. (NCCL honours NCCL_DEBUG_FILE only
+        # above the VERSION level.)
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 

