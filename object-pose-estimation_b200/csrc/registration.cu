@@ -1530,7 +1530,8 @@ __device__ __forceinline__ float box_d2(const float4 lo, const float4 hi, float 
 //                                 boxes and the seed grid are staged once per block
 static constexpr int kSeedG = 12;
 static constexpr int kSeedCells = kSeedG * kSeedG * kSeedG;
-static constexpr int kSaciaHypPerBlock = 8;
+static constexpr int kSaciaHypPerBlock = 16;
+static constexpr int kSaciaScoreThreads = 128;   // points per early-exit check: most hypotheses are out after the first one
 
 // The scoring kernel's work order of the source: along the Morton curve of its bounding box, so that the 32 points of a warp are
 // neighbours (the coarse sample arrives in voxel-key order: rows across the whole model). .w carries the original index: the terms
@@ -1679,7 +1680,7 @@ __global__ void __launch_bounds__(kSaciaThreads) sacia_seed_batch_kernel(SaciaBa
   }
 }
 
-__global__ void __launch_bounds__(kSaciaThreads) sacia_score_batch_kernel(SaciaBatch a) {
+__global__ void __launch_bounds__(kSaciaScoreThreads) sacia_score_batch_kernel(SaciaBatch a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // blockIdx.x = frame (fastest): the hypothesis groups of one frame run one after the other, so the bound below is known early
   const int f = blockIdx.x;
@@ -1692,17 +1693,17 @@ __global__ void __launch_bounds__(kSaciaThreads) sacia_score_batch_kernel(SaciaB
   float* terms = reinterpret_cast<float*>(ghi + n_groups);
   unsigned short* seed = reinterpret_cast<unsigned short*>(terms + a.ns);
   __shared__ Mat4 T;
-  __shared__ float wpart[2][kSaciaThreads / 32];
+  __shared__ float wpart[2][kSaciaScoreThreads / 32];
   __shared__ float s_best[2];
   const unsigned full = 0xffffffffu;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float4* scan = (a.tgt_scan ? a.tgt_scan : a.tgt) + (size_t)f * a.stride;   // a spatially sorted copy makes the boxes tight
-  for (int j = tid; j < nt8; j += kSaciaThreads) tg[j] = j < nt ? __ldg(scan + j) : make_float4(INFINITY, INFINITY, INFINITY, 0.0f);
-  for (int c = tid; c < kSeedCells; c += kSaciaThreads) seed[c] = a.seed_tab[(size_t)f * kSeedCells + c];
+  for (int j = tid; j < nt8; j += kSaciaScoreThreads) tg[j] = j < nt ? __ldg(scan + j) : make_float4(INFINITY, INFINITY, INFINITY, 0.0f);
+  for (int c = tid; c < kSeedCells; c += kSaciaScoreThreads) seed[c] = a.seed_tab[(size_t)f * kSeedCells + c];
   const float4 geo = a.seed_geo[f];
   __syncthreads();
   // boxes of the groups of 8 consecutive target points
-  for (int g = tid; g < n_groups; g += kSaciaThreads) {
+  for (int g = tid; g < n_groups; g += kSaciaScoreThreads) {
     float4 lo = make_float4(INFINITY, INFINITY, INFINITY, 0.0f), hi = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.0f);
     for (int u = 0; u < 8; ++u) {
       const float4 t = tg[8 * g + u];
@@ -1722,7 +1723,7 @@ __global__ void __launch_bounds__(kSaciaThreads) sacia_score_batch_kernel(SaciaB
     // The error is the float sum of the terms IN POINT ORDER (bit-exact with the reference's serial `error += ...`), formed by one
     // thread — but only for a hypothesis that gets that far. The terms are >= 0, so the sum of any subset of them is a lower bound
     // of the total, and ANY summation order is within n * 2^-24 (relative) of the serial one: after every chunk of
-    // kSaciaThreads points the block adds the chunk up in parallel and compares that sum, shrunk by twice that bound, with the lowest
+    // kSaciaScoreThreads points the block adds the chunk up in parallel and compares that sum, shrunk by twice that bound, with the lowest
     // COMPLETE error any hypothesis of this frame has published so far. Once it is larger, the serial total would be larger too:
     // this hypothesis cannot be the first-lowest one and stops (its error is reported as +inf). Which hypotheses stop early
     // depends on timing; the winner, its error and its transform do not.
@@ -1730,7 +1731,7 @@ __global__ void __launch_bounds__(kSaciaThreads) sacia_score_batch_kernel(SaciaB
     bool stop = false;
     int chunk = 0;
     const float shrink = 1.0f - 4.0f * (float)(a.ns + 32) * 5.97e-8f;   // twice the bound 2 n 2^-24 on the gap between two summation orders
-    for (int base = 0; base < a.ns; base += kSaciaThreads, ++chunk) {
+    for (int base = 0; base < a.ns; base += kSaciaScoreThreads, ++chunk) {
       const int i = base + tid;
       float term = 0.0f;
       float x = 0.0f, y = 0.0f, z = 0.0f;
@@ -1793,7 +1794,7 @@ __global__ void __launch_bounds__(kSaciaThreads) sacia_score_batch_kernel(SaciaB
       if (tid == 0) s_best[par] = __uint_as_float(*(volatile unsigned*)frame_best);
       __syncthreads();
 #pragma unroll
-      for (int w = 0; w < kSaciaThreads / 32; ++w) run += wpart[par][w];
+      for (int w = 0; w < kSaciaScoreThreads / 32; ++w) run += wpart[par][w];
       if (a.early_exit && run * shrink > s_best[par]) { stop = true; break; }   // the same values in every thread
     }
     if (tid == 0) {
@@ -2617,7 +2618,7 @@ int sacia_batch_device(ope_ctx* ctx, const SaciaBatch& a_in, int frames, int max
   OPE_TRY(check_launch(ctx, "sacia_seed_batch_kernel"));
   OPE_TRY(dyn_smem(ctx, (const void*)sacia_score_batch_kernel, bytes));
   cudaEventRecord(ctx->kev[1][0], ctx->stream);
-  sacia_score_batch_kernel<<<dim3(frames, (a.H + kSaciaHypPerBlock - 1) / kSaciaHypPerBlock), kSaciaThreads, bytes, ctx->stream>>>(a);
+  sacia_score_batch_kernel<<<dim3(frames, (a.H + kSaciaHypPerBlock - 1) / kSaciaHypPerBlock), kSaciaScoreThreads, bytes, ctx->stream>>>(a);
   cudaEventRecord(ctx->kev[1][1], ctx->stream);
   ctx->kev_valid[1] = true;
   OPE_TRY(check_launch(ctx, "sacia_score_batch_kernel"));
