@@ -61,7 +61,7 @@ def icp_kwargs():
 # iterations, 5.2 MB from DRAM); depth_fused_kernel: DRAM traffic equals the algorithmic bytes.
 NCU_ICP_DRAM_BYTES = 4826624 + 816128
 NCU_DEPTH_DRAM_BYTES = 629331712 + 4976560000
-NCU_ICP_BATCH_DRAM_BYTES = 24823808 + 158464      # icp_small_batch_kernel over 296 frames (profiles/r02_b_batch_kernels_full.txt)
+NCU_ICP_BATCH_DRAM_BYTES = 24792832 + 121856      # icp_small_batch_kernel over 296 frames (profiles/r02_f_batch_kernels_full.txt)
 
 
 def peaks():
@@ -385,12 +385,13 @@ def frame_roofline(ctx, cuda_lib, synth, model, clusters, stream, torch, n=8):
     a = bytes_ / (k_ms * 1e-3) / 1e9
     return {"kernel": "icp_small_batch_kernel (timed on one lane: one launch per chunk of <= 296 frames, nothing else on the device)", "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s",
             "frac": a / peak, "traffic": NCU_ICP_BATCH_DRAM_BYTES, "traffic_source": "ncu --set full of one launch over 296 frames "
-            "(profiles/r02_b_batch_kernels_full.txt): dram__bytes_read.sum + dram__bytes_write.sum", "peak_source": peak_src,
+            "(profiles/r02_f_batch_kernels_full.txt): dram__bytes_read.sum + dram__bytes_write.sum", "peak_source": peak_src,
             "kernel_ms_per_frame": k_ms / len(clusters), "kernel_share_of_step": k_ms / total,
             "stage_ms_per_frame": {k: round(v / len(clusters), 5) for k, v in st.items()},
-            "note": "a frame's fine clouds are ~1.7k + ~1.3k points and live in shared memory for the whole alignment: the launch is "
-                    "issue/latency-bound (ncu: 42 % issue-active, 24 % warps active, DRAM 0.008 %), not HBM-bound (SURVEY 8d); frac is "
-                    "reported against HBM as the contract asks. The HBM-bound stage of the pipeline is depth_to_cloud (below)."}
+            "note": "a frame's fine clouds are ~1.7k + ~1.1k points and live in shared memory for the whole alignment: the launch is "
+                    "issue/latency-bound (ncu: 39 % issue-active, 44 % of the stall samples on barriers, DRAM 0.008 %), not HBM-bound "
+                    "(SURVEY 8d); frac is reported against HBM as the contract asks. Timed on one lane (nothing else on the device); "
+                    "in the headline run eight lanes overlap the launches' tails. The HBM-bound stage is depth_to_cloud (below)."}
 
 
 def frames_cpu_baseline(ctx, cuda_lib, synth, model, clusters, n=24, seed=7):
