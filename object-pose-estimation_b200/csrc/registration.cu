@@ -1695,7 +1695,6 @@ __global__ void __launch_bounds__(kSaciaScoreThreads) sacia_score_batch_kernel(S
   __shared__ Mat4 T;
   __shared__ float wpart[2][kSaciaScoreThreads / 32];
   __shared__ float s_best[2];
-  __shared__ float s_h_best;
   const unsigned full = 0xffffffffu;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float4* scan = (a.tgt_scan ? a.tgt_scan : a.tgt) + (size_t)f * a.stride;   // a spatially sorted copy makes the boxes tight
@@ -1719,10 +1718,8 @@ __global__ void __launch_bounds__(kSaciaScoreThreads) sacia_score_batch_kernel(S
   for (int h = (int)blockIdx.y * kSaciaHypPerBlock; h < h_end; ++h) {
     // (this barrier also closes the previous hypothesis: thread 0's final sum has read the terms)
     if (tid < 16) T.m[tid] = __ldg(a.transforms + ((size_t)f * a.H + h) * 16 + tid);
-    if (tid == 0) s_h_best = __uint_as_float(*(volatile unsigned*)frame_best);
     __syncthreads();
     const Mat4 M = T;
-    const float h_best = s_h_best;   // the frame's lowest complete error when this hypothesis starts (+inf: none yet)
     // The error is the float sum of the terms IN POINT ORDER (bit-exact with the reference's serial `error += ...`), formed by one
     // thread — but only for a hypothesis that gets that far. The terms are >= 0, so the sum of any subset of them is a lower bound
     // of the total, and ANY summation order is within n * 2^-24 (relative) of the serial one: after every chunk of
@@ -1730,91 +1727,76 @@ __global__ void __launch_bounds__(kSaciaScoreThreads) sacia_score_batch_kernel(S
     // COMPLETE error any hypothesis of this frame has published so far. Once it is larger, the serial total would be larger too:
     // this hypothesis cannot be the first-lowest one and stops (its error is reported as +inf). Which hypotheses stop early
     // depends on timing; the winner, its error and its transform do not.
+    float run = 0.0f;
+    bool stop = false;
     int chunk = 0;
     const float shrink = 1.0f - 4.0f * (float)(a.ns + 32) * 5.97e-8f;   // twice the bound 2 n 2^-24 on the gap between two summation orders
-    // One sweep over the source. LB_ONLY: every term is replaced by a lower bound that needs no point distances — the squared
-    // distance to the nearest group BOX among the candidates (every other group is farther than the seed point, see the cull), or
-    // the seed point's distance if that is smaller, shrunk by 1e-4 against float rounding — at a quarter of the cost. The sum of
-    // lower bounds is a lower bound of the error, so the same test stops most hypotheses before a single exact distance is formed;
-    // a hypothesis that survives it is swept again exactly. Returns true when the hypothesis is out.
-    auto sweep = [&](const bool lb_only) -> bool {
-      float run = 0.0f;
-      for (int base = 0; base < a.ns; base += kSaciaScoreThreads, ++chunk) {
-        const int i = base + tid;
-        float term = 0.0f;
-        float x = 0.0f, y = 0.0f, z = 0.0f;
-        bool search = false;
-        int orig = 0;
-        if (i < a.ns) {
-          const float4 p = __ldg(a.src_scan + i);
-          orig = __float_as_int(p.w);
-          xform_point(M, p.x, p.y, p.z, x, y, z);
-          term = 1.0f;
-          search = finite3(x, y, z);
-        }
-        // only the DISTANCE of the nearest neighbour enters the score: ties need no index order
-        float best = FLT_MAX, box_min = FLT_MAX;
-        if (search) {
-          const float fx = fminf(fmaxf((x - geo.x) * geo.w, 0.0f), (float)(kSeedG - 1)), fy = fminf(fmaxf((y - geo.y) * geo.w, 0.0f), (float)(kSeedG - 1)),
-                      fz = fminf(fmaxf((z - geo.z) * geo.w, 0.0f), (float)(kSeedG - 1));
-          const float4 t = tg[seed[((int)fz * kSeedG + (int)fy) * kSeedG + (int)fx]];
-          const float d2 = dist2(x, y, z, t.x, t.y, t.z);
-          if (d2 < best) best = d2;
-        }
-        // the box around the warp's 32 queries (neighbours on the model's Morton curve), grown by the widest bound among them,
-        // against the group boxes, one group per lane; the groups that pass go through the per-thread test. Conservative
-        // comparisons: a float box distance can only be a rounding error above the float distance to a point inside the box.
-        float wlx = search ? x : INFINITY, wly = search ? y : INFINITY, wlz = search ? z : INFINITY;
-        float whx = search ? x : -INFINITY, why = search ? y : -INFINITY, whz = search ? z : -INFINITY;
-        float wb = search ? best : 0.0f;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          wlx = fminf(wlx, __shfl_xor_sync(full, wlx, o)); wly = fminf(wly, __shfl_xor_sync(full, wly, o)); wlz = fminf(wlz, __shfl_xor_sync(full, wlz, o));
-          whx = fmaxf(whx, __shfl_xor_sync(full, whx, o)); why = fmaxf(why, __shfl_xor_sync(full, why, o)); whz = fmaxf(whz, __shfl_xor_sync(full, whz, o));
-          wb = fmaxf(wb, __shfl_xor_sync(full, wb, o));
-        }
-        const float wlim = wb * 1.0002f + 1e-30f;
-        for (int g0 = 0; g0 < n_groups; g0 += 32) {
-          bool near = false;
-          if (g0 + lane < n_groups) {
-            const float4 lo = glo[g0 + lane], hi = ghi[g0 + lane];
-            const float ex = fmaxf(fmaxf(lo.x - whx, wlx - hi.x), 0.0f), ey = fmaxf(fmaxf(lo.y - why, wly - hi.y), 0.0f),
-                        ez = fmaxf(fmaxf(lo.z - whz, wlz - hi.z), 0.0f);
-            near = ex * ex + ey * ey + ez * ez <= wlim;
-          }
-          for (unsigned cand = __ballot_sync(full, near); cand != 0u; cand &= cand - 1u) {
-            const int g = g0 + __ffs(cand) - 1;
-            const float bd2 = box_d2(glo[g], ghi[g], x, y, z);
-            if (lb_only) { box_min = fminf(box_min, bd2); continue; }
-            if (!search || !(bd2 <= best * 1.0001f + 1e-30f)) continue;
-            float d2[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) { const float4 t = tg[8 * g + u]; d2[u] = dist2(x, y, z, t.x, t.y, t.z); }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) best = d2[u] < best ? d2[u] : best;   // NaN / inf (padding, non-finite targets) never wins
-          }
-        }
-        if (lb_only) {
-          if (search) term = fminf(fminf(best, box_min) * 0.9999f / a.threshold, 1.0f);
-        } else {
-          if (search && best <= a.threshold) term = best / a.threshold;
-          if (i < a.ns) terms[orig] = term;
-        }
-        float part = term;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(full, part, o);
-        const int par = chunk & 1;
-        if (lane == 0) wpart[par][warp] = part;
-        if (tid == 0) s_best[par] = __uint_as_float(*(volatile unsigned*)frame_best);
-        __syncthreads();
-#pragma unroll
-        for (int w = 0; w < kSaciaScoreThreads / 32; ++w) run += wpart[par][w];
-        if (a.early_exit && run * shrink > s_best[par]) { ++chunk; return true; }   // the same values in every thread
+    for (int base = 0; base < a.ns; base += kSaciaScoreThreads, ++chunk) {
+      const int i = base + tid;
+      float term = 0.0f;
+      float x = 0.0f, y = 0.0f, z = 0.0f;
+      bool search = false;
+      int orig = 0;
+      if (i < a.ns) {
+        const float4 p = __ldg(a.src_scan + i);
+        orig = __float_as_int(p.w);
+        xform_point(M, p.x, p.y, p.z, x, y, z);
+        term = 1.0f;
+        search = finite3(x, y, z);
       }
-      return false;
-    };
-    bool stop = a.early_exit && h_best < INFINITY && sweep(true);
-    if (!stop) stop = sweep(false);
+      // only the DISTANCE of the nearest neighbour enters the score: ties need no index order
+      float best = FLT_MAX;
+      if (search) {
+        const float fx = fminf(fmaxf((x - geo.x) * geo.w, 0.0f), (float)(kSeedG - 1)), fy = fminf(fmaxf((y - geo.y) * geo.w, 0.0f), (float)(kSeedG - 1)),
+                    fz = fminf(fmaxf((z - geo.z) * geo.w, 0.0f), (float)(kSeedG - 1));
+        const float4 t = tg[seed[((int)fz * kSeedG + (int)fy) * kSeedG + (int)fx]];
+        const float d2 = dist2(x, y, z, t.x, t.y, t.z);
+        if (d2 < best) best = d2;
+      }
+      // the box around the warp's 32 queries (consecutive model points: neighbours), grown by the widest bound among them, against
+      // the group boxes, one group per lane; the groups that pass go through the per-thread test. Conservative comparisons: a
+      // float box distance can only be a rounding error above the float distance to a point inside the box.
+      float wlx = search ? x : INFINITY, wly = search ? y : INFINITY, wlz = search ? z : INFINITY;
+      float whx = search ? x : -INFINITY, why = search ? y : -INFINITY, whz = search ? z : -INFINITY;
+      float wb = search ? best : 0.0f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        wlx = fminf(wlx, __shfl_xor_sync(full, wlx, o)); wly = fminf(wly, __shfl_xor_sync(full, wly, o)); wlz = fminf(wlz, __shfl_xor_sync(full, wlz, o));
+        whx = fmaxf(whx, __shfl_xor_sync(full, whx, o)); why = fmaxf(why, __shfl_xor_sync(full, why, o)); whz = fmaxf(whz, __shfl_xor_sync(full, whz, o));
+        wb = fmaxf(wb, __shfl_xor_sync(full, wb, o));
+      }
+      const float wlim = wb * 1.0002f + 1e-30f;
+      for (int g0 = 0; g0 < n_groups; g0 += 32) {
+        bool near = false;
+        if (g0 + lane < n_groups) {
+          const float4 lo = glo[g0 + lane], hi = ghi[g0 + lane];
+          const float ex = fmaxf(fmaxf(lo.x - whx, wlx - hi.x), 0.0f), ey = fmaxf(fmaxf(lo.y - why, wly - hi.y), 0.0f),
+                      ez = fmaxf(fmaxf(lo.z - whz, wlz - hi.z), 0.0f);
+          near = ex * ex + ey * ey + ez * ez <= wlim;
+        }
+        for (unsigned cand = __ballot_sync(full, near); cand != 0u; cand &= cand - 1u) {
+          const int g = g0 + __ffs(cand) - 1;
+          if (!search || !(box_d2(glo[g], ghi[g], x, y, z) <= best * 1.0001f + 1e-30f)) continue;
+          float d2[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { const float4 t = tg[8 * g + u]; d2[u] = dist2(x, y, z, t.x, t.y, t.z); }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) best = d2[u] < best ? d2[u] : best;   // NaN / inf (padding, non-finite targets) never wins
+        }
+      }
+      if (search && best <= a.threshold) term = best / a.threshold;
+      if (i < a.ns) terms[orig] = term;
+      float part = term;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(full, part, o);
+      const int par = chunk & 1;
+      if (lane == 0) wpart[par][warp] = part;
+      if (tid == 0) s_best[par] = __uint_as_float(*(volatile unsigned*)frame_best);
+      __syncthreads();
+#pragma unroll
+      for (int w = 0; w < kSaciaScoreThreads / 32; ++w) run += wpart[par][w];
+      if (a.early_exit && run * shrink > s_best[par]) { stop = true; break; }   // the same values in every thread
+    }
     if (tid == 0) {
       float error = INFINITY;
       if (!stop) {
