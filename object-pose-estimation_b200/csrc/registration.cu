@@ -2433,29 +2433,30 @@ class LibcRandSession {
     else { ++rptr_; if (rptr_ >= end_) rptr_ = state_; }
     return (int)(v >> 1);
   }
-  // once per process: eight numbers from a borrowed copy against eight from rand(), then the stream is put back where it was
+  // once per process: eight numbers drawn in a borrowed session against the same eight from rand(), the stream rewound after each
+  // (libc ends up on its own state array, in its original state: nothing keeps pointing into this library)
   static bool usable() {
     static std::once_flag once;
     static bool ok = false;
     std::call_once(once, [] {
       if (const char* e = std::getenv("OPE_LIBC_RAND_FAST")) { if (std::atoi(e) == 0) return; }
-      static int32_t rewind[65];   // the stream's state before the test; libc runs on this copy afterwards
+      int32_t saved[65];   // header word + up to 63 state words
       int fast[8], slow[8];
-      {
-        LibcRandSession probe(0);
-        if (!probe.begin()) return;
-        const int words = probe.type_ == 0 ? 2 : (int)(probe.end_ - probe.state_) + 1;
-        probe.end();                                   // encodes the rear pointer into word_[0]; libc is back on its own state
-        std::memcpy(rewind, probe.word_, (size_t)words * sizeof(int32_t));
-        if (!probe.begin()) return;
-        for (int i = 0; i < 8; ++i) fast[i] = probe.step();
-        std::memcpy(probe.word_, rewind, (size_t)words * sizeof(int32_t));   // undo
+      LibcRandSession probe(0);
+      auto rewind = [&](size_t words) {   // borrowed: put the saved state back and return the array to libc
+        std::memcpy(probe.word_, saved, words * sizeof(int32_t));
         probe.state_ = nullptr;
         setstate(reinterpret_cast<char*>(probe.word_));
         borrow_mutex().unlock();
-      }
+      };
+      if (!probe.begin()) return;
+      const size_t words = probe.type_ == 0 ? 2 : (size_t)(probe.end_ - probe.state_) + 1;
+      std::memcpy(saved, probe.word_, words * sizeof(int32_t));   // initstate() has just encoded the rear pointer in the header
+      for (int i = 0; i < 8; ++i) fast[i] = probe.step();
+      rewind(words);
       for (int i = 0; i < 8; ++i) slow[i] = rand();
-      setstate(reinterpret_cast<char*>(rewind));       // rewind: libc continues on the saved copy, eight numbers earlier
+      if (!probe.begin()) return;
+      rewind(words);
       ok = std::memcmp(fast, slow, sizeof(fast)) == 0;
     });
     return ok;
