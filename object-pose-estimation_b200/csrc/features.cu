@@ -72,23 +72,39 @@ __device__ __forceinline__ void normals_smem_body(const float4* __restrict__ pts
   const int lane = threadIdx.x & 31;
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
   const float nan = __int_as_float(0x7fc00000);
-  for (int i = wid; i < n; i += n_warps) {
-    const float4 q = tg_norm[i];
-    const bool ok = finite3(q.x, q.y, q.z);
-    float ld;
-    int li;
-    const int cnt = warp_knn_smem_bounded(tg_norm, n, n_finite, ok, q.x, q.y, q.z, k, FLT_MAX, knn_buf[threadIdx.x >> 5], ld, li);
-    float4 p = make_float4(0, 0, 0, 0);
-    if (lane < cnt) p = tg_norm[li];
-    float r[4] = {nan, nan, nan, nan};
-    if (ok && cnt >= 3) {
-      CovAccum acc;
-      acc.reset();
-      for (int j = 0; j < cnt; ++j)
-        acc.add(__shfl_sync(0xffffffffu, p.x, j), __shfl_sync(0xffffffffu, p.y, j), __shfl_sync(0xffffffffu, p.z, j));
-      normal_from_accum(acc, cnt, q.x, q.y, q.z, vpx, vpy, vpz, r);
+  // The search is a warp's job (one query at a time); the covariance sums — serial over the neighbours in list order, like the
+  // reference's — and the eigenvector are one THREAD's job. So a warp answers 32 queries, parks every neighbour list in shared
+  // memory, and then each lane finishes one query: the serial part runs once per 32 queries instead of once per query with 31
+  // lanes repeating it. Same operations in the same order per query: the same normals, bit for bit.
+  __shared__ unsigned short nbr[kNormThreads / 32][32][34];   // [warp][slot][rank]; 34: lanes reading one rank hit 32 banks
+  const int warp = threadIdx.x >> 5;
+  for (int base = wid; base < n; base += 32 * n_warps) {
+    int my_cnt = 0;
+    bool my_ok = false;
+    for (int slot = 0; slot < 32; ++slot) {
+      const int i = base + slot * n_warps;
+      if (i >= n) break;   // warp-uniform
+      const float4 q = tg_norm[i];
+      const bool ok = finite3(q.x, q.y, q.z);
+      float ld;
+      int li;
+      const int cnt = warp_knn_smem_bounded(tg_norm, n, n_finite, ok, q.x, q.y, q.z, k, FLT_MAX, knn_buf[warp], ld, li);
+      if (lane < cnt) nbr[warp][slot][lane] = (unsigned short)li;
+      if (lane == slot) { my_cnt = cnt; my_ok = ok; }
     }
-    if (lane == 0) out[i] = make_float4(r[0], r[1], r[2], r[3]);
+    __syncwarp();
+    const int i = base + lane * n_warps;
+    if (i < n) {
+      float r[4] = {nan, nan, nan, nan};
+      if (my_ok && my_cnt >= 3) {
+        const float4 q = tg_norm[i];
+        CovAccum acc;
+        acc.reset();
+        for (int j = 0; j < my_cnt; ++j) { const float4 p = tg_norm[nbr[warp][lane][j]]; acc.add(p.x, p.y, p.z); }
+        normal_from_accum(acc, my_cnt, q.x, q.y, q.z, vpx, vpy, vpz, r);
+      }
+      out[i] = make_float4(r[0], r[1], r[2], r[3]);
+    }
     __syncwarp();
   }
 }

@@ -204,3 +204,33 @@ def test_c1_c5_scene_sample_single_and_batched(ctx, orc, synth, cuda_lib, drill)
             assert (p.icp_state, p.icp_converged, p.icp_iterations, p.sacia_best_iteration) == (o_state, o_conv, o_it, o_best), (name, f)
             assert abs(p.fitness - o_fit) < FIT_TOL and abs(p.align_strength - o_strength) < 1e-12, (name, f)
         assert np.abs(src - o_src).max() < 2e-5, f           # alignedSource handed back in place of the source
+
+
+@pytest.mark.gpu
+def test_pose_batch_lanes_and_chunks_do_not_change_results(ctx, synth, cuda_lib, drill, monkeypatch):
+    """ope_pose_batch cuts a batch into chunks and runs them on concurrent lanes (helper threads on worker contexts); tables drawn
+    inside the call from libc rand(). Whatever the cut — one lane and one chunk, many lanes and tiny chunks, sleeping or spinning
+    waits — every frame's result is the same, bit for bit, and the decision tables come from the stream in frame order."""
+    libc = ctypes.CDLL(None)
+    n = 40
+    clusters = [synth.make_frame(drill, 2000 + f)[0] for f in range(n)]
+
+    def run(lanes, chunk, sync=None):
+        monkeypatch.setenv("OPE_BATCH_LANES", str(lanes))
+        monkeypatch.setenv("OPE_BATCH_CHUNK", str(chunk))
+        if sync:
+            monkeypatch.setenv("OPE_BATCH_LANE_SYNC", sync)
+        else:
+            monkeypatch.delenv("OPE_BATCH_LANE_SYNC", raising=False)
+        libc.srand(11)
+        res, status = ctx.pose_batch(drill, clusters, tables=None, workers=8)
+        assert (status == 0).all()
+        tail = libc.rand()   # where the stream stands after the call
+        return [(tuple(r.final_pose), tuple(r.coarse_pose), tuple(r.fine_pose), r.icp_iterations, r.icp_state, r.icp_converged,
+                 r.sacia_best_iteration, r.sacia_best_error, r.fitness, r.align_strength, r.n_src_fine, r.n_tgt_fine) for r in res], tail
+
+    ref, tail = run(1, 64)
+    for lanes, chunk, sync in ((2, 20, None), (4, 7, "block"), (8, 5, "yield"), (3, 13, "spin")):
+        got, t = run(lanes, chunk, sync)
+        assert got == ref, (lanes, chunk, sync)
+        assert t == tail, (lanes, chunk, sync)
