@@ -243,6 +243,7 @@ def run_ours(args):
         return res
 
     libc.srand(1)
+    barrier()   # the first collective builds NCCL's communicator (threads, peer mappings): before the warm-up, not inside the timing
     for _ in range(max(args.warmup, 3)):   # full steps: the chunking (and with it the memory pool's shape) depends on the batch size
         step(targets)
 
@@ -268,6 +269,11 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), ctx.launches - l0, clocks, last
 
+    if os.environ.get("OPE_BENCH_DEBUG_ARMS"):   # diagnosis: both arms, alternating, per-rank ms per step on stderr
+        for name, inp in (("resident", targets), ("host", clusters), ("resident", targets), ("host", clusters)):
+            step(inp)
+            ms, _, _, _ = timed(inp)
+            sys.stderr.write("[arms] rank %d %s %.2f ms/step\n" % (rank, name, ms / args.steps))
     # ---- value: clusters resident in HBM ----
     total_ms, launches, clocks, _ = timed(targets)
     value = N_FRAMES * args.steps / (total_ms / 1e3)
