@@ -247,14 +247,15 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):   # full steps: the chunking (and with it the memory pool's shape) depends on the batch size
         step(targets)
 
-    def timed(inputs):
+    def timed(inputs, steps=None):
+        steps = args.steps if steps is None else steps
         sampler = ClockSampler(local)
         barrier()
         sampler.start()
         l0 = ctx.launches
         ms = []
         last = None
-        for _ in range(args.steps):
+        for _ in range(steps):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
@@ -274,6 +275,9 @@ def run_ours(args):
             step(inp)
             ms, _, _, _ = timed(inp)
             sys.stderr.write("[arms] rank %d %s %.2f ms/step\n" % (rank, name, ms / args.steps))
+    # (untimed dress rehearsal of the timed region itself — barrier, clock sampler, events: at N > 1 the first pass through it was
+    # measured 60 % slower than every later one)
+    timed(targets, 2)
     # ---- value: clusters resident in HBM ----
     total_ms, launches, clocks, _ = timed(targets)
     value = N_FRAMES * args.steps / (total_ms / 1e3)
@@ -292,7 +296,7 @@ def run_ours(args):
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_step": N_FRAMES, "l2": "flushed between steps (256 MiB write)",
-                       "sharding": "frame f -> rank f mod N, no collective", "api": "ope_pose_batch", "workers_per_rank": WORKERS, "chunk_lanes_per_rank": lanes,
+                       "sharding": "frame f -> rank f mod N, no collective", "api": "ope_pose_batch", "workers_per_rank": WORKERS, "chunk_lanes_per_rank": lanes, "untimed_rehearsal_steps": 2,
                        "host_cores_per_rank": cores,
                        "sacia_tables": "drawn from libc rand() inside the timed region (ope_sacia_draw)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
