@@ -326,15 +326,20 @@ OPE_HD bool nn1_fast(const GridView& g, float qx, float qy, float qz, float ux, 
     if (ne[j] - nb[j] > 0) { OPE_COUNT(2); nn1_offer(st, dist2(qx, qy, qz, pa[j].x, pa[j].y, pa[j].z), f2i(pa[j].w)); }
     if (ne[j] - nb[j] > 1) nn1_offer(st, dist2(qx, qy, qz, pb[j].x, pb[j].y, pb[j].z), f2i(pb[j].w));
   }
-  // the rest (cells with more than two points), two loads in flight
+  // the rest (cells with more than two points), OPE_NN1_REST_WIDTH loads in flight (the offers stay in index order; measured on C2:
+  // 2 -> 5.71 ms, 4 -> 5.53, 8 -> 5.55; deferring more of these queries to the warp queue, OPE_NN1_FAST_MAX 32, -> 6.87)
+#ifndef OPE_NN1_REST_WIDTH
+#define OPE_NN1_REST_WIDTH 4
+#endif
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    for (int i = nb[j] + 2; i < ne[j]; i += 2) {
-      const float4 p0 = OPE_LDG(g.pts + i);
-      const bool two = i + 1 < ne[j];
-      const float4 p1 = two ? OPE_LDG(g.pts + i + 1) : p0;
-      nn1_offer(st, dist2(qx, qy, qz, p0.x, p0.y, p0.z), f2i(p0.w));
-      if (two) nn1_offer(st, dist2(qx, qy, qz, p1.x, p1.y, p1.z), f2i(p1.w));
+    for (int i = nb[j] + 2; i < ne[j]; i += OPE_NN1_REST_WIDTH) {
+      float4 pw[OPE_NN1_REST_WIDTH];
+#pragma unroll
+      for (int u = 0; u < OPE_NN1_REST_WIDTH; ++u) pw[u] = OPE_LDG(g.pts + (i + u < ne[j] ? i + u : i));
+#pragma unroll
+      for (int u = 0; u < OPE_NN1_REST_WIDTH; ++u)
+        if (i + u < ne[j]) nn1_offer(st, dist2(qx, qy, qz, pw[u].x, pw[u].y, pw[u].z), f2i(pw[u].w));
     }
   }
   return true;
