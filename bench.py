@@ -316,6 +316,7 @@ def run_ours(args):
         for key, fn in (("icp", lambda: icp_numbers(ctx, cuda_lib, synth, model, stream, torch, flush, args)),
                         ("feature_gemm", lambda: feature_gemm_numbers(ctx)),
                         ("depth_to_cloud", lambda: depth_numbers(ctx, synth, model, stream, torch)),
+                        ("scene_preparation", lambda: scene_numbers(ctx, cuda_lib, synth, model, stream, torch)),
                         ("single_frame", lambda: single_frame_numbers(ctx, cuda_lib, synth, model, clusters, stream, torch))):
             try:
                 line[key] = fn()
@@ -561,6 +562,49 @@ def depth_numbers(ctx, synth, model, stream, torch, frames=1024):
                          "traffic": NCU_DEPTH_DRAM_BYTES if frames == 1024 else None,
                          "traffic_source": "ncu --set full, profiles/r01_e_depth_fused_full.txt", "peak_source": peak_src,
                          "note": "algorithmic = 2 B per pixel in + 16 B per kept pixel out; ncu dram__bytes of the launch equal it (profiles/)"}}
+
+
+def scene_numbers(ctx, cuda_lib, synth, model, stream, torch, frames=(21, 22, 23)):
+    """Scene preparation (SURVEY 8f-2, D&L/src/objectsegmentationplane.cpp): pass-through crop + getSegmentedObjectsOnPlane (table
+    plane RANSAC, polygonal prism, second plane, Euclidean clusters) on full 640x480 frames resident in HBM, device time per frame;
+    the oracle on one host core on the same frames; per-point labels, plane equations and RANSAC iteration counts must be equal."""
+    import orc_py
+    limits = (-0.5, 0.5, -0.5, 0.3, 0.5, 1.6)      # ObjectSegmentationPlane::getFiltered, D&L/src/objectsegmentationplane.cpp:17-18
+    clouds = [synth.make_frame(model, f)[1].reshape(-1, 3) for f in frames]
+    dev = [ctx.upload(c) for c in clouds]
+
+    def gpu(c):
+        filt = ctx.pass_through(c, limits)
+        return filt, ctx.segment_objects_on_plane(filt)
+
+    for c in dev:
+        gpu(c)
+    ms = []
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        got = [gpu(c) for c in dev]
+        e1.record(stream)
+        e1.synchronize()
+        ms.append(e0.elapsed_time(e1) / len(dev))
+    t0 = time.perf_counter()
+    same, kept = True, 0
+    for pts, (filt, g) in zip(clouds, got):
+        keep = np.arange(len(pts), dtype=np.int32)
+        for field, lo, hi in ((2, limits[4], limits[5]), (1, limits[2], limits[3]), (0, limits[0], limits[1])):   # z, y, x
+            keep = keep[orc_py.pass_through(pts[keep], field, lo, hi)]
+        o = orc_py.segment_objects_on_plane(pts[keep])
+        kept += len(keep)
+        same &= bool(np.array_equal(filt.download(), pts[keep]) and np.array_equal(g[0], o[0]) and g[1] == o[1] and
+                     np.array_equal(g[2], o[2]) and np.array_equal(g[3], o[3]) and tuple(g[4]) == tuple(o[4]))
+    cpu_s = (time.perf_counter() - t0) / len(dev)
+    t = float(np.median(ms))
+    return {"workload": "pass-through + getSegmentedObjectsOnPlane on %d full 640x480 frames resident in HBM (%d of 307200 points survive "
+                        "the crop on average)" % (len(dev), kept // len(dev)),
+            "api": "ope_pass_through + ope_segment_objects_on_plane", "ms_per_frame": t, "frames_per_sec": 1e3 / t,
+            "cpu_baseline": {"value": 1.0 / cpu_s, "unit": "frames/s", "cores": 1, "kind": "port",
+                             "sample": "the same %d frames, %.2f s each" % (len(dev), cpu_s)},
+            "parity": {"labels_planes_iterations_equal": same, "ok": same}}
 
 
 def single_frame_numbers(ctx, cuda_lib, synth, model, clusters, stream, torch, n=12):

@@ -221,17 +221,21 @@ __global__ void cell_scatter_kernel(const float4* __restrict__ pts, int n, Binni
     sorted[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
   }
 }
-// order each cell's points by original index (deterministic traversal; cells hold a handful of points)
-__global__ void cell_sort_kernel(const int* __restrict__ cell_start, int64_t ncells, float4* __restrict__ sorted) {
-  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < ncells; c += (int64_t)gridDim.x * blockDim.x) {
+// Order each cell's points by original index (deterministic traversal whatever order the atomics scattered them in): every point
+// counts the points of its cell with a smaller index and goes to that rank in a second array. One thread per point, so a cell of a
+// thousand points (a 5 cm clustering grid over a full-resolution frame) costs its points a thousand cached loads each instead of
+// one thread a million moves.
+__global__ void cell_rank_kernel(const float4* __restrict__ scattered, const int* __restrict__ cell_start, int64_t ncells, Binning bin,
+                                 float4* __restrict__ sorted) {
+  const int total = cell_start[ncells];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const float4 v = scattered[i];
+    const int c = bin_cell(bin, v.x, v.y, v.z);
     const int b = cell_start[c], e = cell_start[c + 1];
-    for (int i = b + 1; i < e; ++i) {
-      float4 v = sorted[i];
-      int key = __float_as_int(v.w);
-      int j = i - 1;
-      while (j >= b && __float_as_int(sorted[j].w) > key) { sorted[j + 1] = sorted[j]; --j; }
-      sorted[j + 1] = v;
-    }
+    const int key = __float_as_int(v.w);
+    int rank = 0;
+    for (int j = b; j < e; ++j) rank += __float_as_int(__ldg(&scattered[j].w)) < key ? 1 : 0;
+    sorted[b + rank] = v;
   }
 }
 
@@ -515,8 +519,13 @@ int build_cells(ope_ctx* ctx, const float4* pts, size_t n, const Binning& bin, i
     cell_scatter_kernel<<<grid_blocks(ctx, n), kThreads, 0, ctx->stream>>>(pts, (int)n, bin, B, S);
     if ((rc = check_launch(ctx, "cell_scatter_kernel")) != OPE_OK) return bail(rc);
     // now B[c] = start of cell c for c in [0, ncells], B[0] = 0
-    cell_sort_kernel<<<grid_blocks(ctx, (size_t)ncells), kThreads, 0, ctx->stream>>>(B, ncells, S);
-    if ((rc = check_launch(ctx, "cell_sort_kernel")) != OPE_OK) return bail(rc);
+    float4* R = nullptr;
+    if ((rc = dalloc(ctx, &R, n)) != OPE_OK) return bail(rc);
+    cell_rank_kernel<<<grid_blocks(ctx, n), kThreads, 0, ctx->stream>>>(S, B, ncells, bin, R);
+    rc = check_launch(ctx, "cell_rank_kernel");
+    dfree(ctx, S);   // stream-ordered: released after the kernel
+    S = R;
+    if (rc != OPE_OK) return bail(rc);
   }
   *cell_start = B;
   *sorted = S;

@@ -130,41 +130,45 @@ __global__ void gather_points_kernel(const float4* __restrict__ pts, const int* 
   if (i < m) out[i] = __ldg(pts + idx[i]);
 }
 // optimizeModelCoefficients: computeMeanAndCovarianceMatrix accumulates nine FLOAT sums over the inliers IN INDEX ORDER, so the
-// sums are order-dependent: thread a (< 9) carries accumulator a through the whole list sequentially (chunks staged in shared
-// memory by the block), thread 0 finishes with eigen33 and d = -n . centroid. One block.
+// sums are order-dependent and each is one serial chain of additions. The chain is all that stays serial: warps 1.. gather the
+// next chunk of inliers and write its nine term arrays (x*x, x*y, ... z) to shared memory while lanes 0..8 of warp 0 — one per
+// accumulator, the same instruction stream for all nine — add up the current chunk. Thread 0 finishes with eigen33 and
+// d = -n . centroid. One block.
+static constexpr int kRefitChunk = 512;
 __global__ void __launch_bounds__(kSegThreads) plane_refit_kernel(const float4* __restrict__ pts, const int* __restrict__ inliers, int m,
                                                                   const float* __restrict__ in, float* __restrict__ out) {
-  __shared__ float4 stage[kSegThreads * 4];
+  __shared__ float terms[2][9][kRefitChunk + 1];   // + 1: the nine lanes of a step read nine different banks
   __shared__ float accu[9];
-  float acc = 0.0f;
-  for (int base = 0; base < m; base += kSegThreads * 4) {
-    const int cnt = min(kSegThreads * 4, m - base);
-    __syncthreads();
-    for (int j = threadIdx.x; j < cnt; j += kSegThreads) stage[j] = __ldg(pts + inliers[base + j]);
-    __syncthreads();
-    if (threadIdx.x < 9) {
-      const int a = threadIdx.x;
-      for (int j = 0; j < cnt; ++j) {
-        const float4 p = stage[j];
-        float term;
-        switch (a) {
-          case 0: term = p.x * p.x; break;
-          case 1: term = p.x * p.y; break;
-          case 2: term = p.x * p.z; break;
-          case 3: term = p.y * p.y; break;
-          case 4: term = p.y * p.z; break;
-          case 5: term = p.z * p.z; break;
-          case 6: term = p.x; break;
-          case 7: term = p.y; break;
-          default: term = p.z; break;
-        }
-        acc += term;
-      }
+  const int tid = threadIdx.x;
+  auto fill = [&](int chunk) {   // by the threads of warps 1..: terms of chunk `chunk` into its buffer
+    const int base = chunk * kRefitChunk;
+    const int cnt = min(kRefitChunk, m - base);
+    float (*t)[kRefitChunk + 1] = terms[chunk & 1];
+    for (int j = tid - 32; j < cnt; j += kSegThreads - 32) {
+      const float4 p = __ldg(pts + inliers[base + j]);
+      t[0][j] = p.x * p.x; t[1][j] = p.x * p.y; t[2][j] = p.x * p.z;
+      t[3][j] = p.y * p.y; t[4][j] = p.y * p.z; t[5][j] = p.z * p.z;
+      t[6][j] = p.x; t[7][j] = p.y; t[8][j] = p.z;
     }
-  }
-  if (threadIdx.x < 9) accu[threadIdx.x] = acc / (float)m;
+  };
+  const int n_chunks = (m + kRefitChunk - 1) / kRefitChunk;
+  float acc = 0.0f;
+  if (tid >= 32 && n_chunks > 0) fill(0);
   __syncthreads();
-  if (threadIdx.x == 0) {
+  for (int c = 0; c < n_chunks; ++c) {
+    if (tid >= 32) {
+      if (c + 1 < n_chunks) fill(c + 1);
+    } else if (tid < 9) {
+      const int cnt = min(kRefitChunk, m - c * kRefitChunk);
+      const float* t = terms[c & 1][tid];
+#pragma unroll 8
+      for (int j = 0; j < cnt; ++j) acc += t[j];
+    }
+    __syncthreads();
+  }
+  if (tid < 9) accu[tid] = acc / (float)m;
+  __syncthreads();
+  if (tid == 0) {
     if (m < 4) { for (int i = 0; i < 4; ++i) out[i] = in[i]; return; }
     float cov[9];
     cov[0] = accu[0] - accu[6] * accu[6]; cov[1] = accu[1] - accu[6] * accu[7]; cov[2] = accu[2] - accu[6] * accu[8];
