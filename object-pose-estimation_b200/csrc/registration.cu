@@ -2384,8 +2384,15 @@ class LibcRandSession {
 #endif
     return rand();
   }
-  // [UPSTREAM ia_ransac.hpp getRandomIndex]: n * (rand() / (RAND_MAX + 1.0)), truncated
-  inline int index(int n) { return (int)(n * (next() / (RAND_MAX + 1.0))); }
+  // [UPSTREAM ia_ransac.hpp getRandomIndex]: n * (rand() / (RAND_MAX + 1.0)), truncated. With RAND_MAX = 2^31 - 1 and 0 <= n <= 2^21
+  // the double product n * r / 2^31 is exact (at most 52 significant bits), so its truncation is the integer (n * r) >> 31.
+  inline int index(int n) {
+    const int r = next();
+#if RAND_MAX == 2147483647
+    if (n >= 0 && n <= (1 << 21)) return (int)(((long long)n * (long long)r) >> 31);
+#endif
+    return (int)(n * (r / (RAND_MAX + 1.0)));
+  }
 
  private:
 #if defined(__GLIBC__)
@@ -2393,12 +2400,15 @@ class LibcRandSession {
   int32_t* state_ = nullptr;   // null: not borrowed, next() calls rand()
   int32_t *fptr_ = nullptr, *rptr_ = nullptr, *end_ = nullptr;
   int type_ = 0;
-  alignas(8) char parked_[128];   // the state libc uses while its own is borrowed (nobody draws from it)
 
   bool begin() {
     static const int kDeg[5] = {0, 7, 15, 31, 63}, kSep[5] = {0, 3, 1, 3, 1};
     borrow_mutex().lock();   // one borrower at a time (concurrent drawers would interleave their numbers anyway)
-    char* prev = initstate(1u, parked_, sizeof(parked_));
+    // the state libc runs on while its own is borrowed (nobody draws from it): seeded once, switched to with setstate() afterwards
+    alignas(8) static char parked[128];
+    static bool parked_ready = false;
+    char* prev = parked_ready ? setstate(parked) : initstate(1u, parked, sizeof(parked));
+    parked_ready = true;
     if (!prev) { borrow_mutex().unlock(); return false; }
     word_ = reinterpret_cast<int32_t*>(prev);
     type_ = word_[0] % 5;
